@@ -1,0 +1,204 @@
+/* vlfs_b200.h - C ABI of the B200-native assembly + solve path for the monolithic
+ * potential-flow / beam / plate weak forms of MonolithicFEMVLFS.jl.
+ *
+ * This is the drop-in boundary behind the Gridap surface the reference calls:
+ *   AffineFEOperator(a,l,X,Y)            src/Yago_freq_domain.jl:167, src/Multi_geo_freq_domain.jl:131,
+ *                                        src/Khabakhpasheva_freq_domain.jl:240
+ *   solve(op)                            src/Yago_freq_domain.jl:171, src/Khabakhpasheva_freq_domain.jl:241
+ *   TransientConstant[Matrix]FEOperator  src/Khabakhpasheva_time_domain.jl:257, src/Periodic_Beam.jl:104
+ *   Newmark(LUSolver(),dt,γ,β) + solve   src/Khabakhpasheva_time_domain.jl:258-266, src/Periodic_Beam.jl:107-116
+ *
+ * The host (Julia shim through `ccall`, or the Python mirror through ctypes) hands over
+ * TABLES - cell coordinates, cell->DOF maps, face->cell glue selectors, reference
+ * shape-function tables at the quadrature points, coefficient fields sampled at the
+ * quadrature points - and a list of TERMS; the library integrates on the GPU, builds the
+ * CSR pattern, scatters, multiplies and solves.  There is no CPU fallback: every compute
+ * entry point fails with VLFS_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Conventions
+ *   - all indices 0-based int32 (DOF ids carry the multi-field offset already);
+ *   - complex numbers are interleaved (re,im) doubles (Julia ComplexF64 / cuDoubleComplex);
+ *   - the caller owns every host buffer; the library copies during the call and never
+ *     keeps a host pointer after returning; all device memory lives behind vlfs_ctx;
+ *   - every function returns a status: 0 ok, <0 argument error, >0 runtime class
+ *     (VLFS_ERR_CUDA, VLFS_ERR_NCCL); VLFS_NOT_CONVERGED is a status, not a failure;
+ *   - one in-flight call per context; no callbacks; no exceptions cross the boundary.
+ */
+#ifndef VLFS_B200_H
+#define VLFS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLFS_OK 0
+#define VLFS_ERR_ARG (-1)
+#define VLFS_ERR_STATE (-2)
+#define VLFS_ERR_CUDA 1
+#define VLFS_ERR_NCCL 2
+#define VLFS_NOT_CONVERGED 3
+
+#define VLFS_MAX_SLOTS 2
+
+/* Operators applied to a basis function at a quadrature point (Gridap: v, ∇(v), ∇(ϕ)⋅e,
+ * Δ(v), ∇∇(v), C⊙∇∇(η), ∇(v)⋅nΛ, (C⊙∇∇(η))⋅nΛ.⁺).  Number of components in brackets,
+ * D = ambient dimension, S = D(D+1)/2. */
+enum {
+  VLFS_OP_VAL = 0,         /* [1] value                                             */
+  VLFS_OP_GRAD = 1,        /* [D] physical gradient                                 */
+  VLFS_OP_DDIR = 2,        /* [1] gradient . dir   (∇ₙ(ϕ) = ∇(ϕ)⋅VectorValue(0,0,1))  */
+  VLFS_OP_LAPL = 3,        /* [1] Laplacian = tr(∇∇)                                */
+  VLFS_OP_HESS = 4,        /* [S] symmetric Hessian components                       */
+  VLFS_OP_CHESS = 5,       /* [S] C⊙∇∇ with the off-diagonal multiplicity folded in,   */
+                           /*     so that HESS . CHESS = ∇∇(v)⊙(C⊙∇∇(η))             */
+  VLFS_OP_GRAD_NOWN = 6,   /* [1] gradient . outward normal of the slot's own cell   */
+  VLFS_OP_CHESS_NPLUS = 7, /* [D] (C⊙∇∇) . outward normal of slot 0's cell           */
+  VLFS_OP_COUNT = 8
+};
+
+enum { VLFS_MEASURE_CELL = 0,   /* sqrt(det(Jt Jt^T)) of the measure slot's cell     */
+       VLFS_MEASURE_FACET = 1   /* |Jt^T t_ref| of the local facet (skeletons; 1 for points) */ };
+
+/* One field (or one side of a skeleton) seen from an integration domain.  The basis lives
+ * in the reference space of `geometry cells` given by `coords`; `variant` selects the
+ * table set per integration cell (local face of the glued volume cell, local edge of the
+ * surface cell on a skeleton); NULL = variant 0. */
+typedef struct {
+  int32_t dref;              /* reference dimension of the geometry cells             */
+  int32_t nv;                /* geometry nodes per cell                               */
+  int32_t nvar;              /* number of table variants                              */
+  int32_t ndofs;             /* local DOFs                                            */
+  const double* coords;      /* [ncells][nv][D]                                       */
+  const int32_t* variant;    /* [ncells] or NULL                                      */
+  const double* geo_grad;    /* [nvar][nq][nv][dref]   reference gradients of the map */
+  const double* val;         /* [nvar][nq][ndofs]                                     */
+  const double* grad;        /* [nvar][nq][ndofs][dref]                               */
+  const double* hess;        /* [nvar][nq][ndofs][dref][dref] or NULL                 */
+  const int32_t* dofs;       /* [ncells][ndofs] global DOF ids                        */
+  const double* ref_normal;  /* [nvar][dref] or NULL (outward reference facet normal) */
+  const double* ref_tangent; /* [nvar][dref] or NULL (reference facet edge vector)    */
+} vlfs_slot_desc;
+
+/* One integration domain = triangulation + measure (Gridap `Measure(trian,degree)`). */
+typedef struct {
+  int32_t D;                 /* ambient dimension                                     */
+  int32_t nq;                /* quadrature points per cell                            */
+  int32_t nslots;            /* 1..VLFS_MAX_SLOTS                                     */
+  int32_t measure_slot;      /* slot whose geometry defines the measure               */
+  int32_t measure_kind;      /* VLFS_MEASURE_*                                        */
+  int32_t nweights;          /* number of coefficient fields                          */
+  int32_t affine;            /* 1: every cell has a constant Jacobian (enables the    */
+                             /*    reference-matrix fast path); 0: general quadrature */
+  int64_t ncells;
+  const double* qweights;    /* [nq]                                                  */
+  const double* weights;     /* [nweights][ncells][nq] coefficient fields at the points */
+  const double* C;           /* [D][D][D][D] or NULL                                  */
+  vlfs_slot_desc slot[VLFS_MAX_SLOTS];
+} vlfs_domain_desc;
+
+/* One bilinear term:  mat += coef * ∫ weight(x) (scale_t . OP_t(test)) . (scale_u . OP_u(trial)) dμ.
+ * The local DOF vector of a domain is the concatenation of its slots; a slot with scale 0
+ * is not touched by the factor.  Touched (test slot, trial slot) blocks are stored in full,
+ * explicit zeros included (Gridap block semantics). */
+typedef struct {
+  int32_t mat;               /* target matrix                                         */
+  int32_t weight;            /* -1 or coefficient-field index                         */
+  double coef_re, coef_im;
+  int32_t test_op, trial_op;
+  double test_scale[VLFS_MAX_SLOTS];
+  double trial_scale[VLFS_MAX_SLOTS];
+  double test_dir[3], trial_dir[3];   /* for VLFS_OP_DDIR                             */
+} vlfs_term_desc;
+
+/* One linear term:  vec += coef * ∫ (w_re + i w_im)(x) (scale . OP(test)) dμ. */
+typedef struct {
+  int32_t vec;               /* target right-hand-side vector                         */
+  int32_t weight_re, weight_im;  /* coefficient-field indices, -1 = absent (1 / 0)    */
+  double coef_re, coef_im;
+  int32_t op;
+  double scale[VLFS_MAX_SLOTS];
+  double dir[3];
+} vlfs_rhs_desc;
+
+typedef struct {
+  int32_t method;            /* VLFS_SOLVER_*                                         */
+  int32_t precond;           /* VLFS_PRECOND_*                                        */
+  int32_t restart;           /* GMRES restart length                                  */
+  int32_t maxit;
+  double rtol;               /* on the true relative residual |b-Ax|/|b|               */
+  int32_t block_size_hint;   /* block-Jacobi / ILU sweeps parameter                   */
+  int32_t sweeps;
+} vlfs_solver_opts;
+
+typedef struct {
+  int32_t iterations;
+  int32_t converged;
+  double rel_residual;
+  double setup_ms, solve_ms;
+} vlfs_solve_stats;
+
+enum { VLFS_SOLVER_GMRES = 0, VLFS_SOLVER_BICGSTAB = 1, VLFS_SOLVER_CG = 2 };
+enum { VLFS_PRECOND_NONE = 0, VLFS_PRECOND_JACOBI = 1, VLFS_PRECOND_BLOCK_ILU0 = 2 };
+
+typedef struct vlfs_ctx vlfs_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int vlfs_version(void);
+int vlfs_device_count(int* n);
+int vlfs_create(vlfs_ctx** ctx, int device);
+int vlfs_destroy(vlfs_ctx* ctx);
+const char* vlfs_last_error(const vlfs_ctx* ctx);
+
+/* ---- problem definition (replaces MultiFieldFESpace + the weak-form closures) ------ */
+/* ndofs: size of the monolithic system; is_complex: vector_type=Vector{ComplexF64};
+ * nmat: matrices sharing one union pattern (1: A;  3: K,C,M of the transient operators);
+ * nvec: right-hand-side vectors. */
+int vlfs_system_init(vlfs_ctx* ctx, int64_t ndofs, int is_complex, int nmat, int nvec);
+int vlfs_add_domain(vlfs_ctx* ctx, const vlfs_domain_desc* desc, int* domain_id);
+int vlfs_add_term(vlfs_ctx* ctx, int domain_id, const vlfs_term_desc* term, int* term_id);
+int vlfs_add_rhs_term(vlfs_ctx* ctx, int domain_id, const vlfs_rhs_desc* term, int* term_id);
+/* frequency sweeps change scalars and coefficient fields only */
+int vlfs_set_term_coef(vlfs_ctx* ctx, int domain_id, int term_id, double re, double im);
+int vlfs_set_rhs_coef(vlfs_ctx* ctx, int domain_id, int term_id, double re, double im);
+int vlfs_set_weights(vlfs_ctx* ctx, int domain_id, int weight, const double* values);
+
+/* ---- SparseMatrixAssembler: symbolic + numeric ------------------------------------ */
+int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo);
+int vlfs_get_pattern(vlfs_ctx* ctx, int32_t* rowptr, int32_t* colind);           /* CSR   */
+int vlfs_get_pattern_csc(vlfs_ctx* ctx, int32_t* colptr, int32_t* rowval, int32_t* csr_slot);
+int vlfs_assemble(vlfs_ctx* ctx);                      /* all matrices and vectors        */
+int vlfs_assemble_matrices(vlfs_ctx* ctx);
+int vlfs_assemble_vectors(vlfs_ctx* ctx);
+int vlfs_get_values(vlfs_ctx* ctx, int mat, void* values);   /* [nnz] real or complex    */
+int vlfs_get_vector(vlfs_ctx* ctx, int vec, void* values);   /* [ndofs]                  */
+/* mat[target] = sum_k coef[k] * mat[src[k]]   (Newmark: K + γ/(βΔt) C + 1/(βΔt²) M)       */
+int vlfs_combine(vlfs_ctx* ctx, int target, int n, const int* src, const double* coef_re_im);
+
+/* ---- algebra -------------------------------------------------------------------- */
+int vlfs_spmv(vlfs_ctx* ctx, int mat, const void* x, void* y);         /* host in/out   */
+int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts);
+int vlfs_solve(vlfs_ctx* ctx, const void* b, void* x, vlfs_solve_stats* stats);   /* host */
+int vlfs_solve_vec(vlfs_ctx* ctx, int vec, void* x, vlfs_solve_stats* stats); /* assembled rhs */
+
+/* ---- Newmark(ls,dt,γ,β) on a constant operator -------------------------------------
+ * Solves (K + γ/(βΔt) C + 1/(βΔt²) M) u_{n+1} = Σ_m g_m(t_{n+1}) b_m - C v* - M a*  for
+ * nsteps steps; mats = {K,C,M} indices, rhs vectors b_m are the assembled vectors 0..nb-1,
+ * tcoef[nsteps][nb] their time factors.  out receives the DOFs [out_lo,out_hi) of every
+ * `out_stride`-th step.  u0,v0,a0 are updated in place to the final state. */
+int vlfs_newmark_run(vlfs_ctx* ctx, int matK, int matC, int matM, int nsteps, double dt,
+                     double gamma, double beta, int nb, const double* tcoef,
+                     double* u0, double* v0, double* a0,
+                     int64_t out_lo, int64_t out_hi, int out_stride, double* out,
+                     vlfs_solve_stats* stats);
+
+/* ---- device-resident benchmarking hooks (no host copies) --------------------------- */
+int vlfs_spmv_device(vlfs_ctx* ctx, int mat, int reps, float* ms_total);
+int vlfs_assemble_timed(vlfs_ctx* ctx, int reps, float* ms_total);
+int vlfs_last_kernel_launches(vlfs_ctx* ctx, int64_t* n);
+int vlfs_device_ptrs(vlfs_ctx* ctx, int mat, void** rowptr, void** colind, void** values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,271 @@
+"""Host-side assembler/operator objects over the C ABI.
+
+`B200System` plays the role of Gridap's `SparseMatrixAssembler(X,Y)` + `AffineFEOperator`
++ `LinearFESolver` for the reference's hot path (src/Yago_freq_domain.jl:167-171,
+src/Khabakhpasheva_time_domain.jl:257-266): it registers integration domains and terms,
+builds the CSR pattern on the GPU, assembles, multiplies and solves.  All arithmetic is in
+libvlfs_b200.so; this file only marshals tables.
+"""
+import ctypes as C
+import numpy as np
+import scipy.sparse as sp
+from . import _lib as L
+
+
+def is_affine(coords, poly):
+    """True when every cell has a constant Jacobian (simplices; parallelotopes)."""
+    if poly.is_simplex or poly.dim <= 1:
+        return True
+    X = coords
+    x0 = X[:, 0]
+    edges = [X[:, 1 << a] - x0 for a in range(poly.dim)]
+    scale = max(float(np.abs(X - x0[:, None, :]).max()), 1e-300)
+    for v, c in enumerate(poly.verts):
+        pred = x0 + sum(c[a] * edges[a] for a in range(poly.dim))
+        if np.abs(pred - X[:, v]).max() > 1e-12 * scale:
+            return False
+    return True
+
+
+class Domain:
+    def __init__(self, system, did, nslots, D):
+        self.system, self.id, self.nslots, self.D = system, did, nslots, D
+        self.nterms = 0
+        self.nrhs = 0
+
+    def _scales(self, spec):
+        out = (C.c_double * L.MAX_SLOTS)()
+        if isinstance(spec, dict):
+            for k, v in spec.items():
+                out[k] = float(v)
+        else:
+            out[int(spec)] = 1.0
+        return out
+
+    def add_term(self, mat, coef, test_op, test_slots, trial_op, trial_slots, weight=-1,
+                 test_dir=(0, 0, 0), trial_dir=(0, 0, 0)):
+        """mat += coef ∫ w (Σ_s scale_s OP_test)(Σ_s scale_s OP_trial) dμ; *_slots is a slot
+        index or a {slot: scale} dict (skeleton jumps/means)."""
+        t = L.TermDesc()
+        t.mat, t.weight = mat, weight
+        t.coef_re, t.coef_im = float(np.real(coef)), float(np.imag(coef))
+        t.test_op, t.trial_op = test_op, trial_op
+        t.test_scale, t.trial_scale = self._scales(test_slots), self._scales(trial_slots)
+        t.test_dir = (C.c_double * 3)(*[float(v) for v in test_dir])
+        t.trial_dir = (C.c_double * 3)(*[float(v) for v in trial_dir])
+        tid = C.c_int(-1)
+        self.system._check(self.system.lib.vlfs_add_term(self.system.ctx, self.id, C.byref(t), C.byref(tid)))
+        self.nterms += 1
+        return tid.value
+
+    def add_rhs(self, vec, coef, op, slots, weight_re=-1, weight_im=-1, direction=(0, 0, 0)):
+        r = L.RhsDesc()
+        r.vec, r.weight_re, r.weight_im = vec, weight_re, weight_im
+        r.coef_re, r.coef_im = float(np.real(coef)), float(np.imag(coef))
+        r.op = op
+        r.scale = self._scales(slots)
+        r.dir = (C.c_double * 3)(*[float(v) for v in direction])
+        tid = C.c_int(-1)
+        self.system._check(self.system.lib.vlfs_add_rhs_term(self.system.ctx, self.id, C.byref(r), C.byref(tid)))
+        self.nrhs += 1
+        return tid.value
+
+    def set_coef(self, term, coef):
+        self.system._check(self.system.lib.vlfs_set_term_coef(
+            self.system.ctx, self.id, term, float(np.real(coef)), float(np.imag(coef))))
+
+    def set_rhs_coef(self, term, coef):
+        self.system._check(self.system.lib.vlfs_set_rhs_coef(
+            self.system.ctx, self.id, term, float(np.real(coef)), float(np.imag(coef))))
+
+    def set_weights(self, index, values):
+        v = L.f64(values)
+        self.system._check(self.system.lib.vlfs_set_weights(self.system.ctx, self.id, index, L.dptr(v)))
+
+
+class B200System:
+    def __init__(self, ndofs, is_complex, nmat=1, nvec=1, device=0):
+        self.lib = L.load()
+        self.ctx = C.c_void_p()
+        rc = self.lib.vlfs_create(C.byref(self.ctx), device)
+        if rc != 0:
+            raise L.VlfsError("vlfs_create failed (status %d): no usable sm_100 GPU; the B200 "
+                              "path has no CPU fallback" % rc)
+        self.ndofs, self.is_complex, self.nmat, self.nvec = int(ndofs), bool(is_complex), nmat, nvec
+        self.dtype = np.complex128 if is_complex else np.float64
+        self._check(self.lib.vlfs_system_init(self.ctx, self.ndofs, int(self.is_complex), nmat, nvec))
+        self.nnz = None
+        self.ncoo = None
+        self.domains = []
+        self._pattern = None
+
+    def close(self):
+        if self.ctx:
+            self.lib.vlfs_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, allow=(0,)):
+        if rc not in allow:
+            msg = self.lib.vlfs_last_error(self.ctx)
+            raise L.VlfsError("libvlfs_b200 status %d: %s" % (rc, msg.decode() if msg else ""))
+        return rc
+
+    # ------------------------------------------------------------------------------
+    def add_domain(self, D, nq, qweights, slots, measure_slot=0, measure_kind=L.MEASURE_CELL,
+                   weights=(), Ctensor=None, affine=False):
+        """slots: list of dicts produced by fe.Measure.*_slot."""
+        d = L.DomainDesc()
+        keep = []
+        ncells = len(slots[0]["dofs"])
+        d.D, d.nq, d.nslots = D, nq, len(slots)
+        d.measure_slot, d.measure_kind = measure_slot, measure_kind
+        d.nweights, d.affine, d.ncells = len(weights), int(bool(affine)), ncells
+        qw = L.f64(qweights); keep.append(qw)
+        d.qweights = L.dptr(qw)
+        if len(weights):
+            w = L.f64(np.stack([np.asarray(x, dtype=np.float64).reshape(ncells, nq) for x in weights]))
+            keep.append(w)
+            d.weights = L.dptr(w)
+        if Ctensor is not None:
+            ct = L.f64(Ctensor); keep.append(ct)
+            assert ct.size == D ** 4
+            d.C = L.dptr(ct)
+        for k, s in enumerate(slots):
+            sd = d.slot[k]
+            sd.dref, sd.nv, sd.nvar, sd.ndofs = s["dref"], s["nv"], s["nvar"], s["ndofs"]
+            arrs = {}
+            for name in ("coords", "geo_grad", "val", "grad", "hess", "ref_normal", "ref_tangent"):
+                arrs[name] = L.f64(s[name]) if s.get(name) is not None else None
+            for name in ("variant", "dofs"):
+                arrs[name] = L.i32(s[name]) if s.get(name) is not None else None
+            assert arrs["coords"].shape == (ncells, sd.nv, D), (arrs["coords"].shape, ncells, sd.nv, D)
+            assert arrs["dofs"].shape == (ncells, sd.ndofs)
+            assert arrs["val"].shape == (sd.nvar, nq, sd.ndofs)
+            assert arrs["grad"].shape == (sd.nvar, nq, sd.ndofs, sd.dref)
+            assert arrs["geo_grad"].shape == (sd.nvar, nq, sd.nv, sd.dref)
+            if arrs["hess"] is not None:
+                assert arrs["hess"].shape == (sd.nvar, nq, sd.ndofs, sd.dref, sd.dref)
+            keep.append(arrs)
+            sd.coords, sd.geo_grad, sd.val = L.dptr(arrs["coords"]), L.dptr(arrs["geo_grad"]), L.dptr(arrs["val"])
+            sd.grad, sd.hess = L.dptr(arrs["grad"]), L.dptr(arrs["hess"])
+            sd.ref_normal, sd.ref_tangent = L.dptr(arrs["ref_normal"]), L.dptr(arrs["ref_tangent"])
+            sd.variant, sd.dofs = L.iptr(arrs["variant"]), L.iptr(arrs["dofs"])
+        did = C.c_int(-1)
+        self._check(self.lib.vlfs_add_domain(self.ctx, C.byref(d), C.byref(did)))
+        dom = Domain(self, did.value, len(slots), D)
+        dom.ncells, dom.nq = ncells, nq
+        self.domains.append(dom)
+        return dom
+
+    # ------------------------------------------------------------------------------
+    def build_pattern(self):
+        nnz, ncoo = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.vlfs_build_pattern(self.ctx, C.byref(nnz), C.byref(ncoo)))
+        self.nnz, self.ncoo = nnz.value, ncoo.value
+        return self.nnz
+
+    def get_pattern(self):
+        if self._pattern is None:
+            rp = np.empty(self.ndofs + 1, dtype=np.int32)
+            ci = np.empty(self.nnz, dtype=np.int32)
+            self._check(self.lib.vlfs_get_pattern(self.ctx, L.iptr(rp), L.iptr(ci)))
+            self._pattern = (rp, ci)
+        return self._pattern
+
+    def get_pattern_csc(self):
+        cp = np.empty(self.ndofs + 1, dtype=np.int32)
+        rv = np.empty(self.nnz, dtype=np.int32)
+        sl = np.empty(self.nnz, dtype=np.int32)
+        self._check(self.lib.vlfs_get_pattern_csc(self.ctx, L.iptr(cp), L.iptr(rv), L.iptr(sl)))
+        return cp, rv, sl
+
+    def assemble(self, matrices=True, vectors=True):
+        if matrices and vectors:
+            self._check(self.lib.vlfs_assemble(self.ctx))
+        elif matrices:
+            self._check(self.lib.vlfs_assemble_matrices(self.ctx))
+        elif vectors:
+            self._check(self.lib.vlfs_assemble_vectors(self.ctx))
+
+    def get_values(self, mat=0):
+        v = np.empty(self.nnz, dtype=self.dtype)
+        self._check(self.lib.vlfs_get_values(self.ctx, mat, v.ctypes.data_as(C.c_void_p)))
+        return v
+
+    def get_matrix(self, mat=0):
+        """CSR matrix (explicit zeros kept), the `get_matrix(op)` of the reference."""
+        rp, ci = self.get_pattern()
+        return sp.csr_matrix((self.get_values(mat), ci.copy(), rp.copy()), shape=(self.ndofs, self.ndofs))
+
+    def get_vector(self, vec=0):
+        v = np.empty(self.ndofs, dtype=self.dtype)
+        self._check(self.lib.vlfs_get_vector(self.ctx, vec, v.ctypes.data_as(C.c_void_p)))
+        return v
+
+    def combine(self, target, sources, coefs):
+        src = L.i32(sources)
+        cf = np.zeros(2 * len(sources))
+        cf[0::2] = np.real(coefs)
+        cf[1::2] = np.imag(coefs)
+        self._check(self.lib.vlfs_combine(self.ctx, target, len(sources), L.iptr(src), L.dptr(cf)))
+
+    def spmv(self, x, mat=0):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        y = np.empty_like(x)
+        self._check(self.lib.vlfs_spmv(self.ctx, mat, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)))
+        return y
+
+    def solver_setup(self, mat=0, method=L.SOLVER_GMRES, precond=L.PRECOND_JACOBI, restart=100,
+                     maxit=5000, rtol=1e-10, block_size_hint=0, sweeps=0):
+        o = L.SolverOpts(method, precond, restart, maxit, rtol, block_size_hint, sweeps)
+        self._check(self.lib.vlfs_solver_setup(self.ctx, mat, C.byref(o)))
+
+    def solve(self, b=None, vec=0, x0=None):
+        x = np.zeros(self.ndofs, dtype=self.dtype) if x0 is None else np.ascontiguousarray(x0, dtype=self.dtype).copy()
+        st = L.SolveStats()
+        if b is None:
+            rc = self.lib.vlfs_solve_vec(self.ctx, vec, x.ctypes.data_as(C.c_void_p), C.byref(st))
+        else:
+            b = np.ascontiguousarray(b, dtype=self.dtype)
+            rc = self.lib.vlfs_solve(self.ctx, b.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), C.byref(st))
+        self._check(rc, allow=(0, L.NOT_CONVERGED))
+        return x, dict(iterations=st.iterations, converged=bool(st.converged), rel_residual=st.rel_residual,
+                       setup_ms=st.setup_ms, solve_ms=st.solve_ms)
+
+    def newmark_run(self, matK, matC, matM, nsteps, dt, gamma, beta, tcoef, u0, v0, a0,
+                    out_range=(0, 0), out_stride=1):
+        tc = L.f64(tcoef).reshape(nsteps, -1) if tcoef is not None and np.size(tcoef) else np.zeros((nsteps, 0))
+        nb = tc.shape[1]
+        u, v, a = (np.ascontiguousarray(z, dtype=np.float64).copy() for z in (u0, v0, a0))
+        lo, hi = out_range
+        nout = nsteps // out_stride
+        out = np.zeros((nout, hi - lo))
+        st = L.SolveStats()
+        rc = self.lib.vlfs_newmark_run(self.ctx, matK, matC, matM, nsteps, dt, gamma, beta, nb,
+                                       L.dptr(tc) if nb else None, L.dptr(u), L.dptr(v), L.dptr(a),
+                                       lo, hi, out_stride, L.dptr(out) if hi > lo else None, C.byref(st))
+        self._check(rc, allow=(0, L.NOT_CONVERGED))
+        return u, v, a, out, dict(iterations=st.iterations, converged=bool(st.converged),
+                                  rel_residual=st.rel_residual, solve_ms=st.solve_ms)
+
+    # device-resident timing hooks
+    def spmv_device_ms(self, mat=0, reps=10):
+        ms = C.c_float(0)
+        self._check(self.lib.vlfs_spmv_device(self.ctx, mat, reps, C.byref(ms)))
+        return ms.value / reps
+
+    def assemble_device_ms(self, reps=1):
+        ms = C.c_float(0)
+        self._check(self.lib.vlfs_assemble_timed(self.ctx, reps, C.byref(ms)))
+        return ms.value / reps
+
+    def launches(self):
+        n = C.c_int64(0)
+        self.lib.vlfs_last_kernel_launches(self.ctx, C.byref(n))
+        return n.value

@@ -1,0 +1,691 @@
+// api.cu - C ABI of libvlfs_b200 (see include/vlfs_b200.h for the reference interfaces
+// each entry point replaces).  Host-side bookkeeping only; every byte of arithmetic runs in
+// the kernels of integrate.cu / pattern.cu / spmv.cu / krylov.cu.
+#include "common.cuh"
+#include "solver.cuh"
+#include <cstring>
+#include <memory>
+
+void build_pattern_device(const std::vector<DomainDev>& doms, long long ndofs,
+                          DevBuf<int>& rowptr, DevBuf<int>& colind, DevBuf<int>& rowind,
+                          DevBuf<int>& dest_all, std::vector<long long>& dest_off,
+                          long long* nnz_out, long long* ncoo_out, cudaStream_t s,
+                          long long* launches);
+void build_csc_device(const int* rowind, const int* colind, long long nnz, long long ndofs,
+                      DevBuf<int>& colptr, DevBuf<int>& rowval, DevBuf<int>& csr_slot,
+                      cudaStream_t s, long long* launches);
+void launch_integrate(const DomainDev& dom, const TermDev* terms_dev, int nterms,
+                      const RhsDev* rhs_dev, int nrhs, const int* dest, double* const* mats,
+                      int nmat, double* const* vecs, int nvec, int is_complex, int do_mat,
+                      int do_vec, int nsm, cudaStream_t s);
+void launch_gradgrad_reference(const DomainDev& dom, double* Sref, cudaStream_t s);
+void launch_gradgrad_affine(const DomainDev& dom, const double* Sref, const int* dest, double* vals,
+                            int is_complex, double cre, double cim, int nsm, cudaStream_t s);
+void launch_spmv(const int* rowptr, const int* colind, const void* vals, const void* x, void* y,
+                 long long nrows, long long nnz, int is_complex, const double* alpha,
+                 const double* beta, int nsm, cudaStream_t s);
+void launch_axpby_vals(double* target, size_t n, int nsrc, double* const* src,
+                       const double* coef_re_im, int is_complex, cudaStream_t s);
+
+namespace {
+
+int op_ncomp(int op, int D) {
+  switch (op) {
+    case VLFS_OP_VAL: case VLFS_OP_DDIR: case VLFS_OP_LAPL: case VLFS_OP_GRAD_NOWN: return 1;
+    case VLFS_OP_GRAD: case VLFS_OP_CHESS_NPLUS: return D;
+    case VLFS_OP_HESS: case VLFS_OP_CHESS: return D * (D + 1) / 2;
+  }
+  return -1;
+}
+bool op_needs_hess(int op) {
+  return op == VLFS_OP_LAPL || op == VLFS_OP_HESS || op == VLFS_OP_CHESS || op == VLFS_OP_CHESS_NPLUS;
+}
+
+struct SlotStore {
+  DevBuf<double> coords, geo_grad, val, grad, hess, ref_normal, ref_tangent;
+  DevBuf<int> variant, dofs;
+};
+
+struct Domain {
+  vlfs_domain_desc desc;      // scalar fields only are meaningful after add
+  DomainDev dev{};
+  SlotStore st[VLFS_MAX_SLOTS];
+  DevBuf<double> qweights, weights, C;
+  std::vector<vlfs_term_desc> terms;
+  std::vector<vlfs_rhs_desc> rhs;
+  std::vector<TermDev> terms_host;
+  std::vector<RhsDev> rhs_host;
+  std::vector<char> term_fast;      // handled by the reference-matrix fast path
+  DevBuf<TermDev> terms_dev;
+  DevBuf<RhsDev> rhs_dev;
+  DevBuf<double> Sref;
+  bool finalized = false;
+  bool coef_dirty = true;
+};
+
+}  // namespace
+
+struct vlfs_ctx {
+  int device = 0;
+  int nsm = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long ndofs = 0;
+  int is_complex = 0, nmat = 0, nvec = 0;
+  std::vector<std::unique_ptr<Domain>> doms;
+  bool pattern_built = false;
+  long long nnz = 0, ncoo = 0;
+  DevBuf<int> rowptr, colind, rowind, dest_all;
+  std::vector<long long> dest_off;
+  std::vector<DevBuf<double>> mats, vecs;
+  long long launches = 0;
+  SolverPtr solver;
+  size_t scalar() const { return is_complex ? 2 : 1; }
+};
+
+namespace {
+
+int fail(vlfs_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+template <typename F>
+int guarded(vlfs_ctx* ctx, F&& f) {
+  if (!ctx) return VLFS_ERR_ARG;
+  try {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) throw CudaError{e, __FILE__, __LINE__};
+    return f();
+  } catch (const CudaError& ce) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d", (int)ce.e, cudaGetErrorString(ce.e),
+             ce.file, ce.line);
+    cudaGetLastError();
+    return fail(ctx, VLFS_ERR_CUDA, buf);
+  } catch (const std::string& s) {
+    return fail(ctx, VLFS_ERR_STATE, s);
+  } catch (const std::bad_alloc&) {
+    return fail(ctx, VLFS_ERR_STATE, "host allocation failed");
+  } catch (...) {
+    return fail(ctx, VLFS_ERR_STATE, "unknown failure");
+  }
+}
+
+int find_or_add_opi(DomainDev& dev, int slot, int op, const double* dir, int D) {
+  for (int o = 0; o < dev.nopi; ++o) {
+    const OpInst& O = dev.opi[o];
+    if (O.slot == slot && O.op == op &&
+        (op != VLFS_OP_DDIR || (O.dir[0] == dir[0] && O.dir[1] == dir[1] && O.dir[2] == dir[2])))
+      return o;
+  }
+  if (dev.nopi >= VLFS_MAX_OPINST) throw std::string("too many distinct operators in one domain");
+  OpInst& O = dev.opi[dev.nopi];
+  O.slot = slot; O.op = op; O.ncomp = op_ncomp(op, D);
+  for (int k = 0; k < 3; ++k) O.dir[k] = dir ? dir[k] : 0.0;
+  O.smem_off = 0;
+  return dev.nopi++;
+}
+
+// derive operator instances, touched blocks, shared-memory layout, device term tables
+void finalize_domain(vlfs_ctx* ctx, Domain& d) {
+  DomainDev& dev = d.dev;
+  const int D = dev.D;
+  dev.nopi = 0;
+  d.terms_host.clear();
+  d.rhs_host.clear();
+  d.term_fast.assign(d.terms.size(), 0);
+  bool touched[VLFS_MAX_SLOTS][VLFS_MAX_SLOTS] = {};
+  for (size_t t = 0; t < d.terms.size(); ++t) {
+    const vlfs_term_desc& T = d.terms[t];
+    int nslots_t = 0, nslots_u = 0;
+    for (int s = 0; s < dev.nslots; ++s) { nslots_t += T.test_scale[s] != 0.0; nslots_u += T.trial_scale[s] != 0.0; }
+    bool fast = dev.affine && T.weight < 0 && T.test_op == VLFS_OP_GRAD && T.trial_op == VLFS_OP_GRAD &&
+                dev.nslots == 1 && dev.slot[0].dref == D && dev.slot[0].nvar == 1 &&
+                dev.slot[0].ndofs * dev.slot[0].ndofs <= 1024;
+    d.term_fast[t] = fast;
+    TermDev td{};
+    td.mat = T.mat; td.weight = T.weight; td.cre = T.coef_re; td.cim = T.coef_im;
+    td.ncomp = op_ncomp(T.test_op, D);
+    for (int s = 0; s < VLFS_MAX_SLOTS; ++s) {
+      td.opi_test[s] = td.opi_trial[s] = -1;
+      td.st[s] = td.su[s] = 0.0;
+    }
+    for (int s = 0; s < dev.nslots; ++s) {
+      if (T.test_scale[s] != 0.0) {
+        td.st[s] = T.test_scale[s];
+        if (!fast) td.opi_test[s] = find_or_add_opi(dev, s, T.test_op, T.test_dir, D);
+      }
+      if (T.trial_scale[s] != 0.0) {
+        td.su[s] = T.trial_scale[s];
+        if (!fast) td.opi_trial[s] = find_or_add_opi(dev, s, T.trial_op, T.trial_dir, D);
+      }
+      for (int u = 0; u < dev.nslots; ++u)
+        if (T.test_scale[s] != 0.0 && T.trial_scale[u] != 0.0) touched[s][u] = true;
+    }
+    if (!fast) d.terms_host.push_back(td);
+  }
+  for (const vlfs_rhs_desc& R : d.rhs) {
+    RhsDev rd{};
+    rd.vec = R.vec; rd.wre = R.weight_re; rd.wim = R.weight_im; rd.cre = R.coef_re; rd.cim = R.coef_im;
+    rd.ncomp = 1;
+    for (int s = 0; s < VLFS_MAX_SLOTS; ++s) { rd.opi[s] = -1; rd.sc[s] = 0.0; }
+    for (int s = 0; s < dev.nslots; ++s)
+      if (R.scale[s] != 0.0) {
+        rd.sc[s] = R.scale[s];
+        rd.opi[s] = find_or_add_opi(dev, s, R.op, R.dir, D);
+      }
+    d.rhs_host.push_back(rd);
+  }
+  // blocks in (test slot, trial slot) order
+  dev.nblocks = 0;
+  int off = 0;
+  for (int s = 0; s < dev.nslots; ++s)
+    for (int u = 0; u < dev.nslots; ++u)
+      if (touched[s][u]) {
+        BlockDev& B = dev.blk[dev.nblocks++];
+        B.ts = s; B.us = u; B.nr = dev.slot[s].ndofs; B.nc = dev.slot[u].ndofs; B.off = off;
+        off += B.nr * B.nc;
+      }
+  dev.entries_per_cell = off;
+  // shared memory layout (doubles)
+  int p = dev.nslots * dev.nq * 12;
+  dev.smem_meas_off = p; p += dev.nq;
+  dev.smem_w_off = p; p += dev.nweights * dev.nq;
+  for (int o = 0; o < dev.nopi; ++o) {
+    OpInst& O = dev.opi[o];
+    if (op_needs_hess(O.op) && !dev.slot[O.slot].hess)
+      throw std::string("a second-derivative operator needs the slot's hess table");
+    if ((O.op == VLFS_OP_CHESS || O.op == VLFS_OP_CHESS_NPLUS) && !dev.C)
+      throw std::string("C tensor missing for a C:Hessian operator");
+    if ((O.op == VLFS_OP_GRAD_NOWN) && !dev.slot[O.slot].ref_normal)
+      throw std::string("ref_normal missing for a normal-derivative operator");
+    if ((O.op == VLFS_OP_CHESS_NPLUS) && !dev.slot[0].ref_normal)
+      throw std::string("ref_normal of slot 0 missing for (C:Hessian).n+");
+    O.smem_off = p;
+    p += dev.nq * O.ncomp * dev.slot[O.slot].ndofs;
+  }
+  dev.smem_total = p;
+  if ((size_t)p * sizeof(double) > 227 * 1024)
+    throw std::string("domain needs more than 227 KB of shared memory per cell");
+  d.terms_dev.upload(d.terms_host.data(), d.terms_host.size(), ctx->stream);
+  d.rhs_dev.upload(d.rhs_host.data(), d.rhs_host.size(), ctx->stream);
+  bool any_fast = false;
+  for (char f : d.term_fast) any_fast |= f != 0;
+  if (any_fast && d.Sref.n == 0) {
+    int nd = dev.slot[0].ndofs, ns = D * (D + 1) / 2;
+    d.Sref.alloc((size_t)ns * nd * nd);
+    launch_gradgrad_reference(dev, d.Sref.p, ctx->stream);
+    ++ctx->launches;
+  }
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  d.finalized = true;
+  d.coef_dirty = false;
+}
+
+void refresh_coefs(vlfs_ctx* ctx, Domain& d) {
+  if (!d.coef_dirty) return;
+  size_t k = 0;
+  for (size_t t = 0; t < d.terms.size(); ++t) {
+    if (d.term_fast[t]) continue;
+    d.terms_host[k].cre = d.terms[t].coef_re;
+    d.terms_host[k].cim = d.terms[t].coef_im;
+    ++k;
+  }
+  for (size_t t = 0; t < d.rhs.size(); ++t) {
+    d.rhs_host[t].cre = d.rhs[t].coef_re;
+    d.rhs_host[t].cim = d.rhs[t].coef_im;
+  }
+  d.terms_dev.upload(d.terms_host.data(), d.terms_host.size(), ctx->stream);
+  d.rhs_dev.upload(d.rhs_host.data(), d.rhs_host.size(), ctx->stream);
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  d.coef_dirty = false;
+}
+
+void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
+  if (!ctx->pattern_built) throw std::string("vlfs_build_pattern must be called first");
+  cudaStream_t s = ctx->stream;
+  std::vector<double*> mp, vp;
+  for (auto& m : ctx->mats) mp.push_back(m.p);
+  for (auto& v : ctx->vecs) vp.push_back(v.p);
+  if (do_mat) for (auto& m : ctx->mats) m.zero(s);
+  if (do_vec) for (auto& v : ctx->vecs) v.zero(s);
+  for (size_t di = 0; di < ctx->doms.size(); ++di) {
+    Domain& d = *ctx->doms[di];
+    refresh_coefs(ctx, d);
+    const int* dest = ctx->dest_all.p + ctx->dest_off[di];
+    bool gen_mat = do_mat && !d.terms_host.empty();
+    bool gen_vec = do_vec && !d.rhs_host.empty();
+    if (gen_mat || gen_vec) {
+      launch_integrate(d.dev, d.terms_dev.p, (int)d.terms_host.size(), d.rhs_dev.p,
+                       (int)d.rhs_host.size(), dest, mp.data(), (int)mp.size(), vp.data(),
+                       (int)vp.size(), ctx->is_complex, gen_mat, gen_vec, ctx->nsm, s);
+      ++ctx->launches;
+    }
+    if (do_mat)
+      for (size_t t = 0; t < d.terms.size(); ++t)
+        if (d.term_fast[t]) {
+          const vlfs_term_desc& T = d.terms[t];
+          launch_gradgrad_affine(d.dev, d.Sref.p, dest, ctx->mats[T.mat].p, ctx->is_complex,
+                                 T.coef_re * T.test_scale[0] * T.trial_scale[0],
+                                 T.coef_im * T.test_scale[0] * T.trial_scale[0], ctx->nsm, s);
+          ++ctx->launches;
+        }
+  }
+}
+
+template <typename T>
+void upload_opt(DevBuf<T>& b, const T* h, size_t n, cudaStream_t s) {
+  if (h && n) b.upload(h, n, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int vlfs_version(void) { return 100; }
+
+int vlfs_device_count(int* n) {
+  if (!n) return VLFS_ERR_ARG;
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) { *n = 0; cudaGetLastError(); return VLFS_ERR_CUDA; }
+  return VLFS_OK;
+}
+
+int vlfs_create(vlfs_ctx** out, int device) {
+  if (!out) return VLFS_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    return VLFS_ERR_CUDA;      // no CPU fallback: without a GPU the library refuses to exist
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VLFS_ERR_CUDA;
+  if (prop.major < 10) return VLFS_ERR_CUDA;   // sm_100a code only
+  vlfs_ctx* c = new (std::nothrow) vlfs_ctx();
+  if (!c) return VLFS_ERR_STATE;
+  c->device = device;
+  c->nsm = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return VLFS_ERR_CUDA;
+  }
+  *out = c;
+  return VLFS_OK;
+}
+
+int vlfs_destroy(vlfs_ctx* ctx) {
+  if (!ctx) return VLFS_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->solver.reset();
+  ctx->doms.clear();
+  ctx->mats.clear();
+  ctx->vecs.clear();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return VLFS_OK;
+}
+
+const char* vlfs_last_error(const vlfs_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int vlfs_system_init(vlfs_ctx* ctx, int64_t ndofs, int is_complex, int nmat, int nvec) {
+  return guarded(ctx, [&]() {
+    if (ndofs <= 0 || ndofs >= (1ll << 31) || nmat < 1 || nmat > 4 || nvec < 0 || nvec > 4)
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_system_init: bad sizes (1<=nmat<=4, 0<=nvec<=4)");
+    ctx->ndofs = ndofs; ctx->is_complex = is_complex ? 1 : 0; ctx->nmat = nmat; ctx->nvec = nvec;
+    ctx->doms.clear(); ctx->mats.clear(); ctx->vecs.clear();
+    ctx->pattern_built = false; ctx->solver.reset();
+    ctx->vecs.resize(nvec);
+    for (auto& v : ctx->vecs) { v.alloc((size_t)ndofs * ctx->scalar()); v.zero(ctx->stream); }
+    return VLFS_OK;
+  });
+}
+
+int vlfs_add_domain(vlfs_ctx* ctx, const vlfs_domain_desc* desc, int* domain_id) {
+  return guarded(ctx, [&]() {
+    if (!desc || !domain_id) return fail(ctx, VLFS_ERR_ARG, "null argument");
+    if (ctx->ndofs == 0) return fail(ctx, VLFS_ERR_STATE, "vlfs_system_init first");
+    if (ctx->pattern_built) return fail(ctx, VLFS_ERR_STATE, "pattern already built");
+    const vlfs_domain_desc& d = *desc;
+    if (d.D < 1 || d.D > 3 || d.nq < 1 || d.nslots < 1 || d.nslots > VLFS_MAX_SLOTS ||
+        d.ncells < 0 || d.measure_slot < 0 || d.measure_slot >= d.nslots ||
+        d.nweights < 0 || d.nweights > VLFS_MAX_WEIGHTS || !d.qweights)
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_add_domain: bad descriptor");
+    auto dom = std::make_unique<Domain>();
+    dom->desc = d;
+    cudaStream_t s = ctx->stream;
+    DomainDev& dev = dom->dev;
+    dev.D = d.D; dev.nq = d.nq; dev.nslots = d.nslots; dev.measure_slot = d.measure_slot;
+    dev.measure_kind = d.measure_kind; dev.nweights = d.nweights; dev.affine = d.affine;
+    dev.ncells = d.ncells;
+    dom->qweights.upload(d.qweights, d.nq, s);
+    dev.qweights = dom->qweights.p;
+    if (d.nweights) {
+      if (!d.weights) return fail(ctx, VLFS_ERR_ARG, "weights missing");
+      dom->weights.upload(d.weights, (size_t)d.nweights * d.ncells * d.nq, s);
+    }
+    dev.weights = dom->weights.p;
+    if (d.C) dom->C.upload(d.C, (size_t)d.D * d.D * d.D * d.D, s);
+    dev.C = dom->C.p;
+    for (int k = 0; k < d.nslots; ++k) {
+      const vlfs_slot_desc& S = d.slot[k];
+      if (S.dref < 0 || S.dref > d.D || S.nv < 1 || S.nvar < 1 || S.ndofs < 1 || !S.coords ||
+          !S.geo_grad || !S.val || !S.dofs || (S.dref > 0 && !S.grad))
+        return fail(ctx, VLFS_ERR_ARG, "vlfs_add_domain: bad slot descriptor");
+      SlotStore& st = dom->st[k];
+      size_t nc = (size_t)d.ncells;
+      st.coords.upload(S.coords, nc * S.nv * d.D, s);
+      upload_opt(st.variant, S.variant, nc, s);
+      st.geo_grad.upload(S.geo_grad, (size_t)S.nvar * d.nq * S.nv * S.dref, s);
+      st.val.upload(S.val, (size_t)S.nvar * d.nq * S.ndofs, s);
+      st.grad.upload(S.grad, (size_t)S.nvar * d.nq * S.ndofs * S.dref, s);
+      upload_opt(st.hess, S.hess, (size_t)S.nvar * d.nq * S.ndofs * S.dref * S.dref, s);
+      st.dofs.upload(S.dofs, nc * S.ndofs, s);
+      upload_opt(st.ref_normal, S.ref_normal, (size_t)S.nvar * S.dref, s);
+      upload_opt(st.ref_tangent, S.ref_tangent, (size_t)S.nvar * S.dref, s);
+      SlotDev& sd = dev.slot[k];
+      sd.dref = S.dref; sd.nv = S.nv; sd.nvar = S.nvar; sd.ndofs = S.ndofs;
+      sd.has_hess = S.hess != nullptr;
+      sd.coords = st.coords.p; sd.variant = st.variant.p; sd.geo_grad = st.geo_grad.p;
+      sd.val = st.val.p; sd.grad = st.grad.p; sd.hess = st.hess.p; sd.dofs = st.dofs.p;
+      sd.ref_normal = st.ref_normal.p; sd.ref_tangent = st.ref_tangent.p;
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *domain_id = (int)ctx->doms.size();
+    ctx->doms.push_back(std::move(dom));
+    return VLFS_OK;
+  });
+}
+
+int vlfs_add_term(vlfs_ctx* ctx, int domain_id, const vlfs_term_desc* term, int* term_id) {
+  return guarded(ctx, [&]() {
+    if (!term || domain_id < 0 || domain_id >= (int)ctx->doms.size())
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_add_term: bad domain");
+    if (ctx->pattern_built) return fail(ctx, VLFS_ERR_STATE, "pattern already built");
+    Domain& d = *ctx->doms[domain_id];
+    const int D = d.dev.D;
+    if (term->mat < 0 || term->mat >= ctx->nmat || term->weight >= d.dev.nweights ||
+        op_ncomp(term->test_op, D) < 0 || op_ncomp(term->trial_op, D) < 0 ||
+        op_ncomp(term->test_op, D) != op_ncomp(term->trial_op, D))
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_add_term: bad term (operators must have equal component counts)");
+    if ((int)d.terms.size() >= VLFS_MAX_TERMS) return fail(ctx, VLFS_ERR_ARG, "too many terms");
+    if (term_id) *term_id = (int)d.terms.size();
+    d.terms.push_back(*term);
+    return VLFS_OK;
+  });
+}
+
+int vlfs_add_rhs_term(vlfs_ctx* ctx, int domain_id, const vlfs_rhs_desc* term, int* term_id) {
+  return guarded(ctx, [&]() {
+    if (!term || domain_id < 0 || domain_id >= (int)ctx->doms.size())
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_add_rhs_term: bad domain");
+    if (ctx->pattern_built) return fail(ctx, VLFS_ERR_STATE, "pattern already built");
+    Domain& d = *ctx->doms[domain_id];
+    if (term->vec < 0 || term->vec >= ctx->nvec || term->weight_re >= d.dev.nweights ||
+        term->weight_im >= d.dev.nweights || op_ncomp(term->op, d.dev.D) != 1)
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_add_rhs_term: bad term (scalar operators only)");
+    if ((int)d.rhs.size() >= VLFS_MAX_TERMS) return fail(ctx, VLFS_ERR_ARG, "too many terms");
+    if (term_id) *term_id = (int)d.rhs.size();
+    d.rhs.push_back(*term);
+    return VLFS_OK;
+  });
+}
+
+int vlfs_set_term_coef(vlfs_ctx* ctx, int domain_id, int term_id, double re, double im) {
+  return guarded(ctx, [&]() {
+    if (domain_id < 0 || domain_id >= (int)ctx->doms.size()) return fail(ctx, VLFS_ERR_ARG, "bad domain");
+    Domain& d = *ctx->doms[domain_id];
+    if (term_id < 0 || term_id >= (int)d.terms.size()) return fail(ctx, VLFS_ERR_ARG, "bad term");
+    d.terms[term_id].coef_re = re; d.terms[term_id].coef_im = im; d.coef_dirty = true;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_set_rhs_coef(vlfs_ctx* ctx, int domain_id, int term_id, double re, double im) {
+  return guarded(ctx, [&]() {
+    if (domain_id < 0 || domain_id >= (int)ctx->doms.size()) return fail(ctx, VLFS_ERR_ARG, "bad domain");
+    Domain& d = *ctx->doms[domain_id];
+    if (term_id < 0 || term_id >= (int)d.rhs.size()) return fail(ctx, VLFS_ERR_ARG, "bad term");
+    d.rhs[term_id].coef_re = re; d.rhs[term_id].coef_im = im; d.coef_dirty = true;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_set_weights(vlfs_ctx* ctx, int domain_id, int weight, const double* values) {
+  return guarded(ctx, [&]() {
+    if (domain_id < 0 || domain_id >= (int)ctx->doms.size() || !values) return fail(ctx, VLFS_ERR_ARG, "bad domain");
+    Domain& d = *ctx->doms[domain_id];
+    if (weight < 0 || weight >= d.dev.nweights) return fail(ctx, VLFS_ERR_ARG, "bad weight index");
+    size_t n = (size_t)d.dev.ncells * d.dev.nq;
+    CUDA_TRY(cudaMemcpyAsync(d.weights.p + (size_t)weight * n, values, n * sizeof(double),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VLFS_OK;
+  });
+}
+
+int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
+  return guarded(ctx, [&]() {
+    if (ctx->doms.empty()) return fail(ctx, VLFS_ERR_STATE, "no domains");
+    std::vector<DomainDev> devs;
+    for (auto& d : ctx->doms) { finalize_domain(ctx, *d); devs.push_back(d->dev); }
+    long long n1 = 0, n2 = 0;
+    build_pattern_device(devs, ctx->ndofs, ctx->rowptr, ctx->colind, ctx->rowind, ctx->dest_all,
+                         ctx->dest_off, &n1, &n2, ctx->stream, &ctx->launches);
+    ctx->nnz = n1; ctx->ncoo = n2;
+    ctx->mats.clear();
+    ctx->mats.resize(ctx->nmat);
+    for (auto& m : ctx->mats) { m.alloc((size_t)n1 * ctx->scalar()); m.zero(ctx->stream); }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->pattern_built = true;
+    if (nnz) *nnz = n1;
+    if (ncoo) *ncoo = n2;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_get_pattern(vlfs_ctx* ctx, int32_t* rowptr, int32_t* colind) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built) return fail(ctx, VLFS_ERR_STATE, "pattern not built");
+    if (rowptr) CUDA_TRY(cudaMemcpy(rowptr, ctx->rowptr.p, (ctx->ndofs + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    if (colind) CUDA_TRY(cudaMemcpy(colind, ctx->colind.p, ctx->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    return VLFS_OK;
+  });
+}
+
+int vlfs_get_pattern_csc(vlfs_ctx* ctx, int32_t* colptr, int32_t* rowval, int32_t* csr_slot) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built) return fail(ctx, VLFS_ERR_STATE, "pattern not built");
+    DevBuf<int> cp, rv, sl;
+    build_csc_device(ctx->rowind.p, ctx->colind.p, ctx->nnz, ctx->ndofs, cp, rv, sl, ctx->stream,
+                     &ctx->launches);
+    if (colptr) CUDA_TRY(cudaMemcpy(colptr, cp.p, (ctx->ndofs + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    if (rowval) CUDA_TRY(cudaMemcpy(rowval, rv.p, ctx->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    if (csr_slot) CUDA_TRY(cudaMemcpy(csr_slot, sl.p, ctx->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    return VLFS_OK;
+  });
+}
+
+int vlfs_assemble(vlfs_ctx* ctx) {
+  return guarded(ctx, [&]() { assemble_impl(ctx, true, true); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); return VLFS_OK; });
+}
+int vlfs_assemble_matrices(vlfs_ctx* ctx) {
+  return guarded(ctx, [&]() { assemble_impl(ctx, true, false); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); return VLFS_OK; });
+}
+int vlfs_assemble_vectors(vlfs_ctx* ctx) {
+  return guarded(ctx, [&]() { assemble_impl(ctx, false, true); CUDA_TRY(cudaStreamSynchronize(ctx->stream)); return VLFS_OK; });
+}
+
+int vlfs_get_values(vlfs_ctx* ctx, int mat, void* values) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !values) return fail(ctx, VLFS_ERR_ARG, "bad matrix");
+    CUDA_TRY(cudaMemcpy(values, ctx->mats[mat].p, ctx->nnz * ctx->scalar() * sizeof(double), cudaMemcpyDeviceToHost));
+    return VLFS_OK;
+  });
+}
+
+int vlfs_get_vector(vlfs_ctx* ctx, int vec, void* values) {
+  return guarded(ctx, [&]() {
+    if (vec < 0 || vec >= ctx->nvec || !values) return fail(ctx, VLFS_ERR_ARG, "bad vector");
+    CUDA_TRY(cudaMemcpy(values, ctx->vecs[vec].p, ctx->ndofs * ctx->scalar() * sizeof(double), cudaMemcpyDeviceToHost));
+    return VLFS_OK;
+  });
+}
+
+int vlfs_combine(vlfs_ctx* ctx, int target, int n, const int* src, const double* coef) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built || target < 0 || target >= ctx->nmat || n < 1 || n > 4 || !src || !coef)
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_combine: bad arguments");
+    double* sp[4];
+    for (int k = 0; k < n; ++k) {
+      if (src[k] < 0 || src[k] >= ctx->nmat) return fail(ctx, VLFS_ERR_ARG, "vlfs_combine: bad source");
+      sp[k] = ctx->mats[src[k]].p;
+    }
+    launch_axpby_vals(ctx->mats[target].p, (size_t)ctx->nnz, n, sp, coef, ctx->is_complex, ctx->stream);
+    ++ctx->launches;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VLFS_OK;
+  });
+}
+
+int vlfs_spmv(vlfs_ctx* ctx, int mat, const void* x, void* y) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !x || !y) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    size_t nb = (size_t)ctx->ndofs * ctx->scalar();
+    DevBuf<double> dx, dy;
+    dx.upload((const double*)x, nb, ctx->stream);
+    dy.alloc(nb);
+    const double one[2] = {1, 0}, zero[2] = {0, 0};
+    launch_spmv(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, dx.p, dy.p, ctx->ndofs, ctx->nnz,
+                ctx->is_complex, one, zero, ctx->nsm, ctx->stream);
+    ++ctx->launches;
+    CUDA_TRY(cudaMemcpyAsync(y, dy.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VLFS_OK;
+  });
+}
+
+int vlfs_spmv_device(vlfs_ctx* ctx, int mat, int reps, float* ms_total) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || reps < 1) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    size_t nb = (size_t)ctx->ndofs * ctx->scalar();
+    DevBuf<double> dx, dy;
+    std::vector<double> hx(nb);
+    for (size_t i = 0; i < (size_t)ctx->ndofs; ++i) {
+      if (ctx->is_complex) { hx[2 * i] = sin(0.1 * (double)i); hx[2 * i + 1] = cos(0.1 * (double)i); }
+      else hx[i] = sin(0.1 * (double)i);
+    }
+    dx.upload(hx.data(), nb, ctx->stream);
+    dy.alloc(nb);
+    const double one[2] = {1, 0}, zero[2] = {0, 0};
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    for (int r = 0; r < reps; ++r)
+      launch_spmv(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, dx.p, dy.p, ctx->ndofs, ctx->nnz,
+                  ctx->is_complex, one, zero, ctx->nsm, ctx->stream);
+    CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->launches += reps;
+    if (ms_total) *ms_total = ms;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_assemble_timed(vlfs_ctx* ctx, int reps, float* ms_total) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built || reps < 1) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    for (int r = 0; r < reps; ++r) assemble_impl(ctx, true, true);
+    CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_total) *ms_total = ms;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_last_kernel_launches(vlfs_ctx* ctx, int64_t* n) {
+  if (!ctx || !n) return VLFS_ERR_ARG;
+  *n = ctx->launches;
+  return VLFS_OK;
+}
+
+int vlfs_device_ptrs(vlfs_ctx* ctx, int mat, void** rowptr, void** colind, void** values) {
+  if (!ctx || !ctx->pattern_built || mat < 0 || mat >= ctx->nmat) return VLFS_ERR_ARG;
+  if (rowptr) *rowptr = ctx->rowptr.p;
+  if (colind) *colind = ctx->colind.p;
+  if (values) *values = ctx->mats[mat].p;
+  return VLFS_OK;
+}
+
+int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !opts) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    ctx->solver = solver_create(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, ctx->ndofs, ctx->nnz,
+                                ctx->is_complex, *opts, ctx->nsm, ctx->stream, &ctx->launches);
+    return VLFS_OK;
+  });
+}
+
+int vlfs_solve(vlfs_ctx* ctx, const void* b, void* x, vlfs_solve_stats* stats) {
+  return guarded(ctx, [&]() {
+    if (!ctx->solver || !b || !x) return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup first");
+    size_t nb = (size_t)ctx->ndofs * ctx->scalar();
+    DevBuf<double> db, dx;
+    db.upload((const double*)b, nb, ctx->stream);
+    dx.upload((const double*)x, nb, ctx->stream);       // initial guess
+    vlfs_solve_stats st{};
+    int rc = solver_solve(*ctx->solver, db.p, dx.p, &st);
+    CUDA_TRY(cudaMemcpyAsync(x, dx.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) *stats = st;
+    return rc;
+  });
+}
+
+int vlfs_solve_vec(vlfs_ctx* ctx, int vec, void* x, vlfs_solve_stats* stats) {
+  return guarded(ctx, [&]() {
+    if (!ctx->solver || vec < 0 || vec >= ctx->nvec || !x) return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup first");
+    size_t nb = (size_t)ctx->ndofs * ctx->scalar();
+    DevBuf<double> dx;
+    dx.upload((const double*)x, nb, ctx->stream);
+    vlfs_solve_stats st{};
+    int rc = solver_solve(*ctx->solver, ctx->vecs[vec].p, dx.p, &st);
+    CUDA_TRY(cudaMemcpyAsync(x, dx.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) *stats = st;
+    return rc;
+  });
+}
+
+int vlfs_newmark_run(vlfs_ctx* ctx, int matK, int matC, int matM, int nsteps, double dt,
+                     double gamma, double beta, int nb, const double* tcoef, double* u0,
+                     double* v0, double* a0, int64_t out_lo, int64_t out_hi, int out_stride,
+                     double* out, vlfs_solve_stats* stats) {
+  return guarded(ctx, [&]() {
+    if (!ctx->solver) return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup first");
+    if (ctx->is_complex) return fail(ctx, VLFS_ERR_ARG, "Newmark stepping is real-valued");
+    if (matK < 0 || matC < 0 || matM < 0 || matK >= ctx->nmat || matC >= ctx->nmat || matM >= ctx->nmat ||
+        nsteps < 1 || nb < 0 || nb > ctx->nvec || (nb && !tcoef) || !u0 || !v0 || !a0 ||
+        out_lo < 0 || out_hi < out_lo || out_hi > ctx->ndofs || out_stride < 1 || (out_hi > out_lo && !out))
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_newmark_run: bad arguments");
+    std::vector<double*> bv;
+    for (int k = 0; k < nb; ++k) bv.push_back(ctx->vecs[k].p);
+    return newmark_run(*ctx->solver, ctx->rowptr.p, ctx->colind.p, ctx->mats[matC].p, ctx->mats[matM].p,
+                       ctx->ndofs, ctx->nnz, nsteps, dt, gamma, beta, nb, bv.data(), tcoef, u0, v0, a0,
+                       out_lo, out_hi, out_stride, out, stats, ctx->nsm, ctx->stream, &ctx->launches);
+  });
+}
+
+}  // extern "C"

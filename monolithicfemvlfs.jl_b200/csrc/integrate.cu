@@ -1,0 +1,515 @@
+// integrate.cu - numeric phase: cell-wise quadrature + scatter-add into the fixed CSR
+// pattern (sm_100a, FP64 throughout).
+//
+// Replaces Gridap's lazy cell-matrix evaluation and COO fill inside
+// `AffineFEOperator(a,l,X,Y)` / `assemble_matrix_and_vector`
+// (reference call sites: src/Yago_freq_domain.jl:161-167,
+// src/Khabakhpasheva_freq_domain.jl:226-240, src/Khabakhpasheva_time_domain.jl:237-257,
+// src/Periodic_Beam.jl:96-104, src/Multi_geo_freq_domain.jl:125-131).
+//
+// Two kernels:
+//  * integrate_cells<D>: one CTA per cell.  Stage 0 builds the Jacobian pseudo-inverse,
+//    measure and normals of every slot at every quadrature point; stage 1 evaluates the
+//    operator instances (value / gradient / directional derivative / Hessian / C:Hessian /
+//    normal contractions) of all local basis functions into shared memory; stage 2 contracts
+//    test x trial rows for every touched block and scatters through `dest`; stage 3 does
+//    the linear forms.
+//  * gradgrad_affine<D>: the memory-bound fast path for ∫∇u·∇v on cells with a constant
+//    Jacobian: thread-per-entry keeps the symmetrised reference matrices in registers and
+//    streams cells, 6 FMAs + one scatter per entry.
+#include "common.cuh"
+
+namespace {
+
+template <int N>
+__device__ __forceinline__ double det_inv(const double (&A)[3][3], double (&I)[3][3]) {
+  if (N == 1) {
+    I[0][0] = 1.0 / A[0][0];
+    return A[0][0];
+  } else if (N == 2) {
+    double d = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+    double r = 1.0 / d;
+    I[0][0] = A[1][1] * r; I[0][1] = -A[0][1] * r;
+    I[1][0] = -A[1][0] * r; I[1][1] = A[0][0] * r;
+    return d;
+  } else {
+    double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
+    double c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2];
+    double c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+    double d = A[0][0] * c00 + A[0][1] * c01 + A[0][2] * c02;
+    double r = 1.0 / d;
+    I[0][0] = c00 * r;
+    I[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * r;
+    I[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * r;
+    I[1][0] = c01 * r;
+    I[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * r;
+    I[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * r;
+    I[2][0] = c02 * r;
+    I[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * r;
+    I[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * r;
+    return d;
+  }
+}
+
+__device__ __forceinline__ double det_inv_n(int n, const double (&A)[3][3], double (&I)[3][3]) {
+  if (n == 1) return det_inv<1>(A, I);
+  if (n == 2) return det_inv<2>(A, I);
+  return det_inv<3>(A, I);
+}
+
+// geometry record in shared memory per (slot, q): pinv[D][3] (9) + normal[3] = 12 doubles
+constexpr int GEO_STRIDE = 12;
+
+template <int D>
+__device__ void slot_geometry(const SlotDev& S, long long cell, int q, int nq, double* rec,
+                              double* meas_out, int measure_kind) {
+  const int var = S.variant ? S.variant[cell] : 0;
+  const double* gg = S.geo_grad + ((size_t)var * nq + q) * S.nv * S.dref;
+  const double* X = S.coords + (size_t)cell * S.nv * D;
+  double Jt[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int v = 0; v < S.nv; ++v)
+    for (int a = 0; a < S.dref; ++a) {
+      double g = gg[v * S.dref + a];
+#pragma unroll
+      for (int b = 0; b < D; ++b) Jt[a][b] = fma(g, X[v * D + b], Jt[a][b]);
+    }
+  double pinv[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};   // [b][a]
+  double meas;
+  if (S.dref == D) {
+    double I[3][3];
+    double d = det_inv_n(D, Jt, I);
+    for (int b = 0; b < D; ++b)
+      for (int a = 0; a < D; ++a) pinv[b][a] = I[b][a];
+    meas = fabs(d);
+  } else {
+    double G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Gi[3][3];
+    for (int a = 0; a < S.dref; ++a)
+      for (int c = 0; c < S.dref; ++c) {
+        double s = 0;
+#pragma unroll
+        for (int b = 0; b < D; ++b) s = fma(Jt[a][b], Jt[c][b], s);
+        G[a][c] = s;
+      }
+    double d = det_inv_n(S.dref, G, Gi);
+    for (int b = 0; b < D; ++b)
+      for (int a = 0; a < S.dref; ++a) {
+        double s = 0;
+        for (int c = 0; c < S.dref; ++c) s = fma(Jt[c][b], Gi[c][a], s);
+        pinv[b][a] = s;
+      }
+    meas = sqrt(d);
+  }
+  for (int b = 0; b < 3; ++b)
+    for (int a = 0; a < 3; ++a) rec[b * 3 + a] = (b < D) ? pinv[b][a] : 0.0;
+  double n[3] = {0, 0, 0};
+  if (S.ref_normal) {
+    const double* nr = S.ref_normal + var * S.dref;
+    double nn = 0;
+    for (int b = 0; b < D; ++b) {
+      double s = 0;
+      for (int a = 0; a < S.dref; ++a) s = fma(pinv[b][a], nr[a], s);
+      n[b] = s;
+      nn = fma(s, s, nn);
+    }
+    nn = 1.0 / sqrt(nn);
+    for (int b = 0; b < D; ++b) n[b] *= nn;
+  }
+  rec[9] = n[0]; rec[10] = n[1]; rec[11] = n[2];
+  if (meas_out) {
+    if (measure_kind == VLFS_MEASURE_FACET) {
+      if (S.ref_tangent) {
+        const double* tr = S.ref_tangent + var * S.dref;
+        double tt = 0;
+        for (int b = 0; b < D; ++b) {
+          double s = 0;
+          for (int a = 0; a < S.dref; ++a) s = fma(tr[a], Jt[a][b], s);
+          tt = fma(s, s, tt);
+        }
+        meas = sqrt(tt);
+      } else {
+        meas = 1.0;
+      }
+    }
+    *meas_out = meas;
+  }
+}
+
+template <int D>
+__device__ __forceinline__ int sym_index(int b, int d) {
+  // components: diagonal first, then (0,1),(0,2),(1,2)
+  if (b == d) return b;
+  if (D == 2) return 2;
+  int lo = b < d ? b : d, hi = b < d ? d : b;
+  return lo == 0 ? (hi == 1 ? 3 : 4) : 5;
+}
+
+template <int D>
+__device__ void eval_op(const DomainDev& dom, const OpInst& O, long long cell, int q, int i,
+                        const double* sm_geo, double* out /* stride nd */) {
+  constexpr int S_ = D * (D + 1) / 2;
+  const SlotDev& S = dom.slot[O.slot];
+  const int nd = S.ndofs, nq = dom.nq;
+  const int var = S.variant ? S.variant[cell] : 0;
+  const double* rec = sm_geo + ((size_t)O.slot * nq + q) * GEO_STRIDE;
+  const size_t tq = ((size_t)var * nq + q) * nd + i;
+  if (O.op == VLFS_OP_VAL) {
+    out[0] = S.val[tq];
+    return;
+  }
+  double g[3] = {0, 0, 0};
+  if (O.op == VLFS_OP_GRAD || O.op == VLFS_OP_DDIR || O.op == VLFS_OP_GRAD_NOWN) {
+    const double* gr = S.grad + tq * S.dref;
+#pragma unroll
+    for (int b = 0; b < D; ++b) {
+      double s = 0;
+      for (int a = 0; a < S.dref; ++a) s = fma(rec[b * 3 + a], gr[a], s);
+      g[b] = s;
+    }
+    if (O.op == VLFS_OP_GRAD) {
+#pragma unroll
+      for (int b = 0; b < D; ++b) out[(size_t)b * nd] = g[b];
+    } else if (O.op == VLFS_OP_DDIR) {
+      double s = 0;
+#pragma unroll
+      for (int b = 0; b < D; ++b) s = fma(g[b], O.dir[b], s);
+      out[0] = s;
+    } else {
+      double s = 0;
+#pragma unroll
+      for (int b = 0; b < D; ++b) s = fma(g[b], rec[9 + b], s);
+      out[0] = s;
+    }
+    return;
+  }
+  // second-derivative operators
+  double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  {
+    const double* hr = S.hess + tq * S.dref * S.dref;
+    double T[3][3];   // T[b][c] = sum_a pinv[b][a] Hr[a][c]
+    for (int b = 0; b < D; ++b)
+      for (int c = 0; c < S.dref; ++c) {
+        double s = 0;
+        for (int a = 0; a < S.dref; ++a) s = fma(rec[b * 3 + a], hr[a * S.dref + c], s);
+        T[b][c] = s;
+      }
+    for (int b = 0; b < D; ++b)
+      for (int d = 0; d < D; ++d) {
+        double s = 0;
+        for (int c = 0; c < S.dref; ++c) s = fma(T[b][c], rec[d * 3 + c], s);
+        H[b][d] = s;
+      }
+  }
+  if (O.op == VLFS_OP_LAPL) {
+    double s = 0;
+#pragma unroll
+    for (int b = 0; b < D; ++b) s += H[b][b];
+    out[0] = s;
+    return;
+  }
+  if (O.op == VLFS_OP_HESS) {
+#pragma unroll
+    for (int b = 0; b < D; ++b)
+#pragma unroll
+      for (int d = b; d < D; ++d) out[(size_t)sym_index<D>(b, d) * nd] = H[b][d];
+    return;
+  }
+  // C : H
+  double CH[3][3];
+  for (int b = 0; b < D; ++b)
+    for (int d = 0; d < D; ++d) {
+      double s = 0;
+      const double* Cbd = dom.C + ((size_t)(b * D + d) * D) * D;
+      for (int e = 0; e < D; ++e)
+        for (int f = 0; f < D; ++f) s = fma(Cbd[e * D + f], H[e][f], s);
+      CH[b][d] = s;
+    }
+  if (O.op == VLFS_OP_CHESS) {
+#pragma unroll
+    for (int b = 0; b < D; ++b)
+#pragma unroll
+      for (int d = b; d < D; ++d)
+        out[(size_t)sym_index<D>(b, d) * nd] = (b == d ? 1.0 : 2.0) * CH[b][d];
+    (void)S_;
+    return;
+  }
+  // VLFS_OP_CHESS_NPLUS: contraction with the normal of slot 0
+  const double* rec0 = sm_geo + ((size_t)0 * nq + q) * GEO_STRIDE;
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    double s = 0;
+#pragma unroll
+    for (int b = 0; b < D; ++b) s = fma(CH[a][b], rec0[9 + b], s);
+    out[(size_t)a * nd] = s;
+  }
+}
+
+struct AsmPtrs {
+  double* mat[4];
+  double* vec[4];
+};
+
+template <int D>
+__global__ void __launch_bounds__(256)
+integrate_cells(DomainDev dom, const TermDev* __restrict__ terms, int nterms,
+                const RhsDev* __restrict__ rhs, int nrhs, const int* __restrict__ dest,
+                AsmPtrs ptrs, int is_complex, int do_mat, int do_vec) {
+  extern __shared__ double sm[];
+  const int nq = dom.nq;
+  double* sm_geo = sm;
+  double* sm_meas = sm + dom.smem_meas_off;
+  double* sm_w = sm + dom.smem_w_off;
+  const int tid = threadIdx.x, nth = blockDim.x;
+
+  for (long long cell = blockIdx.x; cell < dom.ncells; cell += gridDim.x) {
+    // ---- stage 0: geometry + coefficient fields --------------------------------
+    for (int t = tid; t < dom.nslots * nq; t += nth) {
+      int s = t / nq, q = t - s * nq;
+      double m;
+      slot_geometry<D>(dom.slot[s], cell, q, nq, sm_geo + (size_t)t * GEO_STRIDE,
+                       s == dom.measure_slot ? &m : nullptr, dom.measure_kind);
+      if (s == dom.measure_slot) sm_meas[q] = m * dom.qweights[q];
+    }
+    for (int t = tid; t < dom.nweights * nq; t += nth) {
+      int w = t / nq, q = t - w * nq;
+      sm_w[t] = dom.weights[((size_t)w * dom.ncells + cell) * nq + q];
+    }
+    __syncthreads();
+    // ---- stage 1: operator instances ------------------------------------------
+    for (int o = 0; o < dom.nopi; ++o) {
+      const OpInst& O = dom.opi[o];
+      const int nd = dom.slot[O.slot].ndofs;
+      for (int t = tid; t < nq * nd; t += nth) {
+        int q = t / nd, i = t - q * nd;
+        eval_op<D>(dom, O, cell, q, i, sm_geo, sm + O.smem_off + (size_t)q * O.ncomp * nd + i);
+      }
+    }
+    __syncthreads();
+    // ---- stage 2: bilinear terms ----------------------------------------------
+    if (do_mat) {
+      for (int b = 0; b < dom.nblocks; ++b) {
+        const BlockDev B = dom.blk[b];
+        const int* drow = dest + (size_t)cell * dom.entries_per_cell + B.off;
+        for (int idx = tid; idx < B.nr * B.nc; idx += nth) {
+          const int i = idx / B.nc, j = idx - i * B.nc;
+          double are[4] = {0, 0, 0, 0}, aim[4] = {0, 0, 0, 0};
+          unsigned touched_re = 0, touched_im = 0;
+          for (int t = 0; t < nterms; ++t) {
+            const TermDev& T = terms[t];
+            const int oa = T.opi_test[B.ts], ob = T.opi_trial[B.us];
+            if (oa < 0 || ob < 0) continue;
+            const int nda = B.nr, ndb = B.nc, nc = T.ncomp;
+            const double* A = sm + dom.opi[oa].smem_off + i;
+            const double* Bp = sm + dom.opi[ob].smem_off + j;
+            const double* W = T.weight >= 0 ? sm_w + T.weight * nq : nullptr;
+            double acc = 0;
+            for (int q = 0; q < nq; ++q) {
+              double dot = 0;
+              for (int c = 0; c < nc; ++c)
+                dot = fma(A[(size_t)(q * nc + c) * nda], Bp[(size_t)(q * nc + c) * ndb], dot);
+              double w = sm_meas[q];
+              if (W) w *= W[q];
+              acc = fma(w, dot, acc);
+            }
+            acc *= T.st[B.ts] * T.su[B.us];
+            are[T.mat] = fma(T.cre, acc, are[T.mat]);
+            aim[T.mat] = fma(T.cim, acc, aim[T.mat]);
+            if (T.cre != 0.0) touched_re |= 1u << T.mat;
+            if (T.cim != 0.0) touched_im |= 1u << T.mat;
+          }
+          const int slot = drow[idx];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (is_complex) {
+              if (touched_re >> m & 1u) atomicAdd(ptrs.mat[m] + 2 * (size_t)slot, are[m]);
+              if (touched_im >> m & 1u) atomicAdd(ptrs.mat[m] + 2 * (size_t)slot + 1, aim[m]);
+            } else {
+              if (touched_re >> m & 1u) atomicAdd(ptrs.mat[m] + (size_t)slot, are[m]);
+            }
+          }
+        }
+      }
+    }
+    // ---- stage 3: linear terms -------------------------------------------------
+    if (do_vec) {
+      for (int t = 0; t < nrhs; ++t) {
+        const RhsDev& R = rhs[t];
+        for (int s = 0; s < dom.nslots; ++s) {
+          if (R.opi[s] < 0) continue;
+          const int nd = dom.slot[s].ndofs;
+          const double* A = sm + dom.opi[R.opi[s]].smem_off;
+          const double* Wr = R.wre >= 0 ? sm_w + R.wre * nq : nullptr;
+          const double* Wi = R.wim >= 0 ? sm_w + R.wim * nq : nullptr;
+          for (int i = tid; i < nd; i += nth) {
+            double ar = 0, ai = 0;
+            for (int q = 0; q < nq; ++q) {
+              double v = sm_meas[q] * A[(size_t)q * nd + i];
+              ar = fma(Wr ? Wr[q] : 1.0, v, ar);
+              if (Wi) ai = fma(Wi[q], v, ai);
+            }
+            ar *= R.sc[s]; ai *= R.sc[s];
+            double vr = R.cre * ar - R.cim * ai, vi = R.cre * ai + R.cim * ar;
+            const int dof = dom.slot[s].dofs[(size_t)cell * nd + i];
+            if (is_complex) {
+              atomicAdd(ptrs.vec[R.vec] + 2 * (size_t)dof, vr);
+              atomicAdd(ptrs.vec[R.vec] + 2 * (size_t)dof + 1, vi);
+            } else {
+              atomicAdd(ptrs.vec[R.vec] + (size_t)dof, vr);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- fast path: ∫ ∇u·∇v on constant-Jacobian cells --------------------------------
+// reference matrices, symmetrised:  Sref[m][i][j], m over sym components of dref x dref
+template <int DR>
+__global__ void gradgrad_reference(SlotDev S, const double* __restrict__ qw, int nq,
+                                   double* __restrict__ Sref) {
+  constexpr int NS = DR * (DR + 1) / 2;
+  const int nd = S.ndofs;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nd * nd; idx += gridDim.x * blockDim.x) {
+    int i = idx / nd, j = idx - i * nd;
+    double acc[NS];
+#pragma unroll
+    for (int m = 0; m < NS; ++m) acc[m] = 0;
+    for (int q = 0; q < nq; ++q) {
+      const double* gi = S.grad + ((size_t)q * nd + i) * DR;
+      const double* gj = S.grad + ((size_t)q * nd + j) * DR;
+      double w = qw[q];
+      int m = 0;
+#pragma unroll
+      for (int a = 0; a < DR; ++a) { acc[m] = fma(w * gi[a], gj[a], acc[m]); ++m; }
+#pragma unroll
+      for (int a = 0; a < DR; ++a)
+#pragma unroll
+        for (int c = a + 1; c < DR; ++c) {
+          acc[m] = fma(w, gi[a] * gj[c] + gi[c] * gj[a], acc[m]);
+          ++m;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NS; ++m) Sref[(size_t)m * nd * nd + idx] = acc[m];
+  }
+}
+
+constexpr int FAST_BATCH = 32;
+
+template <int D>
+__global__ void __launch_bounds__(1024)
+gradgrad_affine(DomainDev dom, const double* __restrict__ Sref, const int* __restrict__ dest,
+                double* __restrict__ vals, int stride /*1 real, 2 complex*/, double cre, double cim,
+                long long cells_per_cta) {
+  constexpr int NS = D * (D + 1) / 2;
+  __shared__ double sG[FAST_BATCH][NS];
+  const SlotDev& S = dom.slot[0];
+  const int nd = S.ndofs, ne = nd * nd;
+  const int idx = threadIdx.x;
+  double sref[NS];
+#pragma unroll
+  for (int m = 0; m < NS; ++m) sref[m] = idx < ne ? Sref[(size_t)m * ne + idx] : 0.0;
+  const long long c0 = (long long)blockIdx.x * cells_per_cta;
+  long long c1 = c0 + cells_per_cta;
+  if (c1 > dom.ncells) c1 = dom.ncells;
+  for (long long cb = c0; cb < c1; cb += FAST_BATCH) {
+    const int nb = (int)((c1 - cb) < FAST_BATCH ? (c1 - cb) : FAST_BATCH);
+    __syncthreads();
+    if (idx < nb) {
+      double rec[GEO_STRIDE], meas;
+      slot_geometry<D>(S, cb + idx, 0, dom.nq, rec, &meas, VLFS_MEASURE_CELL);
+      // G[a][c] = meas * sum_b pinv[b][a] pinv[b][c]
+      int m = 0;
+      for (int a = 0; a < D; ++a) {
+        double s = 0;
+        for (int b = 0; b < D; ++b) s = fma(rec[b * 3 + a], rec[b * 3 + a], s);
+        sG[idx][m++] = meas * s;
+      }
+      for (int a = 0; a < D; ++a)
+        for (int c = a + 1; c < D; ++c) {
+          double s = 0;
+          for (int b = 0; b < D; ++b) s = fma(rec[b * 3 + a], rec[b * 3 + c], s);
+          sG[idx][m++] = meas * s;
+        }
+    }
+    __syncthreads();
+    if (idx < ne) {
+      const int* dp = dest + (size_t)cb * dom.entries_per_cell + dom.blk[0].off + idx;
+      int slot[4];
+      for (int k0 = 0; k0 < nb; k0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (k0 + u < nb) slot[u] = dp[(size_t)(k0 + u) * dom.entries_per_cell];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k0 + u < nb) {
+            double v = 0;
+#pragma unroll
+            for (int m = 0; m < NS; ++m) v = fma(sG[k0 + u][m], sref[m], v);
+            if (cre != 0.0) atomicAdd(vals + (size_t)stride * slot[u], cre * v);
+            if (cim != 0.0) atomicAdd(vals + (size_t)stride * slot[u] + 1, cim * v);
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+// ---- host-side launchers ------------------------------------------------------------
+void launch_integrate(const DomainDev& dom, const TermDev* terms_dev, int nterms,
+                      const RhsDev* rhs_dev, int nrhs, const int* dest, double* const* mats,
+                      int nmat, double* const* vecs, int nvec, int is_complex, int do_mat,
+                      int do_vec, int nsm, cudaStream_t s) {
+  if (dom.ncells == 0) return;
+  AsmPtrs P{};
+  for (int m = 0; m < nmat && m < 4; ++m) P.mat[m] = mats[m];
+  for (int v = 0; v < nvec && v < 4; ++v) P.vec[v] = vecs[v];
+  size_t smem = (size_t)dom.smem_total * sizeof(double);
+  long long grid = dom.ncells;
+  int per_sm = smem ? (int)((220 * 1024) / (smem + 1024)) : 8;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  long long cap = (long long)nsm * per_sm * 4;
+  if (grid > cap) grid = cap;
+  auto launch = [&](auto kern) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, 256, smem, s>>>(dom, terms_dev, nterms, rhs_dev, nrhs, dest, P,
+                                           is_complex, do_mat, do_vec);
+  };
+  if (dom.D == 1) launch(integrate_cells<1>);
+  else if (dom.D == 2) launch(integrate_cells<2>);
+  else launch(integrate_cells<3>);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_gradgrad_reference(const DomainDev& dom, double* Sref, cudaStream_t s) {
+  const SlotDev& S = dom.slot[0];
+  int ne = S.ndofs * S.ndofs;
+  unsigned grid = (ne + 255) / 256;
+  if (S.dref == 1) gradgrad_reference<1><<<grid, 256, 0, s>>>(S, dom.qweights, dom.nq, Sref);
+  else if (S.dref == 2) gradgrad_reference<2><<<grid, 256, 0, s>>>(S, dom.qweights, dom.nq, Sref);
+  else gradgrad_reference<3><<<grid, 256, 0, s>>>(S, dom.qweights, dom.nq, Sref);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_gradgrad_affine(const DomainDev& dom, const double* Sref, const int* dest, double* vals,
+                            int is_complex, double cre, double cim, int nsm, cudaStream_t s) {
+  if (dom.ncells == 0) return;
+  int ne = dom.slot[0].ndofs * dom.slot[0].ndofs;
+  int threads = ((ne + 31) / 32) * 32;
+  if (threads > 1024) throw std::string("gradgrad_affine: element matrix larger than 1024 entries");
+  // CTAs resident per SM limited by threads; give every SM a few waves of cell chunks
+  long long ctas = (long long)nsm * (2048 / threads) * 4;
+  long long per = (dom.ncells + ctas - 1) / ctas;
+  per = ((per + FAST_BATCH - 1) / FAST_BATCH) * FAST_BATCH;
+  long long grid = (dom.ncells + per - 1) / per;
+  int stride = is_complex ? 2 : 1;
+  if (!is_complex) cim = 0.0;
+  if (dom.D == 1) gradgrad_affine<1><<<(unsigned)grid, threads, 0, s>>>(dom, Sref, dest, vals, stride, cre, cim, per);
+  else if (dom.D == 2) gradgrad_affine<2><<<(unsigned)grid, threads, 0, s>>>(dom, Sref, dest, vals, stride, cre, cim, per);
+  else gradgrad_affine<3><<<(unsigned)grid, threads, 0, s>>>(dom, Sref, dest, vals, stride, cre, cim, per);
+  CUDA_TRY(cudaGetLastError());
+}

@@ -1,0 +1,541 @@
+// krylov.cu - preconditioned Krylov solvers and the Newmark driver (sm_100a, FP64).
+//
+// Stands in for `LUSolver()` behind `solve(op)` (src/Yago_freq_domain.jl:171,
+// src/Khabakhpasheva_freq_domain.jl:241, src/Multi_geo_freq_domain.jl:135) and behind
+// `Newmark(LUSolver(),Δt,γ,β)` (src/Khabakhpasheva_time_domain.jl:258-266,
+// src/Periodic_Beam.jl:107-116).  Restarted right-preconditioned GMRES with CGS2
+// orthogonalisation, BiCGStab and CG; dot products are warp-shuffle reductions batched per
+// iteration (one partials kernel + one finishing kernel, no atomics => deterministic).
+#include "solver.cuh"
+#include <complex>
+#include <cmath>
+
+void launch_spmv(const int* rowptr, const int* colind, const void* vals, const void* x, void* y,
+                 long long nrows, long long nnz, int is_complex, const double* alpha,
+                 const double* beta, int nsm, cudaStream_t s);
+
+namespace {
+
+using cd = std::complex<double>;
+
+template <bool C> struct Sc;
+template <> struct Sc<false> {
+  using T = double;
+  __host__ __device__ static T zero() { return 0.0; }
+  __device__ static T conjmul(T a, T b) { return a * b; }
+  __device__ static T mul(T a, T b) { return a * b; }
+  __device__ static T add(T a, T b) { return a + b; }
+  __device__ static T sub(T a, T b) { return a - b; }
+  __device__ static T shfl(T a, int o) { return __shfl_down_sync(0xffffffffu, a, o); }
+  __device__ static T inv(T a) { return 1.0 / a; }
+  __device__ static T from(double re, double im) { return re; }
+};
+template <> struct Sc<true> {
+  using T = double2;
+  __host__ __device__ static T zero() { return make_double2(0, 0); }
+  __device__ static T conjmul(T a, T b) { return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
+  __device__ static T mul(T a, T b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+  __device__ static T add(T a, T b) { return make_double2(a.x + b.x, a.y + b.y); }
+  __device__ static T sub(T a, T b) { return make_double2(a.x - b.x, a.y - b.y); }
+  __device__ static T shfl(T a, int o) {
+    return make_double2(__shfl_down_sync(0xffffffffu, a.x, o), __shfl_down_sync(0xffffffffu, a.y, o));
+  }
+  __device__ static T inv(T a) { double d = 1.0 / (a.x * a.x + a.y * a.y); return make_double2(a.x * d, -a.y * d); }
+  __device__ static T from(double re, double im) { return make_double2(re, im); }
+};
+
+constexpr int RED_THREADS = 256;
+
+template <bool C>
+__device__ typename Sc<C>::T block_reduce(typename Sc<C>::T v, typename Sc<C>::T* sm) {
+  using S = Sc<C>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = S::add(v, S::shfl(v, o));
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < RED_THREADS / 32 ? sm[lane] : S::zero();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = S::add(v, S::shfl(v, o));
+  }
+  __syncthreads();
+  return v;
+}
+
+// partial[k][b] = sum_{i in chunk b} conj(V_k[i]) * w[i]   for k = 0..nv-1 (grid.y = nv)
+template <bool C>
+__global__ void __launch_bounds__(RED_THREADS)
+multidot_partial(const typename Sc<C>::T* __restrict__ V, size_t ldv, const typename Sc<C>::T* __restrict__ w,
+                 long long n, typename Sc<C>::T* __restrict__ partial) {
+  using S = Sc<C>;
+  __shared__ typename S::T sm[RED_THREADS / 32];
+  const typename S::T* v = V + (size_t)blockIdx.y * ldv;
+  typename S::T acc = S::zero();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc = S::add(acc, S::conjmul(v[i], w[i]));
+  acc = block_reduce<C>(acc, sm);
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
+template <bool C>
+__global__ void __launch_bounds__(RED_THREADS)
+multidot_finish(const typename Sc<C>::T* __restrict__ partial, int nb, typename Sc<C>::T* __restrict__ out) {
+  using S = Sc<C>;
+  __shared__ typename S::T sm[RED_THREADS / 32];
+  typename S::T acc = S::zero();
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) acc = S::add(acc, partial[(size_t)blockIdx.x * nb + b]);
+  acc = block_reduce<C>(acc, sm);
+  if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+
+// w -= sum_k h[k] V_k
+template <bool C>
+__global__ void gemv_sub(const typename Sc<C>::T* __restrict__ V, size_t ldv, const typename Sc<C>::T* __restrict__ h,
+                         int nv, typename Sc<C>::T* __restrict__ w, long long n) {
+  using S = Sc<C>;
+  extern __shared__ double smraw[];
+  typename S::T* sh = reinterpret_cast<typename S::T*>(smraw);
+  for (int k = threadIdx.x; k < nv; k += blockDim.x) sh[k] = h[k];
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    typename S::T acc = w[i];
+    for (int k = 0; k < nv; ++k) acc = S::sub(acc, S::mul(sh[k], V[(size_t)k * ldv + i]));
+    w[i] = acc;
+  }
+}
+
+// y = a*x + b*y  (a, b scalars passed by value as re/im)
+template <bool C>
+__global__ void axpby(double are, double aim, const typename Sc<C>::T* __restrict__ x, double bre, double bim,
+                      typename Sc<C>::T* __restrict__ y, long long n) {
+  using S = Sc<C>;
+  typename S::T a = S::from(are, aim), b = S::from(bre, bim);
+  const bool bzero = (bre == 0.0 && bim == 0.0);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    typename S::T v = S::mul(a, x[i]);
+    if (!bzero) v = S::add(v, S::mul(b, y[i]));
+    y[i] = v;
+  }
+}
+
+// z = d .* r
+template <bool C>
+__global__ void pointwise_mul(const typename Sc<C>::T* __restrict__ d, const typename Sc<C>::T* __restrict__ r,
+                              typename Sc<C>::T* __restrict__ z, long long n) {
+  using S = Sc<C>;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    z[i] = S::mul(d[i], r[i]);
+}
+
+template <bool C>
+__global__ void extract_inv_diag(const int* __restrict__ rowptr, const int* __restrict__ colind,
+                                 const typename Sc<C>::T* __restrict__ vals, typename Sc<C>::T* __restrict__ dinv,
+                                 long long n) {
+  using S = Sc<C>;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    typename S::T d = S::from(1.0, 0.0);
+    for (int p = rowptr[r]; p < rowptr[r + 1]; ++p)
+      if (colind[p] == r) { d = S::inv(vals[p]); break; }
+    dinv[r] = d;
+  }
+}
+
+// target = sum_k coef[k] * src[k]  over matrix value arrays
+template <bool C>
+__global__ void combine_vals(typename Sc<C>::T* __restrict__ target, size_t n, int nsrc,
+                             const typename Sc<C>::T* s0, const typename Sc<C>::T* s1,
+                             const typename Sc<C>::T* s2, const typename Sc<C>::T* s3,
+                             double c0r, double c0i, double c1r, double c1i, double c2r, double c2i,
+                             double c3r, double c3i) {
+  using S = Sc<C>;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    typename S::T v = S::mul(S::from(c0r, c0i), s0[i]);
+    if (nsrc > 1) v = S::add(v, S::mul(S::from(c1r, c1i), s1[i]));
+    if (nsrc > 2) v = S::add(v, S::mul(S::from(c2r, c2i), s2[i]));
+    if (nsrc > 3) v = S::add(v, S::mul(S::from(c3r, c3i), s3[i]));
+    target[i] = v;
+  }
+}
+
+inline unsigned vgrid(long long n, int nsm) {
+  long long g = (n + 255) / 256;
+  long long cap = (long long)nsm * 8;
+  return (unsigned)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace
+
+void launch_axpby_vals(double* target, size_t n, int nsrc, double* const* src, const double* c,
+                       int is_complex, cudaStream_t s) {
+  double cc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const double* sp[4] = {src[0], src[0], src[0], src[0]};
+  for (int k = 0; k < nsrc; ++k) { cc[2 * k] = c[2 * k]; cc[2 * k + 1] = c[2 * k + 1]; sp[k] = src[k]; }
+  unsigned grid = vgrid((long long)n, 148);
+  if (is_complex)
+    combine_vals<true><<<grid, 256, 0, s>>>((double2*)target, n, nsrc, (const double2*)sp[0], (const double2*)sp[1],
+                                           (const double2*)sp[2], (const double2*)sp[3], cc[0], cc[1], cc[2], cc[3],
+                                           cc[4], cc[5], cc[6], cc[7]);
+  else
+    combine_vals<false><<<grid, 256, 0, s>>>(target, n, nsrc, sp[0], sp[1], sp[2], sp[3], cc[0], cc[1], cc[2],
+                                            cc[3], cc[4], cc[5], cc[6], cc[7]);
+  CUDA_TRY(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------
+struct SolverState {
+  const int* rowptr; const int* colind; const double* vals;
+  long long n, nnz;
+  int cplx;
+  vlfs_solver_opts opts;
+  int nsm;
+  cudaStream_t s;
+  long long* launches;
+  size_t sc;                    // doubles per scalar
+  int nred;                     // reduction blocks
+  DevBuf<double> dinv, V, w, z, r, partial, hdev, tmp1, tmp2, tmp3, tmp4;
+  double setup_ms = 0;
+
+  double* vec(DevBuf<double>& b) { if (b.n == 0) b.alloc((size_t)n * sc); return b.p; }
+
+  void spmv(const double* x, double* y, double are = 1.0, double bre = 0.0) {
+    const double a[2] = {are, 0}, b[2] = {bre, 0};
+    launch_spmv(rowptr, colind, vals, x, y, n, nnz, cplx, a, b, nsm, s);
+    ++*launches;
+  }
+  void axpby_(cd a, const double* x, cd b, double* y) {
+    if (cplx) axpby<true><<<vgrid(n, nsm), 256, 0, s>>>(a.real(), a.imag(), (const double2*)x, b.real(), b.imag(), (double2*)y, n);
+    else axpby<false><<<vgrid(n, nsm), 256, 0, s>>>(a.real(), 0, x, b.real(), 0, y, n);
+    ++*launches;
+  }
+  void copy(const double* x, double* y) {
+    CUDA_TRY(cudaMemcpyAsync(y, x, (size_t)n * sc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  // out[k] = <V_k, w>, k < nv   (V rows contiguous with leading dimension n scalars)
+  void multidot(const double* Vp, int nv, const double* wp, cd* out) {
+    dim3 grid(nred, nv);
+    if (cplx) {
+      multidot_partial<true><<<grid, RED_THREADS, 0, s>>>((const double2*)Vp, (size_t)n, (const double2*)wp, n, (double2*)partial.p);
+      multidot_finish<true><<<nv, RED_THREADS, 0, s>>>((const double2*)partial.p, nred, (double2*)hdev.p);
+    } else {
+      multidot_partial<false><<<grid, RED_THREADS, 0, s>>>(Vp, (size_t)n, wp, n, partial.p);
+      multidot_finish<false><<<nv, RED_THREADS, 0, s>>>(partial.p, nred, hdev.p);
+    }
+    *launches += 2;
+    std::vector<double> h((size_t)nv * sc);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), hdev.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int k = 0; k < nv; ++k) out[k] = cplx ? cd(h[2 * k], h[2 * k + 1]) : cd(h[k], 0.0);
+  }
+  cd dot(const double* x, const double* y) { cd v; multidot(x, 1, y, &v); return v; }
+  double nrm2(const double* x) { return std::sqrt(std::abs(dot(x, x).real())); }
+  void gemv_sub_(const double* Vp, int nv, const cd* h, double* wp) {
+    std::vector<double> hh((size_t)nv * sc);
+    for (int k = 0; k < nv; ++k) { if (cplx) { hh[2 * k] = h[k].real(); hh[2 * k + 1] = h[k].imag(); } else hh[k] = h[k].real(); }
+    CUDA_TRY(cudaMemcpyAsync(hdev.p, hh.data(), hh.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    size_t smem = (size_t)nv * sc * sizeof(double);
+    if (cplx) gemv_sub<true><<<vgrid(n, nsm), 256, smem, s>>>((const double2*)Vp, (size_t)n, (const double2*)hdev.p, nv, (double2*)wp, n);
+    else gemv_sub<false><<<vgrid(n, nsm), 256, smem, s>>>(Vp, (size_t)n, hdev.p, nv, wp, n);
+    ++*launches;
+    CUDA_TRY(cudaStreamSynchronize(s));   // hh dies at scope exit
+  }
+  void precond(const double* rin, double* zout) {
+    if (opts.precond == VLFS_PRECOND_NONE) { copy(rin, zout); return; }
+    if (cplx) pointwise_mul<true><<<vgrid(n, nsm), 256, 0, s>>>((const double2*)dinv.p, (const double2*)rin, (double2*)zout, n);
+    else pointwise_mul<false><<<vgrid(n, nsm), 256, 0, s>>>(dinv.p, rin, zout, n);
+    ++*launches;
+  }
+};
+
+SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals,
+                                           long long n, long long nnz, int is_complex,
+                                           const vlfs_solver_opts& opts, int nsm, cudaStream_t s,
+                                           long long* launches) {
+  SolverPtr S(new SolverState());
+  S->rowptr = rowptr; S->colind = colind; S->vals = vals; S->n = n; S->nnz = nnz;
+  S->cplx = is_complex; S->opts = opts; S->nsm = nsm; S->s = s; S->launches = launches;
+  S->sc = is_complex ? 2 : 1;
+  if (S->opts.restart < 1) S->opts.restart = 50;
+  if (S->opts.maxit < 1) S->opts.maxit = 1000;
+  if (S->opts.rtol <= 0) S->opts.rtol = 1e-10;
+  S->nred = nsm * 2;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, s));
+  int m = S->opts.restart;
+  S->partial.alloc((size_t)S->nred * (m + 2) * S->sc);
+  S->hdev.alloc((size_t)(m + 2) * S->sc);
+  if (S->opts.precond != VLFS_PRECOND_NONE) {
+    S->dinv.alloc((size_t)n * S->sc);
+    if (is_complex) extract_inv_diag<true><<<vgrid(n, nsm), 256, 0, s>>>(rowptr, colind, (const double2*)vals, (double2*)S->dinv.p, n);
+    else extract_inv_diag<false><<<vgrid(n, nsm), 256, 0, s>>>(rowptr, colind, vals, S->dinv.p, n);
+    ++*launches;
+  }
+  if (S->opts.method == VLFS_SOLVER_GMRES) S->V.alloc((size_t)(m + 1) * n * S->sc);
+  CUDA_TRY(cudaEventRecord(e1, s));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  S->setup_ms = ms;
+  CUDA_TRY(cudaGetLastError());
+  return S;
+}
+
+void SolverDeleter::operator()(SolverState* p) const { delete p; }
+
+namespace {
+
+int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
+  const int m = S.opts.restart;
+  const long long n = S.n;
+  const size_t ld = (size_t)n * S.sc;
+  double* w = S.vec(S.w);
+  double* z = S.vec(S.z);
+  double* r = S.vec(S.r);
+  const double bnorm = S.nrm2(b);
+  if (bnorm == 0.0) {
+    CUDA_TRY(cudaMemsetAsync(x, 0, ld * sizeof(double), S.s));
+    st->iterations = 0; st->converged = 1; st->rel_residual = 0;
+    return VLFS_OK;
+  }
+  std::vector<cd> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), h(m + 2), h2(m + 2), y(m);
+  int it = 0;
+  double rel = 1.0;
+  while (true) {
+    // r = b - A x
+    S.copy(b, r);
+    S.spmv(x, r, -1.0, 1.0);
+    double beta = S.nrm2(r);
+    rel = beta / bnorm;
+    if (rel <= S.opts.rtol || it >= S.opts.maxit) break;
+    S.axpby_(cd(1.0 / beta, 0), r, cd(0, 0), S.V.p);      // V_0
+    std::fill(g.begin(), g.end(), cd(0, 0));
+    g[0] = beta;
+    int j = 0;
+    for (; j < m && it < S.opts.maxit; ++j, ++it) {
+      double* vj = S.V.p + (size_t)j * ld;
+      S.precond(vj, z);
+      S.spmv(z, w);
+      // CGS2
+      S.multidot(S.V.p, j + 1, w, h.data());
+      S.gemv_sub_(S.V.p, j + 1, h.data(), w);
+      S.multidot(S.V.p, j + 1, w, h2.data());
+      S.gemv_sub_(S.V.p, j + 1, h2.data(), w);
+      for (int k = 0; k <= j; ++k) h[k] += h2[k];
+      double hn = S.nrm2(w);
+      h[j + 1] = hn;
+      if (hn > 0) S.axpby_(cd(1.0 / hn, 0), w, cd(0, 0), S.V.p + (size_t)(j + 1) * ld);
+      // Givens
+      for (int k = 0; k < j; ++k) {
+        cd t = cs[k] * h[k] + sn[k] * h[k + 1];
+        h[k + 1] = -std::conj(sn[k]) * h[k] + cs[k] * h[k + 1];
+        h[k] = t;
+      }
+      {
+        cd a = h[j], bb = h[j + 1];
+        double na = std::abs(a), nb2 = std::abs(bb);
+        double t = std::hypot(na, nb2);
+        if (na == 0.0) { cs[j] = 0.0; sn[j] = 1.0; }
+        else { cs[j] = na / t; sn[j] = (a / na) * std::conj(bb) / t; }
+        h[j] = cs[j] * a + sn[j] * bb;
+        h[j + 1] = 0.0;
+        cd gj = g[j];
+        g[j] = cs[j] * gj;
+        g[j + 1] = -std::conj(sn[j]) * gj;
+      }
+      for (int k = 0; k <= j; ++k) H[(size_t)k * m + j] = h[k];
+      rel = std::abs(g[j + 1]) / bnorm;
+      if (rel <= S.opts.rtol || hn == 0.0) { ++j; ++it; break; }
+    }
+    // y = H^{-1} g ; x += M^{-1} V y
+    for (int k = j - 1; k >= 0; --k) {
+      cd sum = g[k];
+      for (int l = k + 1; l < j; ++l) sum -= H[(size_t)k * m + l] * y[l];
+      y[k] = sum / H[(size_t)k * m + k];
+    }
+    CUDA_TRY(cudaMemsetAsync(w, 0, ld * sizeof(double), S.s));
+    std::vector<cd> ny(j);
+    for (int k = 0; k < j; ++k) ny[k] = -y[k];
+    S.gemv_sub_(S.V.p, j, ny.data(), w);       // w = V y
+    S.precond(w, z);
+    S.axpby_(cd(1, 0), z, cd(1, 0), x);
+  }
+  st->iterations = it;
+  st->rel_residual = rel;
+  st->converged = rel <= S.opts.rtol;
+  return st->converged ? VLFS_OK : VLFS_NOT_CONVERGED;
+}
+
+int bicgstab(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
+  const long long n = S.n;
+  const size_t ld = (size_t)n * S.sc;
+  double* r = S.vec(S.r); double* rh = S.vec(S.w); double* p = S.vec(S.z);
+  double* v = S.vec(S.tmp1); double* sv = S.vec(S.tmp2); double* t = S.vec(S.tmp3); double* ph = S.vec(S.tmp4);
+  const double bnorm = S.nrm2(b);
+  if (bnorm == 0.0) {
+    CUDA_TRY(cudaMemsetAsync(x, 0, ld * sizeof(double), S.s));
+    st->iterations = 0; st->converged = 1; st->rel_residual = 0;
+    return VLFS_OK;
+  }
+  S.copy(b, r);
+  S.spmv(x, r, -1.0, 1.0);
+  S.copy(r, rh);
+  cd rho = 1, alpha = 1, omega = 1;
+  CUDA_TRY(cudaMemsetAsync(p, 0, ld * sizeof(double), S.s));
+  CUDA_TRY(cudaMemsetAsync(v, 0, ld * sizeof(double), S.s));
+  double rel = S.nrm2(r) / bnorm;
+  int it = 0;
+  while (rel > S.opts.rtol && it < S.opts.maxit) {
+    cd rho1 = S.dot(rh, r);
+    if (std::abs(rho1) == 0.0) break;
+    cd beta = (rho1 / rho) * (alpha / omega);
+    // p = r + beta (p - omega v)
+    S.axpby_(-omega, v, cd(1, 0), p);
+    S.axpby_(cd(1, 0), r, beta, p);
+    S.precond(p, ph);
+    S.spmv(ph, v);
+    alpha = rho1 / S.dot(rh, v);
+    S.copy(r, sv);
+    S.axpby_(-alpha, v, cd(1, 0), sv);           // s = r - alpha v
+    S.axpby_(alpha, ph, cd(1, 0), x);
+    double sn = S.nrm2(sv);
+    ++it;
+    if (sn / bnorm <= S.opts.rtol) { rel = sn / bnorm; break; }
+    S.precond(sv, ph);
+    S.spmv(ph, t);
+    omega = S.dot(t, sv) / S.dot(t, t);
+    S.axpby_(omega, ph, cd(1, 0), x);
+    S.copy(sv, r);
+    S.axpby_(-omega, t, cd(1, 0), r);
+    rho = rho1;
+    rel = S.nrm2(r) / bnorm;
+  }
+  // true residual
+  S.copy(b, r);
+  S.spmv(x, r, -1.0, 1.0);
+  rel = S.nrm2(r) / bnorm;
+  st->iterations = it; st->rel_residual = rel; st->converged = rel <= S.opts.rtol * 10;
+  return st->converged ? VLFS_OK : VLFS_NOT_CONVERGED;
+}
+
+int cg(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
+  const long long n = S.n;
+  const size_t ld = (size_t)n * S.sc;
+  double* r = S.vec(S.r); double* z = S.vec(S.z); double* p = S.vec(S.w); double* q = S.vec(S.tmp1);
+  const double bnorm = S.nrm2(b);
+  if (bnorm == 0.0) {
+    CUDA_TRY(cudaMemsetAsync(x, 0, ld * sizeof(double), S.s));
+    st->iterations = 0; st->converged = 1; st->rel_residual = 0;
+    return VLFS_OK;
+  }
+  S.copy(b, r);
+  S.spmv(x, r, -1.0, 1.0);
+  S.precond(r, z);
+  S.copy(z, p);
+  cd rz = S.dot(r, z);
+  double rel = S.nrm2(r) / bnorm;
+  int it = 0;
+  while (rel > S.opts.rtol && it < S.opts.maxit) {
+    S.spmv(p, q);
+    cd alpha = rz / S.dot(p, q);
+    S.axpby_(alpha, p, cd(1, 0), x);
+    S.axpby_(-alpha, q, cd(1, 0), r);
+    S.precond(r, z);
+    cd rz1 = S.dot(r, z);
+    S.axpby_(cd(1, 0), z, rz1 / rz, p);
+    rz = rz1;
+    rel = S.nrm2(r) / bnorm;
+    ++it;
+  }
+  st->iterations = it; st->rel_residual = rel; st->converged = rel <= S.opts.rtol;
+  return st->converged ? VLFS_OK : VLFS_NOT_CONVERGED;
+}
+
+}  // namespace
+
+int solver_solve(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
+  vlfs_solve_stats local{};
+  if (!st) st = &local;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, S.s));
+  int rc;
+  if (S.opts.method == VLFS_SOLVER_GMRES) rc = gmres(S, b, x, st);
+  else if (S.opts.method == VLFS_SOLVER_BICGSTAB) rc = bicgstab(S, b, x, st);
+  else rc = cg(S, b, x, st);
+  CUDA_TRY(cudaEventRecord(e1, S.s));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  st->solve_ms = ms;
+  st->setup_ms = S.setup_ms;
+  return rc;
+}
+
+int newmark_run(SolverState& S, const int* rowptr, const int* colind, const double* Cvals,
+                const double* Mvals, long long n, long long nnz, int nsteps, double dt, double gamma,
+                double beta, int nb, double* const* bvecs, const double* tcoef, double* u0, double* v0,
+                double* a0, long long out_lo, long long out_hi, int out_stride, double* out,
+                vlfs_solve_stats* stats, int nsm, cudaStream_t s, long long* launches) {
+  DevBuf<double> u, v, a, u1, rhs, vs, as;
+  u.upload(u0, n, s); v.upload(v0, n, s); a.upload(a0, n, s);
+  u1.alloc(n); rhs.alloc(n); vs.alloc(n); as.alloc(n);
+  const double c_u = gamma / (beta * dt), c_uu = 1.0 / (beta * dt * dt);
+  const double one[2] = {1, 0}, mone[2] = {-1, 0};
+  vlfs_solve_stats tot{};
+  tot.converged = 1;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, s));
+  const long long nout = out_hi - out_lo;
+  long long kout = 0;
+  int rc_all = VLFS_OK;
+  for (int step = 0; step < nsteps; ++step) {
+    // history states: v* = -c_u u + (1-γ/β) v + dt(1-γ/(2β)) a ;  a* = -c_uu u - v/(β dt) - (1-2β)/(2β) a
+    S.copy(v.p, vs.p);
+    S.axpby_(cd(-c_u, 0), u.p, cd(1.0 - gamma / beta, 0), vs.p);
+    S.axpby_(cd(dt * (1.0 - gamma / (2 * beta)), 0), a.p, cd(1, 0), vs.p);
+    S.copy(a.p, as.p);
+    S.axpby_(cd(-c_uu, 0), u.p, cd(-(1.0 - 2 * beta) / (2 * beta), 0), as.p);
+    S.axpby_(cd(-1.0 / (beta * dt), 0), v.p, cd(1, 0), as.p);
+    // rhs = sum_m g_m b_m - C v* - M a*
+    CUDA_TRY(cudaMemsetAsync(rhs.p, 0, n * sizeof(double), s));
+    for (int m = 0; m < nb; ++m) S.axpby_(cd(tcoef[(size_t)step * nb + m], 0), bvecs[m], cd(1, 0), rhs.p);
+    launch_spmv(rowptr, colind, Cvals, vs.p, rhs.p, n, nnz, 0, mone, one, nsm, s);
+    launch_spmv(rowptr, colind, Mvals, as.p, rhs.p, n, nnz, 0, mone, one, nsm, s);
+    *launches += 2;
+    // initial guess: u + dt v + dt²/2 a
+    S.copy(u.p, u1.p);
+    S.axpby_(cd(dt, 0), v.p, cd(1, 0), u1.p);
+    S.axpby_(cd(0.5 * dt * dt, 0), a.p, cd(1, 0), u1.p);
+    vlfs_solve_stats st{};
+    int rc = solver_solve(S, rhs.p, u1.p, &st);
+    if (rc != VLFS_OK && rc != VLFS_NOT_CONVERGED) return rc;
+    if (rc == VLFS_NOT_CONVERGED) { rc_all = rc; tot.converged = 0; }
+    tot.iterations += st.iterations;
+    if (st.rel_residual > tot.rel_residual) tot.rel_residual = st.rel_residual;
+    // v1 = v* + c_u u1 ; a1 = a* + c_uu u1
+    S.axpby_(cd(c_u, 0), u1.p, cd(1, 0), vs.p);
+    S.axpby_(cd(c_uu, 0), u1.p, cd(1, 0), as.p);
+    S.copy(u1.p, u.p); S.copy(vs.p, v.p); S.copy(as.p, a.p);
+    if (nout > 0 && (step + 1) % out_stride == 0) {
+      CUDA_TRY(cudaMemcpyAsync(out + kout * nout, u.p + out_lo, nout * sizeof(double), cudaMemcpyDeviceToHost, s));
+      ++kout;
+    }
+  }
+  CUDA_TRY(cudaEventRecord(e1, s));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  tot.solve_ms = ms;
+  tot.setup_ms = S.setup_ms;
+  CUDA_TRY(cudaMemcpyAsync(u0, u.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(v0, v.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(a0, a.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (stats) *stats = tot;
+  return rc_all;
+}

@@ -232,7 +232,7 @@ class CellOps:
         dG = geo.gradients(pts)
         if per_cell:
             ne, nq = xref.shape[:2]
-            N = N.reshape(ne, nq, -1)
+            N = N.reshape(ne, nq, reffe.ndofs)
             dN = dN.reshape(ne, nq, reffe.ndofs, poly.dim)
             dG = dG.reshape(ne, nq, geo.ndofs, poly.dim)
             Jt = np.einsum("eqva,evb->eqab", dG, X)
@@ -262,7 +262,7 @@ class CellOps:
         xref = np.asarray(xref, dtype=float)
         if xref.ndim == 3:
             ne, nq = xref.shape[:2]
-            N = geo.values(xref.reshape(-1, poly.dim)).reshape(ne, nq, -1)
+            N = geo.values(xref.reshape(-1, poly.dim)).reshape(ne, nq, geo.ndofs)
             return np.einsum("eqv,evb->eqb", N, X)
         return np.einsum("qv,evb->eqb", geo.values(xref), X)
 
@@ -272,7 +272,7 @@ def phys_points(X, poly, xref):
     xref = np.asarray(xref, dtype=float)
     if xref.ndim == 3:
         ne, nq = xref.shape[:2]
-        N = geo.values(xref.reshape(-1, poly.dim)).reshape(ne, nq, -1)
+        N = geo.values(xref.reshape(-1, poly.dim)).reshape(ne, nq, geo.ndofs)
         return np.einsum("eqv,evb->eqb", N, X)
     return np.einsum("qv,evb->eqb", geo.values(xref), X)
 

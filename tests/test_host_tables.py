@@ -1,0 +1,76 @@
+"""Host-side mirror (vectorised front end + descriptor marshalling) against the oracle's
+independent loop-based front end and literal weak forms - CPU only."""
+import os
+import numpy as np
+import pytest
+import vlfs_b200
+from vlfs_b200 import geometry as G, fe as F
+from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
+from oracle.descriptor_eval import RecordingSystem
+from oracle.cases.yago import YagoCase
+from oracle import model as om, fem as ofem, reffe as orf, polytopes as opt, quadrature as oq
+
+
+def test_reference_tables_match_oracle():
+    rng = np.random.default_rng(0)
+    for name, o in [("SEGMENT", 4), ("QUAD", 4), ("QUAD", 2), ("HEX", 2), ("TRI", 4), ("TET", 2)]:
+        P = G.Polytope(name)
+        a = F.get_reffe(P, o)
+        b = orf.lagrangian(getattr(opt, name), o)
+        assert np.allclose(a.nodes, b.nodes, atol=1e-15)
+        x = rng.random((7, P.dim)) * (0.3 if P.is_simplex else 1.0)
+        v, g, h = a.tabulate(x, need_hess=True)
+        assert np.abs(v - b.values(x)).max() < 1e-11
+        assert np.abs(g - b.gradients(x)).max() < 1e-9
+        assert np.abs(h - b.hessians(x)).max() < 1e-7
+    for name, deg in [("QUAD", 8), ("HEX", 8), ("TRI", 8), ("TET", 4), ("SEGMENT", 4)]:
+        xa, wa = F.quadrature(G.Polytope(name), deg)
+        xb, wb = oq.quadrature(getattr(opt, name), deg)
+        assert np.allclose(xa, xb, atol=1e-15) and np.allclose(wa, wb, atol=1e-16)
+
+
+def test_cartesian_topology_matches_oracle():
+    for kw in [dict(domain=(0, 3, 0, 2), partition=(4, 3)),
+               dict(domain=(0, 3, 0, 2, 0, 1), partition=(3, 2, 2)),
+               dict(domain=(0, 1, 0, 1), partition=(6, 3), isperiodic=(True, False))]:
+        a = G.CartesianDiscreteModel(kw["domain"], kw["partition"], isperiodic=kw.get("isperiodic"))
+        b = om.cartesian_model(kw["domain"], kw["partition"], isperiodic=kw.get("isperiodic"))
+        assert np.array_equal(a.cell_nodes, b.cell_nodes) and np.array_equal(a.cell_vertices, b.cell_vertices)
+        for d in range(1, a.D):
+            assert np.array_equal(a.face_vertices[d], b.face_vertices[d])
+            assert np.array_equal(a.cell_faces[d], b.cell_faces[d])
+        for d in range(a.D + 1):
+            assert np.array_equal(a.face_entity[d], b.face_entity[d])
+
+
+def test_json_model_matches_oracle(golden_dir):
+    a = G.DiscreteModelFromFile(os.path.join(golden_dir, "multi_geo_coarse.json"))
+    b = om.json_model(os.path.join(golden_dir, "multi_geo_coarse.json"))
+    for d in (1, 2):
+        assert np.array_equal(a.face_vertices[d], b.face_vertices[d])
+        assert np.array_equal(a.cell_faces[d], b.cell_faces[d])
+    ga = G.Boundary(a, tags="plate")
+    gb = ofem.boundary(b, "plate")
+    assert np.array_equal(ga.facets, gb.facets) and np.array_equal(ga.cell, gb.cell)
+    assert np.array_equal(ga.lface, gb.lface)
+    sa, sb = G.Skeleton(ga), ofem.SkeletonTriangulation(gb)
+    assert np.array_equal(sa.plus, sb.plus) and np.array_equal(sa.minus, sb.minus)
+    assert np.array_equal(sa.plus_lf, sb.plus_lf) and np.array_equal(sa.minus_lf, sb.minus_lf)
+    va, vb = F.FESpace(ga, 4), ofem.FESpace(gb, 4)
+    assert va.ndofs == vb.ndofs and np.array_equal(va.cell_dofs, vb.cell_dofs)
+
+
+@pytest.mark.parametrize("kw", [dict(nx=2, ny=2, nz=1, order=2, lfactor=0.4, dfactor=3),
+                                dict(nx=1, ny=1, nz=2, order=4, lfactor=0.6, dfactor=4)])
+def test_yago_descriptors_reproduce_oracle_matrix(kw):
+    p = YagoProblem(Yago_freq_domain_params(**kw), system_cls=RecordingSystem)
+    o = YagoCase(**kw)
+    for a, b in [(p.V_Om, o.V_phi), (p.V_Gk, o.V_kap), (p.V_Ge, o.V_eta)]:
+        assert a.ndofs == b.ndofs and np.array_equal(a.cell_dofs, b.cell_dofs)
+    mats, vecs = p.sys.evaluate()
+    A, b = o.assemble()
+    A = A.tocsr(); A.sort_indices()
+    M = mats[0]
+    assert np.array_equal(A.indptr, M.indptr) and np.array_equal(A.indices, M.indices)
+    assert np.abs(A.data - M.data).max() <= 1e-12 * np.abs(A.data).max()
+    assert np.abs(b - vecs[0]).max() <= 1e-12 * np.abs(b).max()
