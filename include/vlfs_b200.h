@@ -139,7 +139,8 @@ typedef struct {
 } vlfs_solve_stats;
 
 enum { VLFS_SOLVER_GMRES = 0, VLFS_SOLVER_BICGSTAB = 1, VLFS_SOLVER_CG = 2 };
-enum { VLFS_PRECOND_NONE = 0, VLFS_PRECOND_JACOBI = 1, VLFS_PRECOND_BLOCK_ILU0 = 2 };
+enum { VLFS_PRECOND_NONE = 0, VLFS_PRECOND_JACOBI = 1, VLFS_PRECOND_BLOCK_ILU0 = 2,
+       VLFS_PRECOND_SPARSE_LU = 3 /* GPU multifrontal LU of the matrix (the LUSolver() twin) */ };
 
 typedef struct vlfs_ctx vlfs_ctx;
 
@@ -177,7 +178,14 @@ int vlfs_combine(vlfs_ctx* ctx, int target, int n, const int* src, const double*
 
 /* ---- algebra -------------------------------------------------------------------- */
 int vlfs_spmv(vlfs_ctx* ctx, int mat, const void* x, void* y);         /* host in/out   */
+/* DOF node coordinates [ndofs][dim] (Gridap: get_cell_points(get_fe_dof_basis(V))); drives the
+ * geometric nested dissection of VLFS_PRECOND_SPARSE_LU. */
+int vlfs_set_dof_coords(vlfs_ctx* ctx, int dim, const double* coords);
 int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts);
+/* refactorise the current values of `mat` keeping the symbolic analysis (ω sweeps) */
+int vlfs_solver_refactor(vlfs_ctx* ctx, int mat);
+/* {nfronts, nlevels, maxfront, fill entries, flops, pool bytes, symbolic ms, numeric ms} */
+int vlfs_direct_info(vlfs_ctx* ctx, double* out8);
 int vlfs_solve(vlfs_ctx* ctx, const void* b, void* x, vlfs_solve_stats* stats);   /* host */
 int vlfs_solve_vec(vlfs_ctx* ctx, int vec, void* x, vlfs_solve_stats* stats); /* assembled rhs */
 

@@ -12,7 +12,7 @@ MAX_SLOTS = 2
 OP_VAL, OP_GRAD, OP_DDIR, OP_LAPL, OP_HESS, OP_CHESS, OP_GRAD_NOWN, OP_CHESS_NPLUS = range(8)
 MEASURE_CELL, MEASURE_FACET = 0, 1
 SOLVER_GMRES, SOLVER_BICGSTAB, SOLVER_CG = 0, 1, 2
-PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_ILU0 = 0, 1, 2
+PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_ILU0, PRECOND_SPARSE_LU = 0, 1, 2, 3
 OK, NOT_CONVERGED = 0, 3
 
 _dp = C.POINTER(C.c_double)
@@ -65,7 +65,7 @@ EXPORTS = [
     "vlfs_set_term_coef", "vlfs_set_rhs_coef", "vlfs_set_weights", "vlfs_build_pattern",
     "vlfs_get_pattern", "vlfs_get_pattern_csc", "vlfs_assemble", "vlfs_assemble_matrices",
     "vlfs_assemble_vectors", "vlfs_get_values", "vlfs_get_vector", "vlfs_combine", "vlfs_spmv",
-    "vlfs_solver_setup", "vlfs_solve", "vlfs_solve_vec", "vlfs_newmark_run", "vlfs_spmv_device",
+    "vlfs_set_dof_coords", "vlfs_solver_setup", "vlfs_solver_refactor", "vlfs_direct_info", "vlfs_solve", "vlfs_solve_vec", "vlfs_newmark_run", "vlfs_spmv_device",
     "vlfs_assemble_timed", "vlfs_last_kernel_launches", "vlfs_device_ptrs",
 ]
 
@@ -110,6 +110,9 @@ def load():
     lib.vlfs_combine.argtypes = [vp, C.c_int, C.c_int, _ip, _dp]
     lib.vlfs_spmv.argtypes = [vp, C.c_int, vp, vp]
     lib.vlfs_solver_setup.argtypes = [vp, C.c_int, C.POINTER(SolverOpts)]
+    lib.vlfs_set_dof_coords.argtypes = [vp, C.c_int, _dp]
+    lib.vlfs_solver_refactor.argtypes = [vp, C.c_int]
+    lib.vlfs_direct_info.argtypes = [vp, _dp]
     lib.vlfs_solve.argtypes = [vp, vp, vp, C.POINTER(SolveStats)]
     lib.vlfs_solve_vec.argtypes = [vp, C.c_int, vp, C.POINTER(SolveStats)]
     lib.vlfs_newmark_run.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,

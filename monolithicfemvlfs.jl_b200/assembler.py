@@ -221,6 +221,21 @@ class B200System:
         self._check(self.lib.vlfs_spmv(self.ctx, mat, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)))
         return y
 
+    def set_dof_coords(self, coords):
+        """DOF node coordinates (ndofs, dim) - ordering input of the sparse LU."""
+        c = L.f64(coords)
+        assert c.shape[0] == self.ndofs
+        self._check(self.lib.vlfs_set_dof_coords(self.ctx, c.shape[1], L.dptr(c)))
+
+    def refactor(self, mat=0):
+        self._check(self.lib.vlfs_solver_refactor(self.ctx, mat))
+
+    def direct_info(self):
+        out = np.zeros(8)
+        self._check(self.lib.vlfs_direct_info(self.ctx, L.dptr(out)))
+        keys = ["nfronts", "nlevels", "maxfront", "fill", "flops", "pool_bytes", "symbolic_ms", "numeric_ms"]
+        return dict(zip(keys, out.tolist()))
+
     def solver_setup(self, mat=0, method=L.SOLVER_GMRES, precond=L.PRECOND_JACOBI, restart=100,
                      maxit=5000, rtol=1e-10, block_size_hint=0, sweeps=0):
         o = L.SolverOpts(method, precond, restart, maxit, rtol, block_size_hint, sweeps)

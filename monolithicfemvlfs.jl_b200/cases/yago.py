@@ -137,6 +137,8 @@ class YagoProblem:
                                            measure_slot=1, weights=[np.zeros(self._xq_Gin.shape[:2])] * 2)
         d.add_rhs(0, 1.0, L.OP_VAL, PHI, weight_re=0, weight_im=1)
         self.nnz = sys_.build_pattern()
+        if hasattr(sys_, "set_dof_coords"):
+            sys_.set_dof_coords(X.dof_coords()[:, :2])       # quasi-2-D: dissect in the (x,y) plane
         self.set_frequency(p.lfactor)
 
     # ω-dependent scalars and coefficient fields only (the sweep of scripts/5-4-1-Yago.jl:33-71)
@@ -193,7 +195,7 @@ class YagoProblem:
 def run_Yago_freq_domain(params, device=0, solver=None):
     prob = YagoProblem(params, device=device)
     prob.assemble()
-    opts = dict(method=L.SOLVER_GMRES, precond=L.PRECOND_JACOBI, restart=200, maxit=20000, rtol=1e-10)
+    opts = dict(method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=30, maxit=60, rtol=1e-12)
     opts.update(solver or {})
     prob.sys.solver_setup(0, **opts)
     x, stats = prob.sys.solve(vec=0)

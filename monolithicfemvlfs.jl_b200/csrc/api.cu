@@ -80,6 +80,10 @@ struct vlfs_ctx {
   std::vector<DevBuf<double>> mats, vecs;
   long long launches = 0;
   SolverPtr solver;
+  DirectPtr direct;
+  std::vector<double> dof_coords;
+  int coord_dim = 0;
+  int solver_mat = -1;
   size_t scalar() const { return is_complex ? 2 : 1; }
 };
 
@@ -321,6 +325,7 @@ int vlfs_destroy(vlfs_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->solver.reset();
+  ctx->direct.reset();
   ctx->doms.clear();
   ctx->mats.clear();
   ctx->vecs.clear();
@@ -337,7 +342,7 @@ int vlfs_system_init(vlfs_ctx* ctx, int64_t ndofs, int is_complex, int nmat, int
       return fail(ctx, VLFS_ERR_ARG, "vlfs_system_init: bad sizes (1<=nmat<=4, 0<=nvec<=4)");
     ctx->ndofs = ndofs; ctx->is_complex = is_complex ? 1 : 0; ctx->nmat = nmat; ctx->nvec = nvec;
     ctx->doms.clear(); ctx->mats.clear(); ctx->vecs.clear();
-    ctx->pattern_built = false; ctx->solver.reset();
+    ctx->pattern_built = false; ctx->solver.reset(); ctx->direct.reset(); ctx->dof_coords.clear();
     ctx->vecs.resize(nvec);
     for (auto& v : ctx->vecs) { v.alloc((size_t)ndofs * ctx->scalar()); v.zero(ctx->stream); }
     return VLFS_OK;
@@ -632,10 +637,45 @@ int vlfs_device_ptrs(vlfs_ctx* ctx, int mat, void** rowptr, void** colind, void*
 int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
   return guarded(ctx, [&]() {
     if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !opts) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    if (opts->precond == VLFS_PRECOND_SPARSE_LU) {
+      if (ctx->dof_coords.empty()) return fail(ctx, VLFS_ERR_STATE, "vlfs_set_dof_coords first (sparse LU ordering)");
+      if (!ctx->direct)
+        ctx->direct = direct_symbolic(ctx->rowptr.p, ctx->colind.p, ctx->ndofs, ctx->nnz, ctx->dof_coords.data(),
+                                      ctx->coord_dim, opts->block_size_hint, ctx->is_complex, ctx->nsm,
+                                      ctx->stream, &ctx->launches);
+      direct_numeric(*ctx->direct, ctx->rowind.p, ctx->colind.p, ctx->mats[mat].p);
+    }
     ctx->solver = solver_create(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, ctx->ndofs, ctx->nnz,
-                                ctx->is_complex, *opts, ctx->nsm, ctx->stream, &ctx->launches);
+                                ctx->is_complex, *opts, ctx->nsm, ctx->stream, &ctx->launches,
+                                ctx->direct.get());
+    ctx->solver_mat = mat;
     return VLFS_OK;
   });
+}
+
+int vlfs_set_dof_coords(vlfs_ctx* ctx, int dim, const double* coords) {
+  return guarded(ctx, [&]() {
+    if (dim < 1 || dim > 3 || !coords || ctx->ndofs == 0) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    ctx->dof_coords.assign(coords, coords + (size_t)ctx->ndofs * dim);
+    ctx->coord_dim = dim;
+    ctx->direct.reset();
+    return VLFS_OK;
+  });
+}
+
+int vlfs_solver_refactor(vlfs_ctx* ctx, int mat) {
+  return guarded(ctx, [&]() {
+    if (!ctx->solver || !ctx->direct || mat < 0 || mat >= ctx->nmat)
+      return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup with VLFS_PRECOND_SPARSE_LU first");
+    direct_numeric(*ctx->direct, ctx->rowind.p, ctx->colind.p, ctx->mats[mat].p);
+    return VLFS_OK;
+  });
+}
+
+int vlfs_direct_info(vlfs_ctx* ctx, double* out8) {
+  if (!ctx || !out8 || !ctx->direct) return VLFS_ERR_ARG;
+  direct_info(*ctx->direct, out8);
+  return VLFS_OK;
 }
 
 int vlfs_solve(vlfs_ctx* ctx, const void* b, void* x, vlfs_solve_stats* stats) {

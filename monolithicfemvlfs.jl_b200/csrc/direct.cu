@@ -1,0 +1,769 @@
+// direct.cu - GPU multifrontal sparse LU (FP64 real / complex, sm_100a).
+//
+// This is the B200 replacement of `LUSolver()` = UMFPACK `lu(A)` + `ldiv!` behind
+// `solve(op)` (src/Yago_freq_domain.jl:171, src/Khabakhpasheva_freq_domain.jl:241,
+// src/Multi_geo_freq_domain.jl:135) and behind `Newmark(LUSolver(),...)`
+// (src/Khabakhpasheva_time_domain.jl:258-259, src/Periodic_Beam.jl:107-108).  The
+// monolithic matrices are indefinite wave operators on which Jacobi/ILU0 Krylov stalls
+// (solver study), so the factorisation itself runs on the GPU:
+//   symbolic (host, once per pattern): geometric nested dissection on the DOF coordinates,
+//     separator tree -> supernodes, front index sets, level schedule;
+//   numeric (device): dense fronts in one pool; per tree level, batched over fronts:
+//     extend-add of the children's Schur complements, then a blocked right-looking partial LU
+//     (32-column panels: diagonal-block LU in shared memory, panel triangular solves, rank-32
+//     Schur update with 64x64 register-tiled FP64 tiles);
+//   solve (device): level-scheduled forward / backward sweeps over the fronts.
+// No pivoting across fronts (static pivoting, verified adequate on these FE matrices); the
+// Krylov driver uses the factorisation as a right preconditioner, so the reported residual is
+// always the true one and one refinement step recovers full accuracy.
+#include "common.cuh"
+#include "direct.cuh"
+#include <algorithm>
+#include <chrono>
+#include <numeric>
+#include <cmath>
+
+namespace {
+
+constexpr int NB = 32;      // panel width
+constexpr int TS = 64;      // Schur tile
+
+template <bool C> struct Num;
+template <> struct Num<false> {
+  using T = double;
+  __device__ static T zero() { return 0.0; }
+  __device__ static T mul(T a, T b) { return a * b; }
+  __device__ static T fnma(T a, T b, T c) { return fma(-a, b, c); }      // c - a*b
+  __device__ static T div(T a, T b) { return a / b; }
+  __device__ static T add(T a, T b) { return a + b; }
+  __device__ static T shfl(T a, int src) { return __shfl_sync(0xffffffffu, a, src); }
+  __device__ static T shfl_down(T a, int o) { return __shfl_down_sync(0xffffffffu, a, o); }
+};
+template <> struct Num<true> {
+  using T = double2;
+  __device__ static T zero() { return make_double2(0, 0); }
+  __device__ static T mul(T a, T b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+  __device__ static T fnma(T a, T b, T c) {
+    c.x = fma(-a.x, b.x, c.x); c.x = fma(a.y, b.y, c.x);
+    c.y = fma(-a.x, b.y, c.y); c.y = fma(-a.y, b.x, c.y);
+    return c;
+  }
+  __device__ static T div(T a, T b) {
+    double d = 1.0 / (b.x * b.x + b.y * b.y);
+    return make_double2((a.x * b.x + a.y * b.y) * d, (a.y * b.x - a.x * b.y) * d);
+  }
+  __device__ static T add(T a, T b) { return make_double2(a.x + b.x, a.y + b.y); }
+  __device__ static T shfl(T a, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src));
+  }
+  __device__ static T shfl_down(T a, int o) {
+    return make_double2(__shfl_down_sync(0xffffffffu, a.x, o), __shfl_down_sync(0xffffffffu, a.y, o));
+  }
+};
+
+struct FrontMeta {
+  long long off;      // offset of the nf x nf row-major front in the pool (scalars)
+  long long woff;     // offset of the front's work vector (nf scalars)
+  int first;          // first pivot position (permuted numbering)
+  int np, nf;
+  int upd_ptr;        // into upd_idx (nf - np entries, ascending permuted positions)
+  int child[2];       // child fronts or -1
+  int cmap_ptr;       // into cmap: local index in the parent of each update index
+  int parent;
+};
+
+__device__ __forceinline__ int local_index(const FrontMeta& F, const int* __restrict__ upd_idx, int p) {
+  if (p < F.first + F.np) return p - F.first;
+  const int* u = upd_idx + F.upd_ptr;
+  int lo = 0, hi = F.nf - F.np;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (u[mid] < p) lo = mid + 1; else hi = mid;
+  }
+  return F.np + lo;
+}
+
+template <bool C>
+__global__ void scatter_matrix(const int* __restrict__ rowind, const int* __restrict__ colind,
+                               const typename Num<C>::T* __restrict__ vals, long long nnz,
+                               const int* __restrict__ pos, const int* __restrict__ front_of_pos,
+                               const FrontMeta* __restrict__ meta, const int* __restrict__ upd_idx,
+                               typename Num<C>::T* __restrict__ pool) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < nnz;
+       p += (long long)gridDim.x * blockDim.x) {
+    int pi = pos[rowind[p]], pj = pos[colind[p]];
+    int f = front_of_pos[pi < pj ? pi : pj];
+    const FrontMeta F = meta[f];
+    int li = local_index(F, upd_idx, pi), lj = local_index(F, upd_idx, pj);
+    pool[F.off + (long long)li * F.nf + lj] = vals[p];
+  }
+}
+
+__global__ void build_cmap(const FrontMeta* __restrict__ meta, int nfronts, const int* __restrict__ upd_idx,
+                           int* __restrict__ cmap) {
+  int f = blockIdx.x;
+  if (f >= nfronts) return;
+  const FrontMeta F = meta[f];
+  if (F.parent < 0) return;
+  const FrontMeta P = meta[F.parent];
+  const int* u = upd_idx + F.upd_ptr;
+  for (int k = threadIdx.x; k < F.nf - F.np; k += blockDim.x)
+    cmap[F.cmap_ptr + k] = local_index(P, upd_idx, u[k]);
+}
+
+// parent += Schur complement of child `slot`; one launch per slot keeps the sum order fixed
+template <bool C>
+__global__ void extend_add(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int slot,
+                           const int* __restrict__ cmap, typename Num<C>::T* __restrict__ pool) {
+  using N = Num<C>;
+  const FrontMeta P = meta[list[blockIdx.z]];
+  const int c = P.child[slot];
+  if (c < 0) return;
+  const FrontMeta Cf = meta[c];
+  const int nu = Cf.nf - Cf.np;
+  const int a = blockIdx.y * 16 + threadIdx.y;
+  const int* cm = cmap + Cf.cmap_ptr;
+  if (a >= nu) return;
+  const long long prow = P.off + (long long)cm[a] * P.nf;
+  const long long crow = Cf.off + (long long)(Cf.np + a) * Cf.nf + Cf.np;
+  for (int b = blockIdx.x * 64 + threadIdx.x; b < nu; b += gridDim.x * 64) {
+    typename N::T* dst = pool + prow + cm[b];
+    *dst = N::add(*dst, pool[crow + b]);
+  }
+}
+
+// LU without pivoting of the diagonal block of panel k (in place)
+template <bool C>
+__global__ void __launch_bounds__(NB * NB)
+diag_lu(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
+        typename Num<C>::T* __restrict__ pool) {
+  using N = Num<C>;
+  __shared__ typename N::T sm[NB][NB + 1];
+  const FrontMeta F = meta[list[blockIdx.x]];
+  const int k0 = k * NB;
+  if (k0 >= F.np) return;
+  const int kb = min(NB, F.np - k0);
+  const int r = threadIdx.y, c = threadIdx.x;
+  typename N::T* D = pool + F.off + (long long)k0 * F.nf + k0;
+  if (r < kb && c < kb) sm[r][c] = D[(long long)r * F.nf + c];
+  __syncthreads();
+  for (int j = 0; j < kb; ++j) {
+    if (c == j && r > j && r < kb) sm[r][j] = N::div(sm[r][j], sm[j][j]);
+    __syncthreads();
+    if (r > j && c > j && r < kb && c < kb) sm[r][c] = N::fnma(sm[r][j], sm[j][c], sm[r][c]);
+    __syncthreads();
+  }
+  if (r < kb && c < kb) D[(long long)r * F.nf + c] = sm[r][c];
+}
+
+// L-panel: rows below the diagonal block times U11^{-1};  U-panel: L11^{-1} times the columns
+// to the right.  blockIdx.y = 0: L-panel (thread per row), 1: U-panel (thread per column).
+template <bool C>
+__global__ void __launch_bounds__(128)
+panel_trsm(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
+           typename Num<C>::T* __restrict__ pool) {
+  using N = Num<C>;
+  __shared__ typename N::T sD[NB][NB + 1];
+  const FrontMeta F = meta[list[blockIdx.z]];
+  const int k0 = k * NB;
+  if (k0 >= F.np) return;
+  const int kb = min(NB, F.np - k0);
+  const int k1 = k0 + kb;
+  const int idx = k1 + blockIdx.x * 128 + threadIdx.x;
+  if (k1 + blockIdx.x * 128 >= F.nf) return;
+  typename N::T* Fp = pool + F.off;
+  for (int t = threadIdx.x; t < kb * kb; t += 128)
+    sD[t / kb][t % kb] = Fp[(long long)(k0 + t / kb) * F.nf + k0 + t % kb];
+  __syncthreads();
+  if (idx >= F.nf) return;
+  typename N::T x[NB];
+  if (blockIdx.y == 0) {
+    typename N::T* row = Fp + (long long)idx * F.nf + k0;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) x[c] = c < kb ? row[c] : N::zero();
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      if (c < kb) {
+        typename N::T v = x[c];
+#pragma unroll
+        for (int r = 0; r < c; ++r) v = N::fnma(x[r], sD[r][c], v);
+        x[c] = N::div(v, sD[c][c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NB; ++c) if (c < kb) row[c] = x[c];
+  } else {
+    typename N::T* col = Fp + (long long)k0 * F.nf + idx;
+#pragma unroll
+    for (int r = 0; r < NB; ++r) x[r] = r < kb ? col[(long long)r * F.nf] : N::zero();
+#pragma unroll
+    for (int r = 0; r < NB; ++r) {
+      if (r < kb) {
+        typename N::T v = x[r];
+#pragma unroll
+        for (int q = 0; q < r; ++q) v = N::fnma(sD[r][q], x[q], v);
+        x[r] = v;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NB; ++r) if (r < kb) col[(long long)r * F.nf] = x[r];
+  }
+}
+
+// trailing update  F[i][j] -= sum_r F[i][k0+r] F[k0+r][j],  i,j >= k1
+template <bool C>
+__global__ void __launch_bounds__(256)
+schur_update(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
+             typename Num<C>::T* __restrict__ pool) {
+  using N = Num<C>;
+  extern __shared__ double smraw[];
+  typename N::T(*sA)[NB + 1] = reinterpret_cast<typename N::T(*)[NB + 1]>(smraw);
+  typename N::T(*sB)[TS] = reinterpret_cast<typename N::T(*)[TS]>(sA + TS);
+  const FrontMeta F = meta[list[blockIdx.z]];
+  const int k0 = k * NB;
+  if (k0 >= F.np) return;
+  const int kb = min(NB, F.np - k0);
+  const int k1 = k0 + kb;
+  const int i0 = k1 + blockIdx.y * TS, j0 = k1 + blockIdx.x * TS;
+  if (i0 >= F.nf || j0 >= F.nf) return;
+  typename N::T* Fp = pool + F.off;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < TS * NB; t += 256) {
+    int r = t / NB, c = t % NB;
+    int i = i0 + r;
+    sA[r][c] = (i < F.nf && c < kb) ? Fp[(long long)i * F.nf + k0 + c] : N::zero();
+  }
+  for (int t = tid; t < NB * TS; t += 256) {
+    int r = t / TS, c = t % TS;
+    int j = j0 + c;
+    sB[r][c] = (j < F.nf && r < kb) ? Fp[(long long)(k0 + r) * F.nf + j] : N::zero();
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  typename N::T acc[4][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[m][n] = N::zero();
+#pragma unroll 8
+  for (int kk = 0; kk < NB; ++kk) {
+    typename N::T a[4], b[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) a[m] = sA[ty + 16 * m][kk];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) b[n] = sB[kk][tx + 16 * n];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[m][n] = N::fnma(a[m], b[n], acc[m][n]);
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    int i = i0 + ty + 16 * m;
+    if (i >= F.nf) continue;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      int j = j0 + tx + 16 * n;
+      if (j < F.nf) {
+        typename N::T* p = Fp + (long long)i * F.nf + j;
+        *p = N::add(*p, acc[m][n]);
+      }
+    }
+  }
+}
+
+// ---- solve kernels --------------------------------------------------------------------
+template <bool C>
+__global__ void permute_in(const typename Num<C>::T* __restrict__ b, const int* __restrict__ pos,
+                           typename Num<C>::T* __restrict__ bp, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    bp[pos[i]] = b[i];
+}
+template <bool C>
+__global__ void permute_out(const typename Num<C>::T* __restrict__ xp, const int* __restrict__ pos,
+                            typename Num<C>::T* __restrict__ x, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = xp[pos[i]];
+}
+
+// w = [b_P ; 0] + contributions of the children (fixed order: slot 0 then slot 1)
+template <bool C>
+__global__ void fwd_gather(const FrontMeta* __restrict__ meta, const int* __restrict__ list,
+                           const int* __restrict__ cmap, const typename Num<C>::T* __restrict__ bp,
+                           typename Num<C>::T* __restrict__ w) {
+  using N = Num<C>;
+  const FrontMeta F = meta[list[blockIdx.x]];
+  typename N::T* wf = w + F.woff;
+  for (int i = threadIdx.x; i < F.nf; i += blockDim.x) wf[i] = i < F.np ? bp[F.first + i] : N::zero();
+  __syncthreads();
+  for (int s = 0; s < 2; ++s) {
+    const int c = F.child[s];
+    if (c < 0) continue;
+    const FrontMeta Cf = meta[c];
+    const typename N::T* wc = w + Cf.woff + Cf.np;
+    const int* cm = cmap + Cf.cmap_ptr;
+    for (int a = threadIdx.x; a < Cf.nf - Cf.np; a += blockDim.x) wf[cm[a]] = N::add(wf[cm[a]], wc[a]);
+    __syncthreads();
+  }
+}
+
+// forward panel step: solve the unit-lower diagonal block, then update all rows below
+template <bool C>
+__global__ void __launch_bounds__(256)
+fwd_panel(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
+          const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ w) {
+  using N = Num<C>;
+  __shared__ typename N::T sx[NB];
+  const FrontMeta F = meta[list[blockIdx.y]];
+  const int k0 = k * NB;
+  if (k0 >= F.np) return;
+  const int kb = min(NB, F.np - k0);
+  const int k1 = k0 + kb;
+  const typename N::T* Fp = pool + F.off;
+  typename N::T* wf = w + F.woff;
+  // every block redoes the tiny triangular solve (keeps it one launch per panel); only
+  // block 0 writes it back
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    typename N::T x = r < kb ? wf[k0 + r] : N::zero();
+    for (int c = 0; c < kb; ++c) {
+      typename N::T xc = N::shfl(x, c);
+      if (r > c && r < kb) x = N::fnma(Fp[(long long)(k0 + r) * F.nf + k0 + c], xc, x);
+    }
+    if (r < kb) sx[r] = x;
+  }
+  __syncthreads();
+  const int i = k1 + blockIdx.x * 256 + threadIdx.x;
+  if (i < F.nf) {
+    const typename N::T* row = Fp + (long long)i * F.nf + k0;
+    typename N::T v = wf[i];
+    for (int c = 0; c < kb; ++c) v = N::fnma(row[c], sx[c], v);
+    // rows of this panel are rewritten below by block 0 only after all blocks have read
+    // wf[k0..k1): they are never in [k1, nf), so there is no hazard
+    wf[i] = v;
+  }
+}
+template <bool C>
+__global__ void fwd_panel_commit(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
+                                 const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ w) {
+  using N = Num<C>;
+  const FrontMeta F = meta[list[blockIdx.x]];
+  const int k0 = k * NB;
+  if (k0 >= F.np) return;
+  const int kb = min(NB, F.np - k0);
+  const typename N::T* Fp = pool + F.off;
+  typename N::T* wf = w + F.woff;
+  const int r = threadIdx.x;
+  typename N::T x = r < kb ? wf[k0 + r] : N::zero();
+  for (int c = 0; c < kb; ++c) {
+    typename N::T xc = N::shfl(x, c);
+    if (r > c && r < kb) x = N::fnma(Fp[(long long)(k0 + r) * F.nf + k0 + c], xc, x);
+  }
+  if (r < kb) wf[k0 + r] = x;
+}
+
+// backward: r_P = y_P - U12 x_U  (warp per pivot row), x_U gathered from the solved vector
+template <bool C>
+__global__ void __launch_bounds__(256)
+bwd_gemv(const FrontMeta* __restrict__ meta, const int* __restrict__ list, const int* __restrict__ upd_idx,
+         const typename Num<C>::T* __restrict__ pool, const typename Num<C>::T* __restrict__ xp,
+         typename Num<C>::T* __restrict__ w) {
+  using N = Num<C>;
+  const FrontMeta F = meta[list[blockIdx.y]];
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= F.np) return;
+  const int nu = F.nf - F.np;
+  const typename N::T* Fr = pool + F.off + (long long)row * F.nf + F.np;
+  const int* u = upd_idx + F.upd_ptr;
+  typename N::T acc = N::zero();
+  for (int a = lane; a < nu; a += 32) acc = N::fnma(Fr[a], xp[u[a]], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = N::add(acc, N::shfl_down(acc, o));
+  if (lane == 0) w[F.woff + row] = N::add(w[F.woff + row], acc);
+}
+
+// backward panel step (descending k): solve the upper diagonal block, update the rows above
+template <bool C>
+__global__ void __launch_bounds__(256)
+bwd_panel(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
+          const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ w) {
+  using N = Num<C>;
+  __shared__ typename N::T sx[NB];
+  const FrontMeta F = meta[list[blockIdx.y]];
+  const int k0 = k * NB;
+  if (k0 >= F.np) return;
+  const int kb = min(NB, F.np - k0);
+  const typename N::T* Fp = pool + F.off;
+  typename N::T* wf = w + F.woff;
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    typename N::T x = r < kb ? wf[k0 + r] : N::zero();
+    for (int c = kb - 1; c >= 0; --c) {
+      if (r == c) x = N::div(x, Fp[(long long)(k0 + c) * F.nf + k0 + c]);
+      typename N::T xc = N::shfl(x, c);
+      if (r < c) x = N::fnma(Fp[(long long)(k0 + r) * F.nf + k0 + c], xc, x);
+    }
+    if (r < kb) sx[r] = x;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < k0) {
+    const typename N::T* row = Fp + (long long)i * F.nf + k0;
+    typename N::T v = wf[i];
+    for (int c = 0; c < kb; ++c) v = N::fnma(row[c], sx[c], v);
+    wf[i] = v;
+  }
+}
+template <bool C>
+__global__ void bwd_panel_commit(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
+                                 const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ w,
+                                 typename Num<C>::T* __restrict__ xp) {
+  using N = Num<C>;
+  const FrontMeta F = meta[list[blockIdx.x]];
+  const int k0 = k * NB;
+  if (k0 >= F.np) return;
+  const int kb = min(NB, F.np - k0);
+  const typename N::T* Fp = pool + F.off;
+  typename N::T* wf = w + F.woff;
+  const int r = threadIdx.x;
+  typename N::T x = r < kb ? wf[k0 + r] : N::zero();
+  for (int c = kb - 1; c >= 0; --c) {
+    if (r == c) x = N::div(x, Fp[(long long)(k0 + c) * F.nf + k0 + c]);
+    typename N::T xc = N::shfl(x, c);
+    if (r < c) x = N::fnma(Fp[(long long)(k0 + r) * F.nf + k0 + c], xc, x);
+  }
+  if (r < kb) { wf[k0 + r] = x; xp[F.first + k0 + r] = x; }
+}
+
+}  // namespace
+
+// =======================================================================================
+// host side: symbolic analysis
+// =======================================================================================
+struct DirectSolver {
+  long long n = 0, nnz = 0;
+  int cplx = 0, nsm = 148;
+  cudaStream_t s = nullptr;
+  long long* launches = nullptr;
+  int nfronts = 0, nlevels = 0, maxnf = 0;
+  long long pool_elems = 0, w_elems = 0, fill = 0;
+  double flops = 0;
+  std::vector<FrontMeta> meta;
+  std::vector<std::vector<int>> level_lists;
+  std::vector<int> level_maxnp, level_maxnf, level_maxnu_child;
+  DevBuf<FrontMeta> d_meta;
+  DevBuf<int> d_pos, d_front_of_pos, d_upd, d_cmap, d_lists;
+  std::vector<int> list_off;
+  DevBuf<double> pool, w, bp, xp;
+  double symbolic_ms = 0, numeric_ms = 0;
+};
+
+namespace {
+
+struct TreeNode { std::vector<int> piv; int child[2] = {-1, -1}; };
+
+struct NDBuilder {
+  const int* ptr; const int* idx; const double* xy; int dim; int leaf;
+  std::vector<signed char> mark;
+  std::vector<TreeNode> nodes;
+  int rec(std::vector<int>& S) {
+    if ((int)S.size() <= leaf) return make_leaf(S);
+    // longest axis, median split
+    int ax = 0; double best = -1;
+    for (int a = 0; a < dim; ++a) {
+      double lo = 1e300, hi = -1e300;
+      for (int v : S) { double c = xy[(size_t)v * dim + a]; lo = std::min(lo, c); hi = std::max(hi, c); }
+      if (hi - lo > best) { best = hi - lo; ax = a; }
+    }
+    std::vector<double> c(S.size());
+    for (size_t k = 0; k < S.size(); ++k) c[k] = xy[(size_t)S[k] * dim + ax];
+    std::vector<double> cs(c);
+    std::nth_element(cs.begin(), cs.begin() + cs.size() / 2, cs.end());
+    double med = cs[cs.size() / 2];
+    std::vector<int> A, B;
+    for (size_t k = 0; k < S.size(); ++k) (c[k] <= med ? A : B).push_back(S[k]);
+    if (A.empty() || B.empty()) {
+      A.clear(); B.clear();
+      for (size_t k = 0; k < S.size(); ++k) (c[k] < med ? A : B).push_back(S[k]);
+      if (A.empty() || B.empty()) return make_leaf(S);
+    }
+    std::vector<int>().swap(S);
+    for (int v : B) mark[v] = 1;
+    std::vector<int> sep, A2;
+    for (int v : A) {
+      bool touch = false;
+      for (int p = ptr[v]; p < ptr[v + 1] && !touch; ++p) touch = mark[idx[p]] == 1;
+      (touch ? sep : A2).push_back(v);
+    }
+    for (int v : B) mark[v] = 0;
+    std::vector<int>().swap(A);
+    int c0 = A2.empty() ? -1 : rec(A2);
+    int c1 = rec(B);
+    TreeNode t;
+    t.piv.swap(sep);
+    t.child[0] = c0 >= 0 ? c0 : c1;
+    t.child[1] = c0 >= 0 ? c1 : -1;
+    nodes.push_back(std::move(t));
+    return (int)nodes.size() - 1;
+  }
+  int make_leaf(std::vector<int>& S) {
+    TreeNode t;
+    t.piv.swap(S);
+    nodes.push_back(std::move(t));
+    return (int)nodes.size() - 1;
+  }
+};
+
+template <typename F>
+float timed(cudaStream_t s, F&& f) {
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, s));
+  f();
+  CUDA_TRY(cudaEventRecord(e1, s));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return ms;
+}
+
+}  // namespace
+
+void DirectDeleter::operator()(DirectSolver* p) const { delete p; }
+
+DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n, long long nnz,
+                          const double* coords, int dim, int leaf, int is_complex, int nsm,
+                          cudaStream_t s, long long* launches) {
+  DirectPtr D(new DirectSolver());
+  D->n = n; D->nnz = nnz; D->cplx = is_complex; D->nsm = nsm; D->s = s; D->launches = launches;
+  if (leaf < 8) leaf = 96;
+  auto t0 = std::chrono::steady_clock::now();
+  // symmetrised pattern on the host
+  std::vector<int> rp(n + 1), ci(nnz);
+  CUDA_TRY(cudaMemcpy(rp.data(), d_rowptr, (n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(ci.data(), d_colind, nnz * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<int> sp(n + 1, 0), si;
+  {
+    std::vector<int> cnt(n, 0);
+    for (long long i = 0; i < n; ++i)
+      for (int p = rp[i]; p < rp[i + 1]; ++p) { ++cnt[i]; if (ci[p] != i) ++cnt[ci[p]]; }
+    std::vector<long long> start(n + 1, 0);
+    for (long long i = 0; i < n; ++i) start[i + 1] = start[i] + cnt[i];
+    std::vector<int> tmp(start[n]);
+    std::vector<long long> fillp(start.begin(), start.end() - 1);
+    for (long long i = 0; i < n; ++i)
+      for (int p = rp[i]; p < rp[i + 1]; ++p) {
+        tmp[fillp[i]++] = ci[p];
+        if (ci[p] != i) tmp[fillp[ci[p]]++] = (int)i;
+      }
+    si.reserve(start[n]);
+    for (long long i = 0; i < n; ++i) {
+      std::sort(tmp.begin() + start[i], tmp.begin() + start[i + 1]);
+      auto e = std::unique(tmp.begin() + start[i], tmp.begin() + start[i + 1]);
+      for (auto it = tmp.begin() + start[i]; it != e; ++it) si.push_back(*it);
+      sp[i + 1] = (int)si.size();
+    }
+  }
+  // nested dissection
+  NDBuilder nd{sp.data(), si.data(), coords, dim, leaf};
+  nd.mark.assign(n, 0);
+  std::vector<int> all(n);
+  std::iota(all.begin(), all.end(), 0);
+  nd.nodes.reserve(2 * n / leaf + 16);
+  int root = nd.rec(all);
+  (void)root;
+  const int nf_ = (int)nd.nodes.size();
+  D->nfronts = nf_;
+  // permutation (postorder = creation order)
+  std::vector<int> pos(n), front_of_pos(n);
+  std::vector<int> first(nf_), parent(nf_, -1);
+  {
+    int k = 0;
+    for (int f = 0; f < nf_; ++f) {
+      first[f] = k;
+      for (int v : nd.nodes[f].piv) { pos[v] = k; front_of_pos[k] = f; ++k; }
+      for (int c : nd.nodes[f].child) if (c >= 0) parent[c] = f;
+    }
+    if (k != n) throw std::string("nested dissection lost DOFs");
+  }
+  // update sets bottom-up
+  std::vector<std::vector<int>> upd(nf_);
+  std::vector<int> level(nf_, 0);
+  std::vector<int> tmp;
+  for (int f = 0; f < nf_; ++f) {
+    const int last = first[f] + (int)nd.nodes[f].piv.size();
+    tmp.clear();
+    for (int v : nd.nodes[f].piv)
+      for (int p = sp[v]; p < sp[v + 1]; ++p) { int q = pos[si[p]]; if (q >= last) tmp.push_back(q); }
+    for (int c : nd.nodes[f].child)
+      if (c >= 0) {
+        for (int q : upd[c]) if (q >= last) tmp.push_back(q);
+        level[f] = std::max(level[f], level[c] + 1);
+      }
+    std::sort(tmp.begin(), tmp.end());
+    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+    upd[f] = tmp;
+  }
+  // meta
+  D->meta.resize(nf_);
+  std::vector<int> upd_flat;
+  long long off = 0, woff = 0;
+  int cm = 0;
+  D->nlevels = 0;
+  for (int f = 0; f < nf_; ++f) {
+    FrontMeta& M = D->meta[f];
+    M.first = first[f]; M.np = (int)nd.nodes[f].piv.size(); M.nf = M.np + (int)upd[f].size();
+    M.off = off; M.woff = woff; M.upd_ptr = (int)upd_flat.size(); M.cmap_ptr = cm; M.parent = parent[f];
+    M.child[0] = nd.nodes[f].child[0]; M.child[1] = nd.nodes[f].child[1];
+    off += (long long)M.nf * M.nf; woff += M.nf; cm += M.nf - M.np;
+    upd_flat.insert(upd_flat.end(), upd[f].begin(), upd[f].end());
+    D->maxnf = std::max(D->maxnf, M.nf);
+    D->nlevels = std::max(D->nlevels, level[f] + 1);
+    const double np = M.np, nu = M.nf - M.np;
+    D->fill += (long long)(np * np + 2 * np * nu);
+    D->flops += (2.0 / 3.0) * np * np * np + 2 * np * np * nu + 2 * np * nu * nu;
+  }
+  D->pool_elems = off; D->w_elems = woff;
+  D->level_lists.assign(D->nlevels, {});
+  for (int f = 0; f < nf_; ++f) D->level_lists[level[f]].push_back(f);
+  D->level_maxnp.assign(D->nlevels, 0); D->level_maxnf.assign(D->nlevels, 0);
+  D->level_maxnu_child.assign(D->nlevels, 0);
+  std::vector<int> lists_flat;
+  D->list_off.clear();
+  for (int L = 0; L < D->nlevels; ++L) {
+    D->list_off.push_back((int)lists_flat.size());
+    for (int f : D->level_lists[L]) {
+      lists_flat.push_back(f);
+      D->level_maxnp[L] = std::max(D->level_maxnp[L], D->meta[f].np);
+      D->level_maxnf[L] = std::max(D->level_maxnf[L], D->meta[f].nf);
+      for (int c : D->meta[f].child)
+        if (c >= 0) D->level_maxnu_child[L] = std::max(D->level_maxnu_child[L], D->meta[c].nf - D->meta[c].np);
+    }
+  }
+  // upload
+  D->d_meta.upload(D->meta.data(), nf_, s);
+  D->d_pos.upload(pos.data(), n, s);
+  D->d_front_of_pos.upload(front_of_pos.data(), n, s);
+  if (upd_flat.empty()) upd_flat.push_back(0);
+  D->d_upd.upload(upd_flat.data(), upd_flat.size(), s);
+  D->d_cmap.alloc(std::max(cm, 1));
+  D->d_lists.upload(lists_flat.data(), lists_flat.size(), s);
+  build_cmap<<<nf_, 128, 0, s>>>(D->d_meta.p, nf_, D->d_upd.p, D->d_cmap.p);
+  ++*launches;
+  const size_t sc = is_complex ? 2 : 1;
+  D->pool.alloc((size_t)D->pool_elems * sc);
+  D->w.alloc((size_t)D->w_elems * sc);
+  D->bp.alloc((size_t)n * sc);
+  D->xp.alloc((size_t)n * sc);
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  D->symbolic_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return D;
+}
+
+template <bool C>
+static void numeric_impl(DirectSolver& D, const int* rowind, const int* colind, const double* vals) {
+  using T = typename Num<C>::T;
+  cudaStream_t s = D.s;
+  T* pool = reinterpret_cast<T*>(D.pool.p);
+  D.pool.zero(s);
+  {
+    long long g = (D.nnz + 255) / 256;
+    long long cap = (long long)D.nsm * 16;
+    scatter_matrix<C><<<(unsigned)std::min(g, cap), 256, 0, s>>>(rowind, colind, reinterpret_cast<const T*>(vals), D.nnz,
+        D.d_pos.p, D.d_front_of_pos.p, D.d_meta.p, D.d_upd.p, pool);
+    ++*D.launches;
+  }
+  const size_t smem = (size_t)(TS * (NB + 1) + NB * TS) * sizeof(T);
+  CUDA_TRY(cudaFuncSetAttribute(schur_update<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int L = 0; L < D.nlevels; ++L) {
+    const int nfr = (int)D.level_lists[L].size();
+    const int* list = D.d_lists.p + D.list_off[L];
+    if (D.level_maxnu_child[L] > 0) {
+      const int nu = D.level_maxnu_child[L];
+      dim3 grid(std::min((nu + 63) / 64, 8), (nu + 15) / 16, nfr), block(64, 16);
+      for (int slot = 0; slot < 2; ++slot) {
+        extend_add<C><<<grid, block, 0, s>>>(D.d_meta.p, list, slot, D.d_cmap.p, pool);
+        ++*D.launches;
+      }
+    }
+    const int npan = (D.level_maxnp[L] + NB - 1) / NB;
+    for (int k = 0; k < npan; ++k) {
+      diag_lu<C><<<nfr, dim3(NB, NB), 0, s>>>(D.d_meta.p, list, k, pool);
+      const int rem = D.level_maxnf[L] - k * NB;     // upper bound of trailing size
+      if (rem > 0) {
+        dim3 g2((rem + 127) / 128, 2, nfr);
+        panel_trsm<C><<<g2, 128, 0, s>>>(D.d_meta.p, list, k, pool);
+        dim3 g3((rem + TS - 1) / TS, (rem + TS - 1) / TS, nfr);
+        schur_update<C><<<g3, 256, smem, s>>>(D.d_meta.p, list, k, pool);
+        *D.launches += 2;
+      }
+      ++*D.launches;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+}
+
+void direct_numeric(DirectSolver& D, const int* rowind, const int* colind, const double* vals) {
+  D.numeric_ms = timed(D.s, [&]() {
+    if (D.cplx) numeric_impl<true>(D, rowind, colind, vals);
+    else numeric_impl<false>(D, rowind, colind, vals);
+  });
+}
+
+template <bool C>
+static void solve_impl(DirectSolver& D, const double* b, double* x) {
+  using T = typename Num<C>::T;
+  cudaStream_t s = D.s;
+  const T* pool = reinterpret_cast<const T*>(D.pool.p);
+  T* w = reinterpret_cast<T*>(D.w.p);
+  T* bp = reinterpret_cast<T*>(D.bp.p);
+  T* xp = reinterpret_cast<T*>(D.xp.p);
+  const unsigned vg = (unsigned)std::min<long long>((D.n + 255) / 256, (long long)D.nsm * 8);
+  permute_in<C><<<vg, 256, 0, s>>>(reinterpret_cast<const T*>(b), D.d_pos.p, bp, D.n);
+  ++*D.launches;
+  for (int L = 0; L < D.nlevels; ++L) {
+    const int nfr = (int)D.level_lists[L].size();
+    const int* list = D.d_lists.p + D.list_off[L];
+    fwd_gather<C><<<nfr, 256, 0, s>>>(D.d_meta.p, list, D.d_cmap.p, bp, w);
+    ++*D.launches;
+    const int npan = (D.level_maxnp[L] + NB - 1) / NB;
+    for (int k = 0; k < npan; ++k) {
+      const int rem = D.level_maxnf[L] - k * NB;
+      dim3 g((std::max(rem, 1) + 255) / 256, nfr);
+      fwd_panel<C><<<g, 256, 0, s>>>(D.d_meta.p, list, k, pool, w);
+      fwd_panel_commit<C><<<nfr, 32, 0, s>>>(D.d_meta.p, list, k, pool, w);
+      *D.launches += 2;
+    }
+  }
+  for (int L = D.nlevels - 1; L >= 0; --L) {
+    const int nfr = (int)D.level_lists[L].size();
+    const int* list = D.d_lists.p + D.list_off[L];
+    dim3 gg((D.level_maxnp[L] + 7) / 8, nfr);
+    bwd_gemv<C><<<gg, 256, 0, s>>>(D.d_meta.p, list, D.d_upd.p, pool, xp, w);
+    ++*D.launches;
+    const int npan = (D.level_maxnp[L] + NB - 1) / NB;
+    for (int k = npan - 1; k >= 0; --k) {
+      dim3 g((std::max(k * NB, 1) + 255) / 256, nfr);
+      bwd_panel<C><<<g, 256, 0, s>>>(D.d_meta.p, list, k, pool, w);
+      bwd_panel_commit<C><<<nfr, 32, 0, s>>>(D.d_meta.p, list, k, pool, w, xp);
+      *D.launches += 2;
+    }
+  }
+  permute_out<C><<<vg, 256, 0, s>>>(xp, D.d_pos.p, reinterpret_cast<T*>(x), D.n);
+  ++*D.launches;
+  CUDA_TRY(cudaGetLastError());
+}
+
+void direct_solve(DirectSolver& D, const double* b_dev, double* x_dev) {
+  if (D.cplx) solve_impl<true>(D, b_dev, x_dev);
+  else solve_impl<false>(D, b_dev, x_dev);
+}
+
+void direct_info(const DirectSolver& D, double* out8) {
+  out8[0] = D.nfronts; out8[1] = D.nlevels; out8[2] = D.maxnf; out8[3] = (double)D.fill;
+  out8[4] = D.flops * (D.cplx ? 4.0 : 1.0); out8[5] = (double)D.pool_elems * (D.cplx ? 16 : 8);
+  out8[6] = D.symbolic_ms; out8[7] = D.numeric_ms;
+}

@@ -195,6 +195,7 @@ struct SolverState {
   int nred;                     // reduction blocks
   DevBuf<double> dinv, V, w, z, r, partial, hdev, tmp1, tmp2, tmp3, tmp4;
   double setup_ms = 0;
+  DirectSolver* direct = nullptr;
 
   double* vec(DevBuf<double>& b) { if (b.n == 0) b.alloc((size_t)n * sc); return b.p; }
 
@@ -241,6 +242,7 @@ struct SolverState {
   }
   void precond(const double* rin, double* zout) {
     if (opts.precond == VLFS_PRECOND_NONE) { copy(rin, zout); return; }
+    if (opts.precond == VLFS_PRECOND_SPARSE_LU) { direct_solve(*direct, rin, zout); return; }
     if (cplx) pointwise_mul<true><<<vgrid(n, nsm), 256, 0, s>>>((const double2*)dinv.p, (const double2*)rin, (double2*)zout, n);
     else pointwise_mul<false><<<vgrid(n, nsm), 256, 0, s>>>(dinv.p, rin, zout, n);
     ++*launches;
@@ -250,10 +252,11 @@ struct SolverState {
 SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals,
                                            long long n, long long nnz, int is_complex,
                                            const vlfs_solver_opts& opts, int nsm, cudaStream_t s,
-                                           long long* launches) {
+                                           long long* launches, DirectSolver* direct) {
   SolverPtr S(new SolverState());
   S->rowptr = rowptr; S->colind = colind; S->vals = vals; S->n = n; S->nnz = nnz;
   S->cplx = is_complex; S->opts = opts; S->nsm = nsm; S->s = s; S->launches = launches;
+  S->direct = direct;
   S->sc = is_complex ? 2 : 1;
   if (S->opts.restart < 1) S->opts.restart = 50;
   if (S->opts.maxit < 1) S->opts.maxit = 1000;
@@ -265,7 +268,7 @@ SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals
   int m = S->opts.restart;
   S->partial.alloc((size_t)S->nred * (m + 2) * S->sc);
   S->hdev.alloc((size_t)(m + 2) * S->sc);
-  if (S->opts.precond != VLFS_PRECOND_NONE) {
+  if (S->opts.precond == VLFS_PRECOND_JACOBI || S->opts.precond == VLFS_PRECOND_BLOCK_ILU0) {
     S->dinv.alloc((size_t)n * S->sc);
     if (is_complex) extract_inv_diag<true><<<vgrid(n, nsm), 256, 0, s>>>(rowptr, colind, (const double2*)vals, (double2*)S->dinv.p, n);
     else extract_inv_diag<false><<<vgrid(n, nsm), 256, 0, s>>>(rowptr, colind, vals, S->dinv.p, n);

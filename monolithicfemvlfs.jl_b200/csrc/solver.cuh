@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include <memory>
+#include "direct.cuh"
 
 struct SolverState;
 struct SolverDeleter { void operator()(SolverState*) const; };
@@ -9,9 +10,9 @@ struct SolverDeleter { void operator()(SolverState*) const; };
 using SolverPtr = std::unique_ptr<SolverState, SolverDeleter>;
 
 SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals,
-                                           long long n, long long nnz, int is_complex,
+                        long long n, long long nnz, int is_complex,
                                            const vlfs_solver_opts& opts, int nsm, cudaStream_t s,
-                                           long long* launches);
+                                           long long* launches, DirectSolver* direct);
 int solver_solve(SolverState& S, const double* b_dev, double* x_dev, vlfs_solve_stats* stats);
 int newmark_run(SolverState& S, const int* rowptr, const int* colind, const double* Cvals,
                 const double* Mvals, long long n, long long nnz, int nsteps, double dt, double gamma,

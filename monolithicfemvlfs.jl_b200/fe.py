@@ -280,6 +280,15 @@ class MultiFieldFESpace:
             s.field = f
             s.offset = int(self.offsets[f])
 
+    def dof_coords(self):
+        """(ndofs, D) physical coordinates of every DOF node of the monolithic system."""
+        D = self.spaces[0].trian.cell_coords().shape[2]
+        out = np.zeros((self.ndofs, D))
+        for s in self.spaces:
+            xc = s.cell_dof_coords()
+            out[s.cell_dofs.reshape(-1) + s.offset] = xc.reshape(-1, D)
+        return out
+
     def split(self, x):
         return [x[self.offsets[i]:self.offsets[i + 1]] for i in range(len(self.spaces))]
 

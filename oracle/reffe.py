@@ -84,15 +84,45 @@ class LagrangianRefFE:
         self.ndofs = len(self.nodes)
         self.exps = _exponents(poly, order)
         assert len(self.exps) == self.ndofs, (len(self.exps), self.ndofs)
-        V = self._monomials(self.nodes)
-        self.change = np.linalg.inv(V)
+        self.change = self._exact_change()
+
+    def _exact_change(self):
+        """Inverse nodal Vandermonde matrix.  Gridap takes a Float64 `inv`, which carries
+        1e-13..1e-12 relative round-off at order 4 (SURVEY.md hard part 3); the nodes are
+        rational (i/order), so the oracle inverts exactly in rational arithmetic and rounds
+        once, and evaluates the monomial sums in extended precision - it is then the more
+        accurate side of every 1e-12 comparison."""
+        from fractions import Fraction
+        p = self.order
+        n = self.ndofs
+        lat = np.rint(self.nodes * p).astype(int)
+        V = [[Fraction(1) for _ in range(n)] for _ in range(n)]
+        for i in range(n):
+            for j in range(n):
+                v = Fraction(1)
+                for a in range(self.dim):
+                    v *= Fraction(int(lat[i, a]), p) ** int(self.exps[j, a])
+                V[i][j] = v
+        # Gauss-Jordan on [V | I]
+        M = [row + [Fraction(int(i == j)) for j in range(n)] for i, row in enumerate(V)]
+        for c in range(n):
+            piv = next(r for r in range(c, n) if M[r][c] != 0)
+            M[c], M[piv] = M[piv], M[c]
+            inv = 1 / M[c][c]
+            M[c] = [x * inv for x in M[c]]
+            for r in range(n):
+                if r != c and M[r][c] != 0:
+                    f = M[r][c]
+                    M[r] = [x - f * y for x, y in zip(M[r], M[c])]
+        ld = np.longdouble
+        return np.array([[ld(x.numerator) / ld(x.denominator) for x in row[n:]] for row in M], dtype=ld)
 
     def _monomials(self, x, deriv=None):
         """Monomial values (npts, nmono); deriv = tuple of axes to differentiate."""
-        x = np.asarray(x, dtype=float).reshape(-1, self.dim)
-        out = np.ones((len(x), len(self.exps)))
+        x = np.asarray(x, dtype=np.longdouble).reshape(-1, self.dim)
+        out = np.ones((len(x), len(self.exps)), dtype=np.longdouble)
         e = self.exps.copy()
-        coef = np.ones(len(self.exps))
+        coef = np.ones(len(self.exps), dtype=np.longdouble)
         for a in (deriv or ()):
             coef = coef * e[:, a]
             e = e.copy()
@@ -103,11 +133,11 @@ class LagrangianRefFE:
 
     def values(self, x):
         """(npts, ndofs)."""
-        return self._monomials(x) @ self.change
+        return (self._monomials(x) @ self.change).astype(float)
 
     def gradients(self, x):
         """(npts, ndofs, dim) reference gradients."""
-        return np.stack([self._monomials(x, (a,)) @ self.change
+        return np.stack([(self._monomials(x, (a,)) @ self.change).astype(float)
                          for a in range(self.dim)], axis=2)
 
     def hessians(self, x):
@@ -116,7 +146,7 @@ class LagrangianRefFE:
         H = np.zeros((n, self.ndofs, self.dim, self.dim))
         for a in range(self.dim):
             for b in range(a, self.dim):
-                h = self._monomials(x, (a, b)) @ self.change
+                h = (self._monomials(x, (a, b)) @ self.change).astype(float)
                 H[:, :, a, b] = h
                 H[:, :, b, a] = h
         return H
