@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 hot path (assembly nnz/s + SpMV GB/s + solve
+s/step on the Yago 3-D case, BASELINE.json) with the CPU restatement timed beside it.
+
+  python bench.py --gpus N --steps K --warmup W [--workload Y1]        (our arm)
+  python bench.py --impl reference --gpus N --steps K --warmup W       (CPU reference arm)
+
+A "step" is one numeric pass of `AffineFEOperator(a,b,X,Y)` for one frequency: zero + cell
+integration of every term + scatter into the fixed CSR pattern (matrix and right-hand side).
+`value` = nnz of the monolithic matrix / step time, inputs resident in HBM.  `e2e` is the
+same metric through the host-buffer C-ABI path: coefficient fields copied host->device, the
+assembly, and the matrix values + rhs copied device->host, all inside the timed region.
+SpMV and solve are timed in the same run and reported in `spmv` / `solve`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (Yago parameters, description)   [scripts/5-4-1-Yago.jl:17-46; SURVEY.md §8(d)]
+    "Y0": dict(nx=2, ny=2, nz=1, order=2, lfactor=0.4, dfactor=3),
+    "Ymid": dict(nx=8, ny=2, nz=2, order=4, lfactor=0.4, dfactor=4),
+    "Y1": dict(nx=32, ny=4, nz=3, order=4, lfactor=0.4, dfactor=4),
+    "Y2": dict(nx=64, ny=8, nz=6, order=4, lfactor=0.4, dfactor=4),
+}
+CPU_SAMPLE = dict(nx=16, ny=2, nz=3, order=4, lfactor=0.4, dfactor=4)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def assembly_bytes(prob, nnz, ncoo, sT):
+    """Algorithmic bytes of one numeric assembly pass: every CSR value written
+    once, the COO->slot permutation read once, DOF maps / coordinates / coefficient fields
+    read once."""
+    tables = 0
+    for t, nd, nv, D in [(prob.Om, 27, 8, 3), (prob.Gf, 27 + prob.V_Gk.reffe.ndofs, 8 + 4, 3),
+                         (prob.Gb, 27 + prob.V_Ge.reffe.ndofs, 8 + 4, 3)]:
+        tables += t.ncells * (4 * nd + 8 * D * nv)
+    tables += prob.Gf.ncells * 25 * 8 * 5
+    return nnz * sT + 4 * ncoo + tables
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import vlfs_b200
+    from vlfs_b200 import _lib as L
+    from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    kw = WORKLOADS[args.workload]
+    t0 = time.time()
+    prob = YagoProblem(Yago_freq_domain_params(**kw), device=local)
+    setup_s = time.time() - t0
+    S = prob.sys
+    nnz, ncoo, N = S.nnz, S.ncoo, S.ndofs
+    sT = 16
+    peak, peak_kind = measured_peaks()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxms(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    launches0 = S.launches()
+    for _ in range(max(args.warmup, 3)):
+        S.assemble()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    launches1 = S.launches()
+    ms = maxms(S.assemble_device_ms(reps=args.steps))
+    launches2 = S.launches()
+    barrier()
+    clk = clocks.stop()
+    value = world * nnz / (ms * 1e-3)
+
+    # per-kernel times (CUDA events on the launching stream) for the roofline of the dominant kernel
+    prof = S.assemble_profile(reps=3)
+    dom_name, dom_ms = max(prof, key=lambda kv: kv[1])
+    ent_vol = prob.Om.ncells * 27 * 27
+    ent_gf = prob.Gf.ncells * (27 + prob.V_Gk.reffe.ndofs) ** 2
+    if dom_name.startswith("gradgrad_affine"):
+        # volume Laplace: one 16-byte RMW on the value + 4-byte dest per COO entry, 192 B coords/cell
+        kbytes = ent_vol * (16 + 4) + prob.Om.ncells * 192
+    else:
+        kbytes = ent_gf * (16 + 4) + prob.Gf.ncells * (12 * 24 + 52 * 4 + 5 * 25 * 8)
+    roof = {"bound": "hbm", "kernel": dom_name, "achieved": kbytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
+            "peak_kind": peak_kind, "unit": "GB/s", "traffic": None,
+            "share_of_step": dom_ms / sum(t for _, t in prof)}
+    roof["frac"] = roof["achieved"] / peak
+    step_bytes = assembly_bytes(prob, nnz, ncoo, sT)
+
+    # SpMV (device resident, x fixed = (sin 0.1 i, cos 0.1 i))
+    S.spmv_device_ms(reps=3)
+    barrier()
+    sp_ms = maxms(S.spmv_device_ms(reps=max(args.steps, 10)))
+    barrier()
+    sp_bytes = nnz * (sT + 4) + 4 * (N + 1) + 2 * N * sT
+    spmv = {"ms": sp_ms, "GBs": world * sp_bytes / (sp_ms * 1e-3) / 1e9, "bytes": sp_bytes}
+    spmv["frac"] = spmv["GBs"] / world / peak
+
+    # solve: sparse LU factorisation + GMRES(1-2 its) per frequency
+    solve = None
+    if not args.no_solve:
+        t0 = time.time()
+        S.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=20, maxit=40, rtol=1e-10)
+        first_s = time.time() - t0
+        info = S.direct_info()
+        t0 = time.time()
+        S.refactor(0)
+        x, st = S.solve(vec=0)
+        step_s = time.time() - t0
+        xs, rao = prob.rao(x)
+        solve = {"s_per_step": step_s, "first_setup_s": first_s, "symbolic_ms": info["symbolic_ms"],
+                 "numeric_ms": info["numeric_ms"], "gmres_iterations": st["iterations"],
+                 "rel_residual": st["rel_residual"], "solve_ms": st["solve_ms"],
+                 "factor_TFLOPs": info["flops"] / (info["numeric_ms"] * 1e-3) / 1e12,
+                 "fill_entries": info["fill"], "fronts": info["nfronts"], "max_front": info["maxfront"],
+                 "rao_max": float(rao.max()) if len(rao) else None}
+
+    # end to end through host buffers: H2D coefficient fields, assemble, D2H values + rhs
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    h2d = 0
+    vals_host = torch.empty(nnz * 2, dtype=torch.float64).pin_memory().numpy().view(np.complex128)
+    rhs_host = torch.empty(N * 2, dtype=torch.float64).pin_memory().numpy().view(np.complex128)
+    import ctypes as C
+
+    def e2e_step():
+        prob.set_frequency(kw["lfactor"])           # H2D of the ω-dependent fields
+        S.assemble()
+        S._check(S.lib.vlfs_get_values(S.ctx, 0, vals_host.ctypes.data_as(C.c_void_p)))
+        S._check(S.lib.vlfs_get_vector(S.ctx, 0, rhs_host.ctypes.data_as(C.c_void_p)))
+    h2d = (5 * prob.Gf.ncells * 25 + 2 * prob.Gin.ncells * 25) * 8
+    d2h = nnz * sT + N * sT
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    nrep = max(2, min(args.steps, 5))
+    for _ in range(nrep):
+        e2e_step()
+    torch.cuda.synchronize()
+    e_ms = maxms((time.perf_counter() - t0) * 1e3 / nrep)
+    barrier()
+    e2e = {"value": world * nnz / (e_ms * 1e-3), "unit": "nnz/s", "ms_per_step": e_ms,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline()
+
+    if rank == 0:
+        out = {
+            "metric": "assembly nnz/s (Yago 3D; + SpMV GB/s + solve s/step in `spmv`/`solve`)",
+            "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 (complex128 matrix)", "data": "synthetic (deterministic Yago mesh, analytic coefficients)",
+            "config": {"workload": "%s: Yago 5-4-1 %s, N=%d, nnz=%d, ncoo=%d; inputs > L2 (values %.2f GB + dest %.2f GB), no flush"
+                       % (args.workload, json.dumps(kw), N, nnz, ncoo, nnz * sT / 1e9, ncoo * 4 / 1e9),
+                       "parallelism": "replicas" if world > 1 else "single"},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches2 - launches1),
+            "roofline": roof, "step_GBs": step_bytes / (ms * 1e-3) / 1e9, "step_frac": step_bytes / (ms * 1e-3) / 1e9 / peak,
+            "kernels_ms": prof, "spmv": spmv, "solve": solve, "cpu_baseline": cpu,
+            "host_setup_s": setup_s,
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sample=None):
+    """The oracle (CPU restatement of Gridap's assembly) timed on the host cores."""
+    import numpy as np
+    from oracle.cases.yago import YagoCase
+    kw = sample or CPU_SAMPLE
+    case = YagoCase(**kw)
+    t0 = time.time()
+    A, b = case.assemble()
+    dt = time.time() - t0
+    return {"value": A.nnz / dt, "unit": "nnz/s", "cores": 1, "kind": "port",
+            "sample": "oracle (NumPy restatement of Gridap cell integration + sparse(I,J,V)) on Yago %s: "
+                      "N=%d nnz=%d in %.1f s" % (json.dumps(kw), A.shape[0], A.nnz, dt), "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_baseline(WORKLOADS["Y0"])
+    c = None
+    for _ in range(max(1, min(args.steps, 3))):
+        c = cpu_baseline()
+        vals.append(c["value"])
+    v = sum(vals) / len(vals)
+    c["value"] = v
+    out = {"impl": "reference", "metric": "assembly nnz/s (Yago 3D; + SpMV GB/s + solve s/step in `spmv`/`solve`)",
+           "value": v, "unit": "nnz/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(vals),
+           "warmup": 1, "ms_per_step": c["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64 (complex128 matrix)", "data": "synthetic",
+           "config": {"workload": "CPU restatement on a bounded sample of the Yago workload: " + c["sample"]},
+           "cpu_baseline": c,
+           "e2e": {"value": v, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="Y1", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

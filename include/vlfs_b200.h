@@ -203,6 +203,8 @@ int vlfs_newmark_run(vlfs_ctx* ctx, int matK, int matC, int matM, int nsteps, do
 /* ---- device-resident benchmarking hooks (no host copies) --------------------------- */
 int vlfs_spmv_device(vlfs_ctx* ctx, int mat, int reps, float* ms_total);
 int vlfs_assemble_timed(vlfs_ctx* ctx, int reps, float* ms_total);
+/* per-kernel CUDA-event times of one assembly pass (averaged over reps); names ';'-joined */
+int vlfs_assemble_profile(vlfs_ctx* ctx, int reps, char* names, int names_cap, float* ms, int ms_cap, int* nrec);
 int vlfs_last_kernel_launches(vlfs_ctx* ctx, int64_t* n);
 int vlfs_device_ptrs(vlfs_ctx* ctx, int mat, void** rowptr, void** colind, void** values);
 

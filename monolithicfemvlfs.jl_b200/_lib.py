@@ -66,7 +66,7 @@ EXPORTS = [
     "vlfs_get_pattern", "vlfs_get_pattern_csc", "vlfs_assemble", "vlfs_assemble_matrices",
     "vlfs_assemble_vectors", "vlfs_get_values", "vlfs_get_vector", "vlfs_combine", "vlfs_spmv",
     "vlfs_set_dof_coords", "vlfs_solver_setup", "vlfs_solver_refactor", "vlfs_direct_info", "vlfs_solve", "vlfs_solve_vec", "vlfs_newmark_run", "vlfs_spmv_device",
-    "vlfs_assemble_timed", "vlfs_last_kernel_launches", "vlfs_device_ptrs",
+    "vlfs_assemble_timed", "vlfs_assemble_profile", "vlfs_last_kernel_launches", "vlfs_device_ptrs",
 ]
 
 _lib = None
@@ -120,6 +120,7 @@ def load():
                                      C.c_int64, C.c_int64, C.c_int, _dp, C.POINTER(SolveStats)]
     lib.vlfs_spmv_device.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     lib.vlfs_assemble_timed.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    lib.vlfs_assemble_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     lib.vlfs_last_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.vlfs_device_ptrs.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     for name in EXPORTS:

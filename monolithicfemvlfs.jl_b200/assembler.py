@@ -280,6 +280,15 @@ class B200System:
         self._check(self.lib.vlfs_assemble_timed(self.ctx, reps, C.byref(ms)))
         return ms.value / reps
 
+    def assemble_profile(self, reps=3):
+        """[(kernel name, avg ms)] of one assembly pass, CUDA events on the launching stream."""
+        names = C.create_string_buffer(4096)
+        ms = (C.c_float * 64)()
+        n = C.c_int(0)
+        self._check(self.lib.vlfs_assemble_profile(self.ctx, reps, names, 4096, ms, 64, C.byref(n)))
+        nm = names.value.decode().split(";")[:n.value]
+        return [(nm[k], float(ms[k])) for k in range(n.value)]
+
     def launches(self):
         n = C.c_int64(0)
         self.lib.vlfs_last_kernel_launches(self.ctx, C.byref(n))

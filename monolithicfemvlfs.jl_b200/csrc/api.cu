@@ -79,6 +79,8 @@ struct vlfs_ctx {
   std::vector<long long> dest_off;
   std::vector<DevBuf<double>> mats, vecs;
   long long launches = 0;
+  bool profile = false;
+  std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
   SolverPtr solver;
   DirectPtr direct;
   std::vector<double> dof_coords;
@@ -246,14 +248,28 @@ void refresh_coefs(vlfs_ctx* ctx, Domain& d) {
   d.coef_dirty = false;
 }
 
+struct ProfScope {
+  vlfs_ctx* ctx; cudaEvent_t e0{}, e1{}; bool on;
+  ProfScope(vlfs_ctx* c, const std::string& name) : ctx(c), on(c->profile) {
+    if (!on) return;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->stream);
+    ctx->prof_events.push_back({name, {e0, e1}});
+  }
+  ~ProfScope() { if (on) cudaEventRecord(e1, ctx->stream); }
+};
+
 void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   if (!ctx->pattern_built) throw std::string("vlfs_build_pattern must be called first");
   cudaStream_t s = ctx->stream;
   std::vector<double*> mp, vp;
   for (auto& m : ctx->mats) mp.push_back(m.p);
   for (auto& v : ctx->vecs) vp.push_back(v.p);
-  if (do_mat) for (auto& m : ctx->mats) m.zero(s);
-  if (do_vec) for (auto& v : ctx->vecs) v.zero(s);
+  {
+    ProfScope ps(ctx, "memset");
+    if (do_mat) for (auto& m : ctx->mats) m.zero(s);
+    if (do_vec) for (auto& v : ctx->vecs) v.zero(s);
+  }
   for (size_t di = 0; di < ctx->doms.size(); ++di) {
     Domain& d = *ctx->doms[di];
     refresh_coefs(ctx, d);
@@ -261,6 +277,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     bool gen_mat = do_mat && !d.terms_host.empty();
     bool gen_vec = do_vec && !d.rhs_host.empty();
     if (gen_mat || gen_vec) {
+      ProfScope ps(ctx, "integrate_cells:dom" + std::to_string(di));
       launch_integrate(d.dev, d.terms_dev.p, (int)d.terms_host.size(), d.rhs_dev.p,
                        (int)d.rhs_host.size(), dest, mp.data(), (int)mp.size(), vp.data(),
                        (int)vp.size(), ctx->is_complex, gen_mat, gen_vec, ctx->nsm, s);
@@ -270,6 +287,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
       for (size_t t = 0; t < d.terms.size(); ++t)
         if (d.term_fast[t]) {
           const vlfs_term_desc& T = d.terms[t];
+          ProfScope ps(ctx, "gradgrad_affine:dom" + std::to_string(di));
           launch_gradgrad_affine(d.dev, d.Sref.p, dest, ctx->mats[T.mat].p, ctx->is_complex,
                                  T.coef_re * T.test_scale[0] * T.trial_scale[0],
                                  T.coef_im * T.test_scale[0] * T.trial_scale[0], ctx->nsm, s);
@@ -616,6 +634,39 @@ int vlfs_assemble_timed(vlfs_ctx* ctx, int reps, float* ms_total) {
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (ms_total) *ms_total = ms;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_assemble_profile(vlfs_ctx* ctx, int reps, char* names, int names_cap, float* ms, int ms_cap, int* nrec) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built || reps < 1 || !names || !ms || !nrec) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    std::vector<std::string> nm;
+    std::vector<double> acc;
+    for (int r = 0; r < reps; ++r) {
+      ctx->profile = true;
+      ctx->prof_events.clear();
+      assemble_impl(ctx, true, true);
+      ctx->profile = false;
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      if (r == 0) { nm.resize(ctx->prof_events.size()); acc.assign(ctx->prof_events.size(), 0.0); }
+      for (size_t k = 0; k < ctx->prof_events.size(); ++k) {
+        float t = 0;
+        cudaEventElapsedTime(&t, ctx->prof_events[k].second.first, ctx->prof_events[k].second.second);
+        acc[k] += t; nm[k] = ctx->prof_events[k].first;
+        cudaEventDestroy(ctx->prof_events[k].second.first);
+        cudaEventDestroy(ctx->prof_events[k].second.second);
+      }
+      ctx->prof_events.clear();
+    }
+    std::string joined;
+    int n = 0;
+    for (size_t k = 0; k < nm.size() && (int)k < ms_cap; ++k) {
+      joined += nm[k]; joined += ";";
+      ms[k] = (float)(acc[k] / reps); ++n;
+    }
+    snprintf(names, names_cap, "%s", joined.c_str());
+    *nrec = n;
     return VLFS_OK;
   });
 }
