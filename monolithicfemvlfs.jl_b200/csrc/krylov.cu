@@ -305,13 +305,21 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
   std::vector<cd> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), h(m + 2), h2(m + 2), y(m);
   int it = 0;
   double rel = 1.0;
+  // With the sparse LU as preconditioner every iteration is a refinement step that gains
+  // many digits; when it stops doing so the attainable accuracy eps*|A||x|/|b| is reached
+  // and further iterations are wasted.
+  const bool direct = S.opts.precond == VLFS_PRECOND_SPARSE_LU;
+  bool stagnated = false;
+  double prev_cycle_rel = 1e300;
   while (true) {
     // r = b - A x
     S.copy(b, r);
     S.spmv(x, r, -1.0, 1.0);
     double beta = S.nrm2(r);
     rel = beta / bnorm;
-    if (rel <= S.opts.rtol || it >= S.opts.maxit) break;
+    if (rel <= S.opts.rtol || it >= S.opts.maxit || stagnated) break;
+    if (direct && rel > 0.25 * prev_cycle_rel) break;
+    prev_cycle_rel = rel;
     S.axpby_(cd(1.0 / beta, 0), r, cd(0, 0), S.V.p);      // V_0
     std::fill(g.begin(), g.end(), cd(0, 0));
     g[0] = beta;
@@ -348,8 +356,10 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
         g[j + 1] = -std::conj(sn[j]) * gj;
       }
       for (int k = 0; k <= j; ++k) H[(size_t)k * m + j] = h[k];
+      const double prev = rel;
       rel = std::abs(g[j + 1]) / bnorm;
       if (rel <= S.opts.rtol || hn == 0.0) { ++j; ++it; break; }
+      if (direct && j >= 1 && rel > 0.25 * prev) { stagnated = true; ++j; ++it; break; }
     }
     // y = H^{-1} g ; x += M^{-1} V y
     for (int k = j - 1; k >= 0; --k) {
