@@ -27,6 +27,24 @@ def is_affine(coords, poly):
     return True
 
 
+def slot_is_affine(coords, dref, nv):
+    """Constant Jacobian on every cell of a slot: simplices always; n-cubes (lexicographic
+    corners) when every vertex is x0 + sum_a c_a (x_{2^a} - x0)."""
+    X = np.asarray(coords, dtype=np.float64)
+    if dref <= 1 or nv == dref + 1 or len(X) == 0:
+        return True
+    if nv != 1 << dref:
+        return False
+    x0 = X[:, 0]
+    edges = [X[:, 1 << a] - x0 for a in range(dref)]
+    scale = max(float(np.abs(X - x0[:, None, :]).max()), 1e-300)
+    for v in range(nv):
+        pred = x0 + sum(edges[a] for a in range(dref) if (v >> a) & 1)
+        if np.abs(pred - X[:, v]).max() > 1e-12 * scale:
+            return False
+    return True
+
+
 class Domain:
     def __init__(self, system, did, nslots, D):
         self.system, self.id, self.nslots, self.D = system, did, nslots, D
@@ -118,8 +136,12 @@ class B200System:
 
     # ------------------------------------------------------------------------------
     def add_domain(self, D, nq, qweights, slots, measure_slot=0, measure_kind=L.MEASURE_CELL,
-                   weights=(), Ctensor=None, affine=False):
-        """slots: list of dicts produced by fe.Measure.*_slot."""
+                   weights=(), Ctensor=None, affine=None):
+        """slots: list of dicts produced by fe.Measure.*_slot.  affine=None: detect whether
+        every slot's cells have a constant Jacobian (enables the cheaper geometry stage and
+        the reference-matrix fast path)."""
+        if affine is None:
+            affine = all(slot_is_affine(s["coords"], s["dref"], s["nv"]) for s in slots)
         d = L.DomainDesc()
         keep = []
         ncells = len(slots[0]["dofs"])

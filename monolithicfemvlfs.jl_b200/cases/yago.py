@@ -6,7 +6,7 @@ from .. import _lib as L
 from ..geometry import (CartesianDiscreteModel, add_tag_from_tags, Interior, Boundary,
                         Triangulation, Skeleton)
 from ..fe import ReferenceFE, TestFESpace, TrialFESpace, MultiFieldFESpace, Measure, lagrangian
-from ..assembler import B200System, is_affine
+from ..assembler import B200System
 
 
 @dataclass
@@ -30,7 +30,9 @@ def wave_constants(L_, H, g, lfactor):
 class YagoProblem:
     """Everything up to and including `op = AffineFEOperator(a,b,X,Y)`."""
 
-    def __init__(self, params, device=0, system_cls=B200System):
+    def __init__(self, params, device=0, system_cls=B200System, affine=None):
+        """affine=None: detect constant-Jacobian domains; False: force the general per-point
+        geometry path everywhere (parity check of the fast paths)."""
         p = self.params = params
         nx, ny, nz, order = p.nx, p.ny, p.nz, p.order
         # fixed parameters (:29-50)
@@ -88,13 +90,13 @@ class YagoProblem:
         ez = (0.0, 0.0, 1.0)
         # ---- Ω : ∫ ∇(ϕ)⋅∇(w) (:162)
         s_phi = dOm.own_slot(V_Om)
-        self.dom_Om = sys_.add_domain(3, dOm.nq, dOm.wq, [s_phi], affine=is_affine(s_phi["coords"], Om.poly))
+        self.dom_Om = sys_.add_domain(3, dOm.nq, dOm.wq, [s_phi], affine=affine)
         self.dom_Om.add_term(0, 1.0, L.OP_GRAD, 0, L.OP_GRAD, 0)
         # ---- Γf (:163): slot 0 = ϕ trace, slot 1 = κ ; weights: 0 = μ₁, 1 = Re/Im of rhs fields
         xq = dGf.points()
         self._xq_Gf = xq[..., 0].copy()
         self.dom_Gf = sys_.add_domain(3, dGf.nq, dGf.wq, [dGf.trace_slot(V_Om), dGf.surface_slot(V_Gk)],
-                                      measure_slot=1, weights=[np.zeros_like(self._xq_Gf)] * 5)
+                                      measure_slot=1, weights=[np.zeros_like(self._xq_Gf)] * 5, affine=affine)
         d = self.dom_Gf
         PHI, KAP = 0, 1
         self.t_Gf = dict(
@@ -113,7 +115,7 @@ class YagoProblem:
         # ---- Γb (:164): slot 0 = ϕ trace, slot 1 = η
         self.dom_Gb = d = sys_.add_domain(3, dGb.nq, dGb.wq,
                                           [dGb.trace_slot(V_Om), dGb.surface_slot(V_Ge, need_hess=True)],
-                                          measure_slot=1, Ctensor=Ct)
+                                          measure_slot=1, Ctensor=Ct, affine=affine)
         ETA = 1
         self.t_Gb = dict(
             vv=d.add_term(0, 0, L.OP_VAL, ETA, L.OP_VAL, ETA),                        # (g-ω²d₀) η v
@@ -123,7 +125,7 @@ class YagoProblem:
         # ---- Λb (:165): slot 0 = η⁺, slot 1 = η⁻
         self.dom_Lb = d = sys_.add_domain(3, dLb.nq, dLb.wq,
                                           [dLb.skeleton_slot(V_Ge, "plus"), dLb.skeleton_slot(V_Ge, "minus")],
-                                          measure_slot=0, measure_kind=L.MEASURE_FACET, Ctensor=Ct)
+                                          measure_slot=0, measure_kind=L.MEASURE_FACET, Ctensor=Ct, affine=affine)
         jump, mean = {0: 1.0, 1: -1.0}, {0: 0.5, 1: 0.5}
         gamma = 1.0 * order * (order + 1) / c["h"]
         d.add_term(0, -1.0, L.OP_GRAD, jump, L.OP_CHESS_NPLUS, mean)
@@ -134,7 +136,7 @@ class YagoProblem:
         V_aux.offset = 0
         self._xq_Gin = dGin.points()
         self.dom_Gin = d = sys_.add_domain(3, dGin.nq, dGin.wq, [dGin.trace_slot(V_Om), dGin.surface_slot(V_aux)],
-                                           measure_slot=1, weights=[np.zeros(self._xq_Gin.shape[:2])] * 2)
+                                           measure_slot=1, weights=[np.zeros(self._xq_Gin.shape[:2])] * 2, affine=affine)
         d.add_rhs(0, 1.0, L.OP_VAL, PHI, weight_re=0, weight_im=1)
         self.nnz = sys_.build_pattern()
         if hasattr(sys_, "set_dof_coords"):

@@ -14,8 +14,8 @@ void build_pattern_device(const std::vector<DomainDev>& doms, long long ndofs,
 void build_csc_device(const int* rowind, const int* colind, long long nnz, long long ndofs,
                       DevBuf<int>& colptr, DevBuf<int>& rowval, DevBuf<int>& csr_slot,
                       cudaStream_t s, long long* launches);
-void launch_integrate(const DomainDev& dom, const TermDev* terms_dev, int nterms,
-                      const RhsDev* rhs_dev, int nrhs, const int* dest, double* const* mats,
+void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, const int* dest,
+                      const int* cell_list, long long ncells_run, double* const* mats,
                       int nmat, double* const* vecs, int nvec, int is_complex, int do_mat,
                       int do_vec, int nsm, cudaStream_t s);
 void launch_gradgrad_reference(const DomainDev& dom, double* Sref, cudaStream_t s);
@@ -56,8 +56,11 @@ struct Domain {
   std::vector<TermDev> terms_host;
   std::vector<RhsDev> rhs_host;
   std::vector<char> term_fast;      // handled by the reference-matrix fast path
-  DevBuf<TermDev> terms_dev;
   DevBuf<RhsDev> rhs_dev;
+  std::vector<TileTarget> targets_host;
+  std::vector<TileProd> prods_host;
+  DevBuf<TileTarget> targets_dev;
+  DevBuf<TileProd> prods_dev;
   DevBuf<double> Sref;
   bool finalized = false;
   bool coef_dirty = true;
@@ -133,6 +136,38 @@ int find_or_add_opi(DomainDev& dev, int slot, int op, const double* dir, int D) 
   return dev.nopi++;
 }
 
+// (block, matrix, re|im) targets of the tiled bilinear stage and their contractions; rebuilt
+// whenever a coefficient changes (a zero coefficient part contributes nothing)
+void build_tile_tables(vlfs_ctx* ctx, Domain& d) {
+  DomainDev& dev = d.dev;
+  d.targets_host.clear();
+  d.prods_host.clear();
+  for (int b = 0; b < dev.nblocks; ++b) {
+    dev.target_first[b] = (int)d.targets_host.size();
+    const BlockDev& B = dev.blk[b];
+    for (int m = 0; m < ctx->nmat; ++m)
+      for (int part = 0; part < (ctx->is_complex ? 2 : 1); ++part) {
+        TileTarget tg{m, part, (int)d.prods_host.size(), 0};
+        for (const TermDev& T : d.terms_host) {
+          if (T.mat != m || T.opi_test[B.ts] < 0 || T.opi_trial[B.us] < 0) continue;
+          const double c = (part == 0 ? T.cre : T.cim) * T.st[B.ts] * T.su[B.us];
+          if (c == 0.0) continue;
+          const OpInst& OA = dev.opi[T.opi_test[B.ts]];
+          const OpInst& OB = dev.opi[T.opi_trial[B.us]];
+          d.prods_host.push_back(TileProd{OA.smem_off, OB.smem_off, OA.buf_stride, OB.buf_stride,
+                                          OA.ndp, OB.ndp, T.ncomp, T.weight, c});
+          ++tg.count;
+        }
+        if (tg.count) d.targets_host.push_back(tg);
+      }
+  }
+  dev.target_first[dev.nblocks] = (int)d.targets_host.size();
+  d.targets_dev.upload(d.targets_host.data(), d.targets_host.size(), ctx->stream);
+  d.prods_dev.upload(d.prods_host.data(), d.prods_host.size(), ctx->stream);
+  dev.targets = d.targets_dev.p;
+  dev.prods = d.prods_dev.p;
+}
+
 // derive operator instances, touched blocks, shared-memory layout, device term tables
 void finalize_domain(vlfs_ctx* ctx, Domain& d) {
   DomainDev& dev = d.dev;
@@ -194,10 +229,13 @@ void finalize_domain(vlfs_ctx* ctx, Domain& d) {
         off += B.nr * B.nc;
       }
   dev.entries_per_cell = off;
-  // shared memory layout (doubles)
-  int p = dev.nslots * dev.nq * 12;
-  dev.smem_meas_off = p; p += dev.nq;
-  dev.smem_w_off = p; p += dev.nweights * dev.nq;
+  // 4x4 tiles of the touched blocks
+  dev.tile_base[0] = 0;
+  for (int b = 0; b < dev.nblocks; ++b) {
+    dev.tiles_j[b] = (dev.blk[b].nc + 3) / 4;
+    dev.tile_base[b + 1] = dev.tile_base[b] + ((dev.blk[b].nr + 3) / 4) * dev.tiles_j[b];
+  }
+  // shared memory layout (doubles); operator arrays start on 32-byte boundaries
   for (int o = 0; o < dev.nopi; ++o) {
     OpInst& O = dev.opi[o];
     if (op_needs_hess(O.op) && !dev.slot[O.slot].hess)
@@ -208,13 +246,37 @@ void finalize_domain(vlfs_ctx* ctx, Domain& d) {
       throw std::string("ref_normal missing for a normal-derivative operator");
     if ((O.op == VLFS_OP_CHESS_NPLUS) && !dev.slot[0].ref_normal)
       throw std::string("ref_normal of slot 0 missing for (C:Hessian).n+");
-    O.smem_off = p;
-    p += dev.nq * O.ncomp * dev.slot[O.slot].ndofs;
+    O.ndp = (dev.slot[O.slot].ndofs + 3) & ~3;
   }
+  dev.nqg = dev.affine ? 1 : dev.nq;
+  dev.smem_meas_off = dev.nslots * dev.nqg * 12;
+  dev.smem_geo_stride = (dev.smem_meas_off + dev.nq + 3) & ~3;
+  int p = 3 * dev.smem_geo_stride;
+  dev.smem_inv_off = p;
+  for (int o = 0; o < dev.nopi; ++o) {         // values of a slot with one table variant do
+    OpInst& O = dev.opi[o];                    // not depend on the cell
+    if (O.op == VLFS_OP_VAL && !dev.slot[O.slot].variant) {
+      O.smem_off = p; O.buf_stride = 0;
+      p += dev.nq * O.ncomp * O.ndp;
+    }
+  }
+  dev.smem_inv_len = p - dev.smem_inv_off;
+  dev.smem_buf_off = p;
+  int q = (dev.nweights * dev.nq + 3) & ~3;
+  for (int o = 0; o < dev.nopi; ++o) {
+    OpInst& O = dev.opi[o];
+    if (O.op == VLFS_OP_VAL && !dev.slot[O.slot].variant) continue;
+    O.smem_off = p + q; O.buf_stride = -1;
+    q += dev.nq * O.ncomp * O.ndp;
+  }
+  dev.smem_buf_stride = q;
+  for (int o = 0; o < dev.nopi; ++o)
+    if (dev.opi[o].buf_stride < 0) dev.opi[o].buf_stride = q;
+  p += 2 * q;
   dev.smem_total = p;
   if ((size_t)p * sizeof(double) > 227 * 1024)
     throw std::string("domain needs more than 227 KB of shared memory per cell");
-  d.terms_dev.upload(d.terms_host.data(), d.terms_host.size(), ctx->stream);
+  build_tile_tables(ctx, d);
   d.rhs_dev.upload(d.rhs_host.data(), d.rhs_host.size(), ctx->stream);
   bool any_fast = false;
   for (char f : d.term_fast) any_fast |= f != 0;
@@ -242,7 +304,7 @@ void refresh_coefs(vlfs_ctx* ctx, Domain& d) {
     d.rhs_host[t].cre = d.rhs[t].coef_re;
     d.rhs_host[t].cim = d.rhs[t].coef_im;
   }
-  d.terms_dev.upload(d.terms_host.data(), d.terms_host.size(), ctx->stream);
+  build_tile_tables(ctx, d);
   d.rhs_dev.upload(d.rhs_host.data(), d.rhs_host.size(), ctx->stream);
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   d.coef_dirty = false;
@@ -278,9 +340,9 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     bool gen_vec = do_vec && !d.rhs_host.empty();
     if (gen_mat || gen_vec) {
       ProfScope ps(ctx, "integrate_cells:dom" + std::to_string(di));
-      launch_integrate(d.dev, d.terms_dev.p, (int)d.terms_host.size(), d.rhs_dev.p,
-                       (int)d.rhs_host.size(), dest, mp.data(), (int)mp.size(), vp.data(),
-                       (int)vp.size(), ctx->is_complex, gen_mat, gen_vec, ctx->nsm, s);
+      launch_integrate(d.dev, d.rhs_dev.p, (int)d.rhs_host.size(), dest, nullptr, d.dev.ncells,
+                       mp.data(), (int)mp.size(), vp.data(), (int)vp.size(), ctx->is_complex,
+                       gen_mat, gen_vec, ctx->nsm, s);
       ++ctx->launches;
     }
     if (do_mat)
@@ -400,17 +462,34 @@ int vlfs_add_domain(vlfs_ctx* ctx, const vlfs_domain_desc* desc, int* domain_id)
         return fail(ctx, VLFS_ERR_ARG, "vlfs_add_domain: bad slot descriptor");
       SlotStore& st = dom->st[k];
       size_t nc = (size_t)d.ncells;
+      // a variant array with one distinct value (e.g. every boundary facet is the same local
+      // face of its cell) selects one table set: upload only that set, so that the value
+      // tables become cell-invariant for the kernel
+      int nvar = S.nvar, v0 = 0;
+      bool uniform = S.variant != nullptr && nc > 0;
+      if (uniform) {
+        v0 = S.variant[0];
+        for (size_t c = 1; c < nc && uniform; ++c) uniform = S.variant[c] == v0;
+      }
+      if (S.variant)
+        for (size_t c = 0; c < nc; ++c)
+          if (S.variant[c] < 0 || S.variant[c] >= S.nvar)
+            return fail(ctx, VLFS_ERR_ARG, "vlfs_add_domain: variant index out of range");
+      if (uniform) nvar = 1; else v0 = 0;
+      const size_t tq = (size_t)d.nq;
       st.coords.upload(S.coords, nc * S.nv * d.D, s);
-      upload_opt(st.variant, S.variant, nc, s);
-      st.geo_grad.upload(S.geo_grad, (size_t)S.nvar * d.nq * S.nv * S.dref, s);
-      st.val.upload(S.val, (size_t)S.nvar * d.nq * S.ndofs, s);
-      st.grad.upload(S.grad, (size_t)S.nvar * d.nq * S.ndofs * S.dref, s);
-      upload_opt(st.hess, S.hess, (size_t)S.nvar * d.nq * S.ndofs * S.dref * S.dref, s);
+      if (!uniform) upload_opt(st.variant, S.variant, nc, s);
+      st.geo_grad.upload(S.geo_grad + v0 * tq * S.nv * S.dref, (size_t)nvar * tq * S.nv * S.dref, s);
+      st.val.upload(S.val + v0 * tq * S.ndofs, (size_t)nvar * tq * S.ndofs, s);
+      st.grad.upload(S.grad + v0 * tq * S.ndofs * S.dref, (size_t)nvar * tq * S.ndofs * S.dref, s);
+      if (S.hess)
+        st.hess.upload(S.hess + v0 * tq * S.ndofs * S.dref * S.dref,
+                       (size_t)nvar * tq * S.ndofs * S.dref * S.dref, s);
       st.dofs.upload(S.dofs, nc * S.ndofs, s);
-      upload_opt(st.ref_normal, S.ref_normal, (size_t)S.nvar * S.dref, s);
-      upload_opt(st.ref_tangent, S.ref_tangent, (size_t)S.nvar * S.dref, s);
+      if (S.ref_normal) st.ref_normal.upload(S.ref_normal + (size_t)v0 * S.dref, (size_t)nvar * S.dref, s);
+      if (S.ref_tangent) st.ref_tangent.upload(S.ref_tangent + (size_t)v0 * S.dref, (size_t)nvar * S.dref, s);
       SlotDev& sd = dev.slot[k];
-      sd.dref = S.dref; sd.nv = S.nv; sd.nvar = S.nvar; sd.ndofs = S.ndofs;
+      sd.dref = S.dref; sd.nv = S.nv; sd.nvar = nvar; sd.ndofs = S.ndofs;
       sd.has_hess = S.hess != nullptr;
       sd.coords = st.coords.p; sd.variant = st.variant.p; sd.geo_grad = st.geo_grad.p;
       sd.val = st.val.p; sd.grad = st.grad.p; sd.hess = st.hess.p; sd.dofs = st.dofs.p;

@@ -64,7 +64,24 @@ struct SlotDev {
 struct OpInst {
   int slot, op, ncomp;
   double dir[3];
-  int smem_off;     // offset (doubles) of the [nq][ncomp][ndofs] array
+  int smem_off;     // offset (doubles) of the [nq][ncomp][ndp] array (multiple of 4)
+  int ndp;          // row stride: local DOF count rounded up to a multiple of 4 (zero padded)
+  int buf_stride;   // 0: cell-invariant table evaluated once per CTA; else distance between
+                    //    the two pipeline buffers of this per-cell table
+};
+
+// One contraction feeding a (block, matrix, re|im) target of the tiled bilinear stage:
+// target += coef * sum_q meas[q] W[q] sum_c A[q][c][i] B[q][c][j]
+struct TileProd {
+  int offA, offB;       // shared-memory offsets of the operator arrays (pipeline buffer 0)
+  int bufA, bufB;       // their pipeline-buffer strides (0 = cell-invariant)
+  int ndpA, ndpB;       // their row strides
+  int ncomp, weight;    // components per point, coefficient-field index or -1
+  double coef;          // coefficient part (re or im) times the slot scales
+};
+struct TileTarget {
+  int mat, part;        // part: 0 = real, 1 = imaginary
+  int first, count;     // range in the TileProd array
 };
 
 struct TermDev {
@@ -100,9 +117,19 @@ struct DomainDev {
   int nblocks;
   BlockDev blk[VLFS_MAX_BLOCKS];
   int entries_per_cell;
-  int smem_geom_off[VLFS_MAX_SLOTS];   // per slot: pinv [nq][D][dref], normal [nq][D]
-  int smem_meas_off;                   // [nq] measure*qweight
-  int smem_w_off;                      // [nweights][nq]
+  int tile_base[VLFS_MAX_BLOCKS + 1];  // prefix of 4x4 tiles per block
+  int tiles_j[VLFS_MAX_BLOCKS];        // tiles along the trial index
+  int target_first[VLFS_MAX_BLOCKS + 1];
+  const TileTarget* targets;
+  const TileProd* prods;
+  // shared-memory layout (doubles).  Geometry records are triple buffered (computed two
+  // cells ahead), per-cell operator tables and coefficient fields double buffered (one cell
+  // ahead), cell-invariant operator tables single.
+  int nqg;                             // geometry points per slot: 1 when affine, else nq
+  int smem_geo_stride;                 // one geometry buffer: [nslots][nqg][12] + meas[nq]
+  int smem_meas_off;                   // offset of meas inside a geometry buffer
+  int smem_inv_off, smem_inv_len;      // cell-invariant operator tables
+  int smem_buf_off, smem_buf_stride;   // per-cell buffers: weights [nweights][nq] + tables
   int smem_total;                      // doubles
 };
 

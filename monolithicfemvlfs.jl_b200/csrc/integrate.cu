@@ -145,13 +145,15 @@ __device__ __forceinline__ int sym_index(int b, int d) {
 
 template <int D>
 __device__ void eval_op(const DomainDev& dom, const OpInst& O, long long cell, int q, int i,
-                        const double* sm_geo, double* out /* stride nd */) {
+                        const double* sm_geo, double* out /* stride ndp */) {
   constexpr int S_ = D * (D + 1) / 2;
   const SlotDev& S = dom.slot[O.slot];
-  const int nd = S.ndofs, nq = dom.nq;
+  const int nq = dom.nq;
+  const int nd = O.ndp;        // component stride of the padded shared-memory rows
   const int var = S.variant ? S.variant[cell] : 0;
-  const double* rec = sm_geo + ((size_t)O.slot * nq + q) * GEO_STRIDE;
-  const size_t tq = ((size_t)var * nq + q) * nd + i;
+  const int qg = dom.nqg == 1 ? 0 : q;
+  const double* rec = sm_geo + ((size_t)O.slot * dom.nqg + qg) * GEO_STRIDE;
+  const size_t tq = ((size_t)var * nq + q) * S.ndofs + i;
   if (O.op == VLFS_OP_VAL) {
     out[0] = S.val[tq];
     return;
@@ -233,7 +235,7 @@ __device__ void eval_op(const DomainDev& dom, const OpInst& O, long long cell, i
     return;
   }
   // VLFS_OP_CHESS_NPLUS: contraction with the normal of slot 0
-  const double* rec0 = sm_geo + ((size_t)0 * nq + q) * GEO_STRIDE;
+  const double* rec0 = sm_geo + (size_t)qg * GEO_STRIDE;
 #pragma unroll
   for (int a = 0; a < D; ++a) {
     double s = 0;
@@ -248,101 +250,152 @@ struct AsmPtrs {
   double* vec[4];
 };
 
+// Pipelined over the cells of a CTA: iteration k computes the geometry of cell k+2, the
+// per-cell operator tables and coefficient fields of cell k+1 and the tiles of cell k, with
+// one barrier per iteration, so the dependent global loads of the preparation stages overlap
+// the FP64 tile contraction of other warps.
 template <int D>
-__global__ void __launch_bounds__(256)
-integrate_cells(DomainDev dom, const TermDev* __restrict__ terms, int nterms,
-                const RhsDev* __restrict__ rhs, int nrhs, const int* __restrict__ dest,
+__global__ void __launch_bounds__(256, 3)
+integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const int* __restrict__ dest,
+                const int* __restrict__ cell_list, long long ncells_run,
                 AsmPtrs ptrs, int is_complex, int do_mat, int do_vec) {
-  extern __shared__ double sm[];
-  const int nq = dom.nq;
-  double* sm_geo = sm;
-  double* sm_meas = sm + dom.smem_meas_off;
-  double* sm_w = sm + dom.smem_w_off;
+  extern __shared__ __align__(16) double sm[];
+  const int nq = dom.nq, nqg = dom.nqg;
   const int tid = threadIdx.x, nth = blockDim.x;
-
-  for (long long cell = blockIdx.x; cell < dom.ncells; cell += gridDim.x) {
-    // ---- stage 0: geometry + coefficient fields --------------------------------
-    for (int t = tid; t < dom.nslots * nq; t += nth) {
-      int s = t / nq, q = t - s * nq;
+  const int vstride = is_complex ? 2 : 1;
+  const long long first = blockIdx.x, step = gridDim.x;
+  auto cell_at = [&](long long k) -> long long {
+    const long long r = first + k * step;
+    if (r >= ncells_run) return -1;
+    return cell_list ? (long long)cell_list[r] : r;
+  };
+  auto geo_buf = [&](long long k) { return sm + (size_t)(k % 3) * dom.smem_geo_stride; };
+  auto stage_geometry = [&](long long cell, double* geo) {
+    if (cell < 0) return;
+    for (int t = tid; t < dom.nslots * nqg; t += nth) {
+      const int s = t / nqg, q = t - s * nqg;
       double m;
-      slot_geometry<D>(dom.slot[s], cell, q, nq, sm_geo + (size_t)t * GEO_STRIDE,
+      slot_geometry<D>(dom.slot[s], cell, q, nq, geo + (size_t)t * GEO_STRIDE,
                        s == dom.measure_slot ? &m : nullptr, dom.measure_kind);
-      if (s == dom.measure_slot) sm_meas[q] = m * dom.qweights[q];
-    }
-    for (int t = tid; t < dom.nweights * nq; t += nth) {
-      int w = t / nq, q = t - w * nq;
-      sm_w[t] = dom.weights[((size_t)w * dom.ncells + cell) * nq + q];
-    }
-    __syncthreads();
-    // ---- stage 1: operator instances ------------------------------------------
-    for (int o = 0; o < dom.nopi; ++o) {
-      const OpInst& O = dom.opi[o];
-      const int nd = dom.slot[O.slot].ndofs;
-      for (int t = tid; t < nq * nd; t += nth) {
-        int q = t / nd, i = t - q * nd;
-        eval_op<D>(dom, O, cell, q, i, sm_geo, sm + O.smem_off + (size_t)q * O.ncomp * nd + i);
+      if (s == dom.measure_slot) {
+        if (nqg == 1) for (int qq = 0; qq < nq; ++qq) geo[dom.smem_meas_off + qq] = m * dom.qweights[qq];
+        else geo[dom.smem_meas_off + q] = m * dom.qweights[q];
       }
     }
-    __syncthreads();
-    // ---- stage 2: bilinear terms ----------------------------------------------
+  };
+  auto stage_tables = [&](long long cell, const double* geo, int par, bool invariant) {
+    if (cell < 0) return;
+    if (!invariant) {
+      double* w = sm + dom.smem_buf_off + (size_t)par * dom.smem_buf_stride;
+      for (int t = tid; t < dom.nweights * nq; t += nth) {
+        const int wi = t / nq, q = t - wi * nq;
+        w[t] = dom.weights[((size_t)wi * dom.ncells + cell) * nq + q];
+      }
+    }
+    for (int o = 0; o < dom.nopi; ++o) {
+      const OpInst& O = dom.opi[o];
+      if ((O.buf_stride == 0) != invariant) continue;
+      const int nd = dom.slot[O.slot].ndofs;
+      double* base = sm + O.smem_off + (size_t)par * O.buf_stride;
+      for (int t = tid; t < nq * nd; t += nth) {
+        const int q = t / nd, i = t - q * nd;
+        eval_op<D>(dom, O, cell, q, i, geo, base + (size_t)q * O.ncomp * O.ndp + i);
+      }
+    }
+  };
+
+  // operator tables are zero padded to a multiple of 4 local DOFs; the padding is never
+  // written again, so clearing once per CTA is enough
+  for (int t = dom.smem_inv_off + tid; t < dom.smem_total; t += nth) sm[t] = 0.0;
+  stage_geometry(cell_at(0), geo_buf(0));
+  __syncthreads();
+  stage_tables(cell_at(0), geo_buf(0), 0, true);     // cell-invariant tables, once
+  stage_tables(cell_at(0), geo_buf(0), 0, false);
+  stage_geometry(cell_at(1), geo_buf(1));
+  __syncthreads();
+
+  for (long long k = 0;; ++k) {
+    const long long cell = cell_at(k);
+    if (cell < 0) break;
+    const int par = (int)(k & 1);
+    stage_geometry(cell_at(k + 2), geo_buf(k + 2));
+    stage_tables(cell_at(k + 1), geo_buf(k + 1), par ^ 1, false);
+    const double* sm_meas = geo_buf(k) + dom.smem_meas_off;
+    const double* sm_w = sm + dom.smem_buf_off + (size_t)par * dom.smem_buf_stride;
+    // ---- bilinear terms, 4x4 register tiles --------------------------------------
+    // Every (block, matrix, re|im) target is a small GEMM  T = A^T diag(w) B over the
+    // (point, component) index; a thread owns a 4x4 tile of one block, reads 4+4 operands per
+    // contraction index with two 128-bit shared loads each and issues 16 DFMAs.
     if (do_mat) {
-      for (int b = 0; b < dom.nblocks; ++b) {
+      const int ntiles = dom.tile_base[dom.nblocks];
+      for (int tile = tid; tile < ntiles; tile += nth) {
+        int b = 0;
+        while (tile >= dom.tile_base[b + 1]) ++b;
         const BlockDev B = dom.blk[b];
+        const int lt = tile - dom.tile_base[b];
+        const int ti = lt / dom.tiles_j[b], tj = lt - ti * dom.tiles_j[b];
+        const int i0 = ti * 4, j0 = tj * 4;
         const int* drow = dest + (size_t)cell * dom.entries_per_cell + B.off;
-        for (int idx = tid; idx < B.nr * B.nc; idx += nth) {
-          const int i = idx / B.nc, j = idx - i * B.nc;
-          double are[4] = {0, 0, 0, 0}, aim[4] = {0, 0, 0, 0};
-          unsigned touched_re = 0, touched_im = 0;
-          for (int t = 0; t < nterms; ++t) {
-            const TermDev& T = terms[t];
-            const int oa = T.opi_test[B.ts], ob = T.opi_trial[B.us];
-            if (oa < 0 || ob < 0) continue;
-            const int nda = B.nr, ndb = B.nc, nc = T.ncomp;
-            const double* A = sm + dom.opi[oa].smem_off + i;
-            const double* Bp = sm + dom.opi[ob].smem_off + j;
-            const double* W = T.weight >= 0 ? sm_w + T.weight * nq : nullptr;
-            double acc = 0;
-            for (int q = 0; q < nq; ++q) {
-              double dot = 0;
-              for (int c = 0; c < nc; ++c)
-                dot = fma(A[(size_t)(q * nc + c) * nda], Bp[(size_t)(q * nc + c) * ndb], dot);
-              double w = sm_meas[q];
-              if (W) w *= W[q];
-              acc = fma(w, dot, acc);
-            }
-            acc *= T.st[B.ts] * T.su[B.us];
-            are[T.mat] = fma(T.cre, acc, are[T.mat]);
-            aim[T.mat] = fma(T.cim, acc, aim[T.mat]);
-            if (T.cre != 0.0) touched_re |= 1u << T.mat;
-            if (T.cim != 0.0) touched_im |= 1u << T.mat;
-          }
-          const int slot = drow[idx];
+        for (int tg = dom.target_first[b]; tg < dom.target_first[b + 1]; ++tg) {
+          const TileTarget T = dom.targets[tg];
+          double acc[4][4];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            if (is_complex) {
-              if (touched_re >> m & 1u) atomicAdd(ptrs.mat[m] + 2 * (size_t)slot, are[m]);
-              if (touched_im >> m & 1u) atomicAdd(ptrs.mat[m] + 2 * (size_t)slot + 1, aim[m]);
-            } else {
-              if (touched_re >> m & 1u) atomicAdd(ptrs.mat[m] + (size_t)slot, are[m]);
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+          for (int pi = T.first; pi < T.first + T.count; ++pi) {
+            const TileProd P = dom.prods[pi];
+            const double* Ap = sm + P.offA + par * P.bufA + i0;
+            const double* Bp = sm + P.offB + par * P.bufB + j0;
+            const double* W = P.weight >= 0 ? sm_w + P.weight * nq : nullptr;
+            const int sa = P.ndpA, sb = P.ndpB, nc = P.ncomp;
+            for (int q = 0; q < nq; ++q) {
+              double w = sm_meas[q] * P.coef;
+              if (W) w *= W[q];
+              for (int c = 0; c < nc; ++c) {
+                const double2 a01 = *reinterpret_cast<const double2*>(Ap);
+                const double2 a23 = *reinterpret_cast<const double2*>(Ap + 2);
+                const double2 b01 = *reinterpret_cast<const double2*>(Bp);
+                const double2 b23 = *reinterpret_cast<const double2*>(Bp + 2);
+                const double av[4] = {a01.x * w, a01.y * w, a23.x * w, a23.y * w};
+                const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) acc[a][e] = fma(av[a], bv[e], acc[a][e]);
+                Ap += sa; Bp += sb;
+              }
+            }
+          }
+          double* out = ptrs.mat[T.mat] + T.part;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int i = i0 + a;
+            if (i >= B.nr) break;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j0 + e;
+              if (j < B.nc) atomicAdd(out + (size_t)vstride * drow[i * B.nc + j], acc[a][e]);
             }
           }
         }
       }
     }
-    // ---- stage 3: linear terms -------------------------------------------------
+    // ---- linear terms ---------------------------------------------------------------
     if (do_vec) {
       for (int t = 0; t < nrhs; ++t) {
         const RhsDev& R = rhs[t];
         for (int s = 0; s < dom.nslots; ++s) {
           if (R.opi[s] < 0) continue;
           const int nd = dom.slot[s].ndofs;
-          const double* A = sm + dom.opi[R.opi[s]].smem_off;
+          const OpInst& O = dom.opi[R.opi[s]];
+          const double* A = sm + O.smem_off + (size_t)par * O.buf_stride;
           const double* Wr = R.wre >= 0 ? sm_w + R.wre * nq : nullptr;
           const double* Wi = R.wim >= 0 ? sm_w + R.wim * nq : nullptr;
           for (int i = tid; i < nd; i += nth) {
             double ar = 0, ai = 0;
             for (int q = 0; q < nq; ++q) {
-              double v = sm_meas[q] * A[(size_t)q * nd + i];
+              double v = sm_meas[q] * A[(size_t)q * O.ndp + i];
               ar = fma(Wr ? Wr[q] : 1.0, v, ar);
               if (Wi) ai = fma(Wi[q], v, ai);
             }
@@ -459,25 +512,35 @@ gradgrad_affine(DomainDev dom, const double* __restrict__ Sref, const int* __res
 }  // namespace
 
 // ---- host-side launchers ------------------------------------------------------------
-void launch_integrate(const DomainDev& dom, const TermDev* terms_dev, int nterms,
-                      const RhsDev* rhs_dev, int nrhs, const int* dest, double* const* mats,
+void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, const int* dest,
+                      const int* cell_list, long long ncells_run, double* const* mats,
                       int nmat, double* const* vecs, int nvec, int is_complex, int do_mat,
                       int do_vec, int nsm, cudaStream_t s) {
-  if (dom.ncells == 0) return;
+  if (ncells_run == 0) return;
   AsmPtrs P{};
   for (int m = 0; m < nmat && m < 4; ++m) P.mat[m] = mats[m];
   for (int v = 0; v < nvec && v < 4; ++v) P.vec[v] = vecs[v];
   size_t smem = (size_t)dom.smem_total * sizeof(double);
-  long long grid = dom.ncells;
-  int per_sm = smem ? (int)((220 * 1024) / (smem + 1024)) : 8;
+  // one thread per 4x4 tile of the cell's touched blocks, whole warps, at most 256
+  int ntiles = do_mat ? dom.tile_base[dom.nblocks] : 0;
+  int threads = ((ntiles + 31) / 32) * 32;
+  if (threads < 64) threads = 64;
+  if (threads > 256) threads = 256;
+  long long grid = ncells_run;
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
-  long long cap = (long long)nsm * per_sm * 4;
+  int by_threads = 2048 / threads;
+  if (per_sm > by_threads) per_sm = by_threads;
+  int by_regs = 65536 / (threads * 80);          // __launch_bounds__(256,3): <= 80 registers
+  if (by_regs < 1) by_regs = 1;
+  if (per_sm > by_regs) per_sm = by_regs;
+  // persistent CTAs: exactly the resident set, each pipelining over its cells
+  long long cap = (long long)nsm * per_sm;
   if (grid > cap) grid = cap;
   auto launch = [&](auto kern) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, 256, smem, s>>>(dom, terms_dev, nterms, rhs_dev, nrhs, dest, P,
-                                           is_complex, do_mat, do_vec);
+    kern<<<(unsigned)grid, threads, smem, s>>>(dom, rhs_dev, nrhs, dest, cell_list, ncells_run, P,
+                                               is_complex, do_mat, do_vec);
   };
   if (dom.D == 1) launch(integrate_cells<1>);
   else if (dom.D == 2) launch(integrate_cells<2>);

@@ -59,7 +59,7 @@ class RecordingSystem:
         self.domains = []
 
     def add_domain(self, D, nq, qweights, slots, measure_slot=0, measure_kind=MEASURE_CELL,
-                   weights=(), Ctensor=None, affine=False):
+                   weights=(), Ctensor=None, affine=None):
         ncells = len(slots[0]["dofs"])
         d = _Dom(D=D, nq=nq, qweights=np.asarray(qweights, float), slots=slots, measure_slot=measure_slot,
                  measure_kind=measure_kind, ncells=ncells, affine=affine,

@@ -125,19 +125,16 @@ def test_krylov_methods_on_spd_block(case):
     assert np.linalg.norm(x - xt) <= 1e-8 * np.linalg.norm(xt)
 
 
-def test_general_quadrature_path_equals_fast_path():
-    """The affine reference-matrix fast path and the general quadrature kernel agree."""
+@pytest.mark.parametrize("kw", [KW0, KW1], ids=["warmup", "order4"])
+def test_general_quadrature_path_equals_fast_path(kw):
+    """The constant-Jacobian paths (reference-matrix Laplace kernel, single geometry record
+    per cell) and the general per-point quadrature kernel agree."""
     from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
-    import vlfs_b200.cases.yago as ymod
-    prob = YagoProblem(Yago_freq_domain_params(**KW0), device=0)
+    prob = YagoProblem(Yago_freq_domain_params(**kw), device=0)
     prob.assemble()
-    v_fast = prob.sys.get_values(0)
-    saved = ymod.is_affine
-    ymod.is_affine = lambda *a, **k: False
-    try:
-        prob2 = YagoProblem(Yago_freq_domain_params(**KW0), device=0)
-    finally:
-        ymod.is_affine = saved
+    v_fast, b_fast = prob.sys.get_values(0), prob.sys.get_vector(0)
+    prob2 = YagoProblem(Yago_freq_domain_params(**kw), device=0, affine=False)
     prob2.assemble()
-    v_gen = prob2.sys.get_values(0)
+    v_gen, b_gen = prob2.sys.get_values(0), prob2.sys.get_vector(0)
     assert np.abs(v_fast - v_gen).max() <= 1e-13 * np.abs(v_gen).max()
+    assert np.abs(b_fast - b_gen).max() <= 1e-13 * np.abs(b_gen).max()
