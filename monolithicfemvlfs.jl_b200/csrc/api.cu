@@ -5,6 +5,7 @@
 #include "solver.cuh"
 #include <cstring>
 #include <memory>
+#include <array>
 
 void build_pattern_device(const std::vector<DomainDev>& doms, long long ndofs,
                           DevBuf<int>& rowptr, DevBuf<int>& colind, DevBuf<int>& rowind,
@@ -14,6 +15,8 @@ void build_pattern_device(const std::vector<DomainDev>& doms, long long ndofs,
 void build_csc_device(const int* rowind, const int* colind, long long nnz, long long ndofs,
                       DevBuf<int>& colptr, DevBuf<int>& rowval, DevBuf<int>& csr_slot,
                       cudaStream_t s, long long* launches);
+void build_tiled_dest(const DomainDev& dom, const int* dest, DevBuf<int>& tiled, cudaStream_t s,
+                      long long* launches);
 void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, const int* dest,
                       const int* cell_list, long long ncells_run, double* const* mats,
                       int nmat, double* const* vecs, int nvec, int is_complex, int do_mat,
@@ -62,6 +65,8 @@ struct Domain {
   DevBuf<TileTarget> targets_dev;
   DevBuf<TileProd> prods_dev;
   DevBuf<double> Sref;
+  DevBuf<int> dest_tiled;           // [cell][tile][4][4] CSR slots for the tiled kernel
+  std::vector<std::array<int, 3>> tref_pairs;   // (test op instance, trial op instance, smem offset)
   bool finalized = false;
   bool coef_dirty = true;
 };
@@ -154,14 +159,27 @@ void build_tile_tables(vlfs_ctx* ctx, Domain& d) {
           if (c == 0.0) continue;
           const OpInst& OA = dev.opi[T.opi_test[B.ts]];
           const OpInst& OB = dev.opi[T.opi_trial[B.us]];
-          d.prods_host.push_back(TileProd{OA.smem_off, OB.smem_off, OA.buf_stride, OB.buf_stride,
-                                          OA.ndp, OB.ndp, T.ncomp, T.weight, c});
+          TileProd P{};
+          P.offA = OA.smem_off; P.offB = OB.smem_off; P.bufA = OA.buf_stride; P.bufB = OB.buf_stride;
+          P.ndpA = OA.ndp; P.ndpB = OB.ndp; P.ncomp = T.ncomp; P.weight = T.weight; P.coef = c;
+          P.tref = -1; P.ldt = OB.ndp; P.nr4 = OA.ndp; P.tref_owner = -1;
+          if (T.weight < 0)
+            for (auto& pr : d.tref_pairs)
+              if (pr[0] == T.opi_test[B.ts] && pr[1] == T.opi_trial[B.us]) P.tref = pr[2];
+          d.prods_host.push_back(P);
           ++tg.count;
         }
         if (tg.count) d.targets_host.push_back(tg);
       }
   }
   dev.target_first[dev.nblocks] = (int)d.targets_host.size();
+  for (size_t k = 0; k < d.prods_host.size(); ++k) {
+    if (d.prods_host[k].tref < 0) continue;
+    size_t owner = k;
+    for (size_t l = 0; l < k; ++l)
+      if (d.prods_host[l].tref == d.prods_host[k].tref) { owner = l; break; }
+    d.prods_host[k].tref_owner = (int)owner;
+  }
   d.targets_dev.upload(d.targets_host.data(), d.targets_host.size(), ctx->stream);
   d.prods_dev.upload(d.prods_host.data(), d.prods_host.size(), ctx->stream);
   dev.targets = d.targets_dev.p;
@@ -181,7 +199,9 @@ void finalize_domain(vlfs_ctx* ctx, Domain& d) {
     const vlfs_term_desc& T = d.terms[t];
     int nslots_t = 0, nslots_u = 0;
     for (int s = 0; s < dev.nslots; ++s) { nslots_t += T.test_scale[s] != 0.0; nslots_u += T.trial_scale[s] != 0.0; }
-    bool fast = dev.affine && T.weight < 0 && T.test_op == VLFS_OP_GRAD && T.trial_op == VLFS_OP_GRAD &&
+    // (single-contribution slots are written with plain stores, so one slot must never be
+    // fed by two kernels: the fast path needs the domain to itself)
+    bool fast = d.terms.size() == 1 && dev.affine && T.weight < 0 && T.test_op == VLFS_OP_GRAD && T.trial_op == VLFS_OP_GRAD &&
                 dev.nslots == 1 && dev.slot[0].dref == D && dev.slot[0].nvar == 1 &&
                 dev.slot[0].ndofs * dev.slot[0].ndofs <= 1024;
     d.term_fast[t] = fast;
@@ -250,8 +270,8 @@ void finalize_domain(vlfs_ctx* ctx, Domain& d) {
   }
   dev.nqg = dev.affine ? 1 : dev.nq;
   dev.smem_meas_off = dev.nslots * dev.nqg * 12;
-  dev.smem_geo_stride = (dev.smem_meas_off + dev.nq + 3) & ~3;
-  int p = 3 * dev.smem_geo_stride;
+  dev.smem_geo_stride = (dev.smem_meas_off + dev.nq + 1 + 3) & ~3;
+  int p = 4 * dev.smem_geo_stride;
   dev.smem_inv_off = p;
   for (int o = 0; o < dev.nopi; ++o) {         // values of a slot with one table variant do
     OpInst& O = dev.opi[o];                    // not depend on the cell
@@ -261,6 +281,23 @@ void finalize_domain(vlfs_ctx* ctx, Domain& d) {
     }
   }
   dev.smem_inv_len = p - dev.smem_inv_off;
+  // reference matrices of contractions between two cell-invariant tables without a coefficient
+  // field on an affine domain: one [nr4][nc4] matrix per distinct (test op, trial op) pair
+  dev.smem_tref_off = p;
+  d.tref_pairs.clear();
+  if (dev.affine)
+    for (const TermDev& T : d.terms_host)
+      for (int b = 0; b < dev.nblocks; ++b) {
+        const int oa = T.opi_test[dev.blk[b].ts], ob = T.opi_trial[dev.blk[b].us];
+        if (oa < 0 || ob < 0 || T.weight >= 0) continue;
+        if (dev.opi[oa].buf_stride != 0 || dev.opi[ob].buf_stride != 0) continue;
+        bool seen = false;
+        for (auto& pr : d.tref_pairs) seen |= pr[0] == oa && pr[1] == ob;
+        if (seen) continue;
+        d.tref_pairs.push_back({oa, ob, p});
+        p += dev.opi[oa].ndp * dev.opi[ob].ndp;
+      }
+  dev.smem_tref_len = p - dev.smem_tref_off;
   dev.smem_buf_off = p;
   int q = (dev.nweights * dev.nq + 3) & ~3;
   for (int o = 0; o < dev.nopi; ++o) {
@@ -272,7 +309,10 @@ void finalize_domain(vlfs_ctx* ctx, Domain& d) {
   dev.smem_buf_stride = q;
   for (int o = 0; o < dev.nopi; ++o)
     if (dev.opi[o].buf_stride < 0) dev.opi[o].buf_stride = q;
-  p += 2 * q;
+  // three table buffers allow the split-phase pipeline barrier; fall back to two when the
+  // per-cell tables are large (second-derivative operators)
+  dev.nbuf = ((size_t)(p + 3 * q) * sizeof(double) <= 200 * 1024) ? 3 : 2;
+  p += dev.nbuf * q;
   dev.smem_total = p;
   if ((size_t)p * sizeof(double) > 227 * 1024)
     throw std::string("domain needs more than 227 KB of shared memory per cell");
@@ -340,7 +380,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     bool gen_vec = do_vec && !d.rhs_host.empty();
     if (gen_mat || gen_vec) {
       ProfScope ps(ctx, "integrate_cells:dom" + std::to_string(di));
-      launch_integrate(d.dev, d.rhs_dev.p, (int)d.rhs_host.size(), dest, nullptr, d.dev.ncells,
+      launch_integrate(d.dev, d.rhs_dev.p, (int)d.rhs_host.size(), d.dest_tiled.p, nullptr, d.dev.ncells,
                        mp.data(), (int)mp.size(), vp.data(), (int)vp.size(), ctx->is_complex,
                        gen_mat, gen_vec, ctx->nsm, s);
       ++ctx->launches;
@@ -578,6 +618,11 @@ int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
     build_pattern_device(devs, ctx->ndofs, ctx->rowptr, ctx->colind, ctx->rowind, ctx->dest_all,
                          ctx->dest_off, &n1, &n2, ctx->stream, &ctx->launches);
     ctx->nnz = n1; ctx->ncoo = n2;
+    for (size_t di = 0; di < ctx->doms.size(); ++di) {
+      Domain& d = *ctx->doms[di];
+      if (!d.terms_host.empty())
+        build_tiled_dest(d.dev, ctx->dest_all.p + ctx->dest_off[di], d.dest_tiled, ctx->stream, &ctx->launches);
+    }
     ctx->mats.clear();
     ctx->mats.resize(ctx->nmat);
     for (auto& m : ctx->mats) { m.alloc((size_t)n1 * ctx->scalar()); m.zero(ctx->stream); }

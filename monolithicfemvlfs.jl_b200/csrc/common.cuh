@@ -11,6 +11,10 @@
 #define VLFS_MAX_TERMS 24
 #define VLFS_MAX_BLOCKS 4
 #define VLFS_MAX_WEIGHTS 8
+// dest encoding: v >= 0 CSR slot; VLFS_DEST_PAD = padding entry of a 4x4 tile.  (Measured on
+// B200: turning single-contribution slots into plain 8-byte stores is SLOWER than reductions -
+// scattered per-lane transactions cost the LSU the same either way and the branch diverges.)
+#define VLFS_DEST_PAD (-1)
 
 struct CudaError { cudaError_t e; const char* file; int line; };
 
@@ -77,6 +81,11 @@ struct TileProd {
   int bufA, bufB;       // their pipeline-buffer strides (0 = cell-invariant)
   int ndpA, ndpB;       // their row strides
   int ncomp, weight;    // components per point, coefficient-field index or -1
+  int tref;             // >= 0: both operators are cell-invariant, no coefficient field and the
+                        // domain is affine: sum_q qw[q] A B was contracted once per CTA into the
+                        // shared-memory matrix at this offset ([nr4][nc4], row stride ldt)
+  int ldt, nr4;         // padded column / row counts of the reference matrix
+  int tref_owner;       // index of the product that computes the shared reference matrix
   double coef;          // coefficient part (re or im) times the slot scales
 };
 struct TileTarget {
@@ -122,14 +131,17 @@ struct DomainDev {
   int target_first[VLFS_MAX_BLOCKS + 1];
   const TileTarget* targets;
   const TileProd* prods;
-  // shared-memory layout (doubles).  Geometry records are triple buffered (computed two
-  // cells ahead), per-cell operator tables and coefficient fields double buffered (one cell
-  // ahead), cell-invariant operator tables single.
+  // shared-memory layout (doubles).  Geometry records have 4 buffers (computed two cells
+  // ahead), per-cell operator tables and coefficient fields 3 (one cell ahead); the extra
+  // buffer of each lets warps skew by one phase under the split-phase pipeline barrier.
+  // Cell-invariant operator tables and reference matrices are single.
   int nqg;                             // geometry points per slot: 1 when affine, else nq
   int smem_geo_stride;                 // one geometry buffer: [nslots][nqg][12] + meas[nq]
   int smem_meas_off;                   // offset of meas inside a geometry buffer
   int smem_inv_off, smem_inv_len;      // cell-invariant operator tables
+  int smem_tref_off, smem_tref_len;    // reference matrices of the invariant contractions
   int smem_buf_off, smem_buf_stride;   // per-cell buffers: weights [nweights][nq] + tables
+  int nbuf;                            // number of per-cell table buffers (3, or 2 if large)
   int smem_total;                      // doubles
 };
 

@@ -18,6 +18,8 @@
 //    Jacobian: thread-per-entry keeps the symmetrised reference matrices in registers and
 //    streams cells, 6 FMAs + one scatter per entry.
 #include "common.cuh"
+#include <cstdlib>
+#include <cuda/barrier>
 
 namespace {
 
@@ -245,6 +247,18 @@ __device__ void eval_op(const DomainDev& dom, const OpInst& O, long long cell, i
   }
 }
 
+// global-space reduction (no generic-address dispatch, no return value)
+__device__ __forceinline__ void red_add(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// add `v` into CSR value `base[stride*slot]`.  Exact zeros (basis functions that vanish on the
+// integration face: the explicitly stored zeros of the pattern) are not sent: x + 0 == x, and
+// every scattered reduction costs the LSU a full lane slot.
+__device__ __forceinline__ void scatter_value(double* base, int stride, int d, double v) {
+  if (d >= 0 && v != 0.0) red_add(base + (size_t)stride * d, v);
+}
+
 struct AsmPtrs {
   double* mat[4];
   double* vec[4];
@@ -269,7 +283,8 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
     if (r >= ncells_run) return -1;
     return cell_list ? (long long)cell_list[r] : r;
   };
-  auto geo_buf = [&](long long k) { return sm + (size_t)(k % 3) * dom.smem_geo_stride; };
+  // 4 geometry buffers: a warp one phase ahead writes cell k+3 while a slow warp still reads cell k
+  auto geo_buf = [&](long long k) { return sm + (size_t)(k & 3) * dom.smem_geo_stride; };
   auto stage_geometry = [&](long long cell, double* geo) {
     if (cell < 0) return;
     for (int t = tid; t < dom.nslots * nqg; t += nth) {
@@ -278,8 +293,12 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
       slot_geometry<D>(dom.slot[s], cell, q, nq, geo + (size_t)t * GEO_STRIDE,
                        s == dom.measure_slot ? &m : nullptr, dom.measure_kind);
       if (s == dom.measure_slot) {
-        if (nqg == 1) for (int qq = 0; qq < nq; ++qq) geo[dom.smem_meas_off + qq] = m * dom.qweights[qq];
-        else geo[dom.smem_meas_off + q] = m * dom.qweights[q];
+        if (nqg == 1) {
+          for (int qq = 0; qq < nq; ++qq) geo[dom.smem_meas_off + qq] = m * dom.qweights[qq];
+          geo[dom.smem_meas_off + nq] = m;       // constant cell measure (reference-matrix terms)
+        } else {
+          geo[dom.smem_meas_off + q] = m * dom.qweights[q];
+        }
       }
     }
   };
@@ -309,17 +328,48 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
   for (int t = dom.smem_inv_off + tid; t < dom.smem_total; t += nth) sm[t] = 0.0;
   stage_geometry(cell_at(0), geo_buf(0));
   __syncthreads();
+  // split-phase barrier: a thread arrives when its share of the preparation of cell k+1 is
+  // written and waits only before it needs those tables, i.e. after its own tiles of cell k;
+  // with triple-buffered tables the tile phases of different warps may skew by a whole phase
+  __shared__ cuda::barrier<cuda::thread_scope_block> pipe_bar;
+  if (tid == 0) init(&pipe_bar, nth);
+  __syncthreads();
   stage_tables(cell_at(0), geo_buf(0), 0, true);     // cell-invariant tables, once
   stage_tables(cell_at(0), geo_buf(0), 0, false);
   stage_geometry(cell_at(1), geo_buf(1));
   __syncthreads();
+  // reference matrices of the cell-invariant contractions, once per CTA
+  if (do_mat && dom.smem_tref_len > 0) {
+    const int nprod = dom.target_first[dom.nblocks] > 0
+        ? dom.targets[dom.target_first[dom.nblocks] - 1].first + dom.targets[dom.target_first[dom.nblocks] - 1].count : 0;
+    for (int pi = 0; pi < nprod; ++pi) {
+      const TileProd P = dom.prods[pi];
+      if (P.tref < 0 || P.tref_owner != pi) continue;
+      const int nr4 = P.nr4, nc4 = P.ldt;
+      for (int t = tid; t < nr4 * nc4; t += nth) {
+        const int i = t / nc4, j = t - i * nc4;
+        double acc = 0.0;
+        for (int q = 0; q < nq; ++q) {
+          double d = 0.0;
+          for (int c = 0; c < P.ncomp; ++c)
+            d = fma(sm[P.offA + (q * P.ncomp + c) * P.ndpA + i], sm[P.offB + (q * P.ncomp + c) * P.ndpB + j], d);
+          acc = fma(dom.qweights[q], d, acc);
+        }
+        sm[P.tref + t] = acc;
+      }
+    }
+    __syncthreads();
+  }
 
   for (long long k = 0;; ++k) {
     const long long cell = cell_at(k);
     if (cell < 0) break;
-    const int par = (int)(k & 1);
+    const int par = (int)(k % dom.nbuf);
     stage_geometry(cell_at(k + 2), geo_buf(k + 2));
-    stage_tables(cell_at(k + 1), geo_buf(k + 1), par ^ 1, false);
+    stage_tables(cell_at(k + 1), geo_buf(k + 1), (int)((k + 1) % dom.nbuf), false);
+    cuda::barrier<cuda::thread_scope_block>::arrival_token token;
+    const bool split = dom.nbuf >= 3;
+    if (split) token = pipe_bar.arrive();
     const double* sm_meas = geo_buf(k) + dom.smem_meas_off;
     const double* sm_w = sm + dom.smem_buf_off + (size_t)par * dom.smem_buf_stride;
     // ---- bilinear terms, 4x4 register tiles --------------------------------------
@@ -331,11 +381,17 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
       for (int tile = tid; tile < ntiles; tile += nth) {
         int b = 0;
         while (tile >= dom.tile_base[b + 1]) ++b;
-        const BlockDev B = dom.blk[b];
         const int lt = tile - dom.tile_base[b];
         const int ti = lt / dom.tiles_j[b], tj = lt - ti * dom.tiles_j[b];
         const int i0 = ti * 4, j0 = tj * 4;
-        const int* drow = dest + (size_t)cell * dom.entries_per_cell + B.off;
+        // the tile's 16 CSR slots (tile-major dest, -1 = padding), fetched before the math
+        const int4* dt = reinterpret_cast<const int4*>(dest) + ((size_t)cell * ntiles + tile) * 4;
+        int slot[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int4 v = __ldg(dt + a);
+          slot[a][0] = v.x; slot[a][1] = v.y; slot[a][2] = v.z; slot[a][3] = v.w;
+        }
         for (int tg = dom.target_first[b]; tg < dom.target_first[b + 1]; ++tg) {
           const TileTarget T = dom.targets[tg];
           double acc[4][4];
@@ -345,6 +401,18 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
             for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
           for (int pi = T.first; pi < T.first + T.count; ++pi) {
             const TileProd P = dom.prods[pi];
+            if (P.tref >= 0) {              // cell measure x coefficient x reference matrix
+              const double w = sm_meas[nq] * P.coef;
+              const double* Tr = sm + P.tref + i0 * P.ldt + j0;
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const double2 t01 = *reinterpret_cast<const double2*>(Tr + a * P.ldt);
+                const double2 t23 = *reinterpret_cast<const double2*>(Tr + a * P.ldt + 2);
+                acc[a][0] = fma(w, t01.x, acc[a][0]); acc[a][1] = fma(w, t01.y, acc[a][1]);
+                acc[a][2] = fma(w, t23.x, acc[a][2]); acc[a][3] = fma(w, t23.y, acc[a][3]);
+              }
+              continue;
+            }
             const double* Ap = sm + P.offA + par * P.bufA + i0;
             const double* Bp = sm + P.offB + par * P.bufB + j0;
             const double* W = P.weight >= 0 ? sm_w + P.weight * nq : nullptr;
@@ -369,15 +437,10 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
           }
           double* out = ptrs.mat[T.mat] + T.part;
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const int i = i0 + a;
-            if (i >= B.nr) break;
+          for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = j0 + e;
-              if (j < B.nc) atomicAdd(out + (size_t)vstride * drow[i * B.nc + j], acc[a][e]);
-            }
-          }
+            for (int e = 0; e < 4; ++e)
+              scatter_value(out, vstride, slot[a][e], acc[a][e]);
         }
       }
     }
@@ -403,16 +466,17 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
             double vr = R.cre * ar - R.cim * ai, vi = R.cre * ai + R.cim * ar;
             const int dof = dom.slot[s].dofs[(size_t)cell * nd + i];
             if (is_complex) {
-              atomicAdd(ptrs.vec[R.vec] + 2 * (size_t)dof, vr);
-              atomicAdd(ptrs.vec[R.vec] + 2 * (size_t)dof + 1, vi);
+              red_add(ptrs.vec[R.vec] + 2 * (size_t)dof, vr);
+              red_add(ptrs.vec[R.vec] + 2 * (size_t)dof + 1, vi);
             } else {
-              atomicAdd(ptrs.vec[R.vec] + (size_t)dof, vr);
+              red_add(ptrs.vec[R.vec] + (size_t)dof, vr);
             }
           }
         }
       }
     }
-    __syncthreads();
+    if (split) pipe_bar.wait(std::move(token));
+    else pipe_bar.arrive_and_wait();       // two table buffers only: full barrier per cell
   }
 }
 
@@ -500,8 +564,8 @@ gradgrad_affine(DomainDev dom, const double* __restrict__ Sref, const int* __res
             double v = 0;
 #pragma unroll
             for (int m = 0; m < NS; ++m) v = fma(sG[k0 + u][m], sref[m], v);
-            if (cre != 0.0) atomicAdd(vals + (size_t)stride * slot[u], cre * v);
-            if (cim != 0.0) atomicAdd(vals + (size_t)stride * slot[u] + 1, cim * v);
+            if (cre != 0.0) scatter_value(vals, stride, slot[u], cre * v);
+            if (cim != 0.0) scatter_value(vals + 1, stride, slot[u], cim * v);
           }
         }
       }
@@ -526,6 +590,10 @@ void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, con
   int threads = ((ntiles + 31) / 32) * 32;
   if (threads < 64) threads = 64;
   if (threads > 256) threads = 256;
+  if (const char* e = getenv("VLFS_ASM_THREADS")) {      // tuning hook
+    int t = atoi(e);
+    if (t >= 32 && t <= 256 && t % 32 == 0) threads = t;
+  }
   long long grid = ncells_run;
   int per_sm = (int)((220 * 1024) / (smem + 1024));
   if (per_sm < 1) per_sm = 1;

@@ -86,6 +86,26 @@ __global__ void split_csc(const uint64_t* __restrict__ keys, int* __restrict__ r
   }
 }
 
+// dest in the order the tiled integration kernel consumes it: [cell][tile][4][4], -1 = padding
+__global__ void retile_dest(DomainDev dom, const int* __restrict__ dest, int* __restrict__ tiled) {
+  const int ntiles = dom.tile_base[dom.nblocks];
+  const long long total = dom.ncells * (long long)ntiles * 16;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long cell = g / (ntiles * 16);
+    const int r = (int)(g - cell * (ntiles * 16));
+    const int tile = r >> 4, a = (r >> 2) & 3, e = r & 3;
+    int b = 0;
+    while (tile >= dom.tile_base[b + 1]) ++b;
+    const BlockDev& B = dom.blk[b];
+    const int lt = tile - dom.tile_base[b];
+    const int ti = lt / dom.tiles_j[b], tj = lt - ti * dom.tiles_j[b];
+    const int i = ti * 4 + a, j = tj * 4 + e;
+    tiled[g] = (i < B.nr && j < B.nc) ? dest[cell * dom.entries_per_cell + B.off + i * B.nc + j]
+                                      : VLFS_DEST_PAD;
+  }
+}
+
 int bits_for(long long n) {
   int b = 1;
   while ((1ll << b) < n) ++b;
@@ -145,6 +165,16 @@ void build_pattern_device(const std::vector<DomainDev>& doms, long long ndofs,
   CUDA_TRY(cudaStreamSynchronize(s));
   *nnz_out = nnz;
   *ncoo_out = ncoo;
+}
+
+void build_tiled_dest(const DomainDev& dom, const int* dest, DevBuf<int>& tiled, cudaStream_t s,
+                      long long* launches) {
+  const long long total = dom.ncells * (long long)dom.tile_base[dom.nblocks] * 16;
+  tiled.alloc((size_t)total);
+  if (total == 0) return;
+  retile_dest<<<grid_for((size_t)total), 256, 0, s>>>(dom, dest, tiled.p);
+  if (launches) ++*launches;
+  CUDA_TRY(cudaGetLastError());
 }
 
 // CSC view of the CSR pattern: colptr, rowval and the CSR slot of every CSC entry
