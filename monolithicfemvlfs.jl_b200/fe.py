@@ -356,7 +356,12 @@ class Measure:
         lfs = sk.plus_lf if side == "plus" else sk.minus_lf
         xv = [face_points_in_cell(sp, k, lf, self.xq) for lf in range(sp.nfaces(k))]
         val, grad, hess, gg, nd = self._tables(sp, space.order, xv, need_hess)
-        pos = cells if space.trian is surf else surf.position_in(space.trian)[cells]
+        if space.trian is surf:
+            pos = cells
+        else:       # look the field up through the common background facet (only these cells)
+            o = np.argsort(space.trian.facets, kind="stable")
+            pos = o[np.searchsorted(space.trian.facets[o], surf.facets[cells])]
+            assert np.all(space.trian.facets[pos] == surf.facets[cells])
         return dict(dref=sp.dim, nv=len(sp.verts), nvar=len(xv), ndofs=nd,
                     coords=surf.cell_coords()[cells], variant=lfs, geo_grad=gg, val=val, grad=grad,
                     hess=hess, dofs=space.cell_dofs[pos] + space.offset,

@@ -74,3 +74,80 @@ def test_yago_descriptors_reproduce_oracle_matrix(kw):
     assert np.array_equal(A.indptr, M.indptr) and np.array_equal(A.indices, M.indices)
     assert np.abs(A.data - M.data).max() <= 1e-12 * np.abs(A.data).max()
     assert np.abs(b - vecs[0]).max() <= 1e-12 * np.abs(b).max()
+
+
+# ---- the other configurations of BASELINE.json: product descriptors vs the oracle's literal forms
+def _same_pattern_and_values(M, A, tol=1e-12):
+    A = A.tocsr(); A.sort_indices()
+    assert np.array_equal(A.indptr, M.indptr) and np.array_equal(A.indices, M.indices)
+    scale = max(np.abs(A.data).max(), 1e-300)
+    assert np.abs(A.data - M.data).max() <= tol * scale
+
+
+@pytest.mark.parametrize("kw", [dict(n=3, dt=0.1, tf=0.2, orderphi=2, ordereta=2, k=1),
+                                dict(n=4, dt=1e-6, tf=1e-4, orderphi=2, ordereta=4, k=15)])
+def test_periodic_beam_descriptors_reproduce_oracle(kw):
+    from vlfs_b200.cases.periodic_beam import PeriodicBeamProblem, Periodic_Beam_params
+    from oracle.cases.periodic_beam import PeriodicBeamCase
+    p = PeriodicBeamProblem(Periodic_Beam_params(**kw), system_cls=RecordingSystem)
+    o = PeriodicBeamCase(**kw)
+    assert np.array_equal(p.V_Om.cell_dofs, o.V_phi.cell_dofs) and np.array_equal(p.V_G.cell_dofs, o.V_eta.cell_dofs)
+    mats, _ = p.sys.evaluate()
+    for M, A in zip(mats[:3], o.assemble()):
+        _same_pattern_and_values(M, A)
+    for d in range(3):
+        assert np.abs(p.interpolate(0.0, d) - o.interpolate(0.0, d)).max() <= 1e-15 * max(np.abs(o.interpolate(0.0, d)).max(), 1)
+
+
+@pytest.mark.parametrize("kw", [dict(nx=10, ny=1, order=2, xi=0.0),          # scripts/5-2-1-...jl:17-28
+                                dict(nx=10, ny=2, order=4, xi=625.0)])
+def test_khabakhpasheva_descriptors_reproduce_oracle(kw):
+    from vlfs_b200.cases.khabakhpasheva import (KhabakhpashevaFreqProblem, KhabakhpashevaTimeProblem,
+                                                Khabakhpasheva_freq_domain_params, Khabakhpasheva_time_domain_params)
+    from oracle.cases.khabakhpasheva import KhabakhpashevaFreqCase, KhabakhpashevaTimeCase
+    p = KhabakhpashevaFreqProblem(Khabakhpasheva_freq_domain_params(**kw), system_cls=RecordingSystem)
+    o = KhabakhpashevaFreqCase(**kw)
+    assert o.Lj.nfaces == 1
+    for a, b in [(p.V_Om, o.V_phi), (p.V_Gk, o.V_kap), (p.V_Ge, o.V_eta)]:
+        assert np.array_equal(a.cell_dofs, b.cell_dofs)
+    mats, vecs = p.sys.evaluate()
+    A, b = o.assemble()
+    _same_pattern_and_values(mats[0], A)
+    assert np.abs(b - vecs[0]).max() <= 1e-12 * np.abs(b).max()
+    pt_ = KhabakhpashevaTimeProblem(Khabakhpasheva_time_domain_params(**kw), system_cls=RecordingSystem)
+    ot = KhabakhpashevaTimeCase(**kw)
+    mats, vecs = pt_.sys.evaluate()
+    for M, A in zip(mats[:3], ot.assemble()):
+        _same_pattern_and_values(M, A)
+    for t in (0.3, 1.7):
+        bt = np.cos(ot.c["om"] * t) * vecs[0] + np.sin(ot.c["om"] * t) * vecs[1]
+        br = ot.rhs(t)
+        assert np.abs(bt - br).max() <= 1e-12 * np.abs(br).max()
+    assert abs(pt_.ah - ot.time_constants()["ah"]) < 1e-15 and abs(pt_.dt - ot.time_constants()["dt"]) < 1e-18
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_multigeo_descriptors_reproduce_oracle(order, golden_dir):
+    from vlfs_b200.cases.multigeo import MultiGeoProblem, MultiGeo_freq_domain_params
+    from oracle.cases.multigeo import MultiGeoCase
+    f = os.path.join(golden_dir, "multi_geo_coarse.json")
+    p = MultiGeoProblem(MultiGeo_freq_domain_params(mesh_file=f, order=order), system_cls=RecordingSystem)
+    o = MultiGeoCase(f, order=order)
+    for a, b in [(p.V_Om, o.V_phi), (p.V_Gk, o.V_kap), (p.V_Ge, o.V_eta)]:
+        assert np.array_equal(a.cell_dofs, b.cell_dofs)
+    mats, vecs = p.sys.evaluate()
+    A, b = o.assemble()
+    _same_pattern_and_values(mats[0], A, tol=2e-12)
+    assert np.abs(b - vecs[0]).max() <= 2e-12 * np.abs(b).max()
+
+
+def test_gmsh_reader_reproduces_golden_json(golden_dir):
+    """The reference's golden pair multi_geo_coarse.msh <-> .json (models/multi_geo.jl:5-7)."""
+    a = G.DiscreteModelFromFile(os.path.join(golden_dir, "multi_geo_coarse.msh"))
+    b = G.DiscreteModelFromFile(os.path.join(golden_dir, "multi_geo_coarse.json"))
+    assert np.array_equal(a.node_coords, b.node_coords) and np.array_equal(a.cell_nodes, b.cell_nodes)
+    for d in (1, 2, 3):
+        assert np.array_equal(a.face_vertices[d], b.face_vertices[d])
+    for d in range(4):
+        assert np.array_equal(a.face_entity[d], b.face_entity[d])
+    assert a.tags == b.tags

@@ -1,0 +1,122 @@
+"""Oracle pinned on what the reference holds: the analytic travelling wave and
+its convergence rates (src/Periodic_Beam.jl:44-45, scripts/5-1-1-...jl:140-141,183-209), the
+analytic energies (src/Periodic_Beam.jl:129-132), the digitised literature curves
+(data/Ref_data/Khabakhpasheva, committed copies under tests/golden/), problem sizes and
+structural identities.  CPU only."""
+import os
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+from oracle.cases.periodic_beam import PeriodicBeamCase
+from oracle.cases.khabakhpasheva import KhabakhpashevaFreqCase, KhabakhpashevaTimeCase
+from oracle.cases.multigeo import MultiGeoCase
+from oracle.cases.yago import YagoCase
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_periodic_beam_spatial_convergence(order):
+    """5-1-1 (scripts/5-1-1-...jl:43-64): dt=1e-6, tf=1e-4, k=15; slope order+1 and errors
+    on the reference's guide lines c*n^-(order+1), c = [2,5,10] (ϕ) / [10,30,80] (η)."""
+    errs = []
+    for n in (8, 16, 32):
+        r = PeriodicBeamCase(n=n, dt=1e-6, tf=1e-4, orderphi=order, ordereta=order, k=15).run()
+        assert len(r["t"]) == 100
+        errs.append((r["e_phi"][-1], r["e_eta"][-1]))
+    rate_phi = np.log2(errs[1][0] / errs[2][0])
+    rate_eta = np.log2(errs[1][1] / errs[2][1])
+    assert rate_phi > order + 1 - 0.45 and rate_eta > order + 1 - 0.45, (rate_phi, rate_eta)
+    cphi, ceta = {2: 2, 3: 5, 4: 10}[order], {2: 10, 3: 30, 4: 80}[order]
+    assert 0.2 * cphi * 32.0 ** -(order + 1) < errs[2][0] < 2.0 * cphi * 32.0 ** -(order + 1)
+    assert 0.2 * ceta * 32.0 ** -(order + 1) < errs[2][1] < 2.0 * ceta * 32.0 ** -(order + 1)
+
+
+def test_periodic_beam_energies_match_analytic_constants():
+    """src/Periodic_Beam.jl:129-132,145-148: the four discrete energies equal the analytic
+    constants (pairwise: fluid kinetic/potential = g η0² L/4, structure = d0 ω² η0² L/4) and
+    their sum is conserved by Newmark(1/2,1/4)."""
+    c = PeriodicBeamCase(n=8, dt=0.002, tf=0.2, orderphi=3, ordereta=3, k=2)
+    r = c.run()
+    E = np.array(r["E"])
+    big, small = r["E0"]["E_kin_s0"], r["E0"]["E_kin_f0"]
+    assert np.all(np.abs(E[:, 0] - big) < 2e-3 * big) and np.all(np.abs(E[:, 1] - big) < 2e-3 * big)
+    assert np.all(np.abs(E[:, 2] - small) < 3e-2 * small) and np.all(np.abs(E[:, 3] - small) < 3e-2 * small)
+    tot = E.sum(axis=1)
+    assert (tot.max() - tot.min()) < 1e-4 * tot.mean()
+
+
+def test_periodic_beam_structure():
+    c = PeriodicBeamCase(n=4, dt=1e-3, tf=2e-3, orderphi=2, ordereta=2, k=1)
+    K, C, M = c.assemble()
+    nphi = c.V_phi.ndofs
+    assert c.V_phi.ndofs == (2 * 2 * 4) * (2 * 4 + 1) and c.V_eta.ndofs == 2 * 2 * 4     # periodic: no duplicate column
+    assert abs(C + C.T).max() < 1e-15                         # c form is skew (:99)
+    Kpp = K[:nphi, :nphi]
+    assert abs(Kpp - Kpp.T).max() < 1e-13
+    assert np.abs(Kpp @ np.ones(nphi)).max() < 1e-12           # constants in the Laplace kernel
+    assert abs(M[:nphi]).max() == 0.0
+
+
+def test_khabakhpasheva_sizes_and_literature(golden_dir):
+    """5-2-1 at the paper's resolution: N = 33 621 + 1 202 + 401 and
+    |η|/η0 on the literature curves (scripts/5-2-1-...jl:43-61) within digitisation accuracy."""
+    for xi, fname in ((0.0, "Khabakhpasheva_with_joint.csv"), (625.0, "Khabakhpasheva_without_joint.csv")):
+        c = KhabakhpashevaFreqCase(nx=20, ny=5, order=4, xi=xi)
+        assert [s.ndofs for s in c.X.spaces] == [33621, 1202, 401]
+        assert (c.Gb1.ncells, c.Gb2.ncells, c.Lb1.nfaces, c.Lb2.nfaces, c.Lj.nfaces) == (20, 80, 19, 79, 1)
+        assert abs(c.c["gamma"] - 96.0) < 1e-12 and abs(c.c["k"] - 2.0186940746) < 1e-9
+        A, b = c.assemble()
+        x = spla.splu(A).solve(b)
+        xs, eta = c.eta_postprocess(x)
+        ref = np.loadtxt(os.path.join(golden_dir, fname), delimiter=",")
+        inner = ref[(ref[:, 0] > 0.08) & (ref[:, 0] < 0.97)]
+        ours = np.array([eta[np.argmin(np.abs(xs - xr))] for xr in inner[:, 0]])
+        assert np.abs(ours - inner[:, 1]).max() < 0.06, np.abs(ours - inner[:, 1]).max()
+
+
+def test_khabakhpasheva_joint_vanishes_for_xi_zero():
+    a = KhabakhpashevaFreqCase(nx=10, ny=1, order=3, xi=0.0)
+    assert a.Lj.nfaces == 1
+    A0, _ = a.assemble()
+    blocks = []
+    a._joint(lambda r, c, v: blocks.append(v), a.X.offsets[2], a.c["kr"], 3, a.degree)
+    assert a.c["kr"] == 0.0 and all(np.all(v == 0) for v in blocks)
+    b = KhabakhpashevaFreqCase(nx=10, ny=1, order=3, xi=625.0)
+    A1, _ = b.assemble()
+    assert np.array_equal(A0.indptr, A1.indptr) and np.array_equal(A0.indices, A1.indices)
+    assert abs(A0 - A1).max() > 0
+
+
+def test_khabakhpasheva_time_rhs_is_separable():
+    """b(t) = cos(ωt) b(0) + sin(ωt) b(T/4): the split the product's Newmark driver relies on."""
+    c = KhabakhpashevaTimeCase(nx=5, ny=1, order=2, xi=0.0)
+    T = c.c["T"]
+    bc, bs = c.rhs(0.0), c.rhs(T / 4)
+    for t in (0.1, 0.77, 2.3):
+        bt = c.rhs(t)
+        assert np.abs(bt - (np.cos(c.c["om"] * t) * bc + np.sin(c.c["om"] * t) * bs)).max() < 1e-13 * np.abs(bt).max()
+
+
+def test_multigeo_sizes(golden_dir):
+    c = MultiGeoCase(os.path.join(golden_dir, "multi_geo_coarse.json"), order=2)
+    assert (c.Om.ncells, c.model.nvertices, c.model.nfaces(1), c.Gb.ncells, c.Gf.ncells) == (132, 57, 241, 29, 51)
+    A, b = c.assemble()
+    assert A.shape[0] == c.X.ndofs == 298 + 137 + 90
+    # the gmsh reader reproduces the JSON model, hence the same operator
+    c2 = MultiGeoCase(os.path.join(golden_dir, "multi_geo_coarse.msh"), order=2)
+    A2, b2 = c2.assemble()
+    assert np.array_equal(A.indptr, A2.indptr) and np.array_equal(A.indices, A2.indices)
+    assert np.array_equal(A.data, A2.data) and np.array_equal(b, b2)
+
+
+def test_yago_sizes_and_laplace_identities():
+    """Yago warm-up (scripts/5-4-1-Yago.jl:17-30): 720 hexes, N = 11 988; the Ω-only Laplace block
+    is symmetric with zero row sums on rows that see no surface term."""
+    c = YagoCase(nx=2, ny=2, nz=1, order=2, lfactor=0.4, dfactor=3)
+    assert c.Om.ncells == 720 and c.X.ndofs == 11988
+    A, b = c.assemble()
+    nphi = c.V_phi.ndofs
+    App = A.tocsr()[:nphi, :nphi]
+    zc = c.V_phi.dof_coords()[:, 2]
+    interior = zc < c.c["H"] * (1 - 1e-12)
+    rs = np.asarray(App.real.sum(axis=1)).ravel()
+    assert np.abs(rs[interior]).max() < 1e-9 * abs(App).max()
