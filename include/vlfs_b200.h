@@ -208,6 +208,28 @@ int vlfs_assemble_profile(vlfs_ctx* ctx, int reps, char* names, int names_cap, f
 int vlfs_last_kernel_launches(vlfs_ctx* ctx, int64_t* n);
 int vlfs_device_ptrs(vlfs_ctx* ctx, int mat, void** rowptr, void** colind, void** values);
 
+/* ---- distributed building blocks (row-partitioned systems, one context per GPU) ------------
+ * A rank registers the cells that touch its owned DOFs with LOCAL DOF ids [owned | ghost]; rows
+ * [0,n_owned) of the local CSR are then complete.  The entry points below take DEVICE pointers
+ * (vectors of the local length, scalars interleaved as elsewhere) and run on the stream given to
+ * vlfs_set_stream (e.g. the caller's torch / CUDA.jl stream); halo exchange and the all-reduce of
+ * the dot products are the caller's (NCCL through torch.distributed in the Python mirror).
+ * Replaces nothing in the (serial) reference: SURVEY.md §8(e). */
+int vlfs_set_stream(vlfs_ctx* ctx, void* cuda_stream);          /* before vlfs_solver_setup     */
+int vlfs_set_owned_rows(vlfs_ctx* ctx, int64_t n_owned);
+int vlfs_dev_spmv(vlfs_ctx* ctx, int mat, const void* x_dev, void* y_dev);   /* owned rows      */
+int vlfs_dev_precond(vlfs_ctx* ctx, const void* r_dev, void* z_dev);         /* owned block     */
+/* out_host[k] = <V_k, w> over n entries (conjugate-linear in V), V_k = V + k*ldv scalars        */
+int vlfs_dev_multidot(vlfs_ctx* ctx, const void* V_dev, int64_t ldv, int nv, const void* w_dev,
+                      int64_t n, void* out_host);
+int vlfs_dev_gemv_sub(vlfs_ctx* ctx, const void* V_dev, int64_t ldv, int nv, const void* h_host,
+                      void* w_dev, int64_t n);                                /* w -= sum h_k V_k */
+int vlfs_dev_axpby(vlfs_ctx* ctx, double a_re, double a_im, const void* x_dev, double b_re,
+                   double b_im, void* y_dev, int64_t n);                      /* y = a x + b y   */
+int vlfs_dev_gather(vlfs_ctx* ctx, int64_t n, const int32_t* idx_dev, const void* src_dev,
+                    void* dst_dev);                                           /* halo pack       */
+int vlfs_get_vector_device(vlfs_ctx* ctx, int vec, void** ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,8 @@ EXPORTS = [
     "vlfs_assemble_vectors", "vlfs_get_values", "vlfs_get_vector", "vlfs_combine", "vlfs_spmv",
     "vlfs_set_dof_coords", "vlfs_solver_setup", "vlfs_solver_refactor", "vlfs_direct_info", "vlfs_solve", "vlfs_solve_vec", "vlfs_newmark_run", "vlfs_spmv_device",
     "vlfs_assemble_timed", "vlfs_assemble_profile", "vlfs_last_kernel_launches", "vlfs_device_ptrs",
+    "vlfs_set_stream", "vlfs_set_owned_rows", "vlfs_dev_spmv", "vlfs_dev_precond", "vlfs_dev_multidot",
+    "vlfs_dev_gemv_sub", "vlfs_dev_axpby", "vlfs_dev_gather", "vlfs_get_vector_device",
 ]
 
 _lib = None
@@ -123,6 +125,15 @@ def load():
     lib.vlfs_assemble_profile.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     lib.vlfs_last_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.vlfs_device_ptrs.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.vlfs_set_stream.argtypes = [vp, vp]
+    lib.vlfs_set_owned_rows.argtypes = [vp, C.c_int64]
+    lib.vlfs_dev_spmv.argtypes = [vp, C.c_int, vp, vp]
+    lib.vlfs_dev_precond.argtypes = [vp, vp, vp]
+    lib.vlfs_dev_multidot.argtypes = [vp, vp, C.c_int64, C.c_int, vp, C.c_int64, vp]
+    lib.vlfs_dev_gemv_sub.argtypes = [vp, vp, C.c_int64, C.c_int, vp, vp, C.c_int64]
+    lib.vlfs_dev_axpby.argtypes = [vp, C.c_double, C.c_double, vp, C.c_double, C.c_double, vp, C.c_int64]
+    lib.vlfs_dev_gather.argtypes = [vp, C.c_int64, vp, vp, vp]
+    lib.vlfs_get_vector_device.argtypes = [vp, C.c_int, C.POINTER(vp)]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

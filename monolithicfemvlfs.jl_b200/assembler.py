@@ -249,6 +249,11 @@ class B200System:
         assert c.shape[0] == self.ndofs
         self._check(self.lib.vlfs_set_dof_coords(self.ctx, c.shape[1], L.dptr(c)))
 
+    def set_owned_rows(self, n_owned):
+        """Distributed systems: rows [0,n_owned) are owned, the rest are ghosts (dist.py)."""
+        self._check(self.lib.vlfs_set_owned_rows(self.ctx, int(n_owned)))
+        self.n_owned = int(n_owned)
+
     def refactor(self, mat=0):
         self._check(self.lib.vlfs_solver_refactor(self.ctx, mat))
 

@@ -196,9 +196,9 @@ class KhabakhpashevaFreqProblem(_Tank):
         d = sys_.add_domain(2, dGin.nq, dGin.wq, [dGin.trace_slot(self.V_Om), dGin.surface_slot(V_aux)],
                             measure_slot=1, weights=[vin.real, vin.imag])
         d.add_rhs(0, 1.0, L.OP_VAL, PHI, weight_re=0, weight_im=1)            # w vᵢₙ
-        self.nnz = sys_.build_pattern()
         if hasattr(sys_, "set_dof_coords"):
             sys_.set_dof_coords(X.dof_coords())
+        self.nnz = sys_.build_pattern()
 
     def assemble(self):
         self.sys.assemble()
@@ -290,9 +290,9 @@ class KhabakhpashevaTimeProblem(_Tank):
                             measure_slot=1, weights=[amp * np.cos(k * x[..., 0]), amp * np.sin(k * x[..., 0])])
         d.add_rhs(0, 1.0, L.OP_VAL, PHI, weight_re=0)
         d.add_rhs(1, 1.0, L.OP_VAL, PHI, weight_re=1)
-        self.nnz = sys_.build_pattern()
         if hasattr(sys_, "set_dof_coords"):
             sys_.set_dof_coords(X.dof_coords())
+        self.nnz = sys_.build_pattern()
 
     def assemble(self):
         self.sys.assemble()

@@ -106,9 +106,9 @@ class MultiGeoProblem:
         d = sys_.add_domain(3, dGin.nq, dGin.wq, [dGin.trace_slot(V_Om), dGin.surface_slot(V_aux)],
                             measure_slot=1, weights=[vin.real, vin.imag])
         d.add_rhs(0, 1.0, L.OP_VAL, PHI, weight_re=0, weight_im=1)
-        self.nnz = sys_.build_pattern()
         if hasattr(sys_, "set_dof_coords"):
             sys_.set_dof_coords(X.dof_coords())
+        self.nnz = sys_.build_pattern()
 
     def assemble(self):
         self.sys.assemble()

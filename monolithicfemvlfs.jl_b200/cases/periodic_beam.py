@@ -85,9 +85,9 @@ class PeriodicBeamProblem:
         d.add_term(MAT_K, -Drho, L.OP_GRAD_NOWN, jump_n, L.OP_LAPL, mean)
         d.add_term(MAT_K, -Drho, L.OP_LAPL, mean, L.OP_GRAD_NOWN, jump_n)
         d.add_term(MAT_K, Drho * gamma / h, L.OP_GRAD_NOWN, jump_n, L.OP_GRAD_NOWN, jump_n)
-        self.nnz = sys_.build_pattern()
         if hasattr(sys_, "set_dof_coords"):
             sys_.set_dof_coords(X.dof_coords())
+        self.nnz = sys_.build_pattern()
 
     # analytic fields (:44-45) and time derivatives, for `interpolate_everywhere` (:111-113)
     def eta_ex(self, x, t, d=0):

@@ -138,9 +138,9 @@ class YagoProblem:
         self.dom_Gin = d = sys_.add_domain(3, dGin.nq, dGin.wq, [dGin.trace_slot(V_Om), dGin.surface_slot(V_aux)],
                                            measure_slot=1, weights=[np.zeros(self._xq_Gin.shape[:2])] * 2, affine=affine)
         d.add_rhs(0, 1.0, L.OP_VAL, PHI, weight_re=0, weight_im=1)
-        self.nnz = sys_.build_pattern()
         if hasattr(sys_, "set_dof_coords"):
-            sys_.set_dof_coords(X.dof_coords()[:, :2])       # quasi-2-D: dissect in the (x,y) plane
+            sys_.set_dof_coords(X.dof_coords()[:, :2])       # quasi-2-D: dissect in the (x,y)
+        self.nnz = sys_.build_pattern()
         self.set_frequency(p.lfactor)
 
     # ω-dependent scalars and coefficient fields only (the sweep of scripts/5-4-1-Yago.jl:33-71)

@@ -94,6 +94,9 @@ struct vlfs_ctx {
   std::vector<double> dof_coords;
   int coord_dim = 0;
   int solver_mat = -1;
+  long long nowned = 0;             // rows [0,nowned) are owned, the rest are ghosts (distributed)
+  bool own_stream = true;
+  DevBuf<double> dev_partial, dev_h;  // scratch of the vlfs_dev_* reductions
   size_t scalar() const { return is_complex ? 2 : 1; }
 };
 
@@ -449,7 +452,7 @@ int vlfs_destroy(vlfs_ctx* ctx) {
   ctx->doms.clear();
   ctx->mats.clear();
   ctx->vecs.clear();
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return VLFS_OK;
 }
@@ -461,6 +464,7 @@ int vlfs_system_init(vlfs_ctx* ctx, int64_t ndofs, int is_complex, int nmat, int
     if (ndofs <= 0 || ndofs >= (1ll << 31) || nmat < 1 || nmat > 4 || nvec < 0 || nvec > 4)
       return fail(ctx, VLFS_ERR_ARG, "vlfs_system_init: bad sizes (1<=nmat<=4, 0<=nvec<=4)");
     ctx->ndofs = ndofs; ctx->is_complex = is_complex ? 1 : 0; ctx->nmat = nmat; ctx->nvec = nvec;
+    ctx->nowned = ndofs;
     ctx->doms.clear(); ctx->mats.clear(); ctx->vecs.clear();
     ctx->pattern_built = false; ctx->solver.reset(); ctx->direct.reset(); ctx->dof_coords.clear();
     ctx->vecs.resize(nvec);
@@ -815,12 +819,12 @@ int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
     if (opts->precond == VLFS_PRECOND_SPARSE_LU) {
       if (ctx->dof_coords.empty()) return fail(ctx, VLFS_ERR_STATE, "vlfs_set_dof_coords first (sparse LU ordering)");
       if (!ctx->direct)
-        ctx->direct = direct_symbolic(ctx->rowptr.p, ctx->colind.p, ctx->ndofs, ctx->nnz, ctx->dof_coords.data(),
+        ctx->direct = direct_symbolic(ctx->rowptr.p, ctx->colind.p, ctx->ndofs, ctx->nowned, ctx->nnz, ctx->dof_coords.data(),
                                       ctx->coord_dim, opts->block_size_hint, ctx->is_complex, ctx->nsm,
                                       ctx->stream, &ctx->launches);
       direct_numeric(*ctx->direct, ctx->rowind.p, ctx->colind.p, ctx->mats[mat].p);
     }
-    ctx->solver = solver_create(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, ctx->ndofs, ctx->nnz,
+    ctx->solver = solver_create(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, ctx->nowned, ctx->nnz,
                                 ctx->is_complex, *opts, ctx->nsm, ctx->stream, &ctx->launches,
                                 ctx->direct.get());
     ctx->solver_mat = mat;
@@ -901,6 +905,103 @@ int vlfs_newmark_run(vlfs_ctx* ctx, int matK, int matC, int matM, int nsteps, do
                        ctx->ndofs, ctx->nnz, nsteps, dt, gamma, beta, nb, bv.data(), tcoef, u0, v0, a0,
                        out_lo, out_hi, out_stride, out, stats, ctx->nsm, ctx->stream, &ctx->launches);
   });
+}
+
+/* ---- distributed building blocks: device pointers in, device pointers out ------------------ */
+int vlfs_set_stream(vlfs_ctx* ctx, void* stream) {
+  return guarded(ctx, [&]() {
+    if (ctx->solver || ctx->direct) return fail(ctx, VLFS_ERR_STATE, "vlfs_set_stream before vlfs_solver_setup");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)stream;
+    ctx->own_stream = false;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_set_owned_rows(vlfs_ctx* ctx, int64_t n_owned) {
+  return guarded(ctx, [&]() {
+    if (n_owned < 1 || n_owned > ctx->ndofs) return fail(ctx, VLFS_ERR_ARG, "vlfs_set_owned_rows: 1 <= n_owned <= ndofs");
+    ctx->nowned = n_owned;
+    ctx->solver.reset(); ctx->direct.reset();
+    return VLFS_OK;
+  });
+}
+
+int vlfs_dev_spmv(vlfs_ctx* ctx, int mat, const void* x_dev, void* y_dev) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !x_dev || !y_dev) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    const double one[2] = {1, 0}, zero[2] = {0, 0};
+    launch_spmv(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, x_dev, y_dev, ctx->nowned, ctx->nnz,
+                ctx->is_complex, one, zero, ctx->nsm, ctx->stream);
+    ++ctx->launches;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_dev_precond(vlfs_ctx* ctx, const void* r_dev, void* z_dev) {
+  return guarded(ctx, [&]() {
+    if (!ctx->solver || !r_dev || !z_dev) return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup first");
+    solver_precond(*ctx->solver, (const double*)r_dev, (double*)z_dev);
+    return VLFS_OK;
+  });
+}
+
+int vlfs_dev_multidot(vlfs_ctx* ctx, const void* V_dev, int64_t ldv, int nv, const void* w_dev, int64_t n,
+                      void* out_host) {
+  return guarded(ctx, [&]() {
+    if (!V_dev || !w_dev || !out_host || nv < 1 || nv > 4096 || n < 0) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    const int nred = ctx->nsm * 2;
+    const size_t sc = ctx->scalar();
+    if (ctx->dev_partial.n < (size_t)nred * nv * sc) ctx->dev_partial.alloc((size_t)nred * nv * sc);
+    if (ctx->dev_h.n < (size_t)nv * sc) ctx->dev_h.alloc((size_t)nv * sc);
+    dev_multidot((const double*)V_dev, (size_t)ldv, nv, (const double*)w_dev, n, ctx->is_complex,
+                 ctx->dev_partial.p, nred, ctx->dev_h.p, ctx->stream);
+    ctx->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(out_host, ctx->dev_h.p, nv * sc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VLFS_OK;
+  });
+}
+
+int vlfs_dev_gemv_sub(vlfs_ctx* ctx, const void* V_dev, int64_t ldv, int nv, const void* h_host, void* w_dev,
+                      int64_t n) {
+  return guarded(ctx, [&]() {
+    if (!V_dev || !w_dev || !h_host || nv < 1 || nv > 4096 || n < 0) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    const size_t sc = ctx->scalar();
+    if (ctx->dev_h.n < (size_t)nv * sc) ctx->dev_h.alloc((size_t)nv * sc);
+    CUDA_TRY(cudaMemcpyAsync(ctx->dev_h.p, h_host, nv * sc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    dev_gemv_sub((const double*)V_dev, (size_t)ldv, nv, ctx->dev_h.p, (double*)w_dev, n, ctx->is_complex,
+                 ctx->nsm, ctx->stream);
+    ++ctx->launches;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));     // h_host may be reused by the caller
+    return VLFS_OK;
+  });
+}
+
+int vlfs_dev_axpby(vlfs_ctx* ctx, double a_re, double a_im, const void* x_dev, double b_re, double b_im,
+                   void* y_dev, int64_t n) {
+  return guarded(ctx, [&]() {
+    if (!x_dev || !y_dev || n < 0) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    dev_axpby(a_re, a_im, (const double*)x_dev, b_re, b_im, (double*)y_dev, n, ctx->is_complex, ctx->nsm, ctx->stream);
+    ++ctx->launches;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_dev_gather(vlfs_ctx* ctx, int64_t n, const int32_t* idx_dev, const void* src_dev, void* dst_dev) {
+  return guarded(ctx, [&]() {
+    if (n < 0 || (n && (!idx_dev || !src_dev || !dst_dev))) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    dev_gather(idx_dev, (const double*)src_dev, (double*)dst_dev, n, ctx->is_complex, ctx->nsm, ctx->stream);
+    ++ctx->launches;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_get_vector_device(vlfs_ctx* ctx, int vec, void** ptr) {
+  if (!ctx || vec < 0 || vec >= ctx->nvec || !ptr) return VLFS_ERR_ARG;
+  *ptr = ctx->vecs[vec].p;
+  return VLFS_OK;
 }
 
 }  // extern "C"

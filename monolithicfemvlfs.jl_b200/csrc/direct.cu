@@ -92,6 +92,7 @@ __global__ void scatter_matrix(const int* __restrict__ rowind, const int* __rest
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < nnz;
        p += (long long)gridDim.x * blockDim.x) {
     int pi = pos[rowind[p]], pj = pos[colind[p]];
+    if (pi < 0 || pj < 0) continue;        // ghost row / column of a distributed system
     int f = front_of_pos[pi < pj ? pi : pj];
     const FrontMeta F = meta[f];
     int li = local_index(F, upd_idx, pi), lj = local_index(F, upd_idx, pj);
@@ -533,9 +534,11 @@ float timed(cudaStream_t s, F&& f) {
 
 void DirectDeleter::operator()(DirectSolver* p) const { delete p; }
 
-DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n, long long nnz,
-                          const double* coords, int dim, int leaf, int is_complex, int nsm,
+DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_total, long long n,
+                          long long nnz, const double* coords, int dim, int leaf, int is_complex, int nsm,
                           cudaStream_t s, long long* launches) {
+  // n_total rows/columns exist in the CSR pattern, the first n (owned block of a distributed
+  // system; n == n_total on one GPU) are factorised
   DirectPtr D(new DirectSolver());
   D->n = n; D->nnz = nnz; D->cplx = is_complex; D->nsm = nsm; D->s = s; D->launches = launches;
   if (leaf < 8) leaf = 96;
@@ -544,6 +547,15 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n,
   std::vector<int> rp(n + 1), ci(nnz);
   CUDA_TRY(cudaMemcpy(rp.data(), d_rowptr, (n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(ci.data(), d_colind, nnz * sizeof(int), cudaMemcpyDeviceToHost));
+  if (n < n_total) {                       // drop ghost columns from the owned rows
+    int w = 0;
+    std::vector<int> rp2(n + 1, 0);
+    for (long long i = 0; i < n; ++i) {
+      for (int q = rp[i]; q < rp[i + 1]; ++q) if (ci[q] < n) ci[w++] = ci[q];
+      rp2[i + 1] = w;
+    }
+    rp.swap(rp2);
+  }
   std::vector<int> sp(n + 1, 0), si;
   {
     std::vector<int> cnt(n, 0);
@@ -577,7 +589,7 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n,
   const int nf_ = (int)nd.nodes.size();
   D->nfronts = nf_;
   // permutation (postorder = creation order)
-  std::vector<int> pos(n), front_of_pos(n);
+  std::vector<int> pos(n_total, -1), front_of_pos(n);
   std::vector<int> first(nf_), parent(nf_, -1);
   {
     int k = 0;
@@ -644,7 +656,7 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n,
   }
   // upload
   D->d_meta.upload(D->meta.data(), nf_, s);
-  D->d_pos.upload(pos.data(), n, s);
+  D->d_pos.upload(pos.data(), n_total, s);
   D->d_front_of_pos.upload(front_of_pos.data(), n, s);
   if (upd_flat.empty()) upd_flat.push_back(0);
   D->d_upd.upload(upd_flat.data(), upd_flat.size(), s);

@@ -182,6 +182,50 @@ void launch_axpby_vals(double* target, size_t n, int nsrc, double* const* src, c
   CUDA_TRY(cudaGetLastError());
 }
 
+namespace {
+// dst[k] = src[idx[k]]  (halo pack)
+template <bool C>
+__global__ void gather_entries(const int* __restrict__ idx, const typename Sc<C>::T* __restrict__ src,
+                               typename Sc<C>::T* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[idx[i]];
+}
+
+}  // namespace
+
+// ---- device-pointer vector algebra (distributed Krylov building blocks; api.cu: vlfs_dev_*) ----
+void dev_multidot(const double* V, size_t ldv, int nv, const double* w, long long n, int cplx,
+                  double* partial, int nred, double* out_dev, cudaStream_t s) {
+  dim3 grid(nred, nv);
+  if (cplx) {
+    multidot_partial<true><<<grid, RED_THREADS, 0, s>>>((const double2*)V, ldv, (const double2*)w, n, (double2*)partial);
+    multidot_finish<true><<<nv, RED_THREADS, 0, s>>>((const double2*)partial, nred, (double2*)out_dev);
+  } else {
+    multidot_partial<false><<<grid, RED_THREADS, 0, s>>>(V, ldv, w, n, partial);
+    multidot_finish<false><<<nv, RED_THREADS, 0, s>>>(partial, nred, out_dev);
+  }
+  CUDA_TRY(cudaGetLastError());
+}
+void dev_gemv_sub(const double* V, size_t ldv, int nv, const double* h_dev, double* w, long long n, int cplx,
+                  int nsm, cudaStream_t s) {
+  size_t smem = (size_t)nv * (cplx ? 2 : 1) * sizeof(double);
+  if (cplx) gemv_sub<true><<<vgrid(n, nsm), 256, smem, s>>>((const double2*)V, ldv, (const double2*)h_dev, nv, (double2*)w, n);
+  else gemv_sub<false><<<vgrid(n, nsm), 256, smem, s>>>(V, ldv, h_dev, nv, w, n);
+  CUDA_TRY(cudaGetLastError());
+}
+void dev_axpby(double are, double aim, const double* x, double bre, double bim, double* y, long long n, int cplx,
+               int nsm, cudaStream_t s) {
+  if (cplx) axpby<true><<<vgrid(n, nsm), 256, 0, s>>>(are, aim, (const double2*)x, bre, bim, (double2*)y, n);
+  else axpby<false><<<vgrid(n, nsm), 256, 0, s>>>(are, 0, x, bre, 0, y, n);
+  CUDA_TRY(cudaGetLastError());
+}
+void dev_gather(const int* idx, const double* src, double* dst, long long n, int cplx, int nsm, cudaStream_t s) {
+  if (n == 0) return;
+  if (cplx) gather_entries<true><<<vgrid(n, nsm), 256, 0, s>>>(idx, (const double2*)src, (double2*)dst, n);
+  else gather_entries<false><<<vgrid(n, nsm), 256, 0, s>>>(idx, src, dst, n);
+  CUDA_TRY(cudaGetLastError());
+}
+
 // ---------------------------------------------------------------------------------------
 struct SolverState {
   const int* rowptr; const int* colind; const double* vals;
@@ -286,6 +330,8 @@ SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals
 }
 
 void SolverDeleter::operator()(SolverState* p) const { delete p; }
+
+void solver_precond(SolverState& S, const double* r_dev, double* z_dev) { S.precond(r_dev, z_dev); }
 
 namespace {
 

@@ -19,3 +19,13 @@ int newmark_run(SolverState& S, const int* rowptr, const int* colind, const doub
                 double beta, int nb, double* const* bvecs, const double* tcoef, double* u0, double* v0,
                 double* a0, long long out_lo, long long out_hi, int out_stride, double* out,
                 vlfs_solve_stats* stats, int nsm, cudaStream_t s, long long* launches);
+
+void solver_precond(SolverState& S, const double* r_dev, double* z_dev);
+// device-pointer vector algebra (krylov.cu)
+void dev_multidot(const double* V, size_t ldv, int nv, const double* w, long long n, int cplx,
+                  double* partial, int nred, double* out_dev, cudaStream_t s);
+void dev_gemv_sub(const double* V, size_t ldv, int nv, const double* h_dev, double* w, long long n, int cplx,
+                  int nsm, cudaStream_t s);
+void dev_axpby(double are, double aim, const double* x, double bre, double bim, double* y, long long n, int cplx,
+               int nsm, cudaStream_t s);
+void dev_gather(const int* idx, const double* src, double* dst, long long n, int cplx, int nsm, cudaStream_t s);
