@@ -208,6 +208,20 @@ int vlfs_assemble_profile(vlfs_ctx* ctx, int reps, char* names, int names_cap, f
 int vlfs_last_kernel_launches(vlfs_ctx* ctx, int64_t* n);
 int vlfs_device_ptrs(vlfs_ctx* ctx, int mat, void** rowptr, void** colind, void** values);
 
+/* ---- functionals of FE functions (the integrals the reference evaluates after each step:
+ * l2(x) = √(∑∫(x⋅x)dΩ) and the energies, src/Periodic_Beam.jl:119-120,141-148) ------------------
+ * value = ∑_cells ∫ | Σ_s scale_s OP(u_h) − f |² dμ on a registered domain; u_h from the DOF
+ * vector x (host, real, length ndofs); f = coefficient-field index of the domain (update it with
+ * vlfs_set_weights, e.g. the analytic solution at the points at time t) or -1. */
+typedef struct {
+  int32_t op;                          /* VLFS_OP_*                                         */
+  int32_t weight_f;                    /* -1 or coefficient-field index (scalar operators)  */
+  double scale[VLFS_MAX_SLOTS];
+  double dir[3];
+} vlfs_functional_desc;
+int vlfs_eval_functional(vlfs_ctx* ctx, int domain_id, const vlfs_functional_desc* f,
+                         const void* x_host, double* value);
+
 /* ---- distributed building blocks (row-partitioned systems, one context per GPU) ------------
  * A rank registers the cells that touch its owned DOFs with LOCAL DOF ids [owned | ghost]; rows
  * [0,n_owned) of the local CSR are then complete.  The entry points below take DEVICE pointers

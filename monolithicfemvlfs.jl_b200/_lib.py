@@ -45,6 +45,11 @@ class RhsDesc(C.Structure):
                 ("scale", C.c_double * MAX_SLOTS), ("dir", C.c_double * 3)]
 
 
+class FunctionalDesc(C.Structure):
+    _fields_ = [("op", C.c_int32), ("weight_f", C.c_int32), ("scale", C.c_double * MAX_SLOTS),
+                ("dir", C.c_double * 3)]
+
+
 class SolverOpts(C.Structure):
     _fields_ = [("method", C.c_int32), ("precond", C.c_int32), ("restart", C.c_int32),
                 ("maxit", C.c_int32), ("rtol", C.c_double), ("block_size_hint", C.c_int32),
@@ -69,6 +74,7 @@ EXPORTS = [
     "vlfs_assemble_timed", "vlfs_assemble_profile", "vlfs_last_kernel_launches", "vlfs_device_ptrs",
     "vlfs_set_stream", "vlfs_set_owned_rows", "vlfs_dev_spmv", "vlfs_dev_precond", "vlfs_dev_multidot",
     "vlfs_dev_gemv_sub", "vlfs_dev_axpby", "vlfs_dev_gather", "vlfs_get_vector_device",
+    "vlfs_eval_functional",
 ]
 
 _lib = None
@@ -134,6 +140,7 @@ def load():
     lib.vlfs_dev_axpby.argtypes = [vp, C.c_double, C.c_double, vp, C.c_double, C.c_double, vp, C.c_int64]
     lib.vlfs_dev_gather.argtypes = [vp, C.c_int64, vp, vp, vp]
     lib.vlfs_get_vector_device.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    lib.vlfs_eval_functional.argtypes = [vp, C.c_int, C.POINTER(FunctionalDesc), vp, _dp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

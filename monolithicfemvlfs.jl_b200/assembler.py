@@ -88,6 +88,19 @@ class Domain:
         self.nrhs += 1
         return tid.value
 
+    def functional(self, x, op, slots, weight_f=-1, direction=(0, 0, 0)):
+        """∑∫ |Σ_s scale_s OP(u_h) − f|² dμ on this domain, u_h from the DOF vector x
+        (`∑(∫(x⋅x)dΩ)` of src/Periodic_Beam.jl:119-120 evaluated on the GPU)."""
+        f = L.FunctionalDesc()
+        f.op, f.weight_f = op, weight_f
+        f.scale = self._scales(slots)
+        f.dir = (C.c_double * 3)(*[float(v) for v in direction])
+        xv = np.ascontiguousarray(x, dtype=np.float64)
+        out = C.c_double(0.0)
+        self.system._check(self.system.lib.vlfs_eval_functional(
+            self.system.ctx, self.id, C.byref(f), xv.ctypes.data_as(C.c_void_p), C.byref(out)))
+        return out.value
+
     def set_coef(self, term, coef):
         self.system._check(self.system.lib.vlfs_set_term_coef(
             self.system.ctx, self.id, term, float(np.real(coef)), float(np.imag(coef))))

@@ -65,12 +65,15 @@ class PeriodicBeamProblem:
 
         sys_ = self.sys = system_cls(X.ndofs, False, nmat=4, nvec=1, device=device)
         # a: ∫ ∇(ϕ)⋅∇(w) dΩ (:100)
-        d = self.dom_Om = sys_.add_domain(2, dOm.nq, dOm.wq, [dOm.own_slot(V_Om)])
+        # (one coefficient field per domain: the analytic solution at the points, for l2_Ω/l2_Γ)
+        self._xq_Om, self._xq_G = dOm.points(), dG.points()
+        d = self.dom_Om = sys_.add_domain(2, dOm.nq, dOm.wq, [dOm.own_slot(V_Om)],
+                                          weights=[np.zeros(self._xq_Om.shape[:2])])
         d.add_term(MAT_K, 1.0, L.OP_GRAD, 0, L.OP_GRAD, 0)
         # Γ: slot 0 = ϕ trace, slot 1 = η  (m :98, c :99, a :101)
         d = self.dom_G = sys_.add_domain(2, dG.nq, dG.wq,
                                          [dG.trace_slot(V_Om), dG.surface_slot(V_G, need_hess=True)],
-                                         measure_slot=1)
+                                         measure_slot=1, weights=[np.zeros(self._xq_G.shape[:2])])
         PHI, ETA = 0, 1
         d.add_term(MAT_K, g, L.OP_VAL, ETA, L.OP_VAL, ETA)              # g η v
         d.add_term(MAT_K, Drho, L.OP_LAPL, ETA, L.OP_LAPL, ETA)         # Dᵨ Δ(η) Δ(v)
@@ -131,3 +134,35 @@ class PeriodicBeamProblem:
             self.interpolate(0.0, 0), self.interpolate(0.0, 1), self.interpolate(0.0, 2),
             out_range=(0, self.X.ndofs if keep_states else 0), out_stride=1)
         return u, v, a, out, st
+
+
+def run_periodic_beam(params, device=0, solver=None):
+    """`run_periodic_beam(params)` (src/Periodic_Beam.jl:23-165): returns
+    (e_ϕ, e_η, E_kin_f, E_pot_f, E_kin_s, E_ela_s, E_kin_f₀, E_kin_s₀, E_pot_f₀, E_ela_s₀, t_global);
+    the per-step integrals (:141-148) are evaluated on the GPU (vlfs_eval_functional)."""
+    prob = PeriodicBeamProblem(params, device=device)
+    prob.assemble()
+    u, v, a, states, prob.stats = prob.solve(solver=solver)
+    c, p = prob.c, params
+    PHI, ETA = 0, 1
+    e_phi, e_eta, Ekf, Epf, Eks, Ees, ts = [], [], [], [], [], [], []
+    prev = prob.interpolate(0.0, 0)
+    for n in range(states.shape[0]):
+        t = (n + 1) * p.dt
+        x = states[n]
+        prob.dom_Om.set_weights(0, prob.phi_ex(prob._xq_Om, t))
+        prob.dom_G.set_weights(0, prob.eta_ex(prob._xq_G, t))
+        e_phi.append(np.sqrt(prob.dom_Om.functional(x, L.OP_VAL, 0, weight_f=0)))
+        e_eta.append(np.sqrt(prob.dom_G.functional(x, L.OP_VAL, ETA, weight_f=0)))
+        Ekf.append(0.5 * prob.dom_Om.functional(x, L.OP_GRAD, 0))
+        Epf.append(0.5 * c["g"] * prob.dom_G.functional(x, L.OP_VAL, ETA))
+        Eks.append(0.5 * c["d0"] * prob.dom_G.functional((x - prev) / p.dt, L.OP_VAL, ETA))
+        Ees.append(0.5 * c["Drho"] * prob.dom_G.functional(x, L.OP_LAPL, ETA))
+        ts.append(t)
+        prev = x
+    E_kin_f0 = 0.25 * c["d0"] * c["om"] ** 2 * c["eta0"] ** 2 * c["L"]
+    E_kin_s0 = 0.25 * c["g"] * c["eta0"] ** 2 * c["L"]
+    E_pot_f0 = 0.25 * c["Drho"] * c["k"] ** 4 * c["eta0"] ** 2 * c["L"]
+    E_ela_s0 = 0.25 * c["g"] * c["eta0"] ** 2 * c["L"]
+    return (np.array(e_phi), np.array(e_eta), np.array(Ekf), np.array(Epf), np.array(Eks), np.array(Ees),
+            E_kin_f0, E_kin_s0, E_pot_f0, E_ela_s0, np.array(ts))

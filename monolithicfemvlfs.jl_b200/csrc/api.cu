@@ -22,6 +22,8 @@ void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, con
                       int nmat, double* const* vecs, int nvec, int is_complex, int do_mat,
                       int do_vec, int nsm, cudaStream_t s);
 void launch_gradgrad_reference(const DomainDev& dom, double* Sref, cudaStream_t s);
+void launch_functional(const DomainDev& dom, const OpInst& O0, const OpInst& O1, double sc0, double sc1,
+                       int wf, const double* x, double* result, int nsm, cudaStream_t s);
 void launch_gradgrad_affine(const DomainDev& dom, const double* Sref, const int* dest, double* vals,
                             int is_complex, double cre, double cim, int nsm, cudaStream_t s);
 void launch_spmv(const int* rowptr, const int* colind, const void* vals, const void* x, void* y,
@@ -1002,6 +1004,41 @@ int vlfs_get_vector_device(vlfs_ctx* ctx, int vec, void** ptr) {
   if (!ctx || vec < 0 || vec >= ctx->nvec || !ptr) return VLFS_ERR_ARG;
   *ptr = ctx->vecs[vec].p;
   return VLFS_OK;
+}
+
+int vlfs_eval_functional(vlfs_ctx* ctx, int domain_id, const vlfs_functional_desc* f, const void* x_host,
+                         double* value) {
+  return guarded(ctx, [&]() {
+    if (!f || !x_host || !value || domain_id < 0 || domain_id >= (int)ctx->doms.size())
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_eval_functional: bad arguments");
+    if (ctx->is_complex) return fail(ctx, VLFS_ERR_ARG, "vlfs_eval_functional: real systems only");
+    Domain& d = *ctx->doms[domain_id];
+    const DomainDev& dev = d.dev;
+    const int nc = op_ncomp(f->op, dev.D);
+    if (nc < 0 || f->weight_f >= dev.nweights || (f->weight_f >= 0 && nc != 1))
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_eval_functional: bad operator / field");
+    OpInst O[2];
+    double sc[2] = {0.0, 0.0};
+    for (int s = 0; s < 2; ++s) {
+      O[s].slot = s < dev.nslots ? s : 0; O[s].op = f->op; O[s].ncomp = nc; O[s].smem_off = 0; O[s].ndp = 1;
+      O[s].buf_stride = 0;
+      for (int k = 0; k < 3; ++k) O[s].dir[k] = f->dir[k];
+      if (s < dev.nslots) sc[s] = f->scale[s];
+      if (sc[s] != 0.0) {
+        if (op_needs_hess(f->op) && !dev.slot[s].hess) return fail(ctx, VLFS_ERR_ARG, "hess table missing");
+        if (f->op == VLFS_OP_GRAD_NOWN && !dev.slot[s].ref_normal) return fail(ctx, VLFS_ERR_ARG, "ref_normal missing");
+        if ((f->op == VLFS_OP_CHESS || f->op == VLFS_OP_CHESS_NPLUS) && !dev.C) return fail(ctx, VLFS_ERR_ARG, "C missing");
+      }
+    }
+    DevBuf<double> dx, res;
+    dx.upload((const double*)x_host, (size_t)ctx->ndofs, ctx->stream);
+    res.alloc(1); res.zero(ctx->stream);
+    launch_functional(dev, O[0], O[1], sc[0], sc[1], f->weight_f, dx.p, res.p, ctx->nsm, ctx->stream);
+    ++ctx->launches;
+    CUDA_TRY(cudaMemcpyAsync(value, res.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VLFS_OK;
+  });
 }
 
 }  // extern "C"

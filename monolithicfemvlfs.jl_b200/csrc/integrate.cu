@@ -480,6 +480,61 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
   }
 }
 
+// ---- functionals of FE functions:  sum_cells ∫ | sum_s scale_s OP(u_h) - f |^2 dμ  ------------
+// (L2 errors and energies of src/Periodic_Beam.jl:119-120,141-148).  One CTA per cell, one thread
+// per quadrature point; u_h is evaluated from the DOF vector x through the same operator code
+// as the assembly.  f = coefficient field sampled at the points, or absent.
+template <int D>
+__global__ void __launch_bounds__(128)
+functional_cells(DomainDev dom, OpInst O0, OpInst O1, double sc0, double sc1, int wf,
+                 const double* __restrict__ x, double* __restrict__ result) {
+  extern __shared__ __align__(16) double sm[];        // geometry records [nslots][nq][12]
+  __shared__ double red[4];
+  const int nq = dom.nq, tid = threadIdx.x;
+  double total = 0.0;
+  for (long long cell = blockIdx.x; cell < dom.ncells; cell += gridDim.x) {
+    __syncthreads();
+    double meas = 0.0;
+    for (int t = tid; t < dom.nslots * nq; t += blockDim.x) {
+      const int s = t / nq, q = t - s * nq;
+      double m;
+      slot_geometry<D>(dom.slot[s], cell, q, nq, sm + (size_t)t * GEO_STRIDE,
+                       s == dom.measure_slot ? &m : nullptr, dom.measure_kind);
+      if (s == dom.measure_slot) sm[(size_t)dom.nslots * nq * GEO_STRIDE + q] = m * dom.qweights[q];
+    }
+    __syncthreads();
+    for (int q = tid; q < nq; q += blockDim.x) {
+      double v[6] = {0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < 2; ++k) {
+        const OpInst& O = k == 0 ? O0 : O1;
+        const double sc = k == 0 ? sc0 : sc1;
+        if (sc == 0.0) continue;
+        const SlotDev& S = dom.slot[O.slot];
+        for (int i = 0; i < S.ndofs; ++i) {
+          double tmp[6];
+          eval_op<D>(dom, O, cell, q, 0 + i, sm, tmp);      // component stride O.ndp == 1
+          const double xi = x[S.dofs[(size_t)cell * S.ndofs + i]] * sc;
+          for (int c = 0; c < O.ncomp; ++c) v[c] = fma(tmp[c], xi, v[c]);
+        }
+      }
+      if (wf >= 0) v[0] -= dom.weights[((size_t)wf * dom.ncells + cell) * nq + q];
+      double s2 = 0.0;
+      for (int c = 0; c < O0.ncomp; ++c) s2 = fma(v[c], v[c], s2);
+      meas = sm[(size_t)dom.nslots * nq * GEO_STRIDE + q];
+      total = fma(meas, s2, total);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_down_sync(0xffffffffu, total, o);
+  if ((tid & 31) == 0) red[tid >> 5] = total;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+    if (t != 0.0) atomicAdd(result, t);
+  }
+}
+
 // ---- fast path: ∫ ∇u·∇v on constant-Jacobian cells --------------------------------
 // reference matrices, symmetrised:  Sref[m][i][j], m over sym components of dref x dref
 template <int DR>
@@ -613,6 +668,23 @@ void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, con
   if (dom.D == 1) launch(integrate_cells<1>);
   else if (dom.D == 2) launch(integrate_cells<2>);
   else launch(integrate_cells<3>);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_functional(const DomainDev& dom_in, const OpInst& O0, const OpInst& O1, double sc0, double sc1,
+                       int wf, const double* x, double* result, int nsm, cudaStream_t s) {
+  if (dom_in.ncells == 0) return;
+  DomainDev dom = dom_in;
+  dom.nqg = dom.nq;                       // per-point geometry records, whatever the domain's flag
+  size_t smem = ((size_t)dom.nslots * dom.nq * GEO_STRIDE + dom.nq) * sizeof(double);
+  long long grid = dom.ncells < (long long)nsm * 8 ? dom.ncells : (long long)nsm * 8;
+  auto launch = [&](auto kern) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, 128, smem, s>>>(dom, O0, O1, sc0, sc1, wf, x, result);
+  };
+  if (dom.D == 1) launch(functional_cells<1>);
+  else if (dom.D == 2) launch(functional_cells<2>);
+  else launch(functional_cells<3>);
   CUDA_TRY(cudaGetLastError());
 }
 

@@ -5,6 +5,7 @@ import os
 import numpy as np
 import pytest
 import scipy.sparse.linalg as spla
+from conftest import lu_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -66,7 +67,7 @@ def test_khabakhpasheva_freq(kw):
     assert np.abs(bb - b).max() <= 1e-12 * np.abs(b).max()
     prob.sys.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=30, maxit=60, rtol=1e-12)
     x, st = prob.sys.solve(vec=0)
-    xr = spla.splu(A.tocsc()).solve(b)
+    xr = lu_reference(A, b)
     assert np.linalg.norm(x - xr) <= 1e-8 * np.linalg.norm(xr)
     xs, eta = prob.postprocess(x)
     xs_r, eta_r = ref.eta_postprocess(xr)
@@ -105,5 +106,22 @@ def test_multigeo_coarse(order, golden_dir):
     assert np.abs(prob.sys.get_vector(0) - b).max() <= 2e-12 * np.abs(b).max()
     prob.sys.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=30, maxit=60, rtol=1e-12)
     x, st = prob.sys.solve(vec=0)
-    xr = spla.splu(A.tocsc()).solve(b)
+    xr = lu_reference(A, b)
     assert np.linalg.norm(x - xr) <= 1e-8 * np.linalg.norm(xr)
+
+
+def test_run_periodic_beam_functionals_on_gpu():
+    """The drop-in `run_periodic_beam`: L2 errors and the four energies evaluated by the GPU
+    functional kernel equal the oracle's (src/Periodic_Beam.jl:141-148)."""
+    from vlfs_b200.cases.periodic_beam import run_periodic_beam, Periodic_Beam_params
+    from oracle.cases.periodic_beam import PeriodicBeamCase
+    kw = dict(n=8, dt=0.002, tf=0.02, orderphi=3, ordereta=3, k=2)
+    out = run_periodic_beam(Periodic_Beam_params(**kw), device=0)
+    r = PeriodicBeamCase(**kw).run()
+    E = np.array(r["E"])
+    assert len(out[10]) == len(r["t"]) and np.allclose(out[10], r["t"], rtol=1e-14)
+    assert np.abs(out[0] - np.array(r["e_phi"])).max() <= 1e-6 * np.max(r["e_phi"])
+    assert np.abs(out[1] - np.array(r["e_eta"])).max() <= 1e-6 * np.max(r["e_eta"])
+    for k in range(4):
+        assert np.abs(out[2 + k] - E[:, k]).max() <= 1e-8 * np.abs(E[:, k]).max(), k
+    assert out[6] == r["E0"]["E_kin_f0"] and out[7] == r["E0"]["E_kin_s0"]

@@ -3,6 +3,7 @@ pattern bit-exact, entries <= 1e-12, SpMV, and solution <= 1e-8 vs the oracle's 
 import numpy as np
 import pytest
 import scipy.sparse.linalg as spla
+from conftest import lu_reference
 
 pytestmark = pytest.mark.gpu
 
@@ -94,7 +95,7 @@ def test_solve_matches_lu(case):
     x, st = prob.sys.solve(vec=0)
     print(prob.sys.direct_info())
     assert st["converged"] and st["iterations"] <= 5
-    xr = spla.splu(A.tocsc()).solve(b)
+    xr = lu_reference(A, b)
     err = np.linalg.norm(x - xr) / np.linalg.norm(xr)
     print("iterations", st["iterations"], "residual", st["rel_residual"], "error", err)
     assert err <= 1e-8
