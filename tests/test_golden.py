@@ -1,0 +1,85 @@
+"""Committed oracle fixtures (tests/golden/oracle_*.npz, made by tests/golden/make_golden.py):
+the CPU half checks that the oracle still reproduces them; the GPU half checks the CUDA path
+against them without re-deriving anything from the oracle at run time."""
+import os
+import numpy as np
+import pytest
+from golden.make_golden import pattern_digest, probe
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _check_probe(g, A, b, tol=1e-12):
+    p = probe(A, b)
+    assert p["n"] == int(g["n"]) and p["nnz"] == int(g["nnz"])
+    assert np.array_equal(p["digest"], g["digest"])                       # pattern bit-exact
+    assert np.abs(p["Ax"] - g["Ax"]).max() <= tol * np.abs(g["Ax"]).max()
+    assert np.abs(p["diag"] - g["diag"]).max() <= tol * np.abs(g["diag"]).max()
+    assert np.abs(p["b"] - g["b"]).max() <= tol * np.abs(g["b"]).max()
+
+
+def test_oracle_reproduces_fixtures(golden_dir):
+    from oracle.cases.yago import YagoCase
+    from oracle.cases.khabakhpasheva import KhabakhpashevaFreqCase
+    from oracle.cases.multigeo import MultiGeoCase
+    _check_probe(_load(golden_dir, "oracle_yago_warmup.npz"),
+                 *YagoCase(nx=2, ny=2, nz=1, order=2, lfactor=0.4, dfactor=3).assemble(), tol=1e-13)
+    _check_probe(_load(golden_dir, "oracle_khab_freq_warmup.npz"),
+                 *KhabakhpashevaFreqCase(nx=10, ny=1, order=2, xi=0.0).assemble(), tol=1e-13)
+    _check_probe(_load(golden_dir, "oracle_multigeo_warmup.npz"),
+                 *MultiGeoCase(os.path.join(golden_dir, "multi_geo_coarse.json"), order=2).assemble(), tol=1e-13)
+
+
+@pytest.mark.gpu
+def test_gpu_yago_warmup_against_fixture(golden_dir):
+    from vlfs_b200 import _lib as L
+    from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
+    g = _load(golden_dir, "oracle_yago_warmup.npz")
+    prob = YagoProblem(Yago_freq_domain_params(nx=2, ny=2, nz=1, order=2, lfactor=0.4, dfactor=3), device=0)
+    prob.assemble()
+    _check_probe(g, prob.sys.get_matrix(0), prob.sys.get_vector(0))
+    prob.sys.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=30, maxit=60, rtol=1e-12)
+    x, st = prob.sys.solve(vec=0)
+    assert np.linalg.norm(x - g["x"]) <= 1e-8 * np.linalg.norm(g["x"])
+    xs, rao = prob.rao(x)
+    assert np.array_equal(xs, g["rao_x"]) and np.abs(rao - g["rao"]).max() <= 1e-8 * np.abs(g["rao"]).max()
+
+
+@pytest.mark.gpu
+def test_gpu_khabakhpasheva_against_fixtures(golden_dir):
+    from vlfs_b200.cases.khabakhpasheva import (run_Khabakhpasheva_freq_domain, run_Khabakhpasheva_time_domain,
+                                                Khabakhpasheva_freq_domain_params, Khabakhpasheva_time_domain_params,
+                                                KhabakhpashevaTimeProblem)
+    g = _load(golden_dir, "oracle_khab_freq_warmup.npz")
+    xs, eta = run_Khabakhpasheva_freq_domain(Khabakhpasheva_freq_domain_params(nx=10, ny=1, order=2, xi=0.0))
+    assert np.array_equal(xs, g["xs"]) and np.abs(eta - g["eta"]).max() <= 1e-8 * g["eta"].max()
+    g = _load(golden_dir, "oracle_khab_time_warmup.npz")
+    prob = KhabakhpashevaTimeProblem(Khabakhpasheva_time_domain_params(nx=10, ny=1, order=2, xi=0.0))
+    prob.assemble()
+    ts, hist, (u, v, a), st = prob.solve(nsteps=40)
+    assert np.allclose(ts, g["ts"], rtol=1e-14, atol=0)
+    assert np.abs(hist - g["eta_hist"]).max() <= 1e-8 * np.abs(g["eta_hist"]).max()
+    assert np.abs(u - g["u"]).max() <= 1e-8 * np.abs(g["u"]).max()
+
+
+@pytest.mark.gpu
+def test_gpu_periodic_beam_and_multigeo_against_fixtures(golden_dir):
+    from vlfs_b200.cases.periodic_beam import run_periodic_beam, Periodic_Beam_params
+    from vlfs_b200.cases.multigeo import MultiGeoProblem, MultiGeo_freq_domain_params
+    from vlfs_b200 import _lib as L
+    g = _load(golden_dir, "oracle_periodic_beam.npz")
+    out = run_periodic_beam(Periodic_Beam_params(n=3, dt=0.5, tf=1.0, orderphi=2, ordereta=2, k=1))
+    assert np.abs(out[0] - g["e_phi"]).max() <= 1e-7 * g["e_phi"].max()
+    assert np.abs(out[1] - g["e_eta"]).max() <= 1e-7 * g["e_eta"].max()
+    out = run_periodic_beam(Periodic_Beam_params(n=8, dt=1e-6, tf=1e-4, orderphi=2, ordereta=2, k=15))
+    assert abs(out[0][-1] - g["conv_e_phi"]) <= 1e-6 * g["conv_e_phi"]
+    assert abs(out[1][-1] - g["conv_e_eta"]) <= 1e-6 * g["conv_e_eta"]
+    g = _load(golden_dir, "oracle_multigeo_warmup.npz")
+    prob = MultiGeoProblem(MultiGeo_freq_domain_params(mesh_file=os.path.join(golden_dir, "multi_geo_coarse.json"), order=2))
+    prob.assemble()
+    _check_probe(g, prob.sys.get_matrix(0), prob.sys.get_vector(0), tol=2e-12)
+    prob.sys.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=30, maxit=60, rtol=1e-12)
+    x, st = prob.sys.solve(vec=0)
+    assert np.linalg.norm(x - g["x"]) <= 1e-8 * np.linalg.norm(g["x"])
