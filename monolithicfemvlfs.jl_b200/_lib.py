@@ -74,7 +74,8 @@ EXPORTS = [
     "vlfs_assemble_timed", "vlfs_assemble_profile", "vlfs_last_kernel_launches", "vlfs_device_ptrs",
     "vlfs_set_stream", "vlfs_set_owned_rows", "vlfs_dev_spmv", "vlfs_dev_precond", "vlfs_dev_multidot",
     "vlfs_dev_gemv_sub", "vlfs_dev_axpby", "vlfs_dev_gather", "vlfs_get_vector_device",
-    "vlfs_eval_functional",
+    "vlfs_eval_functional", "vlfs_set_roles", "vlfs_schur_size", "vlfs_schur_get", "vlfs_schur_forward",
+    "vlfs_schur_backward", "vlfs_dense_factor", "vlfs_dense_solve",
 ]
 
 _lib = None
@@ -141,6 +142,13 @@ def load():
     lib.vlfs_dev_gather.argtypes = [vp, C.c_int64, vp, vp, vp]
     lib.vlfs_get_vector_device.argtypes = [vp, C.c_int, C.POINTER(vp)]
     lib.vlfs_eval_functional.argtypes = [vp, C.c_int, C.POINTER(FunctionalDesc), vp, _dp]
+    lib.vlfs_set_roles.argtypes = [vp, C.POINTER(C.c_int8)]
+    lib.vlfs_schur_size.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.vlfs_schur_get.argtypes = [vp, vp]
+    lib.vlfs_schur_forward.argtypes = [vp, vp, vp]
+    lib.vlfs_schur_backward.argtypes = [vp, vp, vp]
+    lib.vlfs_dense_factor.argtypes = [vp, C.c_int64, vp]
+    lib.vlfs_dense_solve.argtypes = [vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

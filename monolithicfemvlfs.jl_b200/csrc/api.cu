@@ -97,6 +97,8 @@ struct vlfs_ctx {
   int coord_dim = 0;
   int solver_mat = -1;
   long long nowned = 0;             // rows [0,nowned) are owned, the rest are ghosts (distributed)
+  std::vector<signed char> roles;   // sparse-LU role of every unknown (empty: owned = eliminate)
+  DirectPtr dense;                  // dense LU of an interface system (substructuring)
   bool own_stream = true;
   DevBuf<double> dev_partial, dev_h;  // scratch of the vlfs_dev_* reductions
   size_t scalar() const { return is_complex ? 2 : 1; }
@@ -451,6 +453,7 @@ int vlfs_destroy(vlfs_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ctx->solver.reset();
   ctx->direct.reset();
+  ctx->dense.reset();
   ctx->doms.clear();
   ctx->mats.clear();
   ctx->vecs.clear();
@@ -820,10 +823,16 @@ int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
     if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !opts) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
     if (opts->precond == VLFS_PRECOND_SPARSE_LU) {
       if (ctx->dof_coords.empty()) return fail(ctx, VLFS_ERR_STATE, "vlfs_set_dof_coords first (sparse LU ordering)");
-      if (!ctx->direct)
-        ctx->direct = direct_symbolic(ctx->rowptr.p, ctx->colind.p, ctx->ndofs, ctx->nowned, ctx->nnz, ctx->dof_coords.data(),
+      if (!ctx->direct) {
+        std::vector<signed char> role = ctx->roles;
+        if (role.empty()) {
+          role.assign((size_t)ctx->ndofs, 2);
+          for (long long i = 0; i < ctx->nowned; ++i) role[i] = 0;
+        }
+        ctx->direct = direct_symbolic(ctx->rowptr.p, ctx->colind.p, ctx->ndofs, role.data(), ctx->nnz, ctx->dof_coords.data(),
                                       ctx->coord_dim, opts->block_size_hint, ctx->is_complex, ctx->nsm,
                                       ctx->stream, &ctx->launches);
+      }
       direct_numeric(*ctx->direct, ctx->rowind.p, ctx->colind.p, ctx->mats[mat].p);
     }
     ctx->solver = solver_create(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, ctx->nowned, ctx->nnz,
@@ -1037,6 +1046,65 @@ int vlfs_eval_functional(vlfs_ctx* ctx, int domain_id, const vlfs_functional_des
     ++ctx->launches;
     CUDA_TRY(cudaMemcpyAsync(value, res.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VLFS_OK;
+  });
+}
+
+/* ---- substructuring: partial factorisation with a kept boundary + dense interface solve -------- */
+int vlfs_set_roles(vlfs_ctx* ctx, const int8_t* role) {
+  return guarded(ctx, [&]() {
+    if (!role || ctx->ndofs == 0) return fail(ctx, VLFS_ERR_ARG, "vlfs_set_roles: bad arguments");
+    for (long long i = 0; i < ctx->ndofs; ++i)
+      if (role[i] < 0 || role[i] > 2) return fail(ctx, VLFS_ERR_ARG, "vlfs_set_roles: role must be 0, 1 or 2");
+    ctx->roles.assign(role, role + ctx->ndofs);
+    ctx->solver.reset(); ctx->direct.reset();
+    return VLFS_OK;
+  });
+}
+
+int vlfs_schur_size(vlfs_ctx* ctx, int64_t* n_keep) {
+  if (!ctx || !n_keep || !ctx->direct) return VLFS_ERR_ARG;
+  *n_keep = direct_nkeep(*ctx->direct);
+  return VLFS_OK;
+}
+
+int vlfs_schur_get(vlfs_ctx* ctx, void* S_dev) {
+  return guarded(ctx, [&]() {
+    if (!ctx->direct || !S_dev) return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup (sparse LU) first");
+    direct_schur(*ctx->direct, (double*)S_dev);
+    return VLFS_OK;
+  });
+}
+
+int vlfs_schur_forward(vlfs_ctx* ctx, const void* b_dev, void* g_keep_dev) {
+  return guarded(ctx, [&]() {
+    if (!ctx->direct || !b_dev) return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup (sparse LU) first");
+    direct_forward(*ctx->direct, (const double*)b_dev, (double*)g_keep_dev);
+    return VLFS_OK;
+  });
+}
+
+int vlfs_schur_backward(vlfs_ctx* ctx, const void* x_keep_dev, void* x_dev) {
+  return guarded(ctx, [&]() {
+    if (!ctx->direct || !x_dev) return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup (sparse LU) first");
+    direct_backward(*ctx->direct, (const double*)x_keep_dev, (double*)x_dev);
+    return VLFS_OK;
+  });
+}
+
+int vlfs_dense_factor(vlfs_ctx* ctx, int64_t n, const void* S_dev) {
+  return guarded(ctx, [&]() {
+    if (n < 1 || n > 200000 || !S_dev) return fail(ctx, VLFS_ERR_ARG, "vlfs_dense_factor: bad arguments");
+    ctx->dense = direct_dense(n, ctx->is_complex, ctx->nsm, ctx->stream, &ctx->launches);
+    direct_dense_factor(*ctx->dense, (const double*)S_dev);
+    return VLFS_OK;
+  });
+}
+
+int vlfs_dense_solve(vlfs_ctx* ctx, const void* b_dev, void* x_dev) {
+  return guarded(ctx, [&]() {
+    if (!ctx->dense || !b_dev || !x_dev) return fail(ctx, VLFS_ERR_STATE, "vlfs_dense_factor first");
+    direct_solve(*ctx->dense, (const double*)b_dev, (double*)x_dev);
     return VLFS_OK;
   });
 }

@@ -86,13 +86,14 @@ __device__ __forceinline__ int local_index(const FrontMeta& F, const int* __rest
 template <bool C>
 __global__ void scatter_matrix(const int* __restrict__ rowind, const int* __restrict__ colind,
                                const typename Num<C>::T* __restrict__ vals, long long nnz,
-                               const int* __restrict__ pos, const int* __restrict__ front_of_pos,
+                               const int* __restrict__ pos, int n_elim, const int* __restrict__ front_of_pos,
                                const FrontMeta* __restrict__ meta, const int* __restrict__ upd_idx,
                                typename Num<C>::T* __restrict__ pool) {
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < nnz;
        p += (long long)gridDim.x * blockDim.x) {
     int pi = pos[rowind[p]], pj = pos[colind[p]];
-    if (pi < 0 || pj < 0) continue;        // ghost row / column of a distributed system
+    if (pi < 0 || pj < 0) continue;        // ignored row / column (ghosts of a distributed system)
+    if (pi >= n_elim && pj >= n_elim) continue;   // kept x kept: stays outside the factorisation
     int f = front_of_pos[pi < pj ? pi : pj];
     const FrontMeta F = meta[f];
     int li = local_index(F, upd_idx, pi), lj = local_index(F, upd_idx, pj);
@@ -274,17 +275,47 @@ schur_update(const FrontMeta* __restrict__ meta, const int* __restrict__ list, i
 }
 
 // ---- solve kernels --------------------------------------------------------------------
+// b (original numbering, n_total entries) -> bp (eliminated positions only)
 template <bool C>
 __global__ void permute_in(const typename Num<C>::T* __restrict__ b, const int* __restrict__ pos,
-                           typename Num<C>::T* __restrict__ bp, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    bp[pos[i]] = b[i];
+                           typename Num<C>::T* __restrict__ bp, long long n_total, int n_elim) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = pos[i];
+    if (p >= 0 && p < n_elim) bp[p] = b[i];
+  }
 }
+// xp (eliminated + kept positions) -> x (original numbering); ignored entries are left alone
 template <bool C>
 __global__ void permute_out(const typename Num<C>::T* __restrict__ xp, const int* __restrict__ pos,
-                            typename Num<C>::T* __restrict__ x, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    x[i] = xp[pos[i]];
+                            typename Num<C>::T* __restrict__ x, long long n_total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = pos[i];
+    if (p >= 0) x[i] = xp[p];
+  }
+}
+// S[keep a][keep b] += trailing block of a root front (its Schur complement on the kept set)
+template <bool C>
+__global__ void add_root_schur(FrontMeta F, const int* __restrict__ upd_idx, int n_elim, int n_keep,
+                               const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ S) {
+  using N = Num<C>;
+  const int nu = F.nf - F.np;
+  const int* u = upd_idx + F.upd_ptr;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)nu * nu;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(t / nu), b = (int)(t - (long long)a * nu);
+    typename N::T* dst = S + (size_t)(u[a] - n_elim) * n_keep + (u[b] - n_elim);
+    *dst = N::add(*dst, pool[F.off + (long long)(F.np + a) * F.nf + F.np + b]);
+  }
+}
+// g[keep a] += update part of a root's work vector (forward sweep);  xp[kept] = xk (backward)
+template <bool C>
+__global__ void add_root_rhs(FrontMeta F, const int* __restrict__ upd_idx, int n_elim,
+                             const typename Num<C>::T* __restrict__ w, typename Num<C>::T* __restrict__ g) {
+  using N = Num<C>;
+  const int nu = F.nf - F.np;
+  const int* u = upd_idx + F.upd_ptr;
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < nu; a += gridDim.x * blockDim.x)
+    g[u[a] - n_elim] = N::add(g[u[a] - n_elim], w[F.woff + F.np + a]);
 }
 
 // w = [b_P ; 0] + contributions of the children (fixed order: slot 0 then slot 1)
@@ -443,7 +474,10 @@ __global__ void bwd_panel_commit(const FrontMeta* __restrict__ meta, const int* 
 // host side: symbolic analysis
 // =======================================================================================
 struct DirectSolver {
-  long long n = 0, nnz = 0;
+  long long n = 0, nnz = 0;          // n: eliminated unknowns
+  long long n_total = 0, n_keep = 0; // original vector length; kept (Schur boundary) unknowns
+  std::vector<int> roots;
+  bool dense = false;                // single dense front (interface system)
   int cplx = 0, nsm = 148;
   cudaStream_t s = nullptr;
   long long* launches = nullptr;
@@ -534,44 +568,46 @@ float timed(cudaStream_t s, F&& f) {
 
 void DirectDeleter::operator()(DirectSolver* p) const { delete p; }
 
-DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_total, long long n,
-                          long long nnz, const double* coords, int dim, int leaf, int is_complex, int nsm,
-                          cudaStream_t s, long long* launches) {
-  // n_total rows/columns exist in the CSR pattern, the first n (owned block of a distributed
-  // system; n == n_total on one GPU) are factorised
+DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_total,
+                          const signed char* role, long long nnz, const double* coords, int dim, int leaf,
+                          int is_complex, int nsm, cudaStream_t s, long long* launches) {
+  // role[i] (host, n_total entries): 0 = eliminate, 1 = keep as Schur boundary (never a pivot; the
+  // root fronts end with the Schur complement on these unknowns), 2 = ignore (ghosts).
   DirectPtr D(new DirectSolver());
-  D->n = n; D->nnz = nnz; D->cplx = is_complex; D->nsm = nsm; D->s = s; D->launches = launches;
+  std::vector<int> elim, keep;
+  for (long long i = 0; i < n_total; ++i) {
+    if (role[i] == 0) elim.push_back((int)i);
+    else if (role[i] == 1) keep.push_back((int)i);
+  }
+  const long long n = (long long)elim.size();
+  D->n = n; D->n_total = n_total; D->n_keep = (long long)keep.size();
+  D->nnz = nnz; D->cplx = is_complex; D->nsm = nsm; D->s = s; D->launches = launches;
+  if (n == 0) throw std::string("sparse LU: nothing to eliminate");
   if (leaf < 8) leaf = 96;
   auto t0 = std::chrono::steady_clock::now();
-  // symmetrised pattern on the host
-  std::vector<int> rp(n + 1), ci(nnz);
-  CUDA_TRY(cudaMemcpy(rp.data(), d_rowptr, (n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  // symmetrised pattern on the host, original numbering; rows of eliminated unknowns only
+  // (edges to kept unknowns are recorded on the eliminated side)
+  std::vector<int> rp(n_total + 1), ci(nnz);
+  CUDA_TRY(cudaMemcpy(rp.data(), d_rowptr, (n_total + 1) * sizeof(int), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(ci.data(), d_colind, nnz * sizeof(int), cudaMemcpyDeviceToHost));
-  if (n < n_total) {                       // drop ghost columns from the owned rows
-    int w = 0;
-    std::vector<int> rp2(n + 1, 0);
-    for (long long i = 0; i < n; ++i) {
-      for (int q = rp[i]; q < rp[i + 1]; ++q) if (ci[q] < n) ci[w++] = ci[q];
-      rp2[i + 1] = w;
-    }
-    rp.swap(rp2);
-  }
-  std::vector<int> sp(n + 1, 0), si;
+  std::vector<int> sp(n_total + 1, 0), si;
   {
-    std::vector<int> cnt(n, 0);
-    for (long long i = 0; i < n; ++i)
-      for (int p = rp[i]; p < rp[i + 1]; ++p) { ++cnt[i]; if (ci[p] != i) ++cnt[ci[p]]; }
-    std::vector<long long> start(n + 1, 0);
-    for (long long i = 0; i < n; ++i) start[i + 1] = start[i] + cnt[i];
-    std::vector<int> tmp(start[n]);
+    std::vector<int> cnt(n_total, 0);
+    auto edge = [&](long long i, int j, auto&& f) {
+      if (role[i] == 2 || role[j] == 2 || (int)i == j) return;
+      if (role[i] == 0) f((int)i, j);
+      if (role[j] == 0) f(j, (int)i);
+    };
+    for (long long i = 0; i < n_total; ++i)
+      for (int p = rp[i]; p < rp[i + 1]; ++p) edge(i, ci[p], [&](int a, int) { ++cnt[a]; });
+    std::vector<long long> start(n_total + 1, 0);
+    for (long long i = 0; i < n_total; ++i) start[i + 1] = start[i] + cnt[i];
+    std::vector<int> tmp(start[n_total]);
     std::vector<long long> fillp(start.begin(), start.end() - 1);
-    for (long long i = 0; i < n; ++i)
-      for (int p = rp[i]; p < rp[i + 1]; ++p) {
-        tmp[fillp[i]++] = ci[p];
-        if (ci[p] != i) tmp[fillp[ci[p]]++] = (int)i;
-      }
-    si.reserve(start[n]);
-    for (long long i = 0; i < n; ++i) {
+    for (long long i = 0; i < n_total; ++i)
+      for (int p = rp[i]; p < rp[i + 1]; ++p) edge(i, ci[p], [&](int a, int b2) { tmp[fillp[a]++] = b2; });
+    si.reserve(start[n_total]);
+    for (long long i = 0; i < n_total; ++i) {
       std::sort(tmp.begin() + start[i], tmp.begin() + start[i + 1]);
       auto e = std::unique(tmp.begin() + start[i], tmp.begin() + start[i + 1]);
       for (auto it = tmp.begin() + start[i]; it != e; ++it) si.push_back(*it);
@@ -580,9 +616,8 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_
   }
   // nested dissection
   NDBuilder nd{sp.data(), si.data(), coords, dim, leaf};
-  nd.mark.assign(n, 0);
-  std::vector<int> all(n);
-  std::iota(all.begin(), all.end(), 0);
+  nd.mark.assign(n_total, 0);
+  std::vector<int> all(elim);
   nd.nodes.reserve(2 * n / leaf + 16);
   int root = nd.rec(all);
   (void)root;
@@ -599,6 +634,7 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_
       for (int c : nd.nodes[f].child) if (c >= 0) parent[c] = f;
     }
     if (k != n) throw std::string("nested dissection lost DOFs");
+    for (size_t q = 0; q < keep.size(); ++q) pos[keep[q]] = (int)(n + q);
   }
   // update sets bottom-up
   std::vector<std::vector<int>> upd(nf_);
@@ -667,8 +703,10 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_
   const size_t sc = is_complex ? 2 : 1;
   D->pool.alloc((size_t)D->pool_elems * sc);
   D->w.alloc((size_t)D->w_elems * sc);
-  D->bp.alloc((size_t)n * sc);
-  D->xp.alloc((size_t)n * sc);
+  D->bp.alloc((size_t)(n + D->n_keep) * sc);
+  D->xp.alloc((size_t)(n + D->n_keep) * sc);
+  D->xp.zero(s);
+  for (int f = 0; f < nf_; ++f) if (parent[f] < 0) D->roots.push_back(f);
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
   D->symbolic_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -676,18 +714,10 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_
 }
 
 template <bool C>
-static void numeric_impl(DirectSolver& D, const int* rowind, const int* colind, const double* vals) {
+static void factor_levels(DirectSolver& D) {
   using T = typename Num<C>::T;
   cudaStream_t s = D.s;
   T* pool = reinterpret_cast<T*>(D.pool.p);
-  D.pool.zero(s);
-  {
-    long long g = (D.nnz + 255) / 256;
-    long long cap = (long long)D.nsm * 16;
-    scatter_matrix<C><<<(unsigned)std::min(g, cap), 256, 0, s>>>(rowind, colind, reinterpret_cast<const T*>(vals), D.nnz,
-        D.d_pos.p, D.d_front_of_pos.p, D.d_meta.p, D.d_upd.p, pool);
-    ++*D.launches;
-  }
   const size_t smem = (size_t)(TS * (NB + 1) + NB * TS) * sizeof(T);
   CUDA_TRY(cudaFuncSetAttribute(schur_update<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int L = 0; L < D.nlevels; ++L) {
@@ -718,6 +748,22 @@ static void numeric_impl(DirectSolver& D, const int* rowind, const int* colind, 
   CUDA_TRY(cudaGetLastError());
 }
 
+template <bool C>
+static void numeric_impl(DirectSolver& D, const int* rowind, const int* colind, const double* vals) {
+  using T = typename Num<C>::T;
+  cudaStream_t s = D.s;
+  T* pool = reinterpret_cast<T*>(D.pool.p);
+  D.pool.zero(s);
+  {
+    long long g = (D.nnz + 255) / 256;
+    long long cap = (long long)D.nsm * 16;
+    scatter_matrix<C><<<(unsigned)std::min(g, cap), 256, 0, s>>>(rowind, colind, reinterpret_cast<const T*>(vals), D.nnz,
+        D.d_pos.p, (int)D.n, D.d_front_of_pos.p, D.d_meta.p, D.d_upd.p, pool);
+    ++*D.launches;
+  }
+  factor_levels<C>(D);
+}
+
 void direct_numeric(DirectSolver& D, const int* rowind, const int* colind, const double* vals) {
   D.numeric_ms = timed(D.s, [&]() {
     if (D.cplx) numeric_impl<true>(D, rowind, colind, vals);
@@ -725,16 +771,17 @@ void direct_numeric(DirectSolver& D, const int* rowind, const int* colind, const
   });
 }
 
+// forward sweep: y = L^-1 b on the eliminated unknowns; g_keep (optional, accumulated into) receives
+// the update parts of the roots = -A_KE A_EE^-1 b_E
 template <bool C>
-static void solve_impl(DirectSolver& D, const double* b, double* x) {
+static void forward_impl(DirectSolver& D, const double* b, double* g_keep) {
   using T = typename Num<C>::T;
   cudaStream_t s = D.s;
   const T* pool = reinterpret_cast<const T*>(D.pool.p);
   T* w = reinterpret_cast<T*>(D.w.p);
   T* bp = reinterpret_cast<T*>(D.bp.p);
-  T* xp = reinterpret_cast<T*>(D.xp.p);
-  const unsigned vg = (unsigned)std::min<long long>((D.n + 255) / 256, (long long)D.nsm * 8);
-  permute_in<C><<<vg, 256, 0, s>>>(reinterpret_cast<const T*>(b), D.d_pos.p, bp, D.n);
+  const unsigned vg = (unsigned)std::min<long long>((D.n_total + 255) / 256, (long long)D.nsm * 8);
+  permute_in<C><<<vg, 256, 0, s>>>(reinterpret_cast<const T*>(b), D.d_pos.p, bp, D.n_total, (int)D.n);
   ++*D.launches;
   for (int L = 0; L < D.nlevels; ++L) {
     const int nfr = (int)D.level_lists[L].size();
@@ -750,6 +797,28 @@ static void solve_impl(DirectSolver& D, const double* b, double* x) {
       *D.launches += 2;
     }
   }
+  if (g_keep && D.n_keep > 0)
+    for (int f : D.roots) {
+      const FrontMeta& F = D.meta[f];
+      if (F.nf == F.np) continue;
+      add_root_rhs<C><<<(F.nf - F.np + 255) / 256, 256, 0, s>>>(F, D.d_upd.p, (int)D.n, w, reinterpret_cast<T*>(g_keep));
+      ++*D.launches;
+    }
+  CUDA_TRY(cudaGetLastError());
+}
+
+// backward sweep with known kept values x_keep (optional; zero when absent); x in original numbering
+template <bool C>
+static void backward_impl(DirectSolver& D, const double* x_keep, double* x) {
+  using T = typename Num<C>::T;
+  cudaStream_t s = D.s;
+  const T* pool = reinterpret_cast<const T*>(D.pool.p);
+  T* w = reinterpret_cast<T*>(D.w.p);
+  T* xp = reinterpret_cast<T*>(D.xp.p);
+  if (D.n_keep > 0) {
+    if (x_keep) CUDA_TRY(cudaMemcpyAsync(xp + D.n, x_keep, (size_t)D.n_keep * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    else CUDA_TRY(cudaMemsetAsync(xp + D.n, 0, (size_t)D.n_keep * sizeof(T), s));
+  }
   for (int L = D.nlevels - 1; L >= 0; --L) {
     const int nfr = (int)D.level_lists[L].size();
     const int* list = D.d_lists.p + D.list_off[L];
@@ -764,14 +833,79 @@ static void solve_impl(DirectSolver& D, const double* b, double* x) {
       *D.launches += 2;
     }
   }
-  permute_out<C><<<vg, 256, 0, s>>>(xp, D.d_pos.p, reinterpret_cast<T*>(x), D.n);
+  const unsigned vg = (unsigned)std::min<long long>((D.n_total + 255) / 256, (long long)D.nsm * 8);
+  permute_out<C><<<vg, 256, 0, s>>>(xp, D.d_pos.p, reinterpret_cast<T*>(x), D.n_total);
   ++*D.launches;
   CUDA_TRY(cudaGetLastError());
 }
 
+void direct_forward(DirectSolver& D, const double* b_dev, double* g_keep_dev) {
+  if (D.cplx) forward_impl<true>(D, b_dev, g_keep_dev);
+  else forward_impl<false>(D, b_dev, g_keep_dev);
+}
+void direct_backward(DirectSolver& D, const double* x_keep_dev, double* x_dev) {
+  if (D.cplx) backward_impl<true>(D, x_keep_dev, x_dev);
+  else backward_impl<false>(D, x_keep_dev, x_dev);
+}
 void direct_solve(DirectSolver& D, const double* b_dev, double* x_dev) {
-  if (D.cplx) solve_impl<true>(D, b_dev, x_dev);
-  else solve_impl<false>(D, b_dev, x_dev);
+  direct_forward(D, b_dev, nullptr);
+  direct_backward(D, nullptr, x_dev);
+}
+
+long long direct_nkeep(const DirectSolver& D) { return D.n_keep; }
+
+// S (n_keep x n_keep, row-major, accumulated into) += -A_KE A_EE^-1 A_EK after direct_numeric
+void direct_schur(DirectSolver& D, double* S_dev) {
+  for (int f : D.roots) {
+    const FrontMeta& F = D.meta[f];
+    const long long nu = F.nf - F.np;
+    if (nu == 0) continue;
+    const unsigned grid = (unsigned)std::min<long long>((nu * nu + 255) / 256, (long long)D.nsm * 16);
+    if (D.cplx) add_root_schur<true><<<grid, 256, 0, D.s>>>(F, D.d_upd.p, (int)D.n, (int)D.n_keep,
+                                                            reinterpret_cast<const double2*>(D.pool.p), reinterpret_cast<double2*>(S_dev));
+    else add_root_schur<false><<<grid, 256, 0, D.s>>>(F, D.d_upd.p, (int)D.n, (int)D.n_keep, D.pool.p, S_dev);
+    ++*D.launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+}
+
+// ---- one dense n x n system factorised with the front kernels (interface Schur complement) ----
+DirectPtr direct_dense(long long n, int is_complex, int nsm, cudaStream_t s, long long* launches) {
+  DirectPtr D(new DirectSolver());
+  D->n = n; D->n_total = n; D->n_keep = 0; D->nnz = 0; D->cplx = is_complex; D->nsm = nsm; D->s = s;
+  D->launches = launches; D->dense = true;
+  D->nfronts = 1; D->nlevels = 1; D->maxnf = (int)n;
+  FrontMeta M{};
+  M.off = 0; M.woff = 0; M.first = 0; M.np = (int)n; M.nf = (int)n; M.upd_ptr = 0; M.child[0] = M.child[1] = -1;
+  M.cmap_ptr = 0; M.parent = -1;
+  D->meta.assign(1, M);
+  D->level_lists.assign(1, std::vector<int>{0});
+  D->level_maxnp.assign(1, (int)n); D->level_maxnf.assign(1, (int)n); D->level_maxnu_child.assign(1, 0);
+  D->list_off.assign(1, 0);
+  D->roots.assign(1, 0);
+  D->pool_elems = n * n; D->w_elems = n;
+  D->fill = n * n; D->flops = (2.0 / 3.0) * (double)n * n * n;
+  std::vector<int> pos(n), zero1(1, 0);
+  std::iota(pos.begin(), pos.end(), 0);
+  D->d_meta.upload(D->meta.data(), 1, s);
+  D->d_pos.upload(pos.data(), n, s);
+  D->d_front_of_pos.alloc(1);
+  D->d_upd.upload(zero1.data(), 1, s);
+  D->d_cmap.alloc(1);
+  D->d_lists.upload(zero1.data(), 1, s);
+  const size_t sc = is_complex ? 2 : 1;
+  D->pool.alloc((size_t)n * n * sc);
+  D->w.alloc((size_t)n * sc); D->bp.alloc((size_t)n * sc); D->xp.alloc((size_t)n * sc);
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return D;
+}
+
+void direct_dense_factor(DirectSolver& D, const double* S_dev) {
+  const size_t sc = D.cplx ? 2 : 1;
+  D.numeric_ms = timed(D.s, [&]() {
+    CUDA_TRY(cudaMemcpyAsync(D.pool.p, S_dev, (size_t)D.n * D.n * sc * sizeof(double), cudaMemcpyDeviceToDevice, D.s));
+    if (D.cplx) factor_levels<true>(D); else factor_levels<false>(D);
+  });
 }
 
 void direct_info(const DirectSolver& D, double* out8) {

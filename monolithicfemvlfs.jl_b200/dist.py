@@ -243,6 +243,68 @@ class GpuOps:
     def fill_zero(self, x):
         x.zero_()
 
+    # -- substructuring (partial factorisation with a kept boundary) -------------------------
+    def set_roles(self, role):
+        r = np.ascontiguousarray(role, dtype=np.int8)
+        self.sys._check(self.lib.vlfs_set_roles(self.ctx, r.ctypes.data_as(C.POINTER(C.c_int8))))
+
+    def factor(self, **opts):
+        from . import _lib as L
+        self.sys.solver_setup(self.mat, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=2, maxit=2,
+                              rtol=1e-12, **opts)
+
+    def refactor(self):
+        self.sys.refactor(self.mat)
+
+    def schur_block(self, nk):
+        S = self.torch.zeros(nk * nk * self.sc, dtype=self.torch.float64, device=self.device)
+        self.sys._check(self.lib.vlfs_schur_get(self.ctx, self._p(S)))
+        return S
+
+    def schur_forward(self, b, g):
+        self.sys._check(self.lib.vlfs_schur_forward(self.ctx, self._p(b), self._p(g)))
+
+    def schur_backward(self, xk, x):
+        self.sys._check(self.lib.vlfs_schur_backward(self.ctx, self._p(xk), self._p(x)))
+
+    def dense_factor(self, n, S):
+        self.sys._check(self.lib.vlfs_dense_factor(self.ctx, n, self._p(S)))
+
+    def dense_solve(self, b, x):
+        self.sys._check(self.lib.vlfs_dense_solve(self.ctx, self._p(b), self._p(x)))
+
+    def vec(self, n):
+        return self.torch.zeros(n * self.sc, dtype=self.torch.float64, device=self.device)
+
+    def dense_from_host(self, a):
+        """complex/real 2-D NumPy array -> flat device tensor (row-major, interleaved)."""
+        a = np.ascontiguousarray(a, dtype=self.d.dtype)
+        return self.torch.from_numpy(a.reshape(-1).view(np.float64).copy()).to(self.device)
+
+    def add_block(self, S, n, idx, block, nb):
+        """S[idx,idx] += block for flat row-major S (n x n) and block (nb x nb)."""
+        t = self.torch
+        idx_t = t.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(self.device)
+        Sv = S.view(n, n, self.sc)
+        Sv.index_put_((idx_t[:, None], idx_t[None, :]), block.view(nb, nb, self.sc), accumulate=True)
+
+    def take(self, x, idx_t):
+        """entries idx of an interleaved vector -> new flat tensor."""
+        return x.view(-1, self.sc)[idx_t].reshape(-1).contiguous()
+
+    def put(self, x, idx_t, vals, accumulate=False):
+        xv = x.view(-1, self.sc)
+        if accumulate:
+            xv.index_add_(0, idx_t, vals.view(-1, self.sc))
+        else:
+            xv[idx_t] = vals.view(-1, self.sc)
+
+    def long_index(self, idx):
+        return self.torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(self.device)
+
+    def to_index_host(self, idx_t):
+        return idx_t.cpu().numpy()
+
     def empty_buf(self, count):
         return self.torch.empty(count * self.sc, dtype=self.torch.float64, device=self.device)
 
@@ -333,7 +395,7 @@ class Fleet:
     def norm(self, xs):
         return float(np.sqrt(abs(self.dots(xs, 1, xs)[0].real)))
 
-    def gmres(self, bs, xs, restart=50, maxit=500, rtol=1e-10, precond=True):
+    def gmres(self, bs, xs, restart=50, maxit=500, rtol=1e-10, precond=True, apply=None):
         """Right-preconditioned restarted GMRES with CGS2 on distributed vectors (lists with one
         device vector per local member).  Returns dict(iterations, rel_residual, converged)."""
         M = self.members
@@ -365,11 +427,14 @@ class Fleet:
             g = np.zeros(m_ + 1, dtype=dtype); g[0] = beta
             j = 0
             while j < m_ and it < maxit:
-                for mm, Vk, zz in zip(M, V, z):
-                    if precond:
-                        mm.ops.precond(row(Vk, j), zz)
-                    else:
-                        mm.ops.axpby(1.0, row(Vk, j), 0.0, zz)
+                if apply is not None:                      # e.g. SchurSolver.apply (exact)
+                    apply([row(Vk, j) for Vk in V], z)
+                else:
+                    for mm, Vk, zz in zip(M, V, z):
+                        if precond:
+                            mm.ops.precond(row(Vk, j), zz)
+                        else:
+                            mm.ops.axpby(1.0, row(Vk, j), 0.0, zz)
                 self.matvec(z, w)
                 h = self.dots(V, j + 1, w)
                 for mm, Vk, ww in zip(M, V, w):
@@ -410,9 +475,166 @@ class Fleet:
             for mm, Vk, ww, zz, x in zip(M, V, w, z, xs):        # x += M^-1 V y
                 mm.ops.fill_zero(ww)
                 mm.ops.gemv_sub(Vk, j, -y, ww)
-                if precond:
-                    mm.ops.precond(ww, zz)
-                else:
-                    mm.ops.axpby(1.0, ww, 0.0, zz)
+            if apply is not None:
+                apply(w, z)
+            for mm, ww, zz, x in zip(M, w, z, xs):
+                if apply is None:
+                    if precond:
+                        mm.ops.precond(ww, zz)
+                    else:
+                        mm.ops.axpby(1.0, ww, 0.0, zz)
                 mm.ops.axpby(1.0, zz, 1.0, x)
         return dict(iterations=it, rel_residual=rel, converged=rel <= rtol)
+
+
+# ---------------------------------------------------------------------------------------------
+# exact distributed solve: substructuring on the slab interfaces
+# ---------------------------------------------------------------------------------------------
+class SchurSolver:
+    """x = A^-1 b for the row-partitioned system, used as the (exact) preconditioner of
+    `Fleet.gmres` so that one or two iterations give the LU-quality solution:
+
+      * interface Γ = owned unknowns that a LOWER rank holds as ghosts (the first DOF layer of
+        every slab); the remaining owned unknowns I_r of different ranks do not couple;
+      * every rank factorises A[I_r,I_r] with the multifrontal LU keeping B_r = Γ_r ∪ (ghosts owned
+        by higher ranks) as a Schur boundary: the root fronts end with -A[B,I] A[I,I]^-1 A[I,B];
+      * rank 0 assembles S = A[Γ,Γ] + Σ_r blocks (a few thousand unknowns per cut), factorises it
+        densely with the same front kernels, and per application solves S x_Γ = b_Γ + Σ_r g_r with
+        the forward sweeps' boundary parts g_r; the backward sweeps finish x_I on every rank.
+    """
+
+    def __init__(self, fleet, mat=0):
+        self.fleet, self.mat = fleet, mat
+        F = fleet
+        # Γ_r: owned unknowns requested by lower ranks
+        infos = []
+        for m in F.members:
+            d = m.d
+            gam = np.zeros(d.n_local, dtype=bool)
+            for peer, idx in m.send.items():
+                if peer < m.rank:
+                    gam[np.asarray(m.ops.to_index_host(idx))] = True
+            role = np.full(d.n_local, 2, dtype=np.int8)
+            role[:d.n_owned] = 0
+            role[gam] = 1
+            higher = d.owner[d.ghosts] > m.rank
+            role[d.n_owned:][higher] = 1
+            m.role = role
+            m.keep_local = np.nonzero(role == 1)[0]                 # ascending local id
+            m.keep_gids = d.local_gids[m.keep_local]
+            m.gamma_local = np.nonzero(gam)[0]
+            infos.append((m.rank, d.local_gids[m.gamma_local]))
+        if F.dist is not None:
+            gathered = [None] * F.nranks
+            F.dist.all_gather_object(gathered, infos[0])
+            infos = gathered
+        gam_all = np.concatenate([g for _, g in sorted(infos, key=lambda t: t[0])]) if infos else np.zeros(0, int)
+        self.gamma = np.sort(gam_all)                                # global ids of the interface
+        self.ng = len(self.gamma)
+        for m in F.members:
+            m.keep_pos = np.searchsorted(self.gamma, m.keep_gids)    # position of B_r in Γ
+            assert np.array_equal(self.gamma[m.keep_pos], m.keep_gids)
+            m.gamma_pos = np.searchsorted(self.gamma, m.d.local_gids[m.gamma_local])
+            m.keep_t = m.ops.long_index(m.keep_local)
+            m.gamma_t = m.ops.long_index(m.gamma_local)
+            m.ops.set_roles(m.role)
+        self.root = F.by_rank.get(0)
+
+    # gather variable-size device vectors of every rank on rank 0 (list indexed by rank) ------
+    def _gather(self, parts, sizes):
+        F = self.fleet
+        if F.dist is None:
+            return {m.rank: p for m, p in zip(F.members, parts)}
+        import torch
+        m = F.members[0]
+        out = {}
+        if m.rank == 0:
+            out[0] = parts[0]
+            reqs = []
+            for r in range(1, F.nranks):
+                buf = m.ops.vec(sizes[r])
+                out[r] = buf
+                reqs.append(F.dist.irecv(m.ops.as_tensor(buf), src=r))
+            for q in reqs:
+                q.wait()
+        else:
+            F.dist.send(m.ops.as_tensor(parts[0]), dst=0)
+        return out
+
+    def setup(self):
+        F = self.fleet
+        for m in F.members:
+            m.ops.factor()
+        self._assemble_interface()
+
+    def refactor(self):
+        for m in self.fleet.members:
+            m.ops.refactor()
+        self._assemble_interface()
+
+    def _assemble_interface(self):
+        F = self.fleet
+        nks = {m.rank: len(m.keep_local) for m in F.members}
+        pos = {m.rank: m.keep_pos for m in F.members}
+        agg = []
+        for m in F.members:
+            # A[Γ_r rows, Γ columns] from the owner's complete rows (host CSR, setup only)
+            A = m.d.local.get_matrix(self.mat)[m.gamma_local]
+            cols_g = m.d.local_gids[A.indices]
+            inG = np.isin(cols_g, self.gamma)
+            rows = np.repeat(m.gamma_pos, np.diff(A.indptr))[inG]
+            cols = np.searchsorted(self.gamma, cols_g[inG])
+            agg.append((rows, cols, A.data[inG]))
+        if F.dist is not None:
+            meta = [None] * F.nranks
+            F.dist.all_gather_object(meta, (nks[F.members[0].rank], pos[F.members[0].rank], agg[0]))
+            nks = {r: meta[r][0] for r in range(F.nranks)}
+            pos = {r: meta[r][1] for r in range(F.nranks)}
+            agg = [meta[r][2] for r in range(F.nranks)]
+        self.nks, self.pos = nks, pos
+        blocks = [m.ops.schur_block(len(m.keep_local)) for m in F.members]
+        sc = 2 if F.members[0].d.is_complex else 1
+        got = self._gather(blocks, {r: nks[r] * nks[r] for r in nks})
+        if self.root is not None:
+            ops = self.root.ops
+            S = ops.vec(self.ng * self.ng)
+            dense = np.zeros((self.ng, self.ng), dtype=self.root.d.dtype)
+            for rows, cols, vals in agg:
+                np.add.at(dense, (rows, cols), vals)
+            S += ops.dense_from_host(dense)
+            for r, blk in got.items():
+                ops.add_block(S, self.ng, pos[r], blk, nks[r])
+            ops.dense_factor(self.ng, S)
+            self.xg = ops.vec(self.ng)
+            self.gg = ops.vec(self.ng)
+            self.pos_t = {r: ops.long_index(pos[r]) for r in pos}
+        else:
+            m = F.members[0]
+            self.xg = m.ops.vec(self.ng)
+
+    def apply(self, rs, zs):
+        """zs = A^-1 rs on distributed vectors (one device vector per local member)."""
+        F = self.fleet
+        gs = []
+        for m, r in zip(F.members, rs):
+            g = m.ops.vec(len(m.keep_local))
+            m.ops.schur_forward(r, g)                               # g = -A[B,I] A[I,I]^-1 r_I
+            # b_Γ part: the owner adds its own right-hand-side entries
+            own = m.ops.take(r, m.gamma_t)
+            full = m.ops.vec(len(m.keep_local))
+            k_of_gamma = np.searchsorted(m.keep_local, m.gamma_local)
+            m.ops.put(full, m.ops.long_index(k_of_gamma), own)
+            g += full
+            gs.append(g)
+        got = self._gather(gs, self.nks)
+        if self.root is not None:
+            ops = self.root.ops
+            ops.fill_zero(self.gg)
+            for r, g in got.items():
+                ops.put(self.gg, self.pos_t[r], g, accumulate=True)
+            ops.dense_solve(self.gg, self.xg)
+        if F.dist is not None:
+            F.dist.broadcast(F.members[0].ops.as_tensor(self.xg), src=0)
+        for m, z in zip(F.members, zs):          # (in-process fleets share one device)
+            xk = m.ops.take(self.xg, m.ops.long_index(m.keep_pos))
+            m.ops.schur_backward(xk, z)

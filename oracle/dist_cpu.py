@@ -24,6 +24,9 @@ class CpuLocalSystem(RecordingSystem):
     def get_vector(self, vec=0):
         return self.vecs[vec]
 
+    def get_matrix(self, mat=0):
+        return self.mats[mat].tocsr()
+
 
 class CpuOps:
     def __init__(self, dsys, mat=0):
@@ -85,3 +88,61 @@ class CpuOps:
 
     def sync(self):
         pass
+
+    # -- substructuring twin -----------------------------------------------------------------
+    def set_roles(self, role):
+        self.role = np.asarray(role)
+        self.E = np.nonzero(self.role == 0)[0]
+        self.K = np.nonzero(self.role == 1)[0]
+
+    def factor(self, **_):
+        Afull = self.sys.mats[0].tocsr()
+        self.AEE = spla.splu(Afull[self.E][:, self.E].tocsc())
+        self.AKE = Afull[self.K][:, self.E]
+        self.AEK = Afull[self.E][:, self.K]
+
+    refactor = factor
+
+    def schur_block(self, nk):
+        X = self.AEE.solve(self.AEK.toarray().astype(self.d.dtype))
+        return (-(self.AKE @ X)).reshape(-1)
+
+    def schur_forward(self, b, g):
+        self._bE = np.array(b[self.E])
+        g += -(self.AKE @ self.AEE.solve(self._bE))
+
+    def schur_backward(self, xk, x):
+        x[self.E] = self.AEE.solve(self._bE - self.AEK @ xk)
+        x[self.K] = xk
+
+    def dense_factor(self, n, S):
+        import scipy.linalg as sla
+        self._dense = sla.lu_factor(np.asarray(S).reshape(n, n))
+
+    def dense_solve(self, b, x):
+        import scipy.linalg as sla
+        x[...] = sla.lu_solve(self._dense, b)
+
+    def vec(self, n):
+        return np.zeros(n, dtype=self.d.dtype)
+
+    def dense_from_host(self, a):
+        return np.asarray(a, dtype=self.d.dtype).reshape(-1).copy()
+
+    def add_block(self, S, n, idx, block, nb):
+        S.reshape(n, n)[np.ix_(idx, idx)] += np.asarray(block).reshape(nb, nb)
+
+    def take(self, x, idx):
+        return np.array(x[idx])
+
+    def put(self, x, idx, vals, accumulate=False):
+        if accumulate:
+            np.add.at(x, idx, vals)
+        else:
+            x[idx] = vals
+
+    def long_index(self, idx):
+        return np.asarray(idx, dtype=np.int64)
+
+    def to_index_host(self, idx):
+        return np.asarray(idx)

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 KW = dict(nx=2, ny=1, nz=2, order=4, lfactor=0.6, dfactor=4)
 
 
-def _fleet(nranks):
+def _fleet(nranks, block_lu=True):
     from vlfs_b200 import dist as D, _lib as L
     from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
     members, probs = [], []
@@ -22,7 +22,8 @@ def _fleet(nranks):
         ops = D.GpuOps(prob.sys)
         ops.bind_stream()
         prob.assemble()
-        prob.sys.local.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=2, maxit=2, rtol=1e-12)
+        if block_lu:
+            prob.sys.local.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=2, maxit=2, rtol=1e-12)
         members.append(D.Member(prob.sys, ops))
         probs.append(prob)
     return D.Fleet(members, nranks), members, probs
@@ -71,6 +72,27 @@ def test_distributed_gmres_block_lu(nranks, reference):
     st = fleet.gmres(bs, xs, restart=80, maxit=400, rtol=1e-11)
     print(nranks, st)
     assert st["converged"], st
+    x = np.zeros(len(b), dtype=complex)
+    for m, xl in zip(members, xs):
+        m.d.scatter_owned(m.ops.to_host(xl), x)
+    xr = lu_reference(A, b)
+    assert np.linalg.norm(x - xr) <= 1e-8 * np.linalg.norm(xr)
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_substructuring_exact_solve(nranks, reference):
+    """Partial multifrontal factorisations with a kept interface + dense interface LU: one
+    application is the LU-quality solution; as GMRES preconditioner it converges at once."""
+    from vlfs_b200 import dist as D
+    A, b = reference
+    fleet, members, probs = _fleet(nranks, block_lu=False)
+    schur = D.SchurSolver(fleet)
+    schur.setup()
+    bs = [m.ops.rhs_vector() for m in members]
+    xs = [m.ops.zeros() for m in members]
+    st = fleet.gmres(bs, xs, restart=6, maxit=6, rtol=1e-11, apply=schur.apply)
+    print(nranks, "interface", schur.ng, st)
+    assert st["converged"] and st["iterations"] <= 3, st
     x = np.zeros(len(b), dtype=complex)
     for m, xl in zip(members, xs):
         m.d.scatter_owned(m.ops.to_host(xl), x)
