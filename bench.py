@@ -339,24 +339,32 @@ def run_ours_distributed(args):
 
     solve = None
     if not args.no_solve:
+        # exact distributed solve: per-rank partial multifrontal LU (interface kept), dense interface
+        # LU on rank 0, used as the preconditioner of distributed GMRES (1-2 refinement iterations)
         t0 = time.time()
-        S.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=2, maxit=2, rtol=1e-10)
+        schur = D.SchurSolver(fleet)
+        schur.setup()
         torch.cuda.synchronize()
         first_s = allmax(time.time() - t0)
         info = S.direct_info()
         bs, x0 = [ops.rhs_vector()], [ops.zeros()]
         barrier()
         t0 = time.time()
-        S.refactor(0)
-        # full (unrestarted) GMRES, bounded: block-Jacobi without overlap degrades with mesh
-        # refinement; the flag says whether 1e-9 was reached
-        st = fleet.gmres(bs, x0, restart=args.dist_maxit, maxit=args.dist_maxit, rtol=1e-9)
+        schur.refactor()
         torch.cuda.synchronize()
+        factor_s = allmax(time.time() - t0)
+        t1 = time.time()
+        st = fleet.gmres(bs, x0, restart=8, maxit=8, rtol=1e-10, apply=schur.apply, stagnation=0.25)
+        torch.cuda.synchronize()
+        gm_s = allmax(time.time() - t1)
         step_s = allmax(time.time() - t0)
-        solve = {"s_per_step": step_s, "first_setup_s": first_s, "symbolic_ms": info["symbolic_ms"],
-                 "numeric_ms": info["numeric_ms"], "gmres_iterations": st["iterations"],
-                 "rel_residual": st["rel_residual"], "converged": st["converged"],
-                 "method": "GMRES + block-Jacobi (per-rank multifrontal LU of the owned block)",
+        solve = {"s_per_step": step_s, "first_setup_s": first_s, "refactor_s": factor_s, "gmres_s": gm_s,
+                 "symbolic_ms": info["symbolic_ms"], "numeric_ms": info["numeric_ms"],
+                 "gmres_iterations": st["iterations"], "rel_residual": st["rel_residual"],
+                 "converged": st["converged"], "stagnated_at_attainable_accuracy": st["stagnated"],
+                 "interface_unknowns": int(schur.ng),
+                 "method": "substructuring: per-rank partial multifrontal LU + dense interface LU on rank 0, "
+                           "as preconditioner of distributed GMRES",
                  "max_front": info["maxfront"]}
 
     # end to end through host buffers (rank-local): H2D fields, assemble, D2H local values + rhs

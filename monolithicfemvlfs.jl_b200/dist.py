@@ -395,7 +395,7 @@ class Fleet:
     def norm(self, xs):
         return float(np.sqrt(abs(self.dots(xs, 1, xs)[0].real)))
 
-    def gmres(self, bs, xs, restart=50, maxit=500, rtol=1e-10, precond=True, apply=None):
+    def gmres(self, bs, xs, restart=50, maxit=500, rtol=1e-10, precond=True, apply=None, stagnation=None):
         """Right-preconditioned restarted GMRES with CGS2 on distributed vectors (lists with one
         device vector per local member).  Returns dict(iterations, rel_residual, converged)."""
         M = self.members
@@ -412,14 +412,20 @@ class Fleet:
             return dict(iterations=0, rel_residual=0.0, converged=True)
         it, rel = 0, 1.0
         dtype = M[0].d.dtype
+        # stagnation=f: with an exact preconditioner every iteration is a refinement step; stop
+        # when one gains less than a factor 1/f (attainable accuracy eps*|A||x|/|b| reached)
+        stalled, prev_cycle = False, np.inf
         while True:
             self.matvec(xs, r)                                   # r = b - A x
             for mm, rr, b in zip(M, r, bs):
                 mm.ops.axpby(1.0, b, -1.0, rr)
             beta = self.norm(r)
             rel = beta / bnorm
-            if rel <= rtol or it >= maxit:
+            if rel <= rtol or it >= maxit or stalled:
                 break
+            if stagnation and rel > stagnation * prev_cycle:
+                break
+            prev_cycle = rel
             for mm, Vk, rr in zip(M, V, r):
                 mm.ops.axpby(1.0 / beta, rr, 0.0, row(Vk, 0))
             H = np.zeros((m_ + 1, m_), dtype=dtype)
@@ -464,10 +470,14 @@ class Fleet:
                 g[j + 1] = -np.conj(sn[j]) * g[j]
                 g[j] = cs[j] * g[j]
                 H[:j + 2, j] = col[:j + 2]
+                prev = rel
                 rel = abs(g[j + 1]) / bnorm
                 j += 1
                 it += 1
                 if rel <= rtol or hn == 0.0:
+                    break
+                if stagnation and j >= 2 and rel > stagnation * prev:
+                    stalled = True
                     break
             y = np.zeros(j, dtype=dtype)
             for k in range(j - 1, -1, -1):
@@ -484,7 +494,7 @@ class Fleet:
                     else:
                         mm.ops.axpby(1.0, ww, 0.0, zz)
                 mm.ops.axpby(1.0, zz, 1.0, x)
-        return dict(iterations=it, rel_residual=rel, converged=rel <= rtol)
+        return dict(iterations=it, rel_residual=rel, converged=rel <= rtol, stagnated=bool(stalled))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -19,9 +19,10 @@ mk = lambda *a, **k: D.DistributedSystem(*a, rank=rank, nranks=world, **{**k, "d
 prob = YagoProblem(Yago_freq_domain_params(**kw), device=local, system_cls=mk)
 ops = D.GpuOps(prob.sys); ops.bind_stream()
 prob.assemble()
-prob.sys.local.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=2, maxit=2, rtol=1e-12)
 member = D.Member(prob.sys, ops)
 fleet = D.Fleet([member], world, dist=dist)
+schur = D.SchurSolver(fleet)
+schur.setup()
 N = prob.sys.ndofs_global
 # SpMV
 x = np.sin(0.1 * np.arange(N)) + 1j * np.cos(0.1 * np.arange(N))
@@ -31,7 +32,7 @@ fleet.matvec(xs, ys)
 y_owned = ops.to_host(ys[0])[:prob.sys.n_owned]
 # solve
 bs, x0 = [ops.rhs_vector()], [ops.zeros()]
-st = fleet.gmres(bs, x0, restart=100, maxit=400, rtol=1e-11)
+st = fleet.gmres(bs, x0, restart=8, maxit=8, rtol=1e-11, apply=schur.apply)
 x_owned = ops.to_host(x0[0])[:prob.sys.n_owned]
 gathered = [None] * world
 dist.all_gather_object(gathered, (prob.sys.owned, y_owned, x_owned))
@@ -46,7 +47,7 @@ if rank == 0:
         y[owned] = yo; xd[owned] = xo
     out = dict(world=world, N=N, spmv_err=float(np.abs(y - yr).max() / np.abs(yr).max()),
                solve_err=float(np.linalg.norm(xd - xr) / np.linalg.norm(xr)), gmres=st,
-               halo_bytes=fleet.halo_bytes)
+               halo_bytes=fleet.halo_bytes, interface_unknowns=int(schur.ng))
     print(json.dumps(out))
     assert out["spmv_err"] <= 1e-12 and out["solve_err"] <= 1e-8, out
 dist.destroy_process_group()
