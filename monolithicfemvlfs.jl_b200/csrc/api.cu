@@ -4,14 +4,27 @@
 #include "common.cuh"
 #include "solver.cuh"
 #include <cstring>
+#include <cstdlib>
 #include <memory>
 #include <array>
+#include <map>
+#include <cmath>
 
 void build_pattern_device(const std::vector<DomainDev>& doms, long long ndofs,
                           DevBuf<int>& rowptr, DevBuf<int>& colind, DevBuf<int>& rowind,
                           DevBuf<int>& dest_all, std::vector<long long>& dest_off,
+                          DevBuf<uint32_t>& perm_out, DevBuf<uint32_t>& run_start,
                           long long* nnz_out, long long* ncoo_out, cudaStream_t s,
                           long long* launches);
+void launch_cell_geometry(const DomainDev& dom, int want_gradgrad, double* out, cudaStream_t s);
+void launch_mass_reference(const double* valA, int ndA, const double* valB, int ndB, const double* qw, int nq,
+                           double* T, cudaStream_t s);
+void launch_build_class_tables(const GatherDom* doms, int d, long long work, int nmat, int is_complex, cudaStream_t s);
+void launch_pack_gather_records(const uint32_t* perm, long long ncoo, const GatherDom* doms, int ndom,
+                                unsigned long long* rec, cudaStream_t s);
+void launch_gather_reference(const uint32_t* run_start, const unsigned long long* rec, long long nnz,
+                             const GatherDom* doms, int ndom, int nrp_total, long long tab_total,
+                             double* const* mats, int nmat, int is_complex, int nsm, cudaStream_t s);
 void build_csc_device(const int* rowind, const int* colind, long long nnz, long long ndofs,
                       DevBuf<int>& colptr, DevBuf<int>& rowval, DevBuf<int>& csr_slot,
                       cudaStream_t s, long long* launches);
@@ -60,7 +73,18 @@ struct Domain {
   std::vector<vlfs_rhs_desc> rhs;
   std::vector<TermDev> terms_host;
   std::vector<RhsDev> rhs_host;
-  std::vector<char> term_fast;      // handled by the reference-matrix fast path
+  std::vector<char> term_fast;      // 0 general (cell-centric kernel), 1 grad.grad reference, 2 mass reference
+  std::vector<RefProd> refprods_host;   // grouped by block
+  std::vector<int> refprod_term;        // source term of every RefProd (coefficient refresh)
+  std::vector<double> refprod_scale;    // its slot scales
+  int rp_first[VLFS_MAX_BLOCKS + 1] = {0, 0, 0, 0, 0};
+  DevBuf<RefProd> refprods_dev;
+  DevBuf<double> reftabs, cellgeo;
+  int ncls = 0;                         // geometry classes (0: per-cell factors)
+  DevBuf<int> cls;
+  DevBuf<double> cls_geo, ctab;
+  long long ctab_off[VLFS_MAX_BLOCKS] = {0, 0, 0, 0};
+  long long ctab_work = 0;
   DevBuf<RhsDev> rhs_dev;
   std::vector<TileTarget> targets_host;
   std::vector<TileProd> prods_host;
@@ -86,6 +110,11 @@ struct vlfs_ctx {
   bool pattern_built = false;
   long long nnz = 0, ncoo = 0;
   DevBuf<int> rowptr, colind, rowind, dest_all;
+  DevBuf<uint32_t> perm, run_start;     // sorted COO order and first sorted entry of every slot
+  DevBuf<unsigned long long> gather_rec;   // packed (domain, block, local entry, cell) per sorted entry
+  int nrp_total = 0;
+  long long tab_total = 0;
+  DevBuf<GatherDom> gather_doms;
   std::vector<long long> dest_off;
   std::vector<DevBuf<double>> mats, vecs;
   long long launches = 0;
@@ -193,6 +222,106 @@ void build_tile_tables(vlfs_ctx* ctx, Domain& d) {
   dev.prods = d.prods_dev.p;
 }
 
+// reference products per block, their tables and the per-cell geometric factors
+void build_reference_products(vlfs_ctx* ctx, Domain& d) {
+  DomainDev& dev = d.dev;
+  const int D = dev.D, NS = D * (D + 1) / 2;
+  d.refprods_host.clear(); d.refprod_term.clear(); d.refprod_scale.clear();
+  std::vector<std::array<long long, 4>> mass_tabs;     // (slot s, slot u, offset) of built mass tables
+  long long tab_len = 0, gg_off = -1;
+  bool want_gg = false;
+  for (int b = 0; b < dev.nblocks; ++b) {
+    d.rp_first[b] = (int)d.refprods_host.size();
+    const BlockDev& B = dev.blk[b];
+    for (size_t t = 0; t < d.terms.size(); ++t) {
+      const vlfs_term_desc& T = d.terms[t];
+      if (!d.term_fast[t] || T.test_scale[B.ts] == 0.0 || T.trial_scale[B.us] == 0.0) continue;
+      RefProd P{};
+      P.mat = T.mat;
+      const double sc = T.test_scale[B.ts] * T.trial_scale[B.us];
+      P.cre = T.coef_re * sc; P.cim = T.coef_im * sc;
+      if (d.term_fast[t] == 1) {
+        if (gg_off < 0) { gg_off = tab_len; tab_len += (long long)NS * B.nr * B.nc; }
+        P.ntab = NS; P.geo_idx = 1; P.tab_off = gg_off; want_gg = true;
+      } else {
+        long long off = -1;
+        for (auto& m : mass_tabs) if (m[0] == B.ts && m[1] == B.us) off = m[2];
+        if (off < 0) { off = tab_len; tab_len += (long long)B.nr * B.nc; mass_tabs.push_back({B.ts, B.us, off, 0}); }
+        P.ntab = 1; P.geo_idx = 0; P.tab_off = off;
+      }
+      d.refprods_host.push_back(P);
+      d.refprod_term.push_back((int)t);
+      d.refprod_scale.push_back(sc);
+    }
+  }
+  d.rp_first[dev.nblocks] = (int)d.refprods_host.size();
+  for (int b = dev.nblocks + 1; b <= VLFS_MAX_BLOCKS; ++b) d.rp_first[b] = d.rp_first[dev.nblocks];
+  if (d.refprods_host.empty()) return;
+  d.reftabs.alloc((size_t)tab_len);
+  if (gg_off >= 0) { launch_gradgrad_reference(dev, d.reftabs.p + gg_off, ctx->stream); ++ctx->launches; }
+  for (auto& m : mass_tabs) {
+    const SlotDev& A = dev.slot[m[0]];
+    const SlotDev& Bs = dev.slot[m[1]];
+    launch_mass_reference(A.val, A.ndofs, Bs.val, Bs.ndofs, dev.qweights, dev.nq, d.reftabs.p + m[2], ctx->stream);
+    ++ctx->launches;
+  }
+  d.cellgeo.alloc((size_t)dev.ncells * VLFS_CELLGEO);
+  launch_cell_geometry(dev, want_gg ? 1 : 0, d.cellgeo.p, ctx->stream);
+  ++ctx->launches;
+  d.refprods_dev.upload(d.refprods_host.data(), d.refprods_host.size(), ctx->stream);
+  // geometry classes: cells with bitwise identical factors share one tabulated element block
+  {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    std::vector<double> hg((size_t)dev.ncells * VLFS_CELLGEO);
+    CUDA_TRY(cudaMemcpy(hg.data(), d.cellgeo.p, hg.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    // factors are compared after rounding to 2^-46 of the largest magnitude of their component:
+    // cells of a Cartesian mesh differ only by the round-off of their Jacobians (~1e-16), far
+    // below the 1e-12 entry tolerance; every member uses its class representative's factors
+    std::map<std::array<long long, VLFS_CELLGEO>, int> classes;
+    std::vector<int> cls((size_t)dev.ncells);
+    std::vector<double> cg;
+    const int max_cls = 512;
+    bool ok = true;
+    double gmax[VLFS_CELLGEO];
+    for (int k = 0; k < VLFS_CELLGEO; ++k) gmax[k] = 0.0;
+    for (long long e = 0; e < dev.ncells; ++e)
+      for (int k = 0; k < VLFS_CELLGEO; ++k) gmax[k] = std::max(gmax[k], std::fabs(hg[(size_t)e * VLFS_CELLGEO + k]));
+    // the grad.grad factors share one scale (off-diagonal components of boxes are pure round-off)
+    for (int k = 2; k < VLFS_CELLGEO; ++k) gmax[1] = std::max(gmax[1], gmax[k]);
+    for (int k = 2; k < VLFS_CELLGEO; ++k) gmax[k] = gmax[1];
+    for (long long e = 0; e < dev.ncells && ok; ++e) {
+      std::array<long long, VLFS_CELLGEO> key;
+      for (int k = 0; k < VLFS_CELLGEO; ++k)
+        key[k] = gmax[k] > 0 ? std::llround(hg[(size_t)e * VLFS_CELLGEO + k] / gmax[k] * 70368744177664.0) : 0;
+      auto it = classes.find(key);
+      if (it == classes.end()) {
+        if ((int)classes.size() >= max_cls) { ok = false; break; }
+        it = classes.emplace(key, (int)classes.size()).first;
+        cg.insert(cg.end(), hg.begin() + (size_t)e * VLFS_CELLGEO, hg.begin() + (size_t)(e + 1) * VLFS_CELLGEO);
+      }
+      cls[e] = it->second;
+    }
+    d.ncls = ok ? (int)classes.size() : 0;
+    if (getenv("VLFS_DEBUG")) fprintf(stderr, "[vlfs] domain: %lld cells, %d reference products, %d geometry classes\n",
+                                      (long long)dev.ncells, (int)d.refprods_host.size(), d.ncls);
+    if (d.ncls > 0) {
+      d.cls.upload(cls.data(), cls.size(), ctx->stream);
+      d.cls_geo.upload(cg.data(), cg.size(), ctx->stream);
+      long long off = 0;
+      d.ctab_work = 0;
+      const long long per = (long long)ctx->nmat * (ctx->is_complex ? 2 : 1);
+      for (int b = 0; b < dev.nblocks; ++b) {
+        d.ctab_off[b] = off;
+        if (d.rp_first[b + 1] > d.rp_first[b]) {
+          off += (long long)d.ncls * dev.blk[b].nr * dev.blk[b].nc * per;
+          d.ctab_work = std::max(d.ctab_work, (long long)d.ncls * dev.blk[b].nr * dev.blk[b].nc);
+        }
+      }
+      d.ctab.alloc((size_t)off);
+    }
+  }
+}
+
 // derive operator instances, touched blocks, shared-memory layout, device term tables
 void finalize_domain(vlfs_ctx* ctx, Domain& d) {
   DomainDev& dev = d.dev;
@@ -206,12 +335,21 @@ void finalize_domain(vlfs_ctx* ctx, Domain& d) {
     const vlfs_term_desc& T = d.terms[t];
     int nslots_t = 0, nslots_u = 0;
     for (int s = 0; s < dev.nslots; ++s) { nslots_t += T.test_scale[s] != 0.0; nslots_u += T.trial_scale[s] != 0.0; }
-    // (single-contribution slots are written with plain stores, so one slot must never be
-    // fed by two kernels: the fast path needs the domain to itself)
-    bool fast = d.terms.size() == 1 && dev.affine && T.weight < 0 && T.test_op == VLFS_OP_GRAD && T.trial_op == VLFS_OP_GRAD &&
-                dev.nslots == 1 && dev.slot[0].dref == D && dev.slot[0].nvar == 1 &&
-                dev.slot[0].ndofs * dev.slot[0].ndofs <= 1024;
-    d.term_fast[t] = fast;
+    // reference-type terms (constant-Jacobian cells, no coefficient field): the entry is a
+    // per-cell geometric factor times a cell-independent reference matrix; they are evaluated by
+    // the slot-centric gather pass instead of the cell-centric kernel
+    int fast = 0;
+    if (dev.affine && T.weight < 0) {
+      if (T.test_op == VLFS_OP_GRAD && T.trial_op == VLFS_OP_GRAD && dev.nslots == 1 &&
+          dev.slot[0].dref == D && dev.slot[0].nvar == 1 && dev.measure_kind == VLFS_MEASURE_CELL)
+        fast = 1;
+      else if (T.test_op == VLFS_OP_VAL && T.trial_op == VLFS_OP_VAL) {
+        fast = 2;
+        for (int s = 0; s < dev.nslots; ++s)
+          if ((T.test_scale[s] != 0.0 || T.trial_scale[s] != 0.0) && dev.slot[s].variant) fast = 0;
+      }
+    }
+    d.term_fast[t] = (char)fast;
     TermDev td{};
     td.mat = T.mat; td.weight = T.weight; td.cre = T.coef_re; td.cim = T.coef_im;
     td.ncomp = op_ncomp(T.test_op, D);
@@ -325,14 +463,7 @@ void finalize_domain(vlfs_ctx* ctx, Domain& d) {
     throw std::string("domain needs more than 227 KB of shared memory per cell");
   build_tile_tables(ctx, d);
   d.rhs_dev.upload(d.rhs_host.data(), d.rhs_host.size(), ctx->stream);
-  bool any_fast = false;
-  for (char f : d.term_fast) any_fast |= f != 0;
-  if (any_fast && d.Sref.n == 0) {
-    int nd = dev.slot[0].ndofs, ns = D * (D + 1) / 2;
-    d.Sref.alloc((size_t)ns * nd * nd);
-    launch_gradgrad_reference(dev, d.Sref.p, ctx->stream);
-    ++ctx->launches;
-  }
+  build_reference_products(ctx, d);
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   d.finalized = true;
   d.coef_dirty = false;
@@ -353,6 +484,15 @@ void refresh_coefs(vlfs_ctx* ctx, Domain& d) {
   }
   build_tile_tables(ctx, d);
   d.rhs_dev.upload(d.rhs_host.data(), d.rhs_host.size(), ctx->stream);
+  if (!d.refprods_host.empty()) {                 // in place: gather_doms holds this pointer
+    for (size_t k = 0; k < d.refprods_host.size(); ++k) {
+      const vlfs_term_desc& T = d.terms[d.refprod_term[k]];
+      d.refprods_host[k].cre = T.coef_re * d.refprod_scale[k];
+      d.refprods_host[k].cim = T.coef_im * d.refprod_scale[k];
+    }
+    CUDA_TRY(cudaMemcpyAsync(d.refprods_dev.p, d.refprods_host.data(), d.refprods_host.size() * sizeof(RefProd),
+                             cudaMemcpyHostToDevice, ctx->stream));
+  }
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   d.coef_dirty = false;
 }
@@ -374,15 +514,27 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   std::vector<double*> mp, vp;
   for (auto& m : ctx->mats) mp.push_back(m.p);
   for (auto& v : ctx->vecs) vp.push_back(v.p);
+  for (auto& dp : ctx->doms) refresh_coefs(ctx, *dp);
   {
-    ProfScope ps(ctx, "memset");
-    if (do_mat) for (auto& m : ctx->mats) m.zero(s);
+    // slot-centric pass: writes every CSR value (zero fill included) with the reference-type
+    // contributions summed in COO order; the cell-centric kernels then add the rest
+    ProfScope ps(ctx, "gather_reference");
+    if (do_mat) {
+      for (size_t di = 0; di < ctx->doms.size(); ++di)
+        if (ctx->doms[di]->ncls > 0) {
+          launch_build_class_tables(ctx->gather_doms.p, (int)di, ctx->doms[di]->ctab_work, ctx->nmat,
+                                    ctx->is_complex, s);
+          ++ctx->launches;
+        }
+      launch_gather_reference(ctx->run_start.p, ctx->gather_rec.p, ctx->nnz, ctx->gather_doms.p,
+                              (int)ctx->doms.size(), ctx->nrp_total, ctx->tab_total, mp.data(), (int)mp.size(),
+                              ctx->is_complex, ctx->nsm, s);
+      ++ctx->launches;
+    }
     if (do_vec) for (auto& v : ctx->vecs) v.zero(s);
   }
   for (size_t di = 0; di < ctx->doms.size(); ++di) {
     Domain& d = *ctx->doms[di];
-    refresh_coefs(ctx, d);
-    const int* dest = ctx->dest_all.p + ctx->dest_off[di];
     bool gen_mat = do_mat && !d.terms_host.empty();
     bool gen_vec = do_vec && !d.rhs_host.empty();
     if (gen_mat || gen_vec) {
@@ -392,16 +544,6 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
                        gen_mat, gen_vec, ctx->nsm, s);
       ++ctx->launches;
     }
-    if (do_mat)
-      for (size_t t = 0; t < d.terms.size(); ++t)
-        if (d.term_fast[t]) {
-          const vlfs_term_desc& T = d.terms[t];
-          ProfScope ps(ctx, "gradgrad_affine:dom" + std::to_string(di));
-          launch_gradgrad_affine(d.dev, d.Sref.p, dest, ctx->mats[T.mat].p, ctx->is_complex,
-                                 T.coef_re * T.test_scale[0] * T.trial_scale[0],
-                                 T.coef_im * T.test_scale[0] * T.trial_scale[0], ctx->nsm, s);
-          ++ctx->launches;
-        }
   }
 }
 
@@ -625,7 +767,33 @@ int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
     for (auto& d : ctx->doms) { finalize_domain(ctx, *d); devs.push_back(d->dev); }
     long long n1 = 0, n2 = 0;
     build_pattern_device(devs, ctx->ndofs, ctx->rowptr, ctx->colind, ctx->rowind, ctx->dest_all,
-                         ctx->dest_off, &n1, &n2, ctx->stream, &ctx->launches);
+                         ctx->dest_off, ctx->perm, ctx->run_start, &n1, &n2, ctx->stream, &ctx->launches);
+    {
+      std::vector<GatherDom> gd(ctx->doms.size());
+      for (size_t di = 0; di < ctx->doms.size(); ++di) {
+        Domain& d = *ctx->doms[di];
+        GatherDom& G = gd[di];
+        G.coo_lo = ctx->dest_off[di];
+        G.coo_hi = G.coo_lo + d.dev.ncells * (long long)d.dev.entries_per_cell;
+        G.epc = d.dev.entries_per_cell > 0 ? d.dev.entries_per_cell : 1;
+        G.nblocks = d.dev.nblocks;
+        for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) G.blk[b] = d.dev.blk[b];
+        for (int b = 0; b <= VLFS_MAX_BLOCKS; ++b) G.rp_first[b] = d.rp_first[b];
+        G.rp = d.refprods_dev.p; G.geo = d.cellgeo.p; G.tabs = d.reftabs.p; G.tab_len = (int)d.reftabs.n;
+        G.ncls = d.ncls; G.cls = d.cls.p; G.cls_geo = d.cls_geo.p; G.ctab = d.ctab.p;
+        for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) G.ctab_off[b] = d.ctab_off[b];
+      }
+      ctx->gather_doms.upload(gd.data(), gd.size(), ctx->stream);
+      ctx->nrp_total = 0;
+      ctx->tab_total = 0;
+      for (auto& d : ctx->doms) { ctx->nrp_total += (int)d->refprods_host.size(); ctx->tab_total += (long long)d->reftabs.n; }
+      if ((int)ctx->doms.size() > 16) throw std::string("more than 16 integration domains");
+      ctx->gather_rec.alloc((size_t)n2);
+      launch_pack_gather_records(ctx->perm.p, n2, ctx->gather_doms.p, (int)gd.size(), ctx->gather_rec.p, ctx->stream);
+      ++ctx->launches;
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      ctx->perm.release();
+    }
     ctx->nnz = n1; ctx->ncoo = n2;
     for (size_t di = 0; di < ctx->doms.size(); ++di) {
       Domain& d = *ctx->doms[di];

@@ -145,6 +145,33 @@ struct DomainDev {
   int smem_total;                      // doubles
 };
 
+// ---- reference-matrix contributions, gathered slot by slot (integrate.cu: gather_reference) ----
+// value(slot) = sum over the COO entries of the slot of  sum_products coef * sum_m geo[cell][geo_idx+m]
+//               * tabs[tab_off + m*nr*nc + i*nc + j]
+struct RefProd {
+  int mat, ntab, geo_idx;
+  long long tab_off;
+  double cre, cim;
+};
+#define VLFS_CELLGEO 7         // per cell: measure, then the D(D+1)/2 factors meas * (J^-T J^-1) sym
+struct GatherDom {
+  long long coo_lo, coo_hi;
+  int epc, nblocks;
+  BlockDev blk[VLFS_MAX_BLOCKS];
+  int rp_first[VLFS_MAX_BLOCKS + 1];
+  const RefProd* rp;
+  const double* geo;      // [ncells][VLFS_CELLGEO]
+  const double* tabs;
+  int tab_len;            // doubles in tabs
+  // geometry classes (meshes with few distinct cell shapes, e.g. Cartesian): the complete
+  // reference-type element block of every class is tabulated once per assembly
+  int ncls;               // 0: no classes, per-cell factors are used
+  const int* cls;         // [ncells] class of every cell
+  const double* cls_geo;  // [ncls][VLFS_CELLGEO]
+  double* ctab;           // [block][class][local entry][nmat][scalar]
+  long long ctab_off[VLFS_MAX_BLOCKS];
+};
+
 // ---- primitives -------------------------------------------------------------------
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev,
                         cudaStream_t s);

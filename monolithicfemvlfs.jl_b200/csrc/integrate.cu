@@ -628,7 +628,260 @@ gradgrad_affine(DomainDev dom, const double* __restrict__ Sref, const int* __res
   }
 }
 
+// ---- reference-matrix contributions gathered per CSR slot -----------------------------------
+// Geometry-only per-cell factors (computed once per pattern): measure of the measure slot and,
+// for own-cell volume slots, meas * sum_b pinv[b][a] pinv[b][c] in symmetric component order.
+template <int D>
+__global__ void cell_geometry(DomainDev dom, int want_gradgrad, double* __restrict__ out) {
+  constexpr int NS = D * (D + 1) / 2;
+  for (long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x; cell < dom.ncells;
+       cell += (long long)gridDim.x * blockDim.x) {
+    double rec[GEO_STRIDE], meas = 0.0;
+    slot_geometry<D>(dom.slot[dom.measure_slot], cell, 0, dom.nq, rec, &meas, dom.measure_kind);
+    double* o = out + (size_t)cell * VLFS_CELLGEO;
+    o[0] = meas;
+    for (int m = 0; m < NS && m < VLFS_CELLGEO - 1; ++m) o[1 + m] = 0.0;
+    if (want_gradgrad) {
+      double vol = 0.0;
+      slot_geometry<D>(dom.slot[0], cell, 0, dom.nq, rec, &vol, VLFS_MEASURE_CELL);
+      int m = 0;
+      for (int a = 0; a < D; ++a) {
+        double t = 0;
+        for (int b = 0; b < D; ++b) t = fma(rec[b * 3 + a], rec[b * 3 + a], t);
+        o[1 + m++] = vol * t;
+      }
+      for (int a = 0; a < D; ++a)
+        for (int c = a + 1; c < D; ++c) {
+          double t = 0;
+          for (int b = 0; b < D; ++b) t = fma(rec[b * 3 + a], rec[b * 3 + c], t);
+          o[1 + m++] = vol * t;
+        }
+    }
+  }
+}
+
+// T[i][j] = sum_q qw[q] valA[q][i] valB[q][j]   (both value tables cell-invariant)
+__global__ void mass_reference(const double* __restrict__ valA, int ndA, const double* __restrict__ valB, int ndB,
+                               const double* __restrict__ qw, int nq, double* __restrict__ T) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ndA * ndB; idx += gridDim.x * blockDim.x) {
+    const int i = idx / ndB, j = idx - i * ndB;
+    double acc = 0.0;
+    for (int q = 0; q < nq; ++q) acc = fma(qw[q] * valA[(size_t)q * ndA + i], valB[(size_t)q * ndB + j], acc);
+    T[idx] = acc;
+  }
+}
+
+// sorted COO position -> packed (domain:4 | block:2 | local entry:14 | cell:32) record, once per pattern
+__global__ void pack_gather_records(const uint32_t* __restrict__ perm, long long ncoo,
+                                    const GatherDom* __restrict__ doms, int ndom,
+                                    unsigned long long* __restrict__ rec) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < ncoo;
+       p += (long long)gridDim.x * blockDim.x) {
+    const long long g = perm[p];
+    int d = 0;
+    while (d + 1 < ndom && g >= doms[d].coo_hi) ++d;
+    const GatherDom& G = doms[d];
+    const long long r = g - G.coo_lo;
+    const long long e = r / G.epc;
+    const int le = (int)(r - e * G.epc);
+    int b = 0;
+    while (b + 1 < G.nblocks && le >= G.blk[b + 1].off) ++b;
+    const unsigned long long li = (unsigned long long)(le - G.blk[b].off);
+    rec[p] = ((unsigned long long)d << 60) | ((unsigned long long)b << 58) | (li << 32) | (unsigned long long)e;
+  }
+}
+
+// ctab[block][class][li][mat][part] = sum_products coef * sum_m cls_geo[class][geo_idx+m] * tab_m[li]
+__global__ void build_class_tables(const GatherDom* __restrict__ doms, int d, int nmat, int sc) {
+  const GatherDom& G = doms[d];
+  for (int b = 0; b < G.nblocks; ++b) {
+    const int ne = G.blk[b].nr * G.blk[b].nc;
+    const int k0 = G.rp_first[b], k1 = G.rp_first[b + 1];
+    if (k0 == k1) continue;
+    double* out = G.ctab + G.ctab_off[b];
+    const long long total = (long long)G.ncls * ne;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+      const int c = (int)(t / ne), li = (int)(t - (long long)c * ne);
+      const double* geo = G.cls_geo + (size_t)c * VLFS_CELLGEO;
+      double are[4] = {0, 0, 0, 0}, aim[4] = {0, 0, 0, 0};
+      for (int k = k0; k < k1; ++k) {
+        const RefProd P = G.rp[k];
+        double v = 0.0;
+        for (int m = 0; m < P.ntab; ++m) v = fma(geo[P.geo_idx + m], G.tabs[P.tab_off + (size_t)m * ne + li], v);
+        are[P.mat] = fma(P.cre, v, are[P.mat]);
+        aim[P.mat] = fma(P.cim, v, aim[P.mat]);
+      }
+      for (int m = 0; m < nmat; ++m) {
+        out[((size_t)t * nmat + m) * sc] = are[m];
+        if (sc == 2) out[((size_t)t * nmat + m) * sc + 1] = aim[m];
+      }
+    }
+  }
+}
+
+struct GatherSmemDom {
+  const double* geo;
+  const double* tabs;      // global tables, or (tab_smem) their copy in dynamic shared memory
+  int ncls;
+  const int* cls;
+  const double* ctab;
+  long long ctab_off[VLFS_MAX_BLOCKS];
+  int tab_smem;
+  int rp_first[VLFS_MAX_BLOCKS + 1];
+  int ne[VLFS_MAX_BLOCKS];
+};
+constexpr int GATHER_MAX_DOM = 16, GATHER_MAX_RP = 96;
+
+// One thread per CSR slot: sums the reference-type contributions of the slot's COO entries in COO
+// order (deterministic, no atomics) and WRITES the value - this pass also replaces the zero fill.
+template <int NMAT>
+__global__ void __launch_bounds__(256)
+gather_reference(const uint32_t* __restrict__ run_start, const unsigned long long* __restrict__ rec, long long nnz,
+                 const GatherDom* __restrict__ doms, int ndom, int nrp_total, AsmPtrs ptrs, int nmat,
+                 int is_complex, int tabs_in_smem) {
+  // the reference tables are looked up at scattered local entries: from shared memory a warp's 32
+  // different entries cost a few bank-conflict cycles instead of 32 L1 sector accesses
+  extern __shared__ __align__(16) double stab[];
+  __shared__ GatherSmemDom sd[GATHER_MAX_DOM];
+  __shared__ RefProd srp[GATHER_MAX_RP];
+  __shared__ int srp_base[GATHER_MAX_DOM];
+  if (threadIdx.x == 0) {
+    int base = 0;
+    for (int d = 0; d < ndom; ++d) {
+      sd[d].geo = doms[d].geo; sd[d].tabs = doms[d].tabs; sd[d].tab_smem = 0;
+      sd[d].ncls = doms[d].ncls; sd[d].cls = doms[d].cls; sd[d].ctab = doms[d].ctab;
+      for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) sd[d].ctab_off[b] = doms[d].ctab_off[b];
+      for (int b = 0; b <= VLFS_MAX_BLOCKS; ++b) sd[d].rp_first[b] = doms[d].rp_first[b] + base;
+      for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) sd[d].ne[b] = doms[d].blk[b].nr * doms[d].blk[b].nc;
+      srp_base[d] = base;
+      const int n = doms[d].rp_first[doms[d].nblocks];
+      for (int k = 0; k < n; ++k) srp[base + k] = doms[d].rp[k];
+      base += n;
+    }
+  }
+  __syncthreads();
+  if (tabs_in_smem) {
+    int off = 0;
+    for (int d = 0; d < ndom; ++d) {
+      const int len = doms[d].tab_len;
+      for (int t = threadIdx.x; t < len; t += blockDim.x) stab[off + t] = doms[d].tabs[t];
+      if (threadIdx.x == 0) { sd[d].tabs = stab + off; sd[d].tab_smem = 1; }
+      off += len;
+    }
+    __syncthreads();
+  }
+  for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < nnz;
+       slot += (long long)gridDim.x * blockDim.x) {
+    double are[NMAT], aim[NMAT];
+#pragma unroll
+    for (int m = 0; m < NMAT; ++m) are[m] = aim[m] = 0.0;
+    const uint32_t p1 = run_start[slot + 1];
+    // (a 4-way unrolled version that fetches records and class ids ahead was measured slower)
+    for (uint32_t p = run_start[slot]; p < p1; ++p) {
+      const unsigned long long r = rec[p];
+      const int d = (int)(r >> 60), b = (int)((r >> 58) & 3u), li = (int)((r >> 32) & 0x3fffu);
+      const unsigned e = (unsigned)(r & 0xffffffffull);
+      const GatherSmemDom& G = sd[d];
+      const int k0 = G.rp_first[b], k1 = G.rp_first[b + 1];
+      if (k0 == k1) continue;
+      const int ne = G.ne[b];
+      if (G.ncls > 0) {                                    // tabulated element block of the class
+        const int c = __ldg(G.cls + e);
+        const double* t = G.ctab + G.ctab_off[b] + ((size_t)c * ne + li) * NMAT * (is_complex ? 2 : 1);
+        if (is_complex) {
+#pragma unroll
+          for (int m = 0; m < NMAT; ++m) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(t) + m);
+            are[m] += v.x; aim[m] += v.y;
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < NMAT; ++m) are[m] += __ldg(t + m);
+        }
+        continue;
+      }
+      const double* geo = G.geo + (size_t)e * VLFS_CELLGEO;
+      for (int k = k0; k < k1; ++k) {
+        const RefProd& P = srp[k];
+        const double* tab = G.tabs + P.tab_off + li;
+        double v = 0.0;
+        for (int m = 0; m < P.ntab; ++m) v = fma(__ldg(geo + P.geo_idx + m), tab[(size_t)m * ne], v);
+#pragma unroll
+        for (int m = 0; m < NMAT; ++m)          // static indexing keeps the accumulators in registers
+          if (P.mat == m) { are[m] = fma(P.cre, v, are[m]); aim[m] = fma(P.cim, v, aim[m]); }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < NMAT; ++m) {
+      if (is_complex) reinterpret_cast<double2*>(ptrs.mat[m])[slot] = make_double2(are[m], aim[m]);
+      else ptrs.mat[m][slot] = are[m];
+    }
+  }
+}
+
 }  // namespace
+
+void launch_cell_geometry(const DomainDev& dom, int want_gradgrad, double* out, cudaStream_t s) {
+  if (dom.ncells == 0) return;
+  unsigned grid = (unsigned)((dom.ncells + 127) / 128);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (dom.D == 1) cell_geometry<1><<<grid, 128, 0, s>>>(dom, want_gradgrad, out);
+  else if (dom.D == 2) cell_geometry<2><<<grid, 128, 0, s>>>(dom, want_gradgrad, out);
+  else cell_geometry<3><<<grid, 128, 0, s>>>(dom, want_gradgrad, out);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_mass_reference(const double* valA, int ndA, const double* valB, int ndB, const double* qw, int nq,
+                           double* T, cudaStream_t s) {
+  mass_reference<<<(ndA * ndB + 255) / 256, 256, 0, s>>>(valA, ndA, valB, ndB, qw, nq, T);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_build_class_tables(const GatherDom* doms, int d, long long work, int nmat, int is_complex, cudaStream_t s) {
+  if (work == 0) return;
+  long long grid = (work + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  build_class_tables<<<(unsigned)grid, 256, 0, s>>>(doms, d, nmat, is_complex ? 2 : 1);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_pack_gather_records(const uint32_t* perm, long long ncoo, const GatherDom* doms, int ndom,
+                                unsigned long long* rec, cudaStream_t s) {
+  if (ncoo == 0) return;
+  long long grid = (ncoo + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  pack_gather_records<<<(unsigned)grid, 256, 0, s>>>(perm, ncoo, doms, ndom, rec);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_gather_reference(const uint32_t* run_start, const unsigned long long* rec, long long nnz,
+                             const GatherDom* doms, int ndom, int nrp_total, long long tab_total,
+                             double* const* mats, int nmat, int is_complex, int nsm, cudaStream_t s) {
+  if (nnz == 0) return;
+  if (ndom > GATHER_MAX_DOM || nrp_total > GATHER_MAX_RP)
+    throw std::string("gather_reference: too many domains / reference products");
+  AsmPtrs P{};
+  for (int m = 0; m < nmat && m < 4; ++m) P.mat[m] = mats[m];
+  const size_t smem = (size_t)tab_total * sizeof(double);
+  // (measured on B200: staging the tables in shared memory halves the occupancy and is slower)
+  const int in_smem = 0 && tab_total > 0 && smem <= 100 * 1024;
+  long long grid = (nnz + 255) / 256;
+  const long long cap = (long long)nsm * (in_smem ? (smem > 48 * 1024 ? 2 : 4) * 2 : 32);
+  if (grid > cap) grid = cap;
+  auto launch = [&](auto kern) {
+    if (in_smem) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, 256, in_smem ? smem : 0, s>>>(run_start, rec, nnz, doms, ndom, nrp_total, P, nmat,
+                                                        is_complex, in_smem);
+  };
+  switch (nmat) {
+    case 1: launch(gather_reference<1>); break;
+    case 2: launch(gather_reference<2>); break;
+    case 3: launch(gather_reference<3>); break;
+    default: launch(gather_reference<4>); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+}
 
 // ---- host-side launchers ------------------------------------------------------------
 void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, const int* dest,

@@ -40,13 +40,14 @@ __global__ void flag_heads(const uint64_t* __restrict__ keys, uint32_t* __restri
 __global__ void emit_pattern(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
                              const uint32_t* __restrict__ flag, const uint32_t* __restrict__ ex,
                              int* __restrict__ colind, int* __restrict__ rowind,
-                             int* __restrict__ dest, size_t n) {
+                             int* __restrict__ dest, uint32_t* __restrict__ run_start, size_t n) {
   for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < n;
        g += (size_t)gridDim.x * blockDim.x) {
     uint32_t f = flag[g];
     int slot = (int)(ex[g] + f) - 1;
     dest[perm[g]] = slot;
     if (f) {
+      run_start[slot] = (uint32_t)g;
       uint64_t k = keys[g];
       colind[slot] = (int)(uint32_t)(k & 0xffffffffull);
       rowind[slot] = (int)(uint32_t)(k >> 32);
@@ -125,6 +126,7 @@ inline unsigned grid_for(size_t n, int threads = 256) {
 void build_pattern_device(const std::vector<DomainDev>& doms, long long ndofs,
                           DevBuf<int>& rowptr, DevBuf<int>& colind, DevBuf<int>& rowind,
                           DevBuf<int>& dest_all, std::vector<long long>& dest_off,
+                          DevBuf<uint32_t>& perm_out, DevBuf<uint32_t>& run_start,
                           long long* nnz_out, long long* ncoo_out, cudaStream_t s,
                           long long* launches) {
   long long ncoo = 0;
@@ -157,12 +159,16 @@ void build_pattern_device(const std::vector<DomainDev>& doms, long long ndofs,
   long long nnz = nnz32;
   if (nnz >= (1ll << 31)) throw std::string("nnz exceeds int32 range on one GPU");
   colind.alloc(nnz); rowind.alloc(nnz); rowptr.alloc(ndofs + 1); dest_all.alloc(ncoo);
+  run_start.alloc(nnz + 1);
+  const uint32_t ncoo32 = (uint32_t)ncoo;
+  CUDA_TRY(cudaMemcpyAsync(run_start.p + nnz, &ncoo32, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   emit_pattern<<<grid_for(ncoo), 256, 0, s>>>(keys.p, idx.p, flag.p, ex.p, colind.p, rowind.p,
-                                              dest_all.p, (size_t)ncoo);
+                                              dest_all.p, run_start.p, (size_t)ncoo);
   build_rowptr<<<grid_for(ndofs + 1), 256, 0, s>>>(rowind.p, nnz, rowptr.p, ndofs);
   if (launches) *launches += 4;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(s));
+  perm_out = std::move(idx);          // sorted position -> COO index (slot-centric gather)
   *nnz_out = nnz;
   *ncoo_out = ncoo;
 }
