@@ -42,6 +42,16 @@ def emit(obj):
     f.flush()
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel from the committed
+    `ncu --set full` capture (profiles/r1_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -162,16 +172,19 @@ def run_ours(args):
     # per-kernel times (CUDA events on the launching stream) for the roofline of the dominant kernel
     prof = S.assemble_profile(reps=3)
     dom_name, dom_ms = max(prof, key=lambda kv: kv[1])
-    ent_vol = prob.Om.ncells * 27 * 27
     ent_gf = prob.Gf.ncells * (27 + prob.V_Gk.reffe.ndofs) ** 2
-    if dom_name.startswith("gradgrad_affine"):
-        # volume Laplace: one 16-byte RMW on the value + 4-byte dest per COO entry, 192 B coords/cell
-        kbytes = ent_vol * (16 + 4) + prob.Om.ncells * 192
+    if dom_name.startswith("gather_reference"):
+        # slot-centric pass: every value written once, one index per COO entry, one run pointer per slot
+        kbytes = nnz * sT + 4 * ncoo + 4 * nnz
     else:
-        kbytes = ent_gf * (16 + 4) + prob.Gf.ncells * (12 * 24 + 52 * 4 + 5 * 25 * 8)
+        # cell-centric pass on Γf: the coefficient-field products (675 + 675 real, 729 imaginary
+        # entries per cell) reduced into their slots, dest read once, per-cell tables read once
+        nk = prob.V_Gk.reffe.ndofs
+        kbytes = prob.Gf.ncells * ((nk * 27 * 2 + 27 * 27) * 8 + (27 + nk) ** 2 * 4
+                                   + 12 * 24 + (27 + nk) * 4 + 5 * 25 * 8)
     roof = {"bound": "hbm", "kernel": dom_name, "achieved": kbytes / (dom_ms * 1e-3) / 1e9, "peak": peak,
-            "peak_kind": peak_kind, "unit": "GB/s", "traffic": None,
-            "share_of_step": dom_ms / sum(t for _, t in prof)}
+            "peak_kind": peak_kind, "unit": "GB/s", "traffic": ncu_traffic(dom_name),
+            "share_of_step": dom_ms / sum(t for _, t in prof), "algorithmic_bytes": kbytes}
     roof["frac"] = roof["achieved"] / peak
     step_bytes = assembly_bytes(prob, nnz, ncoo, sT)
 
@@ -416,6 +429,8 @@ def cpu_baseline(sample=None):
     A, b = case.assemble()
     dt = time.time() - t0
     return {"value": A.nnz / dt, "unit": "nnz/s", "cores": 1, "kind": "port",
+            "note": "the reference path is single-threaded: Gridap 0.17 integrates and assembles in one Julia "
+                    "thread (SURVEY.md §3); the port is vectorised NumPy + SciPy sum_duplicates on one core",
             "sample": "oracle (NumPy restatement of Gridap cell integration + sparse(I,J,V)) on Yago %s: "
                       "N=%d nnz=%d in %.1f s" % (json.dumps(kw), A.shape[0], A.nnz, dt), "seconds": dt}
 
