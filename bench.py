@@ -356,9 +356,12 @@ def run_ours_distributed(args):
         # LU on rank 0, used as the preconditioner of distributed GMRES (1-2 refinement iterations)
         t0 = time.time()
         schur = D.SchurSolver(fleet)
-        schur.setup()
+        ok = schur.setup()
         torch.cuda.synchronize()
         first_s = allmax(time.time() - t0)
+    if not args.no_solve and not ok:
+        solve = {"error": "a rank could not factorise its subdomain: %s" % (schur.error or "see another rank")}
+    elif not args.no_solve:
         info = S.direct_info()
         bs, x0 = [ops.rhs_vector()], [ops.zeros()]
         barrier()

@@ -504,18 +504,22 @@ struct NDBuilder {
   std::vector<TreeNode> nodes;
   int rec(std::vector<int>& S) {
     if ((int)S.size() <= leaf) return make_leaf(S);
-    // longest axis, median split
-    int ax = 0; double best = -1;
+    // split axis = the one with the most distinct coordinate planes (the best-resolved direction:
+    // its separators are the smallest; the longest geometric extent is a poor guide on strongly
+    // anisotropic meshes such as x-refined slabs), median split
+    int ax = 0; size_t best = 0;
+    std::vector<double> cs, cbest;
     for (int a = 0; a < dim; ++a) {
-      double lo = 1e300, hi = -1e300;
-      for (int v : S) { double c = xy[(size_t)v * dim + a]; lo = std::min(lo, c); hi = std::max(hi, c); }
-      if (hi - lo > best) { best = hi - lo; ax = a; }
+      cs.resize(S.size());
+      for (size_t k = 0; k < S.size(); ++k) cs[k] = xy[(size_t)S[k] * dim + a];
+      std::sort(cs.begin(), cs.end());
+      size_t distinct = 1;
+      for (size_t k = 1; k < cs.size(); ++k) distinct += cs[k] != cs[k - 1];
+      if (distinct > best) { best = distinct; ax = a; cbest.swap(cs); }
     }
     std::vector<double> c(S.size());
     for (size_t k = 0; k < S.size(); ++k) c[k] = xy[(size_t)S[k] * dim + ax];
-    std::vector<double> cs(c);
-    std::nth_element(cs.begin(), cs.begin() + cs.size() / 2, cs.end());
-    double med = cs[cs.size() / 2];
+    double med = cbest[cbest.size() / 2];
     std::vector<int> A, B;
     for (size_t k = 0; k < S.size(); ++k) (c[k] <= med ? A : B).push_back(S[k]);
     if (A.empty() || B.empty()) {
@@ -701,6 +705,17 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_
   build_cmap<<<nf_, 128, 0, s>>>(D->d_meta.p, nf_, D->d_upd.p, D->d_cmap.p);
   ++*launches;
   const size_t sc = is_complex ? 2 : 1;
+  {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const double need = (double)D->pool_elems * sc * sizeof(double);
+    if (need > 0.92 * (double)free_b) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "sparse LU needs %.1f GB for its fronts (largest %d), %.1f GB free",
+               need / 1e9, D->maxnf, free_b / 1e9);
+      throw std::string(buf);
+    }
+  }
   D->pool.alloc((size_t)D->pool_elems * sc);
   D->w.alloc((size_t)D->w_elems * sc);
   D->bp.alloc((size_t)(n + D->n_keep) * sc);

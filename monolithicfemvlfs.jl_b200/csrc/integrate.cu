@@ -287,7 +287,9 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
   auto geo_buf = [&](long long k) { return sm + (size_t)(k & 3) * dom.smem_geo_stride; };
   auto stage_geometry = [&](long long cell, double* geo) {
     if (cell < 0) return;
-    for (int t = tid; t < dom.nslots * nqg; t += nth) {
+    // (reversed thread order: the serial geometry chain and the coefficient-field loads go to the
+    // last warp, whose lanes beyond the tile count have no contraction work)
+    for (int t = nth - 1 - tid; t < dom.nslots * nqg; t += nth) {
       const int s = t / nqg, q = t - s * nqg;
       double m;
       slot_geometry<D>(dom.slot[s], cell, q, nq, geo + (size_t)t * GEO_STRIDE,
@@ -306,7 +308,7 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
     if (cell < 0) return;
     if (!invariant) {
       double* w = sm + dom.smem_buf_off + (size_t)par * dom.smem_buf_stride;
-      for (int t = tid; t < dom.nweights * nq; t += nth) {
+      for (int t = nth - 1 - tid; t < dom.nweights * nq; t += nth) {
         const int wi = t / nq, q = t - wi * nq;
         w[t] = dom.weights[((size_t)wi * dom.ncells + cell) * nq + q];
       }

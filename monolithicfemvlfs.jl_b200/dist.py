@@ -572,10 +572,20 @@ class SchurSolver:
         return out
 
     def setup(self):
+        """Returns False (on every rank) when a rank could not factorise, e.g. out of memory."""
         F = self.fleet
+        oks, self.error = [], None
         for m in F.members:
-            m.ops.factor()
+            try:
+                m.ops.factor()
+                oks.append(np.array([1.0]))
+            except Exception as e:          # keep the ranks in step: agree on the outcome first
+                oks.append(np.array([0.0]))
+                self.error = repr(e)
+        if F.allreduce(oks)[0] < F.nranks - 0.5:
+            return False
         self._assemble_interface()
+        return True
 
     def refactor(self):
         for m in self.fleet.members:
