@@ -139,7 +139,11 @@ typedef struct {
 } vlfs_solve_stats;
 
 enum { VLFS_SOLVER_GMRES = 0, VLFS_SOLVER_BICGSTAB = 1, VLFS_SOLVER_CG = 2 };
-enum { VLFS_PRECOND_NONE = 0, VLFS_PRECOND_JACOBI = 1, VLFS_PRECOND_BLOCK_ILU0 = 2,
+enum { VLFS_PRECOND_NONE = 0, VLFS_PRECOND_JACOBI = 1,
+       VLFS_PRECOND_BLOCK_ILU0 = 2, /* per-GPU block preconditioner; the block (the owned rows of
+                                       this context) is factorised EXACTLY, i.e. identical to
+                                       VLFS_PRECOND_SPARSE_LU - zero-fill ILU stalls on these
+                                       operators */
        VLFS_PRECOND_SPARSE_LU = 3 /* GPU multifrontal LU of the matrix (the LUSolver() twin) */ };
 
 typedef struct vlfs_ctx vlfs_ctx;

@@ -37,8 +37,6 @@ void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, con
 void launch_gradgrad_reference(const DomainDev& dom, double* Sref, cudaStream_t s);
 void launch_functional(const DomainDev& dom, const OpInst& O0, const OpInst& O1, double sc0, double sc1,
                        int wf, const double* x, double* result, int nsm, cudaStream_t s);
-void launch_gradgrad_affine(const DomainDev& dom, const double* Sref, const int* dest, double* vals,
-                            int is_complex, double cre, double cim, int nsm, cudaStream_t s);
 void launch_spmv(const int* rowptr, const int* colind, const void* vals, const void* x, void* y,
                  long long nrows, long long nnz, int is_complex, const double* alpha,
                  const double* beta, int nsm, cudaStream_t s);
@@ -989,6 +987,11 @@ int vlfs_device_ptrs(vlfs_ctx* ctx, int mat, void** rowptr, void** colind, void*
 int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
   return guarded(ctx, [&]() {
     if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !opts) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    vlfs_solver_opts o2 = *opts;
+    // the per-GPU block preconditioner factorises its block exactly (multifrontal LU): ILU(0) and
+    // Jacobi stall on these indefinite operators
+    if (o2.precond == VLFS_PRECOND_BLOCK_ILU0) o2.precond = VLFS_PRECOND_SPARSE_LU;
+    opts = &o2;
     if (opts->precond == VLFS_PRECOND_SPARSE_LU) {
       if (ctx->dof_coords.empty()) return fail(ctx, VLFS_ERR_STATE, "vlfs_set_dof_coords first (sparse LU ordering)");
       if (!ctx->direct) {

@@ -7,16 +7,16 @@
 // src/Khabakhpasheva_freq_domain.jl:226-240, src/Khabakhpasheva_time_domain.jl:237-257,
 // src/Periodic_Beam.jl:96-104, src/Multi_geo_freq_domain.jl:125-131).
 //
-// Two kernels:
+// Kernels:
 //  * integrate_cells<D>: one CTA per cell.  Stage 0 builds the Jacobian pseudo-inverse,
 //    measure and normals of every slot at every quadrature point; stage 1 evaluates the
 //    operator instances (value / gradient / directional derivative / Hessian / C:Hessian /
 //    normal contractions) of all local basis functions into shared memory; stage 2 contracts
 //    test x trial rows for every touched block and scatters through `dest`; stage 3 does
 //    the linear forms.
-//  * gradgrad_affine<D>: the memory-bound fast path for ∫∇u·∇v on cells with a constant
-//    Jacobian: thread-per-entry keeps the symmetrised reference matrices in registers and
-//    streams cells, 6 FMAs + one scatter per entry.
+//  * gather_reference: the slot-centric pass for reference-type terms on constant-Jacobian
+//    cells (∫∇u·∇v, value x value terms without coefficient field): one thread per CSR slot sums
+//    its COO entries in COO order and writes the value once (also the zero fill).
 #include "common.cuh"
 #include <cstdlib>
 #include <cuda/barrier>
@@ -569,67 +569,6 @@ __global__ void gradgrad_reference(SlotDev S, const double* __restrict__ qw, int
   }
 }
 
-constexpr int FAST_BATCH = 32;
-
-template <int D>
-__global__ void __launch_bounds__(1024)
-gradgrad_affine(DomainDev dom, const double* __restrict__ Sref, const int* __restrict__ dest,
-                double* __restrict__ vals, int stride /*1 real, 2 complex*/, double cre, double cim,
-                long long cells_per_cta) {
-  constexpr int NS = D * (D + 1) / 2;
-  __shared__ double sG[FAST_BATCH][NS];
-  const SlotDev& S = dom.slot[0];
-  const int nd = S.ndofs, ne = nd * nd;
-  const int idx = threadIdx.x;
-  double sref[NS];
-#pragma unroll
-  for (int m = 0; m < NS; ++m) sref[m] = idx < ne ? Sref[(size_t)m * ne + idx] : 0.0;
-  const long long c0 = (long long)blockIdx.x * cells_per_cta;
-  long long c1 = c0 + cells_per_cta;
-  if (c1 > dom.ncells) c1 = dom.ncells;
-  for (long long cb = c0; cb < c1; cb += FAST_BATCH) {
-    const int nb = (int)((c1 - cb) < FAST_BATCH ? (c1 - cb) : FAST_BATCH);
-    __syncthreads();
-    if (idx < nb) {
-      double rec[GEO_STRIDE], meas;
-      slot_geometry<D>(S, cb + idx, 0, dom.nq, rec, &meas, VLFS_MEASURE_CELL);
-      // G[a][c] = meas * sum_b pinv[b][a] pinv[b][c]
-      int m = 0;
-      for (int a = 0; a < D; ++a) {
-        double s = 0;
-        for (int b = 0; b < D; ++b) s = fma(rec[b * 3 + a], rec[b * 3 + a], s);
-        sG[idx][m++] = meas * s;
-      }
-      for (int a = 0; a < D; ++a)
-        for (int c = a + 1; c < D; ++c) {
-          double s = 0;
-          for (int b = 0; b < D; ++b) s = fma(rec[b * 3 + a], rec[b * 3 + c], s);
-          sG[idx][m++] = meas * s;
-        }
-    }
-    __syncthreads();
-    if (idx < ne) {
-      const int* dp = dest + (size_t)cb * dom.entries_per_cell + dom.blk[0].off + idx;
-      int slot[4];
-      for (int k0 = 0; k0 < nb; k0 += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (k0 + u < nb) slot[u] = dp[(size_t)(k0 + u) * dom.entries_per_cell];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (k0 + u < nb) {
-            double v = 0;
-#pragma unroll
-            for (int m = 0; m < NS; ++m) v = fma(sG[k0 + u][m], sref[m], v);
-            if (cre != 0.0) scatter_value(vals, stride, slot[u], cre * v);
-            if (cim != 0.0) scatter_value(vals + 1, stride, slot[u], cim * v);
-          }
-        }
-      }
-    }
-  }
-}
-
 // ---- reference-matrix contributions gathered per CSR slot -----------------------------------
 // Geometry-only per-cell factors (computed once per pattern): measure of the measure slot and,
 // for own-cell volume slots, meas * sum_b pinv[b][a] pinv[b][c] in symmetric component order.
@@ -953,21 +892,3 @@ void launch_gradgrad_reference(const DomainDev& dom, double* Sref, cudaStream_t 
   CUDA_TRY(cudaGetLastError());
 }
 
-void launch_gradgrad_affine(const DomainDev& dom, const double* Sref, const int* dest, double* vals,
-                            int is_complex, double cre, double cim, int nsm, cudaStream_t s) {
-  if (dom.ncells == 0) return;
-  int ne = dom.slot[0].ndofs * dom.slot[0].ndofs;
-  int threads = ((ne + 31) / 32) * 32;
-  if (threads > 1024) throw std::string("gradgrad_affine: element matrix larger than 1024 entries");
-  // CTAs resident per SM limited by threads; give every SM a few waves of cell chunks
-  long long ctas = (long long)nsm * (2048 / threads) * 4;
-  long long per = (dom.ncells + ctas - 1) / ctas;
-  per = ((per + FAST_BATCH - 1) / FAST_BATCH) * FAST_BATCH;
-  long long grid = (dom.ncells + per - 1) / per;
-  int stride = is_complex ? 2 : 1;
-  if (!is_complex) cim = 0.0;
-  if (dom.D == 1) gradgrad_affine<1><<<(unsigned)grid, threads, 0, s>>>(dom, Sref, dest, vals, stride, cre, cim, per);
-  else if (dom.D == 2) gradgrad_affine<2><<<(unsigned)grid, threads, 0, s>>>(dom, Sref, dest, vals, stride, cre, cim, per);
-  else gradgrad_affine<3><<<(unsigned)grid, threads, 0, s>>>(dom, Sref, dest, vals, stride, cre, cim, per);
-  CUDA_TRY(cudaGetLastError());
-}

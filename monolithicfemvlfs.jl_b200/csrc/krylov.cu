@@ -352,7 +352,7 @@ SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals
   int m = S->opts.restart;
   S->partial.alloc((size_t)S->nred * (m + 2) * S->sc);
   S->hdev.alloc((size_t)(m + 2) * S->sc);
-  if (S->opts.precond == VLFS_PRECOND_JACOBI || S->opts.precond == VLFS_PRECOND_BLOCK_ILU0) {
+  if (S->opts.precond == VLFS_PRECOND_JACOBI) {
     S->dinv.alloc((size_t)n * S->sc);
     if (is_complex) extract_inv_diag<true><<<vgrid(n, nsm), 256, 0, s>>>(rowptr, colind, (const double2*)vals, (double2*)S->dinv.p, n);
     else extract_inv_diag<false><<<vgrid(n, nsm), 256, 0, s>>>(rowptr, colind, vals, S->dinv.p, n);
