@@ -9,6 +9,7 @@
 #include <array>
 #include <map>
 #include <cmath>
+#include <algorithm>
 
 void build_pattern_device(const std::vector<DomainDev>& doms, long long ndofs,
                           DevBuf<int>& rowptr, DevBuf<int>& colind, DevBuf<int>& rowind,
@@ -19,6 +20,10 @@ void build_pattern_device(const std::vector<DomainDev>& doms, long long ndofs,
 void launch_cell_geometry(const DomainDev& dom, int want_gradgrad, double* out, cudaStream_t s);
 void launch_mass_reference(const double* valA, int ndA, const double* valB, int ndB, const double* qw, int nq,
                            double* T, cudaStream_t s);
+void launch_cell_jacobians(const DomainDev& dom, double* out, cudaStream_t s);
+void launch_rhs_affine(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, const double* cellgeo,
+                       double* const* vecs, int nvec, int is_complex, int nsm, cudaStream_t s);
+void launch_class_dest(const DomainDev& dom, int nreps, const GatherDom& G, int* tiled, cudaStream_t s);
 void launch_build_class_tables(const GatherDom* doms, int d, long long work, int nmat, int is_complex, cudaStream_t s);
 void launch_pack_gather_records(const uint32_t* perm, long long ncoo, const GatherDom* doms, int ndom,
                                 unsigned long long* rec, cudaStream_t s);
@@ -33,7 +38,7 @@ void build_tiled_dest(const DomainDev& dom, const int* dest, DevBuf<int>& tiled,
 void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, const int* dest,
                       const int* cell_list, long long ncells_run, double* const* mats,
                       int nmat, double* const* vecs, int nvec, int is_complex, int do_mat,
-                      int do_vec, int nsm, cudaStream_t s);
+                      int do_vec, int nsm, cudaStream_t s, int dest_by_run = 0, unsigned stage_mask = ~0u);
 void launch_gradgrad_reference(const DomainDev& dom, double* Sref, cudaStream_t s);
 void launch_functional(const DomainDev& dom, const OpInst& O0, const OpInst& O1, double sc0, double sc1,
                        int wf, const double* x, double* result, int nsm, cudaStream_t s);
@@ -60,6 +65,7 @@ bool op_needs_hess(int op) {
 struct SlotStore {
   DevBuf<double> coords, geo_grad, val, grad, hess, ref_normal, ref_tangent;
   DevBuf<int> variant, dofs;
+  std::vector<int> variant_host;      // kept when the slot has a per-cell variant (classification)
 };
 
 struct Domain {
@@ -78,11 +84,17 @@ struct Domain {
   int rp_first[VLFS_MAX_BLOCKS + 1] = {0, 0, 0, 0, 0};
   DevBuf<RefProd> refprods_dev;
   DevBuf<double> reftabs, cellgeo;
-  int ncls = 0;                         // geometry classes (0: per-cell factors)
-  DevBuf<int> cls;
-  DevBuf<double> cls_geo, ctab;
-  long long ctab_off[VLFS_MAX_BLOCKS] = {0, 0, 0, 0};
-  long long ctab_work = 0;
+  // element-block classes: cells with the same Jacobians, table variants and coefficient-field
+  // values have the same element block; it is tabulated once per class and assembly
+  int ncls = 0;                         // 0: no classes (per-cell paths)
+  bool cls_full = false;                // the general (quadrature) terms are tabulated per class too
+  bool rhs_fast = false;                // linear forms through the barrier-free affine kernel
+  bool cls_dirty = true;
+  DevBuf<int> cls, reps, dest_cls;
+  DevBuf<double> cls_geo, ctab_m[4], jt_dev;
+  std::vector<double> jt_host, cellgeo_host, weights_host;
+  long long ctab_off[VLFS_MAX_BLOCKS] = {-1, -1, -1, -1};
+  long long ctab_entries = 0, ctab_work = 0;
   DevBuf<RhsDev> rhs_dev;
   std::vector<TileTarget> targets_host;
   std::vector<TileProd> prods_host;
@@ -254,6 +266,16 @@ void build_reference_products(vlfs_ctx* ctx, Domain& d) {
   }
   d.rp_first[dev.nblocks] = (int)d.refprods_host.size();
   for (int b = dev.nblocks + 1; b <= VLFS_MAX_BLOCKS; ++b) d.rp_first[b] = d.rp_first[dev.nblocks];
+  // linear forms: value tables without per-cell variant on constant-Jacobian cells
+  d.rhs_fast = dev.affine && !d.rhs.empty();
+  for (const vlfs_rhs_desc& R : d.rhs)
+    for (int sl = 0; sl < dev.nslots; ++sl)
+      if (R.scale[sl] != 0.0 && (R.op != VLFS_OP_VAL || dev.slot[sl].variant)) d.rhs_fast = false;
+  if (d.refprods_host.empty() && d.rhs_fast) {
+    d.cellgeo.alloc((size_t)dev.ncells * VLFS_CELLGEO);
+    launch_cell_geometry(dev, 0, d.cellgeo.p, ctx->stream);
+    ++ctx->launches;
+  }
   if (d.refprods_host.empty()) return;
   d.reftabs.alloc((size_t)tab_len);
   if (gg_off >= 0) { launch_gradgrad_reference(dev, d.reftabs.p + gg_off, ctx->stream); ++ctx->launches; }
@@ -267,57 +289,99 @@ void build_reference_products(vlfs_ctx* ctx, Domain& d) {
   launch_cell_geometry(dev, want_gg ? 1 : 0, d.cellgeo.p, ctx->stream);
   ++ctx->launches;
   d.refprods_dev.upload(d.refprods_host.data(), d.refprods_host.size(), ctx->stream);
-  // geometry classes: cells with bitwise identical factors share one tabulated element block
-  {
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  d.cellgeo_host.resize((size_t)dev.ncells * VLFS_CELLGEO);
+  CUDA_TRY(cudaMemcpy(d.cellgeo_host.data(), d.cellgeo.p, d.cellgeo_host.size() * sizeof(double), cudaMemcpyDeviceToHost));
+}
+
+// Groups the cells of a constant-Jacobian domain into element-block classes and lays out the
+// per-class tables.  Key = Jacobians of every slot rounded to 2^-46 of their largest entry (cells
+// of a regular mesh differ only by round-off, ~1e-16, far below the 1e-12 entry tolerance; every
+// member uses its representative's block), table variants, and the exact bits of the coefficient
+// fields the bilinear terms use.  Worth it when there are few classes (regular meshes); otherwise
+// the per-cell paths stay.
+void classify_domain(vlfs_ctx* ctx, Domain& d) {
+  DomainDev& dev = d.dev;
+  d.cls_dirty = false;
+  d.ncls = 0; d.cls_full = false;
+  for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) d.ctab_off[b] = -1;
+  const bool any_general = !d.terms_host.empty();
+  if (!dev.affine || dev.ncells == 0 || (d.refprods_host.empty() && !any_general)) return;
+  if (d.jt_host.empty()) {
+    d.jt_dev.alloc((size_t)dev.ncells * dev.nslots * 9);
+    launch_cell_jacobians(dev, d.jt_dev.p, ctx->stream);
+    ++ctx->launches;
+    d.jt_host.resize(d.jt_dev.n);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    std::vector<double> hg((size_t)dev.ncells * VLFS_CELLGEO);
-    CUDA_TRY(cudaMemcpy(hg.data(), d.cellgeo.p, hg.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    // factors are compared after rounding to 2^-46 of the largest magnitude of their component:
-    // cells of a Cartesian mesh differ only by the round-off of their Jacobians (~1e-16), far
-    // below the 1e-12 entry tolerance; every member uses its class representative's factors
-    std::map<std::array<long long, VLFS_CELLGEO>, int> classes;
-    std::vector<int> cls((size_t)dev.ncells);
-    std::vector<double> cg;
-    const int max_cls = 512;
-    bool ok = true;
-    double gmax[VLFS_CELLGEO];
-    for (int k = 0; k < VLFS_CELLGEO; ++k) gmax[k] = 0.0;
-    for (long long e = 0; e < dev.ncells; ++e)
-      for (int k = 0; k < VLFS_CELLGEO; ++k) gmax[k] = std::max(gmax[k], std::fabs(hg[(size_t)e * VLFS_CELLGEO + k]));
-    // the grad.grad factors share one scale (off-diagonal components of boxes are pure round-off)
-    for (int k = 2; k < VLFS_CELLGEO; ++k) gmax[1] = std::max(gmax[1], gmax[k]);
-    for (int k = 2; k < VLFS_CELLGEO; ++k) gmax[k] = gmax[1];
-    for (long long e = 0; e < dev.ncells && ok; ++e) {
-      std::array<long long, VLFS_CELLGEO> key;
-      for (int k = 0; k < VLFS_CELLGEO; ++k)
-        key[k] = gmax[k] > 0 ? std::llround(hg[(size_t)e * VLFS_CELLGEO + k] / gmax[k] * 70368744177664.0) : 0;
-      auto it = classes.find(key);
-      if (it == classes.end()) {
-        if ((int)classes.size() >= max_cls) { ok = false; break; }
-        it = classes.emplace(key, (int)classes.size()).first;
-        cg.insert(cg.end(), hg.begin() + (size_t)e * VLFS_CELLGEO, hg.begin() + (size_t)(e + 1) * VLFS_CELLGEO);
+    CUDA_TRY(cudaMemcpy(d.jt_host.data(), d.jt_dev.p, d.jt_host.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    d.jt_dev.release();
+  }
+  std::vector<int> wused;
+  for (const vlfs_term_desc& T : d.terms)
+    if (T.weight >= 0 && std::find(wused.begin(), wused.end(), T.weight) == wused.end()) wused.push_back(T.weight);
+  const int njt = dev.nslots * 9;
+  std::vector<double> jmax(dev.nslots, 0.0);
+  for (long long e = 0; e < dev.ncells; ++e)
+    for (int k = 0; k < njt; ++k) jmax[k / 9] = std::max(jmax[k / 9], std::fabs(d.jt_host[(size_t)e * njt + k]));
+  const size_t klen = (size_t)njt + dev.nslots + wused.size() * dev.nq;
+  std::map<std::vector<long long>, int> classes;
+  std::vector<int> cls((size_t)dev.ncells), reps;
+  std::vector<long long> key(klen);
+  const int max_cls = 4096;
+  const size_t wstride = (size_t)dev.ncells * dev.nq;
+  for (long long e = 0; e < dev.ncells; ++e) {
+    size_t p = 0;
+    for (int k = 0; k < njt; ++k)
+      key[p++] = jmax[k / 9] > 0 ? std::llround(d.jt_host[(size_t)e * njt + k] / jmax[k / 9] * 70368744177664.0) : 0;
+    for (int sl = 0; sl < dev.nslots; ++sl) key[p++] = d.st[sl].variant_host.empty() ? 0 : d.st[sl].variant_host[e];
+    for (int w : wused)
+      for (int q = 0; q < dev.nq; ++q) {
+        long long bits;
+        memcpy(&bits, &d.weights_host[(size_t)w * wstride + (size_t)e * dev.nq + q], sizeof bits);
+        key[p++] = bits;
       }
-      cls[e] = it->second;
+    auto it = classes.find(key);
+    if (it == classes.end()) {
+      if ((int)classes.size() >= max_cls) { classes.clear(); break; }
+      it = classes.emplace(key, (int)classes.size()).first;
+      reps.push_back((int)e);
     }
-    d.ncls = ok ? (int)classes.size() : 0;
-    if (getenv("VLFS_DEBUG")) fprintf(stderr, "[vlfs] domain: %lld cells, %d reference products, %d geometry classes\n",
-                                      (long long)dev.ncells, (int)d.refprods_host.size(), d.ncls);
-    if (d.ncls > 0) {
-      d.cls.upload(cls.data(), cls.size(), ctx->stream);
-      d.cls_geo.upload(cg.data(), cg.size(), ctx->stream);
-      long long off = 0;
-      d.ctab_work = 0;
-      const long long per = (long long)ctx->nmat * (ctx->is_complex ? 2 : 1);
-      for (int b = 0; b < dev.nblocks; ++b) {
-        d.ctab_off[b] = off;
-        if (d.rp_first[b + 1] > d.rp_first[b]) {
-          off += (long long)d.ncls * dev.blk[b].nr * dev.blk[b].nc * per;
-          d.ctab_work = std::max(d.ctab_work, (long long)d.ncls * dev.blk[b].nr * dev.blk[b].nc);
-        }
-      }
-      d.ctab.alloc((size_t)off);
+    cls[e] = it->second;
+  }
+  const int ncls = (int)classes.size();
+  if (getenv("VLFS_DEBUG")) fprintf(stderr, "[vlfs] domain: %lld cells, %d reference products, %d general terms, %d classes\n",
+                                    (long long)dev.ncells, (int)d.refprods_host.size(), (int)d.terms_host.size(), ncls);
+  if (ncls == 0) return;
+  d.ncls = ncls;
+  d.cls_full = any_general && (long long)ncls * 4 <= dev.ncells;
+  d.cls.upload(cls.data(), cls.size(), ctx->stream);
+  d.reps.upload(reps.data(), reps.size(), ctx->stream);
+  if (!d.cellgeo_host.empty()) {
+    std::vector<double> cg((size_t)ncls * VLFS_CELLGEO);
+    for (int c = 0; c < ncls; ++c)
+      memcpy(&cg[(size_t)c * VLFS_CELLGEO], &d.cellgeo_host[(size_t)reps[c] * VLFS_CELLGEO], VLFS_CELLGEO * sizeof(double));
+    d.cls_geo.upload(cg.data(), cg.size(), ctx->stream);
+  }
+  long long off = 0;
+  d.ctab_work = 0;
+  for (int b = 0; b < dev.nblocks; ++b) {
+    if (d.cls_full || d.rp_first[b + 1] > d.rp_first[b]) {
+      d.ctab_off[b] = off;
+      const long long ne = (long long)dev.blk[b].nr * dev.blk[b].nc;
+      off += ncls * ne;
+      d.ctab_work = std::max(d.ctab_work, ncls * ne);
     }
   }
+  d.ctab_entries = off;
+  for (int m = 0; m < ctx->nmat; ++m) d.ctab_m[m].alloc((size_t)off * ctx->scalar());
+  if (d.cls_full) {
+    GatherDom G{};
+    for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) G.ctab_off[b] = d.ctab_off[b];
+    d.dest_cls.alloc((size_t)ncls * dev.tile_base[dev.nblocks] * 16);
+    launch_class_dest(dev, ncls, G, d.dest_cls.p, ctx->stream);
+    ++ctx->launches;
+  }
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
 }
 
 // derive operator instances, touched blocks, shared-memory layout, device term tables
@@ -506,6 +570,27 @@ struct ProfScope {
   ~ProfScope() { if (on) cudaEventRecord(e1, ctx->stream); }
 };
 
+void upload_gather_doms(vlfs_ctx* ctx) {
+  std::vector<GatherDom> gd(ctx->doms.size());
+  for (size_t di = 0; di < ctx->doms.size(); ++di) {
+    Domain& d = *ctx->doms[di];
+    GatherDom& G = gd[di];
+    G.coo_lo = ctx->dest_off[di];
+    G.coo_hi = G.coo_lo + d.dev.ncells * (long long)d.dev.entries_per_cell;
+    G.epc = d.dev.entries_per_cell > 0 ? d.dev.entries_per_cell : 1;
+    G.nblocks = d.dev.nblocks;
+    for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) G.blk[b] = d.dev.blk[b];
+    for (int b = 0; b <= VLFS_MAX_BLOCKS; ++b) G.rp_first[b] = d.rp_first[b];
+    G.rp = d.refprods_dev.p; G.geo = d.cellgeo.p; G.tabs = d.reftabs.p; G.tab_len = (int)d.reftabs.n;
+    G.ncls = d.ncls; G.cls = d.cls.p; G.cls_geo = d.cls_geo.p;
+    for (int m = 0; m < 4; ++m) G.ctab_m[m] = d.ctab_m[m].p;
+    for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) G.ctab_off[b] = d.ctab_off[b];
+  }
+  if (ctx->gather_doms.n != gd.size()) ctx->gather_doms.alloc(gd.size());
+  CUDA_TRY(cudaMemcpyAsync(ctx->gather_doms.p, gd.data(), gd.size() * sizeof(GatherDom), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+}
+
 void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   if (!ctx->pattern_built) throw std::string("vlfs_build_pattern must be called first");
   cudaStream_t s = ctx->stream;
@@ -514,16 +599,33 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   for (auto& v : ctx->vecs) vp.push_back(v.p);
   for (auto& dp : ctx->doms) refresh_coefs(ctx, *dp);
   {
-    // slot-centric pass: writes every CSR value (zero fill included) with the reference-type
-    // contributions summed in COO order; the cell-centric kernels then add the rest
+    bool reclass = false;
+    for (auto& dp : ctx->doms)
+      if (dp->cls_dirty) { classify_domain(ctx, *dp); reclass = true; }
+    if (reclass) upload_gather_doms(ctx);
+  }
+  if (do_mat) {
+    // per-class element blocks: reference products tabulated directly, general (quadrature) terms
+    // integrated on the class representatives only, reduced into the class tables
+    ProfScope ps(ctx, "class_tables");
+    for (size_t di = 0; di < ctx->doms.size(); ++di) {
+      Domain& d = *ctx->doms[di];
+      if (d.ncls == 0) continue;
+      launch_build_class_tables(ctx->gather_doms.p, (int)di, d.ctab_work, ctx->nmat, ctx->is_complex, s);
+      ++ctx->launches;
+      if (d.cls_full) {
+        double* cm[4] = {d.ctab_m[0].p, d.ctab_m[1].p, d.ctab_m[2].p, d.ctab_m[3].p};
+        launch_integrate(d.dev, d.rhs_dev.p, 0, d.dest_cls.p, d.reps.p, d.ncls, cm, ctx->nmat, vp.data(),
+                         (int)vp.size(), ctx->is_complex, 1, 0, ctx->nsm, s, 1);
+        ++ctx->launches;
+      }
+    }
+  }
+  {
+    // slot-centric pass: writes every CSR value (zero fill included) with the tabulated /
+    // reference-type contributions summed in COO order; the cell-centric kernels then add the rest
     ProfScope ps(ctx, "gather_reference");
     if (do_mat) {
-      for (size_t di = 0; di < ctx->doms.size(); ++di)
-        if (ctx->doms[di]->ncls > 0) {
-          launch_build_class_tables(ctx->gather_doms.p, (int)di, ctx->doms[di]->ctab_work, ctx->nmat,
-                                    ctx->is_complex, s);
-          ++ctx->launches;
-        }
       launch_gather_reference(ctx->run_start.p, ctx->gather_rec.p, ctx->nnz, ctx->gather_doms.p,
                               (int)ctx->doms.size(), ctx->nrp_total, ctx->tab_total, mp.data(), (int)mp.size(),
                               ctx->is_complex, ctx->nsm, s);
@@ -533,13 +635,26 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   }
   for (size_t di = 0; di < ctx->doms.size(); ++di) {
     Domain& d = *ctx->doms[di];
-    bool gen_mat = do_mat && !d.terms_host.empty();
+    bool gen_mat = do_mat && !d.terms_host.empty() && !d.cls_full;
     bool gen_vec = do_vec && !d.rhs_host.empty();
+    if (gen_vec && d.rhs_fast) {
+      ProfScope ps(ctx, "rhs_affine:dom" + std::to_string(di));
+      launch_rhs_affine(d.dev, d.rhs_dev.p, (int)d.rhs_host.size(), d.cellgeo.p, vp.data(), (int)vp.size(),
+                        ctx->is_complex, ctx->nsm, s);
+      ++ctx->launches;
+      gen_vec = false;
+    }
     if (gen_mat || gen_vec) {
       ProfScope ps(ctx, "integrate_cells:dom" + std::to_string(di));
+      unsigned mask = ~0u;
+      if (!gen_mat) {                      // vector-only pass: stage the linear terms' operators only
+        mask = 0u;
+        for (const RhsDev& R : d.rhs_host)
+          for (int sl = 0; sl < d.dev.nslots; ++sl) if (R.opi[sl] >= 0) mask |= 1u << R.opi[sl];
+      }
       launch_integrate(d.dev, d.rhs_dev.p, (int)d.rhs_host.size(), d.dest_tiled.p, nullptr, d.dev.ncells,
                        mp.data(), (int)mp.size(), vp.data(), (int)vp.size(), ctx->is_complex,
-                       gen_mat, gen_vec, ctx->nsm, s);
+                       gen_mat, gen_vec, ctx->nsm, s, 0, mask);
       ++ctx->launches;
     }
   }
@@ -640,6 +755,7 @@ int vlfs_add_domain(vlfs_ctx* ctx, const vlfs_domain_desc* desc, int* domain_id)
     if (d.nweights) {
       if (!d.weights) return fail(ctx, VLFS_ERR_ARG, "weights missing");
       dom->weights.upload(d.weights, (size_t)d.nweights * d.ncells * d.nq, s);
+      dom->weights_host.assign(d.weights, d.weights + (size_t)d.nweights * d.ncells * d.nq);
     }
     dev.weights = dom->weights.p;
     if (d.C) dom->C.upload(d.C, (size_t)d.D * d.D * d.D * d.D, s);
@@ -668,6 +784,7 @@ int vlfs_add_domain(vlfs_ctx* ctx, const vlfs_domain_desc* desc, int* domain_id)
       const size_t tq = (size_t)d.nq;
       st.coords.upload(S.coords, nc * S.nv * d.D, s);
       if (!uniform) upload_opt(st.variant, S.variant, nc, s);
+      if (!uniform && S.variant) st.variant_host.assign(S.variant, S.variant + nc);
       st.geo_grad.upload(S.geo_grad + v0 * tq * S.nv * S.dref, (size_t)nvar * tq * S.nv * S.dref, s);
       st.val.upload(S.val + v0 * tq * S.ndofs, (size_t)nvar * tq * S.ndofs, s);
       st.grad.upload(S.grad + v0 * tq * S.ndofs * S.dref, (size_t)nvar * tq * S.ndofs * S.dref, s);
@@ -753,6 +870,12 @@ int vlfs_set_weights(vlfs_ctx* ctx, int domain_id, int weight, const double* val
     size_t n = (size_t)d.dev.ncells * d.dev.nq;
     CUDA_TRY(cudaMemcpyAsync(d.weights.p + (size_t)weight * n, values, n * sizeof(double),
                              cudaMemcpyHostToDevice, ctx->stream));
+    // a changed field that a bilinear term uses changes the element-block classes
+    if (memcmp(d.weights_host.data() + (size_t)weight * n, values, n * sizeof(double)) != 0) {
+      memcpy(d.weights_host.data() + (size_t)weight * n, values, n * sizeof(double));
+      for (const vlfs_term_desc& T : d.terms)
+        if (T.weight == weight) d.cls_dirty = true;
+    }
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return VLFS_OK;
   });
@@ -767,27 +890,14 @@ int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
     build_pattern_device(devs, ctx->ndofs, ctx->rowptr, ctx->colind, ctx->rowind, ctx->dest_all,
                          ctx->dest_off, ctx->perm, ctx->run_start, &n1, &n2, ctx->stream, &ctx->launches);
     {
-      std::vector<GatherDom> gd(ctx->doms.size());
-      for (size_t di = 0; di < ctx->doms.size(); ++di) {
-        Domain& d = *ctx->doms[di];
-        GatherDom& G = gd[di];
-        G.coo_lo = ctx->dest_off[di];
-        G.coo_hi = G.coo_lo + d.dev.ncells * (long long)d.dev.entries_per_cell;
-        G.epc = d.dev.entries_per_cell > 0 ? d.dev.entries_per_cell : 1;
-        G.nblocks = d.dev.nblocks;
-        for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) G.blk[b] = d.dev.blk[b];
-        for (int b = 0; b <= VLFS_MAX_BLOCKS; ++b) G.rp_first[b] = d.rp_first[b];
-        G.rp = d.refprods_dev.p; G.geo = d.cellgeo.p; G.tabs = d.reftabs.p; G.tab_len = (int)d.reftabs.n;
-        G.ncls = d.ncls; G.cls = d.cls.p; G.cls_geo = d.cls_geo.p; G.ctab = d.ctab.p;
-        for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) G.ctab_off[b] = d.ctab_off[b];
-      }
-      ctx->gather_doms.upload(gd.data(), gd.size(), ctx->stream);
+      for (auto& d : ctx->doms) classify_domain(ctx, *d);
+      upload_gather_doms(ctx);
       ctx->nrp_total = 0;
       ctx->tab_total = 0;
       for (auto& d : ctx->doms) { ctx->nrp_total += (int)d->refprods_host.size(); ctx->tab_total += (long long)d->reftabs.n; }
       if ((int)ctx->doms.size() > 16) throw std::string("more than 16 integration domains");
       ctx->gather_rec.alloc((size_t)n2);
-      launch_pack_gather_records(ctx->perm.p, n2, ctx->gather_doms.p, (int)gd.size(), ctx->gather_rec.p, ctx->stream);
+      launch_pack_gather_records(ctx->perm.p, n2, ctx->gather_doms.p, (int)ctx->doms.size(), ctx->gather_rec.p, ctx->stream);
       ++ctx->launches;
       CUDA_TRY(cudaStreamSynchronize(ctx->stream));
       ctx->perm.release();
@@ -795,6 +905,7 @@ int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
     ctx->nnz = n1; ctx->ncoo = n2;
     for (size_t di = 0; di < ctx->doms.size(); ++di) {
       Domain& d = *ctx->doms[di];
+      // (kept also for class-tabulated domains: a coefficient field may later break the classes)
       if (!d.terms_host.empty())
         build_tiled_dest(d.dev, ctx->dest_all.p + ctx->dest_off[di], d.dest_tiled, ctx->stream, &ctx->launches);
     }

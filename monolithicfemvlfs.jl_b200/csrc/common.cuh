@@ -168,8 +168,8 @@ struct GatherDom {
   int ncls;               // 0: no classes, per-cell factors are used
   const int* cls;         // [ncells] class of every cell
   const double* cls_geo;  // [ncls][VLFS_CELLGEO]
-  double* ctab;           // [block][class][local entry][nmat][scalar]
-  long long ctab_off[VLFS_MAX_BLOCKS];
+  double* ctab_m[4];      // per matrix: [block][class][local entry] scalars
+  long long ctab_off[VLFS_MAX_BLOCKS];   // entry offset of every block inside a class table
 };
 
 // ---- primitives -------------------------------------------------------------------

@@ -272,7 +272,7 @@ template <int D>
 __global__ void __launch_bounds__(256, 3)
 integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const int* __restrict__ dest,
                 const int* __restrict__ cell_list, long long ncells_run,
-                AsmPtrs ptrs, int is_complex, int do_mat, int do_vec) {
+                AsmPtrs ptrs, int is_complex, int do_mat, int do_vec, int dest_by_run, unsigned stage_mask) {
   extern __shared__ __align__(16) double sm[];
   const int nq = dom.nq, nqg = dom.nqg;
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -316,6 +316,7 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
     for (int o = 0; o < dom.nopi; ++o) {
       const OpInst& O = dom.opi[o];
       if ((O.buf_stride == 0) != invariant) continue;
+      if (!(stage_mask >> o & 1u)) continue;          // vector-only pass: tables of the linear terms
       const int nd = dom.slot[O.slot].ndofs;
       double* base = sm + O.smem_off + (size_t)par * O.buf_stride;
       for (int t = tid; t < nq * nd; t += nth) {
@@ -387,7 +388,8 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
         const int ti = lt / dom.tiles_j[b], tj = lt - ti * dom.tiles_j[b];
         const int i0 = ti * 4, j0 = tj * 4;
         // the tile's 16 CSR slots (tile-major dest, -1 = padding), fetched before the math
-        const int4* dt = reinterpret_cast<const int4*>(dest) + ((size_t)cell * ntiles + tile) * 4;
+        const int4* dt = reinterpret_cast<const int4*>(dest) +
+                         ((size_t)(dest_by_run ? first + k * step : cell) * ntiles + tile) * 4;
         int slot[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -601,6 +603,87 @@ __global__ void cell_geometry(DomainDev dom, int want_gradgrad, double* __restri
   }
 }
 
+// Linear forms on constant-Jacobian cells whose operators are cell-invariant value tables:
+// vec[dof] += coef * sc * meas(cell) * sum_q qw[q] (W_re + i W_im)(cell,q) N_i(q).  One warp per
+// cell, lanes over the local DOFs, tables through the read-only path; no shared memory, no barrier
+// (the general kernel pays its whole per-cell pipeline for a handful of FMAs here).
+__global__ void __launch_bounds__(256)
+rhs_affine(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const double* __restrict__ cellgeo,
+           AsmPtrs ptrs, int is_complex) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nq = dom.nq;
+  for (long long cell = warp; cell < dom.ncells; cell += nwarps) {
+    const double meas = cellgeo[(size_t)cell * VLFS_CELLGEO];
+    for (int t = 0; t < nrhs; ++t) {
+      const RhsDev R = rhs[t];
+      const double* Wr = R.wre >= 0 ? dom.weights + ((size_t)R.wre * dom.ncells + cell) * nq : nullptr;
+      const double* Wi = R.wim >= 0 ? dom.weights + ((size_t)R.wim * dom.ncells + cell) * nq : nullptr;
+      for (int s = 0; s < dom.nslots; ++s) {
+        if (R.opi[s] < 0) continue;
+        const SlotDev& S = dom.slot[s];
+        for (int i = lane; i < S.ndofs; i += 32) {
+          double ar = 0.0, ai = 0.0;
+          for (int q = 0; q < nq; ++q) {
+            const double v = dom.qweights[q] * __ldg(S.val + (size_t)q * S.ndofs + i);
+            ar = fma(Wr ? Wr[q] : 1.0, v, ar);
+            if (Wi) ai = fma(Wi[q], v, ai);
+          }
+          ar *= meas * R.sc[s]; ai *= meas * R.sc[s];
+          const double vr = R.cre * ar - R.cim * ai, vi = R.cre * ai + R.cim * ar;
+          const int dof = S.dofs[(size_t)cell * S.ndofs + i];
+          if (is_complex) {
+            if (vr != 0.0) red_add(ptrs.vec[R.vec] + 2 * (size_t)dof, vr);
+            if (vi != 0.0) red_add(ptrs.vec[R.vec] + 2 * (size_t)dof + 1, vi);
+          } else if (vr != 0.0) {
+            red_add(ptrs.vec[R.vec] + (size_t)dof, vr);
+          }
+        }
+      }
+    }
+  }
+}
+
+// Jacobian (transposed, [dref][D] padded to 3x3) of every slot at the first point: the complete
+// geometric description of a constant-Jacobian cell (classification key, computed once)
+template <int D>
+__global__ void cell_jacobians(DomainDev dom, double* __restrict__ out) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < dom.ncells * dom.nslots;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long cell = t / dom.nslots;
+    const SlotDev& S = dom.slot[(int)(t - cell * dom.nslots)];
+    const int var = S.variant ? S.variant[cell] : 0;
+    const double* gg = S.geo_grad + ((size_t)var * dom.nq) * S.nv * S.dref;
+    const double* X = S.coords + (size_t)cell * S.nv * D;
+    double Jt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int v = 0; v < S.nv; ++v)
+      for (int a = 0; a < S.dref; ++a)
+        for (int b = 0; b < D; ++b) Jt[a * 3 + b] = fma(gg[v * S.dref + a], X[v * D + b], Jt[a * 3 + b]);
+    for (int k = 0; k < 9; ++k) out[(size_t)t * 9 + k] = Jt[k];
+  }
+}
+
+// dest of the class representatives: entry (block, li) of representative r -> ctab_off[b] + r*ne + li
+__global__ void class_dest(DomainDev dom, int nreps, GatherDom G, int* __restrict__ tiled) {
+  const int ntiles = dom.tile_base[dom.nblocks];
+  const long long total = (long long)nreps * ntiles * 16;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long r = g / (ntiles * 16);
+    const int w = (int)(g - r * (ntiles * 16));
+    const int tile = w >> 4, a = (w >> 2) & 3, e = w & 3;
+    int b = 0;
+    while (tile >= dom.tile_base[b + 1]) ++b;
+    const BlockDev& B = dom.blk[b];
+    const int lt = tile - dom.tile_base[b];
+    const int ti = lt / dom.tiles_j[b], tj = lt - ti * dom.tiles_j[b];
+    const int i = ti * 4 + a, j = tj * 4 + e;
+    tiled[g] = (i < B.nr && j < B.nc) ? (int)(G.ctab_off[b] + r * (long long)(B.nr * B.nc) + i * B.nc + j)
+                                      : VLFS_DEST_PAD;
+  }
+}
+
 // T[i][j] = sum_q qw[q] valA[q][i] valB[q][j]   (both value tables cell-invariant)
 __global__ void mass_reference(const double* __restrict__ valA, int ndA, const double* __restrict__ valB, int ndB,
                                const double* __restrict__ qw, int nq, double* __restrict__ T) {
@@ -638,8 +721,7 @@ __global__ void build_class_tables(const GatherDom* __restrict__ doms, int d, in
   for (int b = 0; b < G.nblocks; ++b) {
     const int ne = G.blk[b].nr * G.blk[b].nc;
     const int k0 = G.rp_first[b], k1 = G.rp_first[b + 1];
-    if (k0 == k1) continue;
-    double* out = G.ctab + G.ctab_off[b];
+    if (G.ctab_off[b] < 0) continue;
     const long long total = (long long)G.ncls * ne;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
@@ -654,8 +736,9 @@ __global__ void build_class_tables(const GatherDom* __restrict__ doms, int d, in
         aim[P.mat] = fma(P.cim, v, aim[P.mat]);
       }
       for (int m = 0; m < nmat; ++m) {
-        out[((size_t)t * nmat + m) * sc] = are[m];
-        if (sc == 2) out[((size_t)t * nmat + m) * sc + 1] = aim[m];
+        double* out = G.ctab_m[m] + (size_t)(G.ctab_off[b] + t) * sc;
+        out[0] = are[m];
+        if (sc == 2) out[1] = aim[m];
       }
     }
   }
@@ -666,8 +749,9 @@ struct GatherSmemDom {
   const double* tabs;      // global tables, or (tab_smem) their copy in dynamic shared memory
   int ncls;
   const int* cls;
-  const double* ctab;
+  const double* ctab_m[4];
   long long ctab_off[VLFS_MAX_BLOCKS];
+  int has_ctab[VLFS_MAX_BLOCKS];      // block tabulated per class (reference products or all terms)
   int tab_smem;
   int rp_first[VLFS_MAX_BLOCKS + 1];
   int ne[VLFS_MAX_BLOCKS];
@@ -691,8 +775,12 @@ gather_reference(const uint32_t* __restrict__ run_start, const unsigned long lon
     int base = 0;
     for (int d = 0; d < ndom; ++d) {
       sd[d].geo = doms[d].geo; sd[d].tabs = doms[d].tabs; sd[d].tab_smem = 0;
-      sd[d].ncls = doms[d].ncls; sd[d].cls = doms[d].cls; sd[d].ctab = doms[d].ctab;
-      for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) sd[d].ctab_off[b] = doms[d].ctab_off[b];
+      sd[d].ncls = doms[d].ncls; sd[d].cls = doms[d].cls;
+      for (int m = 0; m < 4; ++m) sd[d].ctab_m[m] = doms[d].ctab_m[m];
+      for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) {
+        sd[d].ctab_off[b] = doms[d].ctab_off[b];
+        sd[d].has_ctab[b] = doms[d].ncls > 0 && doms[d].ctab_off[b] >= 0;
+      }
       for (int b = 0; b <= VLFS_MAX_BLOCKS; ++b) sd[d].rp_first[b] = doms[d].rp_first[b] + base;
       for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) sd[d].ne[b] = doms[d].blk[b].nr * doms[d].blk[b].nc;
       srp_base[d] = base;
@@ -725,23 +813,23 @@ gather_reference(const uint32_t* __restrict__ run_start, const unsigned long lon
       const unsigned e = (unsigned)(r & 0xffffffffull);
       const GatherSmemDom& G = sd[d];
       const int k0 = G.rp_first[b], k1 = G.rp_first[b + 1];
-      if (k0 == k1) continue;
       const int ne = G.ne[b];
-      if (G.ncls > 0) {                                    // tabulated element block of the class
+      if (G.has_ctab[b]) {                                 // tabulated element block of the class
         const int c = __ldg(G.cls + e);
-        const double* t = G.ctab + G.ctab_off[b] + ((size_t)c * ne + li) * NMAT * (is_complex ? 2 : 1);
+        const size_t t = (size_t)G.ctab_off[b] + (size_t)c * ne + li;
         if (is_complex) {
 #pragma unroll
           for (int m = 0; m < NMAT; ++m) {
-            const double2 v = __ldg(reinterpret_cast<const double2*>(t) + m);
+            const double2 v = __ldg(reinterpret_cast<const double2*>(G.ctab_m[m]) + t);
             are[m] += v.x; aim[m] += v.y;
           }
         } else {
 #pragma unroll
-          for (int m = 0; m < NMAT; ++m) are[m] += __ldg(t + m);
+          for (int m = 0; m < NMAT; ++m) are[m] += __ldg(G.ctab_m[m] + t);
         }
         continue;
       }
+      if (k0 == k1) continue;
       const double* geo = G.geo + (size_t)e * VLFS_CELLGEO;
       for (int k = k0; k < k1; ++k) {
         const RefProd& P = srp[k];
@@ -770,6 +858,36 @@ void launch_cell_geometry(const DomainDev& dom, int want_gradgrad, double* out, 
   if (dom.D == 1) cell_geometry<1><<<grid, 128, 0, s>>>(dom, want_gradgrad, out);
   else if (dom.D == 2) cell_geometry<2><<<grid, 128, 0, s>>>(dom, want_gradgrad, out);
   else cell_geometry<3><<<grid, 128, 0, s>>>(dom, want_gradgrad, out);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_rhs_affine(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, const double* cellgeo,
+                       double* const* vecs, int nvec, int is_complex, int nsm, cudaStream_t s) {
+  if (dom.ncells == 0 || nrhs == 0) return;
+  AsmPtrs P{};
+  for (int v = 0; v < nvec && v < 4; ++v) P.vec[v] = vecs[v];
+  long long grid = (dom.ncells + 7) / 8;
+  if (grid > (long long)nsm * 16) grid = (long long)nsm * 16;
+  rhs_affine<<<(unsigned)grid, 256, 0, s>>>(dom, rhs_dev, nrhs, cellgeo, P, is_complex);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_cell_jacobians(const DomainDev& dom, double* out, cudaStream_t s) {
+  if (dom.ncells == 0) return;
+  unsigned grid = (unsigned)((dom.ncells * dom.nslots + 127) / 128);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (dom.D == 1) cell_jacobians<1><<<grid, 128, 0, s>>>(dom, out);
+  else if (dom.D == 2) cell_jacobians<2><<<grid, 128, 0, s>>>(dom, out);
+  else cell_jacobians<3><<<grid, 128, 0, s>>>(dom, out);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_class_dest(const DomainDev& dom, int nreps, const GatherDom& G, int* tiled, cudaStream_t s) {
+  const long long total = (long long)nreps * dom.tile_base[dom.nblocks] * 16;
+  if (total == 0) return;
+  unsigned grid = (unsigned)((total + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  class_dest<<<grid, 256, 0, s>>>(dom, nreps, G, tiled);
   CUDA_TRY(cudaGetLastError());
 }
 
@@ -828,7 +946,7 @@ void launch_gather_reference(const uint32_t* run_start, const unsigned long long
 void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, const int* dest,
                       const int* cell_list, long long ncells_run, double* const* mats,
                       int nmat, double* const* vecs, int nvec, int is_complex, int do_mat,
-                      int do_vec, int nsm, cudaStream_t s) {
+                      int do_vec, int nsm, cudaStream_t s, int dest_by_run, unsigned stage_mask) {
   if (ncells_run == 0) return;
   AsmPtrs P{};
   for (int m = 0; m < nmat && m < 4; ++m) P.mat[m] = mats[m];
@@ -857,7 +975,7 @@ void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, con
   auto launch = [&](auto kern) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, threads, smem, s>>>(dom, rhs_dev, nrhs, dest, cell_list, ncells_run, P,
-                                               is_complex, do_mat, do_vec);
+                                               is_complex, do_mat, do_vec, dest_by_run, stage_mask);
   };
   if (dom.D == 1) launch(integrate_cells<1>);
   else if (dom.D == 2) launch(integrate_cells<2>);
