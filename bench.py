@@ -378,8 +378,8 @@ def run_ours_distributed(args):
                  "symbolic_ms": info["symbolic_ms"], "numeric_ms": info["numeric_ms"],
                  "gmres_iterations": st["iterations"], "rel_residual": st["rel_residual"],
                  "converged": st["converged"], "stagnated_at_attainable_accuracy": st["stagnated"],
-                 "interface_unknowns": int(schur.ng),
-                 "method": "substructuring: per-rank partial multifrontal LU + dense interface LU on rank 0, "
+                 "interface_unknowns": int(schur.ng), "interface_solver": schur.interface_solver,
+                 "method": "substructuring: per-rank partial multifrontal LU + interface LU on rank 0, "
                            "as preconditioner of distributed GMRES",
                  "max_front": info["maxfront"]}
 

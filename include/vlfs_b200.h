@@ -253,13 +253,16 @@ int vlfs_get_vector_device(vlfs_ctx* ctx, int vec, void** ptr);
  * partial: vlfs_schur_get accumulates S += -A_KE A_EE^-1 A_EK into an n_keep x n_keep row-major
  * device matrix (kept unknowns in ascending local id), vlfs_schur_forward accumulates
  * g += -A_KE A_EE^-1 b_E, vlfs_schur_backward solves the eliminated unknowns for given kept values.
- * vlfs_dense_factor / vlfs_dense_solve: LU of the assembled interface system on one GPU. */
+ * vlfs_dense_factor / vlfs_chain_factor + vlfs_dense_solve: LU of the assembled interface system
+ * (dense, or block tridiagonal by cuts) on one GPU. */
 int vlfs_set_roles(vlfs_ctx* ctx, const int8_t* role);
 int vlfs_schur_size(vlfs_ctx* ctx, int64_t* n_keep);
 int vlfs_schur_get(vlfs_ctx* ctx, void* S_dev);
 int vlfs_schur_forward(vlfs_ctx* ctx, const void* b_dev, void* g_keep_dev);
 int vlfs_schur_backward(vlfs_ctx* ctx, const void* x_keep_dev, void* x_dev);
 int vlfs_dense_factor(vlfs_ctx* ctx, int64_t n, const void* S_dev);
+/* block-tridiagonal S (slab cuts in rank order, blocks of `sizes`): chain of fronts, O(sum n_r^3) */
+int vlfs_chain_factor(vlfs_ctx* ctx, int nblocks, const int64_t* sizes, const void* S_dev);
 int vlfs_dense_solve(vlfs_ctx* ctx, const void* b_dev, void* x_dev);
 
 #ifdef __cplusplus

@@ -75,7 +75,7 @@ EXPORTS = [
     "vlfs_set_stream", "vlfs_set_owned_rows", "vlfs_dev_spmv", "vlfs_dev_precond", "vlfs_dev_multidot",
     "vlfs_dev_gemv_sub", "vlfs_dev_axpby", "vlfs_dev_gather", "vlfs_get_vector_device",
     "vlfs_eval_functional", "vlfs_set_roles", "vlfs_schur_size", "vlfs_schur_get", "vlfs_schur_forward",
-    "vlfs_schur_backward", "vlfs_dense_factor", "vlfs_dense_solve",
+    "vlfs_schur_backward", "vlfs_dense_factor", "vlfs_chain_factor", "vlfs_dense_solve",
 ]
 
 _lib = None
@@ -148,6 +148,7 @@ def load():
     lib.vlfs_schur_forward.argtypes = [vp, vp, vp]
     lib.vlfs_schur_backward.argtypes = [vp, vp, vp]
     lib.vlfs_dense_factor.argtypes = [vp, C.c_int64, vp]
+    lib.vlfs_chain_factor.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), vp]
     lib.vlfs_dense_solve.argtypes = [vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)

@@ -1383,6 +1383,17 @@ int vlfs_dense_factor(vlfs_ctx* ctx, int64_t n, const void* S_dev) {
   });
 }
 
+int vlfs_chain_factor(vlfs_ctx* ctx, int nblocks, const int64_t* sizes, const void* S_dev) {
+  return guarded(ctx, [&]() {
+    if (nblocks < 1 || nblocks > 4096 || !sizes || !S_dev) return fail(ctx, VLFS_ERR_ARG, "vlfs_chain_factor: bad arguments");
+    std::vector<long long> sz(sizes, sizes + nblocks);
+    for (long long v : sz) if (v < 1) return fail(ctx, VLFS_ERR_ARG, "vlfs_chain_factor: empty block");
+    ctx->dense = direct_chain(nblocks, sz.data(), ctx->is_complex, ctx->nsm, ctx->stream, &ctx->launches);
+    direct_chain_factor(*ctx->dense, (const double*)S_dev);
+    return VLFS_OK;
+  });
+}
+
 int vlfs_dense_solve(vlfs_ctx* ctx, const void* b_dev, void* x_dev) {
   return guarded(ctx, [&]() {
     if (!ctx->dense || !b_dev || !x_dev) return fail(ctx, VLFS_ERR_STATE, "vlfs_dense_factor first");

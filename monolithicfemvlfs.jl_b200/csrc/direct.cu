@@ -307,6 +307,19 @@ __global__ void add_root_schur(FrontMeta F, const int* __restrict__ upd_idx, int
     *dst = N::add(*dst, pool[F.off + (long long)(F.np + a) * F.nf + F.np + b]);
   }
 }
+// front of a block-tridiagonal chain <- dense interface matrix S (ng x ng): pivots [o, o+np), update
+// [o+np, o+nf); the update x update corner belongs to the next front
+template <bool C>
+__global__ void chain_fill(FrontMeta F, const typename Num<C>::T* __restrict__ S, long long ng,
+                           typename Num<C>::T* __restrict__ pool) {
+  using N = Num<C>;
+  const long long total = (long long)F.nf * F.nf;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / F.nf), j = (int)(t - (long long)i * F.nf);
+    pool[F.off + t] = (i >= F.np && j >= F.np) ? N::zero() : S[(long long)(F.first + i) * ng + F.first + j];
+  }
+}
+
 // g[keep a] += update part of a root's work vector (forward sweep);  xp[kept] = xk (backward)
 template <bool C>
 __global__ void add_root_rhs(FrontMeta F, const int* __restrict__ upd_idx, int n_elim,
@@ -913,6 +926,71 @@ DirectPtr direct_dense(long long n, int is_complex, int nsm, cudaStream_t s, lon
   D->w.alloc((size_t)n * sc); D->bp.alloc((size_t)n * sc); D->xp.alloc((size_t)n * sc);
   CUDA_TRY(cudaStreamSynchronize(s));
   return D;
+}
+
+// ---- block-tridiagonal interface system (slab cuts in rank order): a chain of fronts, front r has
+// the unknowns of cut r as pivots and those of cut r+1 as update set - the same kernels, O(sum n_r^3)
+DirectPtr direct_chain(int nblocks, const long long* sizes, int is_complex, int nsm, cudaStream_t s,
+                       long long* launches) {
+  DirectPtr D(new DirectSolver());
+  long long n = 0;
+  for (int r = 0; r < nblocks; ++r) n += sizes[r];
+  D->n = n; D->n_total = n; D->n_keep = 0; D->nnz = 0; D->cplx = is_complex; D->nsm = nsm; D->s = s;
+  D->launches = launches; D->dense = true;
+  D->nfronts = nblocks; D->nlevels = nblocks;
+  D->meta.resize(nblocks);
+  std::vector<int> upd_flat, lists(nblocks);
+  long long off = 0, woff = 0, o = 0;
+  int cm = 0;
+  D->level_lists.assign(nblocks, {});
+  D->level_maxnp.assign(nblocks, 0); D->level_maxnf.assign(nblocks, 0); D->level_maxnu_child.assign(nblocks, 0);
+  D->list_off.resize(nblocks);
+  for (int r = 0; r < nblocks; ++r) {
+    FrontMeta& M = D->meta[r];
+    M.first = (int)o; M.np = (int)sizes[r]; M.nf = M.np + (r + 1 < nblocks ? (int)sizes[r + 1] : 0);
+    M.off = off; M.woff = woff; M.upd_ptr = (int)upd_flat.size(); M.cmap_ptr = cm;
+    M.parent = r + 1 < nblocks ? r + 1 : -1; M.child[0] = r > 0 ? r - 1 : -1; M.child[1] = -1;
+    for (int k = M.np; k < M.nf; ++k) upd_flat.push_back((int)(o + k));
+    off += (long long)M.nf * M.nf; woff += M.nf; cm += M.nf - M.np; o += sizes[r];
+    D->maxnf = std::max(D->maxnf, M.nf);
+    D->level_lists[r].push_back(r); lists[r] = r; D->list_off[r] = r;
+    D->level_maxnp[r] = M.np; D->level_maxnf[r] = M.nf;
+    D->level_maxnu_child[r] = r > 0 ? D->meta[r - 1].nf - D->meta[r - 1].np : 0;
+    const double np = M.np, nu = M.nf - M.np;
+    D->fill += (long long)(np * np + 2 * np * nu);
+    D->flops += (2.0 / 3.0) * np * np * np + 2 * np * np * nu + 2 * np * nu * nu;
+  }
+  D->roots.assign(1, nblocks - 1);
+  D->pool_elems = off; D->w_elems = woff;
+  std::vector<int> pos(n);
+  std::iota(pos.begin(), pos.end(), 0);
+  if (upd_flat.empty()) upd_flat.push_back(0);
+  D->d_meta.upload(D->meta.data(), nblocks, s);
+  D->d_pos.upload(pos.data(), n, s);
+  D->d_front_of_pos.alloc(1);
+  D->d_upd.upload(upd_flat.data(), upd_flat.size(), s);
+  D->d_cmap.alloc(std::max(cm, 1));
+  D->d_lists.upload(lists.data(), lists.size(), s);
+  build_cmap<<<nblocks, 128, 0, s>>>(D->d_meta.p, nblocks, D->d_upd.p, D->d_cmap.p);
+  const size_t sc = is_complex ? 2 : 1;
+  D->pool.alloc((size_t)off * sc);
+  D->w.alloc((size_t)woff * sc); D->bp.alloc((size_t)n * sc); D->xp.alloc((size_t)n * sc);
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaGetLastError());
+  return D;
+}
+
+void direct_chain_factor(DirectSolver& D, const double* S_dev) {
+  D.numeric_ms = timed(D.s, [&]() {
+    for (int r = 0; r < D.nfronts; ++r) {
+      const FrontMeta& F = D.meta[r];
+      const unsigned grid = (unsigned)std::min<long long>(((long long)F.nf * F.nf + 255) / 256, (long long)D.nsm * 16);
+      if (D.cplx) chain_fill<true><<<grid, 256, 0, D.s>>>(F, reinterpret_cast<const double2*>(S_dev), D.n, reinterpret_cast<double2*>(D.pool.p));
+      else chain_fill<false><<<grid, 256, 0, D.s>>>(F, S_dev, D.n, D.pool.p);
+      ++*D.launches;
+    }
+    if (D.cplx) factor_levels<true>(D); else factor_levels<false>(D);
+  });
 }
 
 void direct_dense_factor(DirectSolver& D, const double* S_dev) {

@@ -23,5 +23,9 @@ long long direct_nkeep(const DirectSolver& D);
 // dense n x n LU with the same front kernels (interface system)
 DirectPtr direct_dense(long long n, int is_complex, int nsm, cudaStream_t s, long long* launches);
 void direct_dense_factor(DirectSolver& D, const double* S_dev);
+// block-tridiagonal n x n system (blocks of the given sizes, dense row-major S): chain of fronts
+DirectPtr direct_chain(int nblocks, const long long* sizes, int is_complex, int nsm, cudaStream_t s,
+                       long long* launches);
+void direct_chain_factor(DirectSolver& D, const double* S_dev);
 // {nfronts, nlevels, maxfront, fill(entries), flops, pool bytes, symbolic ms, numeric ms}
 void direct_info(const DirectSolver& D, double* out8);

@@ -270,8 +270,20 @@ class GpuOps:
     def dense_factor(self, n, S):
         self.sys._check(self.lib.vlfs_dense_factor(self.ctx, n, self._p(S)))
 
+    def chain_factor(self, sizes, S):
+        sz = np.ascontiguousarray(sizes, dtype=np.int64)
+        self.sys._check(self.lib.vlfs_chain_factor(self.ctx, len(sz), sz.ctypes.data_as(C.POINTER(C.c_int64)), self._p(S)))
+
     def dense_solve(self, b, x):
         self.sys._check(self.lib.vlfs_dense_solve(self.ctx, self._p(b), self._p(x)))
+
+    def add_triplets(self, S, n, rows, cols, vals):
+        """S[rows, cols] += vals on the device (flat row-major n x n)."""
+        t = self.torch
+        r = t.from_numpy(np.ascontiguousarray(rows, dtype=np.int64)).to(self.device)
+        c = t.from_numpy(np.ascontiguousarray(cols, dtype=np.int64)).to(self.device)
+        v = self.from_host(np.ascontiguousarray(vals, dtype=self.d.dtype)).view(-1, self.sc)
+        S.view(n, n, self.sc).index_put_((r, c), v, accumulate=True)
 
     def vec(self, n):
         return self.torch.zeros(n * self.sc, dtype=self.torch.float64, device=self.device)
@@ -538,17 +550,30 @@ class SchurSolver:
             gathered = [None] * F.nranks
             F.dist.all_gather_object(gathered, infos[0])
             infos = gathered
-        gam_all = np.concatenate([g for _, g in sorted(infos, key=lambda t: t[0])]) if infos else np.zeros(0, int)
-        self.gamma = np.sort(gam_all)                                # global ids of the interface
+        # interface unknowns grouped by cut (= owner rank), ascending global id inside a cut: the
+        # interface matrix is block tridiagonal in this order (a cut couples only to its neighbours)
+        per_rank = [np.sort(g) for _, g in sorted(infos, key=lambda t: t[0])]
+        self.block_sizes = [len(g) for g in per_rank if len(g)]
+        self.gamma = np.concatenate(per_rank) if per_rank else np.zeros(0, dtype=np.int64)
+        self.block_of = np.repeat(np.arange(len(self.block_sizes)), self.block_sizes)
         self.ng = len(self.gamma)
+        order = np.argsort(self.gamma, kind="stable")
+        gsorted = self.gamma[order]
+        self._gsorted, self._gorder = gsorted, order
+
+        def position(gids):
+            p = order[np.searchsorted(gsorted, gids)]
+            assert np.array_equal(self.gamma[p], gids)
+            return p
+        self.position = position
         for m in F.members:
-            m.keep_pos = np.searchsorted(self.gamma, m.keep_gids)    # position of B_r in Γ
-            assert np.array_equal(self.gamma[m.keep_pos], m.keep_gids)
-            m.gamma_pos = np.searchsorted(self.gamma, m.d.local_gids[m.gamma_local])
+            m.keep_pos = position(m.keep_gids)                       # position of B_r in Γ
+            m.gamma_pos = position(m.d.local_gids[m.gamma_local])
             m.keep_t = m.ops.long_index(m.keep_local)
             m.gamma_t = m.ops.long_index(m.gamma_local)
             m.ops.set_roles(m.role)
         self.root = F.by_rank.get(0)
+        self.interface_solver = None
 
     # gather variable-size device vectors of every rank on rank 0 (list indexed by rank) ------
     def _gather(self, parts, sizes):
@@ -601,9 +626,9 @@ class SchurSolver:
             # A[Γ_r rows, Γ columns] from the owner's complete rows (host CSR, setup only)
             A = m.d.local.get_matrix(self.mat)[m.gamma_local]
             cols_g = m.d.local_gids[A.indices]
-            inG = np.isin(cols_g, self.gamma)
+            inG = np.isin(cols_g, self._gsorted)
             rows = np.repeat(m.gamma_pos, np.diff(A.indptr))[inG]
-            cols = np.searchsorted(self.gamma, cols_g[inG])
+            cols = self.position(cols_g[inG])
             agg.append((rows, cols, A.data[inG]))
         if F.dist is not None:
             meta = [None] * F.nranks
@@ -618,13 +643,20 @@ class SchurSolver:
         if self.root is not None:
             ops = self.root.ops
             S = ops.vec(self.ng * self.ng)
-            dense = np.zeros((self.ng, self.ng), dtype=self.root.d.dtype)
+            tridiag = True
             for rows, cols, vals in agg:
-                np.add.at(dense, (rows, cols), vals)
-            S += ops.dense_from_host(dense)
+                ops.add_triplets(S, self.ng, rows, cols, vals)
+                tridiag &= bool(np.all(np.abs(self.block_of[rows] - self.block_of[cols]) <= 1))
             for r, blk in got.items():
                 ops.add_block(S, self.ng, pos[r], blk, nks[r])
-            ops.dense_factor(self.ng, S)
+                bl = self.block_of[pos[r]]
+                tridiag &= bool(len(bl) == 0 or bl.max() - bl.min() <= 1)
+            if tridiag and len(self.block_sizes) > 1:
+                ops.chain_factor(self.block_sizes, S)      # O(sum n_r^3): chain of fronts
+                self.interface_solver = "block-tridiagonal chain of %d fronts" % len(self.block_sizes)
+            else:
+                ops.dense_factor(self.ng, S)
+                self.interface_solver = "dense"
             self.xg = ops.vec(self.ng)
             self.gg = ops.vec(self.ng)
             self.pos_t = {r: ops.long_index(pos[r]) for r in pos}

@@ -119,6 +119,13 @@ class CpuOps:
         import scipy.linalg as sla
         self._dense = sla.lu_factor(np.asarray(S).reshape(n, n))
 
+    def chain_factor(self, sizes, S):
+        assert sum(sizes) * sum(sizes) == len(S)
+        self.dense_factor(int(sum(sizes)), S)
+
+    def add_triplets(self, S, n, rows, cols, vals):
+        np.add.at(S.reshape(n, n), (rows, cols), vals)
+
     def dense_solve(self, b, x):
         import scipy.linalg as sla
         x[...] = sla.lu_solve(self._dense, b)
