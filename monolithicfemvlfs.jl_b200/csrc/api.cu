@@ -27,8 +27,10 @@ void launch_class_dest(const DomainDev& dom, int nreps, const GatherDom& G, int*
 void launch_build_class_tables(const GatherDom* doms, int d, long long work, int nmat, int is_complex, cudaStream_t s);
 void launch_pack_gather_records(const uint32_t* perm, long long ncoo, const GatherDom* doms, int ndom,
                                 unsigned long long* rec, cudaStream_t s);
-void launch_gather_reference(const uint32_t* run_start, const unsigned long long* rec, long long nnz,
-                             const GatherDom* doms, int ndom, int nrp_total, long long tab_total,
+void launch_compact_gather_records(const unsigned long long* rec, long long ncoo, const GatherDom* doms,
+                                   uint32_t* out, cudaStream_t s);
+void launch_gather_reference(const uint32_t* run_start, const unsigned long long* rec, const uint32_t* rec32,
+                             long long nnz, const GatherDom* doms, int ndom, int nrp_total, long long tab_total,
                              double* const* mats, int nmat, int is_complex, int nsm, cudaStream_t s);
 void build_csc_device(const int* rowind, const int* colind, long long nnz, long long ndofs,
                       DevBuf<int>& colptr, DevBuf<int>& rowval, DevBuf<int>& csr_slot,
@@ -122,6 +124,8 @@ struct vlfs_ctx {
   DevBuf<int> rowptr, colind, rowind, dest_all;
   DevBuf<uint32_t> perm, run_start;     // sorted COO order and first sorted entry of every slot
   DevBuf<unsigned long long> gather_rec;   // packed (domain, block, local entry, cell) per sorted entry
+  DevBuf<uint32_t> gather_rec32;           // (domain, block, local entry, class) when every domain has classes
+  bool rec32_valid = false;
   int nrp_total = 0;
   long long tab_total = 0;
   DevBuf<GatherDom> gather_doms;
@@ -580,6 +584,9 @@ void upload_gather_doms(vlfs_ctx* ctx) {
     G.epc = d.dev.entries_per_cell > 0 ? d.dev.entries_per_cell : 1;
     G.nblocks = d.dev.nblocks;
     for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) G.blk[b] = d.dev.blk[b];
+    for (int b = 0; b < d.dev.nblocks; ++b)
+      if (d.dev.blk[b].nr * d.dev.blk[b].nc > 16384)
+        throw std::string("a touched block has more than 16384 entries per cell (gather record field)");
     for (int b = 0; b <= VLFS_MAX_BLOCKS; ++b) G.rp_first[b] = d.rp_first[b];
     G.rp = d.refprods_dev.p; G.geo = d.cellgeo.p; G.tabs = d.reftabs.p; G.tab_len = (int)d.reftabs.n;
     G.ncls = d.ncls; G.cls = d.cls.p; G.cls_geo = d.cls_geo.p;
@@ -589,6 +596,23 @@ void upload_gather_doms(vlfs_ctx* ctx) {
   if (ctx->gather_doms.n != gd.size()) ctx->gather_doms.alloc(gd.size());
   CUDA_TRY(cudaMemcpyAsync(ctx->gather_doms.p, gd.data(), gd.size() * sizeof(GatherDom), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+}
+
+// 32-bit class records: possible when every domain that owns COO entries is class-tabulated and
+// the fields fit (8 domains, 4 blocks, 16 384 local entries, 8 192 classes)
+void rebuild_compact_records(vlfs_ctx* ctx) {
+  ctx->rec32_valid = false;
+  if (ctx->gather_rec.n == 0 || ctx->doms.size() > 8) return;
+  for (auto& d : ctx->doms) {
+    if (d->dev.ncells * (long long)d->dev.entries_per_cell == 0) continue;
+    if (d->ncls == 0 || d->ncls > 8192) return;
+  }
+  if (ctx->gather_rec32.n != ctx->gather_rec.n) ctx->gather_rec32.alloc(ctx->gather_rec.n);
+  launch_compact_gather_records(ctx->gather_rec.p, (long long)ctx->gather_rec.n, ctx->gather_doms.p,
+                                ctx->gather_rec32.p, ctx->stream);
+  ++ctx->launches;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->rec32_valid = true;
 }
 
 void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
@@ -602,7 +626,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     bool reclass = false;
     for (auto& dp : ctx->doms)
       if (dp->cls_dirty) { classify_domain(ctx, *dp); reclass = true; }
-    if (reclass) upload_gather_doms(ctx);
+    if (reclass) { upload_gather_doms(ctx); rebuild_compact_records(ctx); }
   }
   if (do_mat) {
     // per-class element blocks: reference products tabulated directly, general (quadrature) terms
@@ -626,7 +650,8 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     // reference-type contributions summed in COO order; the cell-centric kernels then add the rest
     ProfScope ps(ctx, "gather_reference");
     if (do_mat) {
-      launch_gather_reference(ctx->run_start.p, ctx->gather_rec.p, ctx->nnz, ctx->gather_doms.p,
+      launch_gather_reference(ctx->run_start.p, ctx->gather_rec.p,
+                              ctx->rec32_valid ? ctx->gather_rec32.p : nullptr, ctx->nnz, ctx->gather_doms.p,
                               (int)ctx->doms.size(), ctx->nrp_total, ctx->tab_total, mp.data(), (int)mp.size(),
                               ctx->is_complex, ctx->nsm, s);
       ++ctx->launches;
@@ -901,6 +926,7 @@ int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
       ++ctx->launches;
       CUDA_TRY(cudaStreamSynchronize(ctx->stream));
       ctx->perm.release();
+      rebuild_compact_records(ctx);
     }
     ctx->nnz = n1; ctx->ncoo = n2;
     for (size_t di = 0; di < ctx->doms.size(); ++di) {

@@ -744,6 +744,20 @@ __global__ void build_class_tables(const GatherDom* __restrict__ doms, int d, in
   }
 }
 
+// 64-bit (domain, block, entry, cell) records -> 32-bit (domain:3 | block:2 | entry:14 | class:13)
+// records, valid when every domain is class-tabulated: the gather then needs no per-cell load at all
+__global__ void compact_gather_records(const unsigned long long* __restrict__ rec, long long ncoo,
+                                       const GatherDom* __restrict__ doms, uint32_t* __restrict__ out) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < ncoo;
+       p += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long r = rec[p];
+    const unsigned d = (unsigned)(r >> 60), b = (unsigned)((r >> 58) & 3u), li = (unsigned)((r >> 32) & 0x3fffu);
+    const unsigned e = (unsigned)(r & 0xffffffffull);
+    const unsigned c = doms[d].ncls > 0 ? (unsigned)doms[d].cls[e] : 0u;
+    out[p] = (d << 29) | (b << 27) | (li << 13) | c;
+  }
+}
+
 struct GatherSmemDom {
   const double* geo;
   const double* tabs;      // global tables, or (tab_smem) their copy in dynamic shared memory
@@ -760,9 +774,10 @@ constexpr int GATHER_MAX_DOM = 16, GATHER_MAX_RP = 96;
 
 // One thread per CSR slot: sums the reference-type contributions of the slot's COO entries in COO
 // order (deterministic, no atomics) and WRITES the value - this pass also replaces the zero fill.
-template <int NMAT>
+template <int NMAT, bool COMPACT>
 __global__ void __launch_bounds__(256)
-gather_reference(const uint32_t* __restrict__ run_start, const unsigned long long* __restrict__ rec, long long nnz,
+gather_reference(const uint32_t* __restrict__ run_start, const unsigned long long* __restrict__ rec,
+                 const uint32_t* __restrict__ rec32, long long nnz,
                  const GatherDom* __restrict__ doms, int ndom, int nrp_total, AsmPtrs ptrs, int nmat,
                  int is_complex, int tabs_in_smem) {
   // the reference tables are looked up at scattered local entries: from shared memory a warp's 32
@@ -808,6 +823,25 @@ gather_reference(const uint32_t* __restrict__ run_start, const unsigned long lon
     const uint32_t p1 = run_start[slot + 1];
     // (a 4-way unrolled version that fetches records and class ids ahead was measured slower)
     for (uint32_t p = run_start[slot]; p < p1; ++p) {
+      if (COMPACT) {                       // every domain is class-tabulated: record -> table entry
+        const uint32_t r = rec32[p];
+        const int d = (int)(r >> 29), b = (int)((r >> 27) & 3u), li = (int)((r >> 13) & 0x3fffu);
+        const int c = (int)(r & 0x1fffu);
+        const GatherSmemDom& G = sd[d];
+        if (!G.has_ctab[b]) continue;
+        const size_t t = (size_t)G.ctab_off[b] + (size_t)c * G.ne[b] + li;
+        if (is_complex) {
+#pragma unroll
+          for (int m = 0; m < NMAT; ++m) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(G.ctab_m[m]) + t);
+            are[m] += v.x; aim[m] += v.y;
+          }
+        } else {
+#pragma unroll
+          for (int m = 0; m < NMAT; ++m) are[m] += __ldg(G.ctab_m[m] + t);
+        }
+        continue;
+      }
       const unsigned long long r = rec[p];
       const int d = (int)(r >> 60), b = (int)((r >> 58) & 3u), li = (int)((r >> 32) & 0x3fffu);
       const unsigned e = (unsigned)(r & 0xffffffffull);
@@ -914,8 +948,17 @@ void launch_pack_gather_records(const uint32_t* perm, long long ncoo, const Gath
   CUDA_TRY(cudaGetLastError());
 }
 
-void launch_gather_reference(const uint32_t* run_start, const unsigned long long* rec, long long nnz,
-                             const GatherDom* doms, int ndom, int nrp_total, long long tab_total,
+void launch_compact_gather_records(const unsigned long long* rec, long long ncoo, const GatherDom* doms,
+                                   uint32_t* out, cudaStream_t s) {
+  if (ncoo == 0) return;
+  long long grid = (ncoo + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  compact_gather_records<<<(unsigned)grid, 256, 0, s>>>(rec, ncoo, doms, out);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_gather_reference(const uint32_t* run_start, const unsigned long long* rec, const uint32_t* rec32,
+                             long long nnz, const GatherDom* doms, int ndom, int nrp_total, long long tab_total,
                              double* const* mats, int nmat, int is_complex, int nsm, cudaStream_t s) {
   if (nnz == 0) return;
   if (ndom > GATHER_MAX_DOM || nrp_total > GATHER_MAX_RP)
@@ -930,14 +973,23 @@ void launch_gather_reference(const uint32_t* run_start, const unsigned long long
   if (grid > cap) grid = cap;
   auto launch = [&](auto kern) {
     if (in_smem) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, 256, in_smem ? smem : 0, s>>>(run_start, rec, nnz, doms, ndom, nrp_total, P, nmat,
+    kern<<<(unsigned)grid, 256, in_smem ? smem : 0, s>>>(run_start, rec, rec32, nnz, doms, ndom, nrp_total, P, nmat,
                                                         is_complex, in_smem);
   };
-  switch (nmat) {
-    case 1: launch(gather_reference<1>); break;
-    case 2: launch(gather_reference<2>); break;
-    case 3: launch(gather_reference<3>); break;
-    default: launch(gather_reference<4>); break;
+  if (rec32) {
+    switch (nmat) {
+      case 1: launch(gather_reference<1, true>); break;
+      case 2: launch(gather_reference<2, true>); break;
+      case 3: launch(gather_reference<3, true>); break;
+      default: launch(gather_reference<4, true>); break;
+    }
+  } else {
+    switch (nmat) {
+      case 1: launch(gather_reference<1, false>); break;
+      case 2: launch(gather_reference<2, false>); break;
+      case 3: launch(gather_reference<3, false>); break;
+      default: launch(gather_reference<4, false>); break;
+    }
   }
   CUDA_TRY(cudaGetLastError());
 }
