@@ -115,6 +115,8 @@ struct vlfs_ctx {
   int device = 0;
   int nsm = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // class tables of different domains in parallel
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   std::string err;
   long long ndofs = 0;
   int is_complex = 0, nmat = 0, nvec = 0;
@@ -630,20 +632,39 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   }
   if (do_mat) {
     // per-class element blocks: reference products tabulated directly, general (quadrature) terms
-    // integrated on the class representatives only, reduced into the class tables
+    // integrated on the class representatives only, reduced into the class tables.  These are
+    // small latency-bound launches: the domains run side by side on auxiliary streams.
     ProfScope ps(ctx, "class_tables");
+    if (!ctx->ev_fork) {
+      CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      for (int k = 0; k < 3; ++k) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming));
+      }
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev_fork, s));
+    bool used[3] = {false, false, false};
+    int k = 0;
     for (size_t di = 0; di < ctx->doms.size(); ++di) {
       Domain& d = *ctx->doms[di];
       if (d.ncls == 0) continue;
-      launch_build_class_tables(ctx->gather_doms.p, (int)di, d.ctab_work, ctx->nmat, ctx->is_complex, s);
+      cudaStream_t a = ctx->aux[k % 3];
+      if (!used[k % 3]) { CUDA_TRY(cudaStreamWaitEvent(a, ctx->ev_fork, 0)); used[k % 3] = true; }
+      ++k;
+      launch_build_class_tables(ctx->gather_doms.p, (int)di, d.ctab_work, ctx->nmat, ctx->is_complex, a);
       ++ctx->launches;
       if (d.cls_full) {
         double* cm[4] = {d.ctab_m[0].p, d.ctab_m[1].p, d.ctab_m[2].p, d.ctab_m[3].p};
         launch_integrate(d.dev, d.rhs_dev.p, 0, d.dest_cls.p, d.reps.p, d.ncls, cm, ctx->nmat, vp.data(),
-                         (int)vp.size(), ctx->is_complex, 1, 0, ctx->nsm, s, 1);
+                         (int)vp.size(), ctx->is_complex, 1, 0, ctx->nsm, a, 1);
         ++ctx->launches;
       }
     }
+    for (int q = 0; q < 3; ++q)
+      if (used[q]) {
+        CUDA_TRY(cudaEventRecord(ctx->ev_join[q], ctx->aux[q]));
+        CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
+      }
   }
   {
     // slot-centric pass: writes every CSR value (zero fill included) with the tabulated /
@@ -738,6 +759,11 @@ int vlfs_destroy(vlfs_ctx* ctx) {
   ctx->mats.clear();
   ctx->vecs.clear();
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  for (int k = 0; k < 3; ++k) {
+    if (ctx->aux[k]) cudaStreamDestroy(ctx->aux[k]);
+    if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   delete ctx;
   return VLFS_OK;
 }
