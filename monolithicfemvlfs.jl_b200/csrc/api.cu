@@ -117,6 +117,8 @@ struct vlfs_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // class tables of different domains in parallel
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t aux_vec = nullptr;                      // linear forms next to the matrix passes
+  cudaEvent_t ev_vec_fork = nullptr, ev_vec_join = nullptr;
   std::string err;
   long long ndofs = 0;
   int is_complex = 0, nmat = 0, nvec = 0;
@@ -630,6 +632,32 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
       if (dp->cls_dirty) { classify_domain(ctx, *dp); reclass = true; }
     if (reclass) { upload_gather_doms(ctx); rebuild_compact_records(ctx); }
   }
+  // linear forms of constant-Jacobian domains touch only the vectors: they run on their own stream
+  // beside the matrix passes (when both are assembled and nobody is timing kernels one by one)
+  const bool vec_aside = do_vec && do_mat && !ctx->profile;
+  bool vec_join_early = false;
+  if (vec_aside) {
+    if (!ctx->aux_vec) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux_vec, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_vec_fork, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_vec_join, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev_vec_fork, s));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->aux_vec, ctx->ev_vec_fork, 0));
+    for (auto& v : ctx->vecs) v.zero(ctx->aux_vec);
+    for (size_t di = 0; di < ctx->doms.size(); ++di) {
+      Domain& d = *ctx->doms[di];
+      if (d.rhs_host.empty() || !d.rhs_fast) continue;
+      launch_rhs_affine(d.dev, d.rhs_dev.p, (int)d.rhs_host.size(), d.cellgeo.p, vp.data(), (int)vp.size(),
+                        ctx->is_complex, ctx->nsm, ctx->aux_vec);
+      ++ctx->launches;
+    }
+    CUDA_TRY(cudaEventRecord(ctx->ev_vec_join, ctx->aux_vec));
+    // general vector passes (if any) run on the main stream and need the zero fill: join now;
+    // otherwise the join is the last thing this function does
+    for (auto& dp : ctx->doms) if (!dp->rhs_host.empty() && !dp->rhs_fast) vec_join_early = true;
+    if (vec_join_early) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_vec_join, 0));
+  }
   if (do_mat) {
     // per-class element blocks: reference products tabulated directly, general (quadrature) terms
     // integrated on the class representatives only, reduced into the class tables.  These are
@@ -677,12 +705,13 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
                               ctx->is_complex, ctx->nsm, s);
       ++ctx->launches;
     }
-    if (do_vec) for (auto& v : ctx->vecs) v.zero(s);
+    if (do_vec && !vec_aside) for (auto& v : ctx->vecs) v.zero(s);
   }
   for (size_t di = 0; di < ctx->doms.size(); ++di) {
     Domain& d = *ctx->doms[di];
     bool gen_mat = do_mat && !d.terms_host.empty() && !d.cls_full;
     bool gen_vec = do_vec && !d.rhs_host.empty();
+    if (gen_vec && d.rhs_fast && vec_aside) gen_vec = false;      // done on the side stream
     if (gen_vec && d.rhs_fast) {
       ProfScope ps(ctx, "rhs_affine:dom" + std::to_string(di));
       launch_rhs_affine(d.dev, d.rhs_dev.p, (int)d.rhs_host.size(), d.cellgeo.p, vp.data(), (int)vp.size(),
@@ -704,6 +733,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
       ++ctx->launches;
     }
   }
+  if (vec_aside && !vec_join_early) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_vec_join, 0));
 }
 
 template <typename T>
@@ -759,6 +789,9 @@ int vlfs_destroy(vlfs_ctx* ctx) {
   ctx->mats.clear();
   ctx->vecs.clear();
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->aux_vec) cudaStreamDestroy(ctx->aux_vec);
+  if (ctx->ev_vec_fork) cudaEventDestroy(ctx->ev_vec_fork);
+  if (ctx->ev_vec_join) cudaEventDestroy(ctx->ev_vec_join);
   for (int k = 0; k < 3; ++k) {
     if (ctx->aux[k]) cudaStreamDestroy(ctx->aux[k]);
     if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
