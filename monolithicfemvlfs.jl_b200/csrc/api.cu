@@ -30,7 +30,7 @@ void launch_pack_gather_records(const uint32_t* perm, long long ncoo, const Gath
 void launch_compact_gather_records(const unsigned long long* rec, long long ncoo, const GatherDom* doms,
                                    uint32_t* out, cudaStream_t s);
 void launch_gather_reference(const uint32_t* run_start, const unsigned long long* rec, const uint32_t* rec32,
-                             long long nnz, const GatherDom* doms, int ndom, int nrp_total, long long tab_total,
+                             double* const* ctab_all, long long nnz, const GatherDom* doms, int ndom, int nrp_total, long long tab_total,
                              double* const* mats, int nmat, int is_complex, int nsm, cudaStream_t s);
 void build_csc_device(const int* rowind, const int* colind, long long nnz, long long ndofs,
                       DevBuf<int>& colptr, DevBuf<int>& rowval, DevBuf<int>& csr_slot,
@@ -93,7 +93,9 @@ struct Domain {
   bool rhs_fast = false;                // linear forms through the barrier-free affine kernel
   bool cls_dirty = true;
   DevBuf<int> cls, reps, dest_cls;
-  DevBuf<double> cls_geo, ctab_m[4], jt_dev;
+  DevBuf<double> cls_geo, jt_dev;
+  double* ctab_ptr[4] = {nullptr, nullptr, nullptr, nullptr};   // this domain's slice of vlfs_ctx::ctab_all
+  long long ctab_base = 0;                                      // its first entry there
   std::vector<double> jt_host, cellgeo_host, weights_host;
   long long ctab_off[VLFS_MAX_BLOCKS] = {-1, -1, -1, -1};
   long long ctab_entries = 0, ctab_work = 0;
@@ -128,7 +130,8 @@ struct vlfs_ctx {
   DevBuf<int> rowptr, colind, rowind, dest_all;
   DevBuf<uint32_t> perm, run_start;     // sorted COO order and first sorted entry of every slot
   DevBuf<unsigned long long> gather_rec;   // packed (domain, block, local entry, cell) per sorted entry
-  DevBuf<uint32_t> gather_rec32;           // (domain, block, local entry, class) when every domain has classes
+  DevBuf<uint32_t> gather_rec32;           // index of the entry's class-table value (all domains tabulated)
+  DevBuf<double> ctab_all[4];              // per matrix: the class tables of all domains, contiguous
   bool rec32_valid = false;
   int nrp_total = 0;
   long long tab_total = 0;
@@ -381,7 +384,6 @@ void classify_domain(vlfs_ctx* ctx, Domain& d) {
     }
   }
   d.ctab_entries = off;
-  for (int m = 0; m < ctx->nmat; ++m) d.ctab_m[m].alloc((size_t)off * ctx->scalar());
   if (d.cls_full) {
     GatherDom G{};
     for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) G.ctab_off[b] = d.ctab_off[b];
@@ -578,7 +580,21 @@ struct ProfScope {
   ~ProfScope() { if (on) cudaEventRecord(e1, ctx->stream); }
 };
 
+// one contiguous class-table array per matrix: domain slices in domain order
+void layout_class_tables(vlfs_ctx* ctx) {
+  long long total = 0;
+  for (auto& d : ctx->doms) {
+    d->ctab_base = total;
+    if (d->ncls > 0) total += d->ctab_entries;
+  }
+  for (int m = 0; m < ctx->nmat; ++m) {
+    if (ctx->ctab_all[m].n != (size_t)total * ctx->scalar()) ctx->ctab_all[m].alloc((size_t)total * ctx->scalar());
+    for (auto& d : ctx->doms) d->ctab_ptr[m] = d->ncls > 0 ? ctx->ctab_all[m].p + (size_t)d->ctab_base * ctx->scalar() : nullptr;
+  }
+}
+
 void upload_gather_doms(vlfs_ctx* ctx) {
+  layout_class_tables(ctx);
   std::vector<GatherDom> gd(ctx->doms.size());
   for (size_t di = 0; di < ctx->doms.size(); ++di) {
     Domain& d = *ctx->doms[di];
@@ -594,7 +610,8 @@ void upload_gather_doms(vlfs_ctx* ctx) {
     for (int b = 0; b <= VLFS_MAX_BLOCKS; ++b) G.rp_first[b] = d.rp_first[b];
     G.rp = d.refprods_dev.p; G.geo = d.cellgeo.p; G.tabs = d.reftabs.p; G.tab_len = (int)d.reftabs.n;
     G.ncls = d.ncls; G.cls = d.cls.p; G.cls_geo = d.cls_geo.p;
-    for (int m = 0; m < 4; ++m) G.ctab_m[m] = d.ctab_m[m].p;
+    for (int m = 0; m < 4; ++m) G.ctab_m[m] = d.ctab_ptr[m];
+    G.ctab_base = d.ctab_base;
     for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) G.ctab_off[b] = d.ctab_off[b];
   }
   if (ctx->gather_doms.n != gd.size()) ctx->gather_doms.alloc(gd.size());
@@ -602,15 +619,18 @@ void upload_gather_doms(vlfs_ctx* ctx) {
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
 }
 
-// 32-bit class records: possible when every domain that owns COO entries is class-tabulated and
-// the fields fit (8 domains, 4 blocks, 16 384 local entries, 8 192 classes)
+// 32-bit class records (the index of the COO entry's value in the contiguous class tables):
+// possible when every domain that owns COO entries is class-tabulated
 void rebuild_compact_records(vlfs_ctx* ctx) {
   ctx->rec32_valid = false;
-  if (ctx->gather_rec.n == 0 || ctx->doms.size() > 8) return;
+  if (ctx->gather_rec.n == 0) return;
+  long long total = 0;
   for (auto& d : ctx->doms) {
     if (d->dev.ncells * (long long)d->dev.entries_per_cell == 0) continue;
-    if (d->ncls == 0 || d->ncls > 8192) return;
+    if (d->ncls == 0) return;
+    total += d->ctab_entries;
   }
+  if (total >= 0xffffffffll) return;
   if (ctx->gather_rec32.n != ctx->gather_rec.n) ctx->gather_rec32.alloc(ctx->gather_rec.n);
   launch_compact_gather_records(ctx->gather_rec.p, (long long)ctx->gather_rec.n, ctx->gather_doms.p,
                                 ctx->gather_rec32.p, ctx->stream);
@@ -682,7 +702,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
       launch_build_class_tables(ctx->gather_doms.p, (int)di, d.ctab_work, ctx->nmat, ctx->is_complex, a);
       ++ctx->launches;
       if (d.cls_full) {
-        double* cm[4] = {d.ctab_m[0].p, d.ctab_m[1].p, d.ctab_m[2].p, d.ctab_m[3].p};
+        double* cm[4] = {d.ctab_ptr[0], d.ctab_ptr[1], d.ctab_ptr[2], d.ctab_ptr[3]};
         launch_integrate(d.dev, d.rhs_dev.p, 0, d.dest_cls.p, d.reps.p, d.ncls, cm, ctx->nmat, vp.data(),
                          (int)vp.size(), ctx->is_complex, 1, 0, ctx->nsm, a, 1);
         ++ctx->launches;
@@ -699,8 +719,9 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     // reference-type contributions summed in COO order; the cell-centric kernels then add the rest
     ProfScope ps(ctx, "gather_reference");
     if (do_mat) {
+      double* ca[4] = {ctx->ctab_all[0].p, ctx->ctab_all[1].p, ctx->ctab_all[2].p, ctx->ctab_all[3].p};
       launch_gather_reference(ctx->run_start.p, ctx->gather_rec.p,
-                              ctx->rec32_valid ? ctx->gather_rec32.p : nullptr, ctx->nnz, ctx->gather_doms.p,
+                              ctx->rec32_valid ? ctx->gather_rec32.p : nullptr, ca, ctx->nnz, ctx->gather_doms.p,
                               (int)ctx->doms.size(), ctx->nrp_total, ctx->tab_total, mp.data(), (int)mp.size(),
                               ctx->is_complex, ctx->nsm, s);
       ++ctx->launches;

@@ -169,6 +169,7 @@ struct GatherDom {
   const int* cls;         // [ncells] class of every cell
   const double* cls_geo;  // [ncls][VLFS_CELLGEO]
   double* ctab_m[4];      // per matrix: [block][class][local entry] scalars
+  long long ctab_base;    // first entry of this domain in the context-wide contiguous tables
   long long ctab_off[VLFS_MAX_BLOCKS];   // entry offset of every block inside a class table
 };
 

@@ -744,8 +744,9 @@ __global__ void build_class_tables(const GatherDom* __restrict__ doms, int d, in
   }
 }
 
-// 64-bit (domain, block, entry, cell) records -> 32-bit (domain:3 | block:2 | entry:14 | class:13)
-// records, valid when every domain is class-tabulated: the gather then needs no per-cell load at all
+// 64-bit (domain, block, entry, cell) records -> 32-bit index of the entry's value in the
+// contiguous class tables (valid when every domain is class-tabulated; 0xffffffff = block without a
+// table): the gather then needs one load per COO entry besides the record itself
 __global__ void compact_gather_records(const unsigned long long* __restrict__ rec, long long ncoo,
                                        const GatherDom* __restrict__ doms, uint32_t* __restrict__ out) {
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < ncoo;
@@ -753,8 +754,11 @@ __global__ void compact_gather_records(const unsigned long long* __restrict__ re
     const unsigned long long r = rec[p];
     const unsigned d = (unsigned)(r >> 60), b = (unsigned)((r >> 58) & 3u), li = (unsigned)((r >> 32) & 0x3fffu);
     const unsigned e = (unsigned)(r & 0xffffffffull);
-    const unsigned c = doms[d].ncls > 0 ? (unsigned)doms[d].cls[e] : 0u;
-    out[p] = (d << 29) | (b << 27) | (li << 13) | c;
+    const GatherDom& G = doms[d];
+    if (G.ncls > 0 && G.ctab_off[b] >= 0)
+      out[p] = (uint32_t)(G.ctab_base + G.ctab_off[b] + (long long)G.cls[e] * (G.blk[b].nr * G.blk[b].nc) + li);
+    else
+      out[p] = 0xffffffffu;
   }
 }
 
@@ -775,9 +779,9 @@ constexpr int GATHER_MAX_DOM = 16, GATHER_MAX_RP = 96;
 // One thread per CSR slot: sums the reference-type contributions of the slot's COO entries in COO
 // order (deterministic, no atomics) and WRITES the value - this pass also replaces the zero fill.
 template <int NMAT, bool COMPACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 gather_reference(const uint32_t* __restrict__ run_start, const unsigned long long* __restrict__ rec,
-                 const uint32_t* __restrict__ rec32, long long nnz,
+                 const uint32_t* __restrict__ rec32, AsmPtrs ctab_all, long long nnz,
                  const GatherDom* __restrict__ doms, int ndom, int nrp_total, AsmPtrs ptrs, int nmat,
                  int is_complex, int tabs_in_smem) {
   // the reference tables are looked up at scattered local entries: from shared memory a warp's 32
@@ -823,22 +827,18 @@ gather_reference(const uint32_t* __restrict__ run_start, const unsigned long lon
     const uint32_t p1 = run_start[slot + 1];
     // (a 4-way unrolled version that fetches records and class ids ahead was measured slower)
     for (uint32_t p = run_start[slot]; p < p1; ++p) {
-      if (COMPACT) {                       // every domain is class-tabulated: record -> table entry
+      if (COMPACT) {                       // every domain is class-tabulated: record = table index
         const uint32_t r = rec32[p];
-        const int d = (int)(r >> 29), b = (int)((r >> 27) & 3u), li = (int)((r >> 13) & 0x3fffu);
-        const int c = (int)(r & 0x1fffu);
-        const GatherSmemDom& G = sd[d];
-        if (!G.has_ctab[b]) continue;
-        const size_t t = (size_t)G.ctab_off[b] + (size_t)c * G.ne[b] + li;
+        if (r == 0xffffffffu) continue;
         if (is_complex) {
 #pragma unroll
           for (int m = 0; m < NMAT; ++m) {
-            const double2 v = __ldg(reinterpret_cast<const double2*>(G.ctab_m[m]) + t);
+            const double2 v = __ldg(reinterpret_cast<const double2*>(ctab_all.mat[m]) + r);
             are[m] += v.x; aim[m] += v.y;
           }
         } else {
 #pragma unroll
-          for (int m = 0; m < NMAT; ++m) are[m] += __ldg(G.ctab_m[m] + t);
+          for (int m = 0; m < NMAT; ++m) are[m] += __ldg(ctab_all.mat[m] + r);
         }
         continue;
       }
@@ -958,13 +958,14 @@ void launch_compact_gather_records(const unsigned long long* rec, long long ncoo
 }
 
 void launch_gather_reference(const uint32_t* run_start, const unsigned long long* rec, const uint32_t* rec32,
-                             long long nnz, const GatherDom* doms, int ndom, int nrp_total, long long tab_total,
-                             double* const* mats, int nmat, int is_complex, int nsm, cudaStream_t s) {
+                             double* const* ctab_all, long long nnz, const GatherDom* doms, int ndom,
+                             int nrp_total, long long tab_total, double* const* mats, int nmat, int is_complex,
+                             int nsm, cudaStream_t s) {
   if (nnz == 0) return;
   if (ndom > GATHER_MAX_DOM || nrp_total > GATHER_MAX_RP)
     throw std::string("gather_reference: too many domains / reference products");
-  AsmPtrs P{};
-  for (int m = 0; m < nmat && m < 4; ++m) P.mat[m] = mats[m];
+  AsmPtrs P{}, CT{};
+  for (int m = 0; m < nmat && m < 4; ++m) { P.mat[m] = mats[m]; CT.mat[m] = ctab_all[m]; }
   const size_t smem = (size_t)tab_total * sizeof(double);
   // (measured on B200: staging the tables in shared memory halves the occupancy and is slower)
   const int in_smem = 0 && tab_total > 0 && smem <= 100 * 1024;
@@ -973,8 +974,8 @@ void launch_gather_reference(const uint32_t* run_start, const unsigned long long
   if (grid > cap) grid = cap;
   auto launch = [&](auto kern) {
     if (in_smem) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, 256, in_smem ? smem : 0, s>>>(run_start, rec, rec32, nnz, doms, ndom, nrp_total, P, nmat,
-                                                        is_complex, in_smem);
+    kern<<<(unsigned)grid, 256, in_smem ? smem : 0, s>>>(run_start, rec, rec32, CT, nnz, doms, ndom, nrp_total, P,
+                                                        nmat, is_complex, in_smem);
   };
   if (rec32) {
     switch (nmat) {
