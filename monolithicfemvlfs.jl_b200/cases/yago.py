@@ -144,11 +144,12 @@ class YagoProblem:
         self.set_frequency(p.lfactor)
 
     # ω-dependent scalars and coefficient fields only (the sweep of scripts/5-4-1-Yago.jl:33-71)
-    def set_frequency(self, lfactor):
+    def frequency_inputs(self, lfactor):
+        """Host evaluation of everything that depends on ω (scripts/5-4-1-Yago.jl:33-71): the
+        coefficient fields at the quadrature points and the scalar coefficients of the terms."""
         c = self.c
         g, H = c["g"], c["H"]
         k, om = wave_constants(c["L"], H, g, lfactor)
-        self.k, self.om = k, om
         bh = c["bh"]
         ah = -1j * om / g * (1 - bh) / bh
         x1 = self._xq_Gf
@@ -158,27 +159,35 @@ class YagoProblem:
         vz_in = -1j * om * c["eta0"] * np.exp(1j * k * x1)
         eta_d = mu1 * k * eta_in * (x1 < c["xd0"])
         dphi_d = mu1 * vz_in * (x1 < c["xd0"])
-        d = self.dom_Gf
-        d.set_weights(0, mu1)
-        d.set_weights(1, eta_d.real); d.set_weights(2, eta_d.imag)
-        d.set_weights(3, dphi_d.real); d.set_weights(4, dphi_d.imag)
-        t = self.t_Gf
-        d.set_coef(t["uk"], bh * g)
-        d.set_coef(t["up"], -1j * om * bh)
-        d.set_coef(t["wk"], bh * g * ah + 1j * om)
-        d.set_coef(t["wkm"], -k)
-        d.set_coef(t["wp"], -1j * om * bh * ah)
-        d.set_coef(t["wpn"], ah)
-        d.set_rhs_coef(self.r_Gf["w2"], ah)
-        d = self.dom_Gb
-        t = self.t_Gb
-        d.set_coef(t["vv"], g - om ** 2 * c["d0"])
-        d.set_coef(t["vp"], -1j * om)
-        d.set_coef(t["we"], 1j * om)
         x = self._xq_Gin
         vin = (c["eta0"] * om) * (np.cosh(k * x[..., 2]) / np.sinh(k * H)) * np.exp(1j * k * x[..., 0])
-        self.dom_Gin.set_weights(0, vin.real)
-        self.dom_Gin.set_weights(1, vin.imag)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        t, tb = self.t_Gf, self.t_Gb
+        return dict(
+            k=k, om=om,
+            weights_Gf=[f64(mu1), f64(eta_d.real), f64(eta_d.imag), f64(dphi_d.real), f64(dphi_d.imag)],
+            weights_Gin=[f64(vin.real), f64(vin.imag)],
+            coef_Gf={t["uk"]: bh * g, t["up"]: -1j * om * bh, t["wk"]: bh * g * ah + 1j * om, t["wkm"]: -k,
+                     t["wp"]: -1j * om * bh * ah, t["wpn"]: ah},
+            rhs_Gf={self.r_Gf["w2"]: ah},
+            coef_Gb={tb["vv"]: g - om ** 2 * c["d0"], tb["vp"]: -1j * om, tb["we"]: 1j * om})
+
+    def apply_frequency_inputs(self, inp):
+        """Host → device: `vlfs_set_weights` / `vlfs_set_term_coef` / `vlfs_set_rhs_coef`."""
+        self.k, self.om = inp["k"], inp["om"]
+        for i, w in enumerate(inp["weights_Gf"]):
+            self.dom_Gf.set_weights(i, w)
+        for tid, v in inp["coef_Gf"].items():
+            self.dom_Gf.set_coef(tid, v)
+        for rid, v in inp["rhs_Gf"].items():
+            self.dom_Gf.set_rhs_coef(rid, v)
+        for tid, v in inp["coef_Gb"].items():
+            self.dom_Gb.set_coef(tid, v)
+        for i, w in enumerate(inp["weights_Gin"]):
+            self.dom_Gin.set_weights(i, w)
+
+    def set_frequency(self, lfactor):
+        self.apply_frequency_inputs(self.frequency_inputs(lfactor))
 
     def assemble(self):
         self.sys.assemble()
