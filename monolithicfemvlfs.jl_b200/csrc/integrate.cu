@@ -272,7 +272,8 @@ template <int D>
 __global__ void __launch_bounds__(256, 3)
 integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const int* __restrict__ dest,
                 const int* __restrict__ cell_list, long long ncells_run,
-                AsmPtrs ptrs, int is_complex, int do_mat, int do_vec, int dest_by_run, unsigned stage_mask) {
+                AsmPtrs ptrs, int is_complex, int do_mat, int do_vec, int dest_by_run, unsigned stage_mask,
+                int use_tref) {
   extern __shared__ __align__(16) double sm[];
   const int nq = dom.nq, nqg = dom.nqg;
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -341,8 +342,10 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
   stage_tables(cell_at(0), geo_buf(0), 0, false);
   stage_geometry(cell_at(1), geo_buf(1));
   __syncthreads();
-  // reference matrices of the cell-invariant contractions, once per CTA
-  if (do_mat && dom.smem_tref_len > 0) {
+  // reference matrices of the cell-invariant contractions, once per CTA (not worth it when the
+  // CTA integrates a single cell, e.g. class representatives: the untiled precompute costs more
+  // than the tiled contraction it saves - ncu source page: 50-60 % of such launches)
+  if (do_mat && use_tref && dom.smem_tref_len > 0) {
     const int nprod = dom.target_first[dom.nblocks] > 0
         ? dom.targets[dom.target_first[dom.nblocks] - 1].first + dom.targets[dom.target_first[dom.nblocks] - 1].count : 0;
     for (int pi = 0; pi < nprod; ++pi) {
@@ -405,7 +408,7 @@ integrate_cells(DomainDev dom, const RhsDev* __restrict__ rhs, int nrhs, const i
             for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
           for (int pi = T.first; pi < T.first + T.count; ++pi) {
             const TileProd P = dom.prods[pi];
-            if (P.tref >= 0) {              // cell measure x coefficient x reference matrix
+            if (use_tref && P.tref >= 0) {  // cell measure x coefficient x reference matrix
               const double w = sm_meas[nq] * P.coef;
               const double* Tr = sm + P.tref + i0 * P.ldt + j0;
 #pragma unroll
@@ -1107,10 +1110,11 @@ void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, con
   // persistent CTAs: exactly the resident set, each pipelining over its cells
   long long cap = (long long)nsm * per_sm;
   if (grid > cap) grid = cap;
+  const int use_tref = ncells_run >= 2 * grid;      // at least two cells per CTA
   auto launch = [&](auto kern) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, threads, smem, s>>>(dom, rhs_dev, nrhs, dest, cell_list, ncells_run, P,
-                                               is_complex, do_mat, do_vec, dest_by_run, stage_mask);
+                                               is_complex, do_mat, do_vec, dest_by_run, stage_mask, use_tref);
   };
   if (dom.D == 1) launch(integrate_cells<1>);
   else if (dom.D == 2) launch(integrate_cells<2>);
