@@ -28,7 +28,7 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 def label(name, seen):
     for key, lab in (("build_class_tables", "class_tables:build"), ("integrate_cells", "class_tables:integrate"),
-                     ("gather_reference", "gather_reference"), ("rhs_affine", "rhs_affine"), ("csr_spmv", "csr_spmv")):
+                     ("gather_compact", "gather_reference"), ("gather_reference", "gather_reference"), ("rhs_affine", "rhs_affine"), ("csr_spmv", "csr_spmv")):
         if key in name:
             seen[lab] = seen.get(lab, 0) + 1
             return lab, seen[lab]
