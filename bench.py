@@ -64,14 +64,47 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  The timed region of this
+    workload is a few milliseconds, so the sampler polls NVML in a thread (≈ 0.3 ms period)
+    instead of `nvidia-smi -lms` (100 ms); nvidia-smi stays as the fallback."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm_mhz, reasons bitmask)
         self.proc = None
+        self.nv = None
+        self.run = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while self.run:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    why = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((mhz, why))
+            except Exception:
+                pass
+            time.sleep(0.0003)
 
     def start(self):
+        if self.nv is not None:
+            self.run = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -89,6 +122,15 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.run = False
+            self.thread.join(timeout=1.0)
+            nv = self.nv
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            sm = sorted(r[0] for r in self.rows)
+            reasons = sorted(nm for nm, bit in bits.items() if any(r[1] & bit for r in self.rows))
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                    "samples": len(sm), "sampler": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -100,13 +142,12 @@ class ClockSampler:
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
-            for k, nm in enumerate(names):
+            for k, nm in enumerate(self.NAMES):
                 if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampler": "nvidia-smi"}
 
 
 def assembly_bytes(prob, nnz, ncoo, sT):

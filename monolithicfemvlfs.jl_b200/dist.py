@@ -436,6 +436,7 @@ class Fleet:
             if rel <= rtol or it >= maxit or stalled:
                 break
             if stagnation and rel > stagnation * prev_cycle:
+                stalled = True                                   # a whole cycle gained less than 1/f
                 break
             prev_cycle = rel
             for mm, Vk, rr in zip(M, V, r):
