@@ -1,0 +1,128 @@
+"""Full-size checks on the headline workload (Yago 5-4-1 at the paper's resolution,
+scripts/5-4-1-Yago.jl:34-46: N = 1 021 112, 77.5 M complex nonzeros), where the NumPy oracle would
+take minutes: size-independent properties instead of entry-by-entry oracle parity.
+
+  * the sizes SURVEY.md §8 derives from the reference parameters;
+  * the pattern is a valid CSR (sorted, duplicate-free rows) and its CSC view is its transpose;
+  * two independent code paths of the library agree entry by entry: element-block classes +
+    slot-centric gather (the default on constant-Jacobian meshes) against per-point general
+    quadrature + scattered reductions (`affine=False`);
+  * assembly is bitwise repeatable (no atomics on the default path);
+  * the Ω Laplace rows of interior fluid DOFs sum to zero (constants are in the kernel of ∇ϕ·∇w);
+  * SpMV equals SciPy on the downloaded matrix and is linear;
+  * solve round trip: b = A x, solve, compare (tolerance 1e-8, the north star's solution bar).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(nx=32, ny=4, nz=3, order=4, lfactor=0.4, dfactor=4)
+
+
+@pytest.fixture(scope="module")
+def y1():
+    from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
+    prob = YagoProblem(Yago_freq_domain_params(**KW), device=0)
+    prob.assemble()
+    rp, ci = prob.sys.get_pattern()
+    v = prob.sys.get_values(0)
+    return prob, rp, ci, v
+
+
+def test_sizes_from_reference_parameters(y1):
+    prob, rp, ci, v = y1
+    o = prob.X.offsets
+    assert prob.X.ndofs == 1021112
+    assert (o[1] - o[0], o[2] - o[1], o[3] - o[2]) == (650615, 368304, 2193)
+    assert prob.Om.ncells == 69120 and prob.Gf.ncells == 22912 and prob.Gb.ncells == 128
+    assert prob.sys.nnz == len(ci) == rp[-1] and prob.sys.ncoo == 113145328
+
+
+def test_pattern_is_sorted_csr_and_csc_is_its_transpose(y1):
+    prob, rp, ci, v = y1
+    n = prob.X.ndofs
+    assert rp[0] == 0 and np.all(np.diff(rp) > 0)                     # no empty row: every DOF has a diagonal
+    inner = np.ones(len(ci), bool)
+    inner[rp[1:-1]] = False                                          # first entry of every row but the first
+    assert np.all(np.diff(ci.astype(np.int64))[inner[1:]] > 0)        # strictly increasing inside rows
+    assert ci.min() >= 0 and ci.max() == n - 1
+    cp, rv, slot = prob.sys.get_pattern_csc()
+    assert cp[-1] == len(ci) and np.array_equal(np.sort(slot), np.arange(len(ci)))
+    rows = np.repeat(np.arange(n, dtype=np.int32), np.diff(rp))
+    assert np.array_equal(rows[slot], rv)                             # same entries, column-major
+    cols = np.repeat(np.arange(n, dtype=np.int32), np.diff(cp))
+    assert np.array_equal(ci[slot], cols)
+
+
+def test_class_gather_path_equals_general_quadrature_path(y1):
+    prob, rp, ci, v = y1
+    from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
+    prob2 = YagoProblem(Yago_freq_domain_params(**KW), device=0, affine=False)
+    prob2.assemble()
+    rp2, ci2 = prob2.sys.get_pattern()
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2)
+    v2 = prob2.sys.get_values(0)
+    b1, b2 = prob.sys.get_vector(0), prob2.sys.get_vector(0)
+    del prob2
+    o = prob.X.offsets
+    rows = np.repeat(np.arange(prob.X.ndofs, dtype=np.int32), np.diff(rp))
+    for fi in range(3):
+        rm = (rows >= o[fi]) & (rows < o[fi + 1])
+        for fj in range(3):
+            m = rm & (ci >= o[fj]) & (ci < o[fj + 1])
+            if m.any() and np.abs(v2[m]).max() > 0:
+                assert np.abs(v[m] - v2[m]).max() <= 1e-12 * np.abs(v2[m]).max(), (fi, fj)
+    assert np.abs(b1 - b2).max() <= 1e-12 * np.abs(b2).max()
+
+
+def test_assembly_is_bitwise_repeatable(y1):
+    prob, rp, ci, v = y1
+    prob.assemble()
+    assert np.array_equal(prob.sys.get_values(0).view(np.uint64), v.view(np.uint64))
+
+
+def test_interior_laplace_rows_sum_to_zero(y1):
+    prob, rp, ci, v = y1
+    # fluid DOFs that no surface cell touches: their rows hold only ∫∇ϕ·∇w
+    touched = np.zeros(prob.X.ndofs, bool)
+    for tri in (prob.Gf, prob.Gb, prob.Gin):
+        touched[np.unique(prob.V_Om.cell_dofs[tri.cell])] = True       # fluid field: offset 0
+    o = prob.X.offsets
+    interior = np.flatnonzero(~touched[o[0]:o[1]])
+    assert len(interior) > 300000           # nz = 3: four of the seven node layers are below the top cells
+    A = sp.csr_matrix((v, ci, rp), shape=(prob.X.ndofs,) * 2)
+    s = np.asarray(A[interior].sum(axis=1)).ravel()
+    scale = np.abs(A[interior]).sum(axis=1).max()
+    assert np.abs(s).max() <= 1e-12 * scale
+    assert np.abs(A[interior].imag).max() == 0.0
+
+
+def test_spmv_equals_scipy_and_is_linear(y1):
+    prob, rp, ci, v = y1
+    n = prob.X.ndofs
+    A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    i = np.arange(n)
+    x = np.sin(0.1 * i) + 1j * np.cos(0.1 * i)
+    y = np.cos(0.37 * i) - 0.5j * np.sin(0.11 * i)
+    Ax, Ay = prob.sys.spmv(x), prob.sys.spmv(y)
+    ref = A @ x
+    assert np.abs(Ax - ref).max() <= 1e-12 * np.abs(ref).max()
+    al, be = 0.75 - 0.5j, -1.25 + 2j
+    lin = prob.sys.spmv(al * x + be * y)
+    assert np.abs(lin - (al * Ax + be * Ay)).max() <= 1e-12 * np.abs(lin).max()
+
+
+def test_solve_round_trip(y1):
+    prob, rp, ci, v = y1
+    from vlfs_b200 import _lib as L
+    n = prob.X.ndofs
+    i = np.arange(n)
+    xt = (1.0 + 0.5 * np.sin(0.01 * i)) + 1j * np.cos(0.013 * i)
+    b = prob.sys.spmv(xt)
+    prob.sys.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=20, maxit=40, rtol=1e-12)
+    x, st = prob.sys.solve(b=b)
+    r = prob.sys.spmv(x) - b
+    assert np.linalg.norm(r) <= 1e-9 * np.linalg.norm(b)
+    assert np.linalg.norm(x - xt) <= 1e-8 * np.linalg.norm(xt)
