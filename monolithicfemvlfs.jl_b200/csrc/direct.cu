@@ -212,61 +212,74 @@ panel_trsm(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int
   }
 }
 
-// trailing update  F[i][j] -= sum_r F[i][k0+r] F[k0+r][j],  i,j >= k1
+// Blocked right-looking update  F[i][j] -= sum_{r in [d0,d1)} F[i][r] F[r][j]  over one region of
+// the front.  The pivots advance in outer blocks of `outer` panels; inside an outer block ending
+// at Kend only the block's own column strip (mode 1: i >= d1, d1 <= j < Kend) and row strip
+// (mode 2: d1 <= i < Kend, j >= Kend) are updated after every 32-wide panel, with depth 32; the
+// trailing matrix (mode 0: i, j >= Kend) is visited ONCE per outer block with the whole block as
+// depth, so its tiles are read and written `outer` times less often and a CTA amortises its
+// prologue over `outer` x 32 contraction steps.
 template <bool C>
 __global__ void __launch_bounds__(256)
-schur_update(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
-             typename Num<C>::T* __restrict__ pool) {
+schur_update(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int kf, int nk, int mode,
+             int kend_panel, typename Num<C>::T* __restrict__ pool) {
   using N = Num<C>;
   extern __shared__ double smraw[];
   typename N::T(*sA)[NB + 1] = reinterpret_cast<typename N::T(*)[NB + 1]>(smraw);
   typename N::T(*sB)[TS] = reinterpret_cast<typename N::T(*)[TS]>(sA + TS);
   const FrontMeta F = meta[list[blockIdx.z]];
-  const int k0 = k * NB;
-  if (k0 >= F.np) return;
-  const int kb = min(NB, F.np - k0);
-  const int k1 = k0 + kb;
-  const int i0 = k1 + blockIdx.y * TS, j0 = k1 + blockIdx.x * TS;
-  if (i0 >= F.nf || j0 >= F.nf) return;
+  const int d0 = kf * NB;
+  if (d0 >= F.np) return;
+  const int d1 = min((kf + nk) * NB, F.np);
+  const int Kend = min(kend_panel * NB, F.np);
+  int i0, j0, ilim, jlim;
+  if (mode == 0) { i0 = Kend + blockIdx.y * TS; j0 = Kend + blockIdx.x * TS; ilim = F.nf; jlim = F.nf; }
+  else if (mode == 1) { i0 = d1 + blockIdx.y * TS; j0 = d1 + blockIdx.x * TS; ilim = F.nf; jlim = Kend; }
+  else { i0 = d1 + blockIdx.y * TS; j0 = Kend + blockIdx.x * TS; ilim = Kend; jlim = F.nf; }
+  if (i0 >= ilim || j0 >= jlim) return;
   typename N::T* Fp = pool + F.off;
   const int tid = threadIdx.x;
-  for (int t = tid; t < TS * NB; t += 256) {
-    int r = t / NB, c = t % NB;
-    int i = i0 + r;
-    sA[r][c] = (i < F.nf && c < kb) ? Fp[(long long)i * F.nf + k0 + c] : N::zero();
-  }
-  for (int t = tid; t < NB * TS; t += 256) {
-    int r = t / TS, c = t % TS;
-    int j = j0 + c;
-    sB[r][c] = (j < F.nf && r < kb) ? Fp[(long long)(k0 + r) * F.nf + j] : N::zero();
-  }
-  __syncthreads();
   const int tx = tid & 15, ty = tid >> 4;
   typename N::T acc[4][4];
 #pragma unroll
   for (int m = 0; m < 4; ++m)
 #pragma unroll
     for (int n = 0; n < 4; ++n) acc[m][n] = N::zero();
+  for (int kb0 = d0; kb0 < d1; kb0 += NB) {
+    const int kb = min(NB, d1 - kb0);
+    if (kb0 > d0) __syncthreads();
+    for (int t = tid; t < TS * NB; t += 256) {
+      int r = t / NB, c = t % NB;
+      int i = i0 + r;
+      sA[r][c] = (i < ilim && c < kb) ? Fp[(long long)i * F.nf + kb0 + c] : N::zero();
+    }
+    for (int t = tid; t < NB * TS; t += 256) {
+      int r = t / TS, c = t % TS;
+      int j = j0 + c;
+      sB[r][c] = (j < jlim && r < kb) ? Fp[(long long)(kb0 + r) * F.nf + j] : N::zero();
+    }
+    __syncthreads();
 #pragma unroll 8
-  for (int kk = 0; kk < NB; ++kk) {
-    typename N::T a[4], b[4];
+    for (int kk = 0; kk < NB; ++kk) {
+      typename N::T a[4], b[4];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) a[m] = sA[ty + 16 * m][kk];
+      for (int m = 0; m < 4; ++m) a[m] = sA[ty + 16 * m][kk];
 #pragma unroll
-    for (int n = 0; n < 4; ++n) b[n] = sB[kk][tx + 16 * n];
+      for (int n = 0; n < 4; ++n) b[n] = sB[kk][tx + 16 * n];
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+      for (int m = 0; m < 4; ++m)
 #pragma unroll
-      for (int n = 0; n < 4; ++n) acc[m][n] = N::fnma(a[m], b[n], acc[m][n]);
+        for (int n = 0; n < 4; ++n) acc[m][n] = N::fnma(a[m], b[n], acc[m][n]);
+    }
   }
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     int i = i0 + ty + 16 * m;
-    if (i >= F.nf) continue;
+    if (i >= ilim) continue;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       int j = j0 + tx + 16 * n;
-      if (j < F.nf) {
+      if (j < jlim) {
         typename N::T* p = Fp + (long long)i * F.nf + j;
         *p = N::add(*p, acc[m][n]);
       }
@@ -352,30 +365,43 @@ __global__ void fwd_gather(const FrontMeta* __restrict__ meta, const int* __rest
   }
 }
 
-// forward panel step: solve the unit-lower diagonal block, then update all rows below
+// forward panel step: solve the unit-lower diagonal block, then update all rows below.  Every
+// block redoes the tiny triangular solve (one launch per panel); the diagonal block is staged in
+// shared memory first so that the 32-step shuffle chain carries no global-memory latency.
+// Block 0 stores the solved pivots y into `bp` (whose pivot part the front's gather has already
+// consumed): nothing in this launch reads it, so no second "commit" launch is needed.
 template <bool C>
 __global__ void __launch_bounds__(256)
 fwd_panel(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
-          const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ w) {
+          const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ w,
+          typename Num<C>::T* __restrict__ bp) {
   using N = Num<C>;
   __shared__ typename N::T sx[NB];
+  __shared__ typename N::T sD[NB][NB + 1];
   const FrontMeta F = meta[list[blockIdx.y]];
   const int k0 = k * NB;
   if (k0 >= F.np) return;
   const int kb = min(NB, F.np - k0);
   const int k1 = k0 + kb;
+  if (blockIdx.x > 0 && k1 + blockIdx.x * 256 >= F.nf) return;
   const typename N::T* Fp = pool + F.off;
   typename N::T* wf = w + F.woff;
-  // every block redoes the tiny triangular solve (keeps it one launch per panel); only
-  // block 0 writes it back
+  for (int t = threadIdx.x; t < kb * kb; t += 256) {
+    const int r = t / kb, c = t - r * kb;
+    sD[r][c] = Fp[(long long)(k0 + r) * F.nf + k0 + c];
+  }
+  __syncthreads();
   if (threadIdx.x < 32) {
     const int r = threadIdx.x;
     typename N::T x = r < kb ? wf[k0 + r] : N::zero();
     for (int c = 0; c < kb; ++c) {
       typename N::T xc = N::shfl(x, c);
-      if (r > c && r < kb) x = N::fnma(Fp[(long long)(k0 + r) * F.nf + k0 + c], xc, x);
+      if (r > c && r < kb) x = N::fnma(sD[r][c], xc, x);
     }
-    if (r < kb) sx[r] = x;
+    if (r < kb) {
+      sx[r] = x;
+      if (blockIdx.x == 0) bp[F.first + k0 + r] = x;
+    }
   }
   __syncthreads();
   const int i = k1 + blockIdx.x * 256 + threadIdx.x;
@@ -383,36 +409,17 @@ fwd_panel(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int 
     const typename N::T* row = Fp + (long long)i * F.nf + k0;
     typename N::T v = wf[i];
     for (int c = 0; c < kb; ++c) v = N::fnma(row[c], sx[c], v);
-    // rows of this panel are rewritten below by block 0 only after all blocks have read
-    // wf[k0..k1): they are never in [k1, nf), so there is no hazard
     wf[i] = v;
   }
 }
-template <bool C>
-__global__ void fwd_panel_commit(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
-                                 const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ w) {
-  using N = Num<C>;
-  const FrontMeta F = meta[list[blockIdx.x]];
-  const int k0 = k * NB;
-  if (k0 >= F.np) return;
-  const int kb = min(NB, F.np - k0);
-  const typename N::T* Fp = pool + F.off;
-  typename N::T* wf = w + F.woff;
-  const int r = threadIdx.x;
-  typename N::T x = r < kb ? wf[k0 + r] : N::zero();
-  for (int c = 0; c < kb; ++c) {
-    typename N::T xc = N::shfl(x, c);
-    if (r > c && r < kb) x = N::fnma(Fp[(long long)(k0 + r) * F.nf + k0 + c], xc, x);
-  }
-  if (r < kb) wf[k0 + r] = x;
-}
 
-// backward: r_P = y_P - U12 x_U  (warp per pivot row), x_U gathered from the solved vector
+// backward: r_P = y_P - U12 x_U  (warp per pivot row), x_U gathered from the solved vector, y_P
+// from the forward sweep (stored in the permuted right-hand side)
 template <bool C>
 __global__ void __launch_bounds__(256)
 bwd_gemv(const FrontMeta* __restrict__ meta, const int* __restrict__ list, const int* __restrict__ upd_idx,
          const typename Num<C>::T* __restrict__ pool, const typename Num<C>::T* __restrict__ xp,
-         typename Num<C>::T* __restrict__ w) {
+         const typename Num<C>::T* __restrict__ y, typename Num<C>::T* __restrict__ w) {
   using N = Num<C>;
   const FrontMeta F = meta[list[blockIdx.y]];
   const int lane = threadIdx.x & 31;
@@ -425,31 +432,43 @@ bwd_gemv(const FrontMeta* __restrict__ meta, const int* __restrict__ list, const
   for (int a = lane; a < nu; a += 32) acc = N::fnma(Fr[a], xp[u[a]], acc);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc = N::add(acc, N::shfl_down(acc, o));
-  if (lane == 0) w[F.woff + row] = N::add(w[F.woff + row], acc);
+  if (lane == 0) w[F.woff + row] = N::add(y[F.first + row], acc);
 }
 
-// backward panel step (descending k): solve the upper diagonal block, update the rows above
+// backward panel step (descending k): solve the upper diagonal block, update the rows above;
+// block 0 stores the solution of the panel into the permuted solution vector
 template <bool C>
 __global__ void __launch_bounds__(256)
 bwd_panel(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
-          const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ w) {
+          const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ w,
+          typename Num<C>::T* __restrict__ xp) {
   using N = Num<C>;
   __shared__ typename N::T sx[NB];
+  __shared__ typename N::T sD[NB][NB + 1];
   const FrontMeta F = meta[list[blockIdx.y]];
   const int k0 = k * NB;
   if (k0 >= F.np) return;
+  if (blockIdx.x > 0 && blockIdx.x * 256 >= k0) return;
   const int kb = min(NB, F.np - k0);
   const typename N::T* Fp = pool + F.off;
   typename N::T* wf = w + F.woff;
+  for (int t = threadIdx.x; t < kb * kb; t += 256) {
+    const int r = t / kb, c = t - r * kb;
+    sD[r][c] = Fp[(long long)(k0 + r) * F.nf + k0 + c];
+  }
+  __syncthreads();
   if (threadIdx.x < 32) {
     const int r = threadIdx.x;
     typename N::T x = r < kb ? wf[k0 + r] : N::zero();
     for (int c = kb - 1; c >= 0; --c) {
-      if (r == c) x = N::div(x, Fp[(long long)(k0 + c) * F.nf + k0 + c]);
+      if (r == c) x = N::div(x, sD[c][c]);
       typename N::T xc = N::shfl(x, c);
-      if (r < c) x = N::fnma(Fp[(long long)(k0 + r) * F.nf + k0 + c], xc, x);
+      if (r < c) x = N::fnma(sD[r][c], xc, x);
     }
-    if (r < kb) sx[r] = x;
+    if (r < kb) {
+      sx[r] = x;
+      if (blockIdx.x == 0) xp[F.first + k0 + r] = x;
+    }
   }
   __syncthreads();
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -459,26 +478,6 @@ bwd_panel(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int 
     for (int c = 0; c < kb; ++c) v = N::fnma(row[c], sx[c], v);
     wf[i] = v;
   }
-}
-template <bool C>
-__global__ void bwd_panel_commit(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
-                                 const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ w,
-                                 typename Num<C>::T* __restrict__ xp) {
-  using N = Num<C>;
-  const FrontMeta F = meta[list[blockIdx.x]];
-  const int k0 = k * NB;
-  if (k0 >= F.np) return;
-  const int kb = min(NB, F.np - k0);
-  const typename N::T* Fp = pool + F.off;
-  typename N::T* wf = w + F.woff;
-  const int r = threadIdx.x;
-  typename N::T x = r < kb ? wf[k0 + r] : N::zero();
-  for (int c = kb - 1; c >= 0; --c) {
-    if (r == c) x = N::div(x, Fp[(long long)(k0 + c) * F.nf + k0 + c]);
-    typename N::T xc = N::shfl(x, c);
-    if (r < c) x = N::fnma(Fp[(long long)(k0 + r) * F.nf + k0 + c], xc, x);
-  }
-  if (r < kb) { wf[k0 + r] = x; xp[F.first + k0 + r] = x; }
 }
 
 }  // namespace
@@ -748,6 +747,8 @@ static void factor_levels(DirectSolver& D) {
   T* pool = reinterpret_cast<T*>(D.pool.p);
   const size_t smem = (size_t)(TS * (NB + 1) + NB * TS) * sizeof(T);
   CUDA_TRY(cudaFuncSetAttribute(schur_update<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const int outer_env = getenv("VLFS_LU_OUTER") ? atoi(getenv("VLFS_LU_OUTER")) : 4;
+  const int outer = outer_env < 1 ? 1 : outer_env;   // panels per outer block (4 = 128 pivots)
   for (int L = 0; L < D.nlevels; ++L) {
     const int nfr = (int)D.level_lists[L].size();
     const int* list = D.d_lists.p + D.list_off[L];
@@ -760,17 +761,32 @@ static void factor_levels(DirectSolver& D) {
       }
     }
     const int npan = (D.level_maxnp[L] + NB - 1) / NB;
-    for (int k = 0; k < npan; ++k) {
-      diag_lu<C><<<nfr, dim3(NB, NB), 0, s>>>(D.d_meta.p, list, k, pool);
-      const int rem = D.level_maxnf[L] - k * NB;     // upper bound of trailing size
-      if (rem > 0) {
+    const int maxnf = D.level_maxnf[L];
+    for (int K0 = 0; K0 < npan; K0 += outer) {
+      const int K1 = std::min(K0 + outer, npan);          // outer block = panels [K0, K1)
+      for (int k = K0; k < K1; ++k) {
+        diag_lu<C><<<nfr, dim3(NB, NB), 0, s>>>(D.d_meta.p, list, k, pool);
+        ++*D.launches;
+        const int rem = maxnf - k * NB;                   // upper bound of the rows/columns from panel k on
+        if (rem <= 0) continue;
         dim3 g2((rem + 127) / 128, 2, nfr);
         panel_trsm<C><<<g2, 128, 0, s>>>(D.d_meta.p, list, k, pool);
-        dim3 g3((rem + TS - 1) / TS, (rem + TS - 1) / TS, nfr);
-        schur_update<C><<<g3, 256, smem, s>>>(D.d_meta.p, list, k, pool);
-        *D.launches += 2;
+        ++*D.launches;
+        const int strip = (K1 - k - 1) * NB;              // rest of the outer block after panel k
+        if (strip > 0) {
+          dim3 gc((strip + TS - 1) / TS, (rem + TS - 1) / TS, nfr);
+          schur_update<C><<<gc, 256, smem, s>>>(D.d_meta.p, list, k, 1, 1, K1, pool);
+          dim3 gr((rem + TS - 1) / TS, (strip + TS - 1) / TS, nfr);
+          schur_update<C><<<gr, 256, smem, s>>>(D.d_meta.p, list, k, 1, 2, K1, pool);
+          *D.launches += 2;
+        }
       }
-      ++*D.launches;
+      const int rem = maxnf - K0 * NB;                    // >= nf - Kend of every front still active
+      if (rem > 0) {
+        dim3 g3((rem + TS - 1) / TS, (rem + TS - 1) / TS, nfr);
+        schur_update<C><<<g3, 256, smem, s>>>(D.d_meta.p, list, K0, K1 - K0, 0, K1, pool);
+        ++*D.launches;
+      }
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -820,9 +836,8 @@ static void forward_impl(DirectSolver& D, const double* b, double* g_keep) {
     for (int k = 0; k < npan; ++k) {
       const int rem = D.level_maxnf[L] - k * NB;
       dim3 g((std::max(rem, 1) + 255) / 256, nfr);
-      fwd_panel<C><<<g, 256, 0, s>>>(D.d_meta.p, list, k, pool, w);
-      fwd_panel_commit<C><<<nfr, 32, 0, s>>>(D.d_meta.p, list, k, pool, w);
-      *D.launches += 2;
+      fwd_panel<C><<<g, 256, 0, s>>>(D.d_meta.p, list, k, pool, w, bp);
+      ++*D.launches;
     }
   }
   if (g_keep && D.n_keep > 0)
@@ -851,14 +866,13 @@ static void backward_impl(DirectSolver& D, const double* x_keep, double* x) {
     const int nfr = (int)D.level_lists[L].size();
     const int* list = D.d_lists.p + D.list_off[L];
     dim3 gg((D.level_maxnp[L] + 7) / 8, nfr);
-    bwd_gemv<C><<<gg, 256, 0, s>>>(D.d_meta.p, list, D.d_upd.p, pool, xp, w);
+    bwd_gemv<C><<<gg, 256, 0, s>>>(D.d_meta.p, list, D.d_upd.p, pool, xp, reinterpret_cast<const T*>(D.bp.p), w);
     ++*D.launches;
     const int npan = (D.level_maxnp[L] + NB - 1) / NB;
     for (int k = npan - 1; k >= 0; --k) {
       dim3 g((std::max(k * NB, 1) + 255) / 256, nfr);
-      bwd_panel<C><<<g, 256, 0, s>>>(D.d_meta.p, list, k, pool, w);
-      bwd_panel_commit<C><<<nfr, 32, 0, s>>>(D.d_meta.p, list, k, pool, w, xp);
-      *D.launches += 2;
+      bwd_panel<C><<<g, 256, 0, s>>>(D.d_meta.p, list, k, pool, w, xp);
+      ++*D.launches;
     }
   }
   const unsigned vg = (unsigned)std::min<long long>((D.n_total + 255) / 256, (long long)D.nsm * 8);
