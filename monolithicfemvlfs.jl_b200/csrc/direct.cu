@@ -113,24 +113,37 @@ __global__ void build_cmap(const FrontMeta* __restrict__ meta, int nfronts, cons
     cmap[F.cmap_ptr + k] = local_index(P, upd_idx, u[k]);
 }
 
-// parent += Schur complement of child `slot`; one launch per slot keeps the sum order fixed
+// parent += Schur complement of child `slot`; one launch per slot keeps the sum order fixed.
+// A CTA of 64 x 4 threads covers 16 rows: four independent read-modify-write chains per thread.
 template <bool C>
-__global__ void extend_add(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int slot,
-                           const int* __restrict__ cmap, typename Num<C>::T* __restrict__ pool) {
+__global__ void __launch_bounds__(256)
+extend_add(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int slot,
+           const int* __restrict__ cmap, typename Num<C>::T* __restrict__ pool) {
   using N = Num<C>;
   const FrontMeta P = meta[list[blockIdx.z]];
   const int c = P.child[slot];
   if (c < 0) return;
   const FrontMeta Cf = meta[c];
   const int nu = Cf.nf - Cf.np;
-  const int a = blockIdx.y * 16 + threadIdx.y;
+  const int a0 = blockIdx.y * 16 + threadIdx.y;
+  if (blockIdx.y * 16 >= nu) return;
   const int* cm = cmap + Cf.cmap_ptr;
-  if (a >= nu) return;
-  const long long prow = P.off + (long long)cm[a] * P.nf;
-  const long long crow = Cf.off + (long long)(Cf.np + a) * Cf.nf + Cf.np;
+  long long prow[4], crow[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a = a0 + 4 * i;
+    prow[i] = a < nu ? P.off + (long long)cm[a] * P.nf : -1;
+    crow[i] = Cf.off + (long long)(Cf.np + a) * Cf.nf + Cf.np;
+  }
   for (int b = blockIdx.x * 64 + threadIdx.x; b < nu; b += gridDim.x * 64) {
-    typename N::T* dst = pool + prow + cm[b];
-    *dst = N::add(*dst, pool[crow + b]);
+    const int cb = cm[b];
+    typename N::T v[4], d[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (prow[i] >= 0) { v[i] = pool[crow[i] + b]; d[i] = pool[prow[i] + cb]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (prow[i] >= 0) pool[prow[i] + cb] = N::add(d[i], v[i]);
   }
 }
 
@@ -754,7 +767,7 @@ static void factor_levels(DirectSolver& D) {
     const int* list = D.d_lists.p + D.list_off[L];
     if (D.level_maxnu_child[L] > 0) {
       const int nu = D.level_maxnu_child[L];
-      dim3 grid(std::min((nu + 63) / 64, 8), (nu + 15) / 16, nfr), block(64, 16);
+      dim3 grid(std::min((nu + 63) / 64, 8), (nu + 15) / 16, nfr), block(64, 4);
       for (int slot = 0; slot < 2; ++slot) {
         extend_add<C><<<grid, block, 0, s>>>(D.d_meta.p, list, slot, D.d_cmap.p, pool);
         ++*D.launches;

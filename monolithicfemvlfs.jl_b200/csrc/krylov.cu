@@ -277,7 +277,7 @@ struct SolverState {
   long long* launches;
   size_t sc;                    // doubles per scalar
   int nred;                     // reduction blocks
-  DevBuf<double> dinv, V, w, z, r, partial, hdev, tmp1, tmp2, tmp3, tmp4;
+  DevBuf<double> dinv, V, Z, w, z, r, partial, hdev, tmp1, tmp2, tmp3, tmp4;
   double setup_ms = 0;
   DirectSolver* direct = nullptr;
 
@@ -395,6 +395,7 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
   // many digits; when it stops doing so the attainable accuracy eps*|A||x|/|b| is reached
   // and further iterations are wasted.
   const bool direct = S.opts.precond == VLFS_PRECOND_SPARSE_LU;
+  if (direct && S.Z.n != (size_t)m * ld) S.Z.alloc((size_t)m * ld);
   bool stagnated = false;
   double prev_cycle_rel = 1e300;
   while (true) {
@@ -412,8 +413,9 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
     int j = 0;
     for (; j < m && it < S.opts.maxit; ++j, ++it) {
       double* vj = S.V.p + (size_t)j * ld;
-      S.precond(vj, z);
-      S.spmv(z, w);
+      double* zj = direct ? S.Z.p + (size_t)j * ld : z;     // flexible variant: keep M^-1 v_j
+      S.precond(vj, zj);
+      S.spmv(zj, w);
       // CGS2
       S.multidot(S.V.p, j + 1, w, h.data());
       S.gemv_sub_(S.V.p, j + 1, h.data(), w);
@@ -456,9 +458,14 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
     CUDA_TRY(cudaMemsetAsync(w, 0, ld * sizeof(double), S.s));
     std::vector<cd> ny(j);
     for (int k = 0; k < j; ++k) ny[k] = -y[k];
-    S.gemv_sub_(S.V.p, j, ny.data(), w);       // w = V y
-    S.precond(w, z);
-    S.axpby_(cd(1, 0), z, cd(1, 0), x);
+    if (direct) {                               // x += Z y: no further application of the LU sweeps
+      S.gemv_sub_(S.Z.p, j, ny.data(), w);
+      S.axpby_(cd(1, 0), w, cd(1, 0), x);
+    } else {
+      S.gemv_sub_(S.V.p, j, ny.data(), w);     // w = V y
+      S.precond(w, z);
+      S.axpby_(cd(1, 0), z, cd(1, 0), x);
+    }
   }
   st->iterations = it;
   st->rel_residual = rel;
