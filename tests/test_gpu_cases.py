@@ -125,3 +125,30 @@ def test_run_periodic_beam_functionals_on_gpu():
     for k in range(4):
         assert np.abs(out[2 + k] - E[:, k]).max() <= 1e-8 * np.abs(E[:, k]).max(), k
     assert out[6] == r["E0"]["E_kin_f0"] and out[7] == r["E0"]["E_kin_s0"]
+
+
+@pytest.mark.parametrize("omega", [0.4, 0.8])                                 # scripts/5-3-1-Liu.jl:20-32
+def test_liu(omega, golden_dir):
+    """5-3-1 on the reference's own model file (6 016 P4 triangles, variable bathymetry): matrix and
+    right-hand side against the oracle, solution against its LU, |η|/η0 against Liu et al.'s curve."""
+    from vlfs_b200 import _lib as L
+    from vlfs_b200.cases.liu import LiuProblem, Liu_params, run_Liu
+    from oracle.cases.liu import LiuCase
+    f = os.path.join(golden_dir, "Liu.json")
+    prob = LiuProblem(Liu_params(omega=omega, mesh_file=f), device=0)
+    prob.assemble()
+    ref = LiuCase(f, omega=omega)
+    A, b = ref.assemble()
+    assert prob.sys.ncoo == ref.ncoo
+    A = _check_matrix(prob.sys, 0, A)
+    assert np.abs(prob.sys.get_vector(0) - b).max() <= 1e-12 * np.abs(b).max()
+    prob.sys.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=30, maxit=60, rtol=1e-12)
+    x, st = prob.sys.solve(vec=0)
+    xr = lu_reference(A, b)
+    assert np.linalg.norm(x - xr) <= 1e-8 * np.linalg.norm(xr)
+    xs, eta = run_Liu(Liu_params(omega=omega, mesh_file=f), device=0)
+    xs_r, eta_r = ref.postprocess(xr)
+    assert np.array_equal(xs, xs_r) and np.abs(eta - eta_r).max() <= 1e-7 * eta_r.max()
+    lit = np.loadtxt(os.path.join(golden_dir, "Liu_omega_0%d.csv" % round(omega * 10)), delimiter=",")
+    xu, iu = np.unique(xs, return_index=True)
+    assert np.abs(np.interp(lit[:, 0], xu, eta[iu]) - lit[:, 1]).max() < 0.02

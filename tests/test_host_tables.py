@@ -151,3 +151,19 @@ def test_gmsh_reader_reproduces_golden_json(golden_dir):
     for d in range(4):
         assert np.array_equal(a.face_entity[d], b.face_entity[d])
     assert a.tags == b.tags
+
+
+def test_liu_descriptors_reproduce_oracle(golden_dir):
+    """Configuration 5-3-1 on the reference's own model file (models/Liu.json, 6 016 triangles)."""
+    from vlfs_b200.cases.liu import LiuProblem, Liu_params
+    from oracle.cases.liu import LiuCase
+    f = os.path.join(golden_dir, "Liu.json")
+    p = LiuProblem(Liu_params(omega=0.4, mesh_file=f), system_cls=RecordingSystem)
+    o = LiuCase(f, omega=0.4)
+    assert abs(p.c["k"] - o.c["k"]) <= 1e-15
+    for a, b in [(p.V_Om, o.V_phi), (p.V_Gk, o.V_kap), (p.V_Ge, o.V_eta)]:
+        assert a.ndofs == b.ndofs and np.array_equal(a.cell_dofs, b.cell_dofs)
+    mats, vecs = p.sys.evaluate()
+    A, b = o.assemble()
+    _same_pattern_and_values(mats[0], A)
+    assert np.abs(b - vecs[0]).max() <= 1e-12 * np.abs(b).max()

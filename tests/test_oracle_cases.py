@@ -120,3 +120,21 @@ def test_yago_sizes_and_laplace_identities():
     interior = zc < c.c["H"] * (1 - 1e-12)
     rs = np.asarray(App.real.sum(axis=1)).ravel()
     assert np.abs(rs[interior]).max() < 1e-9 * abs(App).max()
+
+
+def test_liu_sizes_and_literature(golden_dir):
+    """5-3-1 on the reference's model file (scripts/5-3-1-Liu.jl:20-32): sizes, dispersion root and
+    |η|/η0 against the digitised curves of Liu et al. (data/Ref_data/Liu) for ω = 0.4 and 0.8."""
+    from oracle.cases.liu import LiuCase
+    for om, fname, lam_over_L in ((0.4, "Liu_omega_04.csv", 1.0633), (0.8, "Liu_omega_08.csv", 0.32078)):
+        c = LiuCase(os.path.join(golden_dir, "Liu.json"), omega=om)
+        assert (c.Om.ncells, c.Gb.ncells, c.Gf.ncells, c.Gd1.ncells, c.Gd2.ncells, c.Gin.ncells, c.Lb.nfaces) == \
+            (6016, 49, 198, 199, 199, 9, 48)
+        assert [s.ndofs for s in c.X.spaces] == [50089, 2386, 197]
+        k = c.c["k"]
+        assert abs(np.sqrt(9.81 * k * np.tanh(k * 60)) - om) < 1e-14 and abs(2 * np.pi / k / 300 - lam_over_L) < 1e-4
+        x, (xs, eta) = c.solve()
+        ref = np.loadtxt(os.path.join(golden_dir, fname), delimiter=",")
+        xu, iu = np.unique(xs, return_index=True)
+        ours = np.interp(ref[:, 0], xu, eta[iu])
+        assert np.abs(ours - ref[:, 1]).max() < 0.02, np.abs(ours - ref[:, 1]).max()
