@@ -77,3 +77,29 @@ for f, order in ((os.path.join(ROOT, "tests/golden/multi_geo_coarse.json"), 2),
     emit(config="5-5-1", mesh=os.path.basename(f), order=order, N=prob.X.ndofs, nnz=prob.nnz, host_setup_s=ts,
          assemble_s=ta, factor_s=tf, solve_s=tsol, iterations=st["iterations"], rel_residual=st["rel_residual"],
          eta_absmax=float(np.abs(eta).max()))
+
+# 5-3-1 Liu: the reference's triangular model, ω = 0.4 and 0.8 (scripts/5-3-1-Liu.jl:20-32)
+from vlfs_b200.cases.liu import LiuProblem, Liu_params
+for om in (0.4, 0.8):
+    prob, ts = t(lambda: LiuProblem(Liu_params(omega=om, mesh_file=os.path.join(ROOT, "tests/golden/Liu.json"))))
+    _, ta = t(prob.assemble)
+    _, tf = t(lambda: prob.sys.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=30, maxit=60, rtol=1e-12))
+    (x, st), tsol = t(lambda: prob.sys.solve(vec=0))
+    xs, eta = prob.postprocess(x)
+    emit(config="5-3-1", omega=om, N=prob.X.ndofs, nnz=prob.nnz, host_setup_s=ts, assemble_s=ta, factor_s=tf, solve_s=tsol,
+         iterations=st["iterations"], rel_residual=st["rel_residual"], eta_max=float(eta.max()), eta_mean=float(eta.mean()))
+
+# 5-1-4 periodic beam with free surface: n = 64, order 4, one wave period at T/40
+# (scripts/5-1-4-periodic-beam-free-surface-energy.jl:73-86 uses n = 128, dt = T/200... scaled down)
+from vlfs_b200.cases.periodic_beam_fs import PeriodicBeamFSProblem, Periodic_Beam_FS_params, run_periodic_beam_FS
+kfs = 15
+Tfs = 2 * np.pi / np.sqrt(9.81 * kfs * np.tanh(kfs * 1.0))
+p = Periodic_Beam_FS_params(n=64, dt=Tfs / 40, tf=Tfs, order=4, k=kfs)
+prob, ts = t(lambda: PeriodicBeamFSProblem(p))
+_, ta = t(prob.assemble)
+(u, v, a, states, st), tsolve = t(prob.solve)
+out, tall = t(lambda: run_periodic_beam_FS(p))
+emit(config="5-1-4", n=64, order=4, N=prob.X.ndofs, nnz=prob.nnz, host_setup_s=ts, assemble_s=ta,
+     newmark_steps=int(states.shape[0]), newmark_s=tsolve, ms_per_step=st["solve_ms"] / max(states.shape[0], 1),
+     e_phi=float(out[0][-1]), e_eta=float(out[1][-1]), E_kin_f_rel=float(out[2][-1] / out[6]),
+     E_pot_f_rel=float(out[3][-1] / out[8]), run_periodic_beam_FS_s=tall)

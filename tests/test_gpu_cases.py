@@ -152,3 +152,35 @@ def test_liu(omega, golden_dir):
     lit = np.loadtxt(os.path.join(golden_dir, "Liu_omega_0%d.csv" % round(omega * 10)), delimiter=",")
     xu, iu = np.unique(xs, return_index=True)
     assert np.abs(np.interp(lit[:, 0], xu, eta[iu]) - lit[:, 1]).max() < 0.02
+
+
+@pytest.mark.parametrize("kw", [dict(n=4, dt=0.01, tf=0.05, order=2, k=1),    # scripts/5-1-4-...jl:37-46 (coarse)
+                                dict(n=6, dt=1e-3, tf=1e-2, order=4, k=3)])
+def test_periodic_beam_fs(kw):
+    """5-1-4: K, C, M and the Newmark matrix against the oracle, the stepped states, and the
+    reference's tuple of errors and energies with the GPU functionals (src/Periodic_Beam_FS.jl:191-198)."""
+    from vlfs_b200.cases.periodic_beam_fs import PeriodicBeamFSProblem, Periodic_Beam_FS_params, run_periodic_beam_FS
+    from vlfs_b200.cases.periodic_beam import MAT_K, MAT_C, MAT_M, MAT_A
+    from oracle.cases.periodic_beam_fs import PeriodicBeamFSCase
+    prob = PeriodicBeamFSProblem(Periodic_Beam_FS_params(**kw), device=0)
+    prob.assemble()
+    ref = PeriodicBeamFSCase(**kw)
+    K, C, M = ref.assemble()
+    for mat, A in ((MAT_K, K), (MAT_C, C), (MAT_M, M)):
+        _check_matrix(prob.sys, mat, A)
+    cu, cuu = 0.5 / (0.25 * kw["dt"]), 1.0 / (0.25 * kw["dt"] ** 2)
+    _check_matrix(prob.sys, MAT_A, K + cu * C + cuu * M)
+    u, v, a, states, st = prob.solve()
+    r = ref.run(keep_states=True)
+    sref = np.array(r["states"])
+    assert states.shape == sref.shape
+    assert np.abs(states - sref).max() <= 1e-8 * np.abs(sref).max()
+    out = run_periodic_beam_FS(Periodic_Beam_FS_params(**kw), device=0)
+    E = np.array(r["E"])
+    assert np.allclose(out[10], r["t"], rtol=1e-14)
+    assert np.abs(out[0] - np.array(r["e_phi"])).max() <= 1e-6 * np.max(r["e_phi"])
+    assert np.abs(out[1] - np.array(r["e_eta"])).max() <= 1e-6 * np.max(r["e_eta"])
+    for k in range(4):
+        assert np.abs(out[2 + k] - E[:, k]).max() <= 1e-7 * np.abs(E[:, k]).max(), k
+    assert out[6] == r["E0"]["E_kin_f0"] and out[7] == r["E0"]["E_kin_s0"]
+    assert out[8] == r["E0"]["E_pot_f0"] and out[9] == r["E0"]["E_ela_s0"]

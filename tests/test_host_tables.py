@@ -167,3 +167,21 @@ def test_liu_descriptors_reproduce_oracle(golden_dir):
     A, b = o.assemble()
     _same_pattern_and_values(mats[0], A)
     assert np.abs(b - vecs[0]).max() <= 1e-12 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("kw", [dict(n=4, dt=0.01, tf=0.02, order=2, k=1),
+                                dict(n=6, dt=1e-3, tf=2e-3, order=4, k=3)])
+def test_periodic_beam_fs_descriptors_reproduce_oracle(kw):
+    """Configuration 5-1-4 (src/Periodic_Beam_FS.jl): beam on half the surface, three fields."""
+    from vlfs_b200.cases.periodic_beam_fs import PeriodicBeamFSProblem, Periodic_Beam_FS_params
+    from oracle.cases.periodic_beam_fs import PeriodicBeamFSCase
+    p = PeriodicBeamFSProblem(Periodic_Beam_FS_params(**kw), system_cls=RecordingSystem)
+    o = PeriodicBeamFSCase(**kw)
+    assert o.Gb.ncells == kw["n"] and o.Gfs.ncells == kw["n"] and o.Lb.nfaces == kw["n"] - 1
+    for a, b in [(p.V_Om, o.V_phi), (p.V_Gfs, o.V_kap), (p.V_Gb, o.V_eta)]:
+        assert np.array_equal(a.cell_dofs, b.cell_dofs)
+    mats, _ = p.sys.evaluate()
+    for M, A in zip(mats[:3], o.assemble()):
+        _same_pattern_and_values(M, A)
+    for d in range(3):
+        assert np.abs(p.interpolate(0.0, d) - o.interpolate(0.0, d)).max() <= 1e-15 * max(np.abs(o.interpolate(0.0, d)).max(), 1)

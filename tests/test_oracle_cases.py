@@ -138,3 +138,21 @@ def test_liu_sizes_and_literature(golden_dir):
         xu, iu = np.unique(xs, return_index=True)
         ours = np.interp(ref[:, 0], xu, eta[iu])
         assert np.abs(ours - ref[:, 1]).max() < 0.02, np.abs(ours - ref[:, 1]).max()
+
+
+def test_periodic_beam_fs_energies_near_analytic_constants():
+    """5-1-4 (scripts/5-1-4-...jl:37-46 with a coarser mesh): after one period the four energies sit
+    near the analytic constants of src/Periodic_Beam_FS.jl:177-180 and their sum is conserved."""
+    from oracle.cases.periodic_beam_fs import PeriodicBeamFSCase
+    k = 2
+    om = np.sqrt(9.81 * k * np.tanh(k * 1.0))
+    T = 2 * np.pi / om
+    c = PeriodicBeamFSCase(n=8, dt=T / 40, tf=T, order=4, k=k)
+    assert (c.Gb.ncells, c.Gfs.ncells, c.Lb.nfaces) == (8, 8, 7)
+    r = c.run()
+    E = np.array(r["E"])
+    E0 = r["E0"]
+    assert abs(E[:, 0].mean() / E0["E_kin_f0"] - 1) < 0.02 and abs(E[:, 1].mean() / E0["E_pot_f0"] - 1) < 0.02
+    tot = E.sum(axis=1)
+    assert np.abs(tot / tot[0] - 1).max() < 5e-3
+    assert r["e_phi"][-1] < 5e-4 and r["e_eta"][-1] < 5e-3
