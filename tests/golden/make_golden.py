@@ -65,6 +65,22 @@ def main():
     A, b = c.assemble()
     x = spla.splu(A.tocsc()).solve(b)
     np.savez_compressed(os.path.join(HERE, "oracle_multigeo_warmup.npz"), x=x, **probe(A, b))
+    # 5-3-1 Liu, ω = 0.4 (scripts/5-3-1-Liu.jl:20-24) on the reference's model file; the value
+    # functionals are kept at every 16th entry to keep the fixture small
+    from oracle.cases.liu import LiuCase
+    from oracle.cases.periodic_beam_fs import PeriodicBeamFSCase
+    c = LiuCase(os.path.join(HERE, "Liu.json"), omega=0.4)
+    A, b = c.assemble()
+    x = spla.splu(A.tocsc()).solve(b)
+    xs, eta = c.postprocess(x)
+    pr = probe(A, b)
+    np.savez_compressed(os.path.join(HERE, "oracle_liu_omega04.npz"), n=pr["n"], nnz=pr["nnz"], digest=pr["digest"],
+                        Ax=pr["Ax"][::16], diag=pr["diag"][::16], b=pr["b"][::16], xs=xs, eta=eta,
+                        eta_dofs=x[c.X.offsets[2]:c.X.offsets[3]])
+    # 5-1-4 on a coarse mesh: the reference's tuple of errors and energies
+    r = PeriodicBeamFSCase(n=4, dt=0.01, tf=0.05, order=2, k=1).run()
+    np.savez_compressed(os.path.join(HERE, "oracle_periodic_beam_fs.npz"), u=r["u"], e_phi=r["e_phi"],
+                        e_eta=r["e_eta"], E=np.array(r["E"]))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

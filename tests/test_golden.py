@@ -32,6 +32,43 @@ def test_oracle_reproduces_fixtures(golden_dir):
                  *MultiGeoCase(os.path.join(golden_dir, "multi_geo_coarse.json"), order=2).assemble(), tol=1e-13)
 
 
+def _check_liu(g, A, b, tol):
+    p = probe(A, b)
+    assert p["n"] == int(g["n"]) and p["nnz"] == int(g["nnz"]) and np.array_equal(p["digest"], g["digest"])
+    for key in ("Ax", "diag", "b"):
+        assert np.abs(p[key][::16] - g[key]).max() <= tol * np.abs(g[key]).max(), key
+
+
+def test_oracle_reproduces_liu_and_fs_fixtures(golden_dir):
+    from oracle.cases.liu import LiuCase
+    from oracle.cases.periodic_beam_fs import PeriodicBeamFSCase
+    _check_liu(_load(golden_dir, "oracle_liu_omega04.npz"),
+               *LiuCase(os.path.join(golden_dir, "Liu.json"), omega=0.4).assemble(), tol=1e-13)
+    g = _load(golden_dir, "oracle_periodic_beam_fs.npz")
+    r = PeriodicBeamFSCase(n=4, dt=0.01, tf=0.05, order=2, k=1).run()
+    assert np.abs(r["u"] - g["u"]).max() <= 1e-12 * np.abs(g["u"]).max()
+    assert np.abs(np.array(r["E"]) - g["E"]).max() <= 1e-11 * np.abs(g["E"]).max()
+
+
+@pytest.mark.gpu
+def test_gpu_liu_and_fs_against_fixtures(golden_dir):
+    from vlfs_b200.cases.liu import LiuProblem, Liu_params, run_Liu
+    from vlfs_b200.cases.periodic_beam_fs import run_periodic_beam_FS, Periodic_Beam_FS_params
+    g = _load(golden_dir, "oracle_liu_omega04.npz")
+    par = Liu_params(omega=0.4, mesh_file=os.path.join(golden_dir, "Liu.json"))
+    prob = LiuProblem(par)
+    prob.assemble()
+    _check_liu(g, prob.sys.get_matrix(0), prob.sys.get_vector(0), tol=1e-12)
+    xs, eta = run_Liu(par)
+    assert np.array_equal(xs, g["xs"]) and np.abs(eta - g["eta"]).max() <= 1e-7 * g["eta"].max()
+    g = _load(golden_dir, "oracle_periodic_beam_fs.npz")
+    out = run_periodic_beam_FS(Periodic_Beam_FS_params(n=4, dt=0.01, tf=0.05, order=2, k=1))
+    assert np.abs(out[0] - g["e_phi"]).max() <= 1e-7 * g["e_phi"].max()
+    assert np.abs(out[1] - g["e_eta"]).max() <= 1e-7 * g["e_eta"].max()
+    for k in range(4):
+        assert np.abs(out[2 + k] - g["E"][:, k]).max() <= 1e-7 * np.abs(g["E"][:, k]).max(), k
+
+
 @pytest.mark.gpu
 def test_gpu_yago_warmup_against_fixture(golden_dir):
     from vlfs_b200 import _lib as L
