@@ -18,6 +18,7 @@
 // always the true one and one refinement step recovers full accuracy.
 #include "common.cuh"
 #include "direct.cuh"
+#include "symbolic_host.hpp"
 #include <algorithm>
 #include <chrono>
 #include <numeric>
@@ -521,64 +522,6 @@ struct DirectSolver {
 
 namespace {
 
-struct TreeNode { std::vector<int> piv; int child[2] = {-1, -1}; };
-
-struct NDBuilder {
-  const int* ptr; const int* idx; const double* xy; int dim; int leaf;
-  std::vector<signed char> mark;
-  std::vector<TreeNode> nodes;
-  int rec(std::vector<int>& S) {
-    if ((int)S.size() <= leaf) return make_leaf(S);
-    // split axis = the one with the most distinct coordinate planes (the best-resolved direction:
-    // its separators are the smallest; the longest geometric extent is a poor guide on strongly
-    // anisotropic meshes such as x-refined slabs), median split
-    int ax = 0; size_t best = 0;
-    std::vector<double> cs, cbest;
-    for (int a = 0; a < dim; ++a) {
-      cs.resize(S.size());
-      for (size_t k = 0; k < S.size(); ++k) cs[k] = xy[(size_t)S[k] * dim + a];
-      std::sort(cs.begin(), cs.end());
-      size_t distinct = 1;
-      for (size_t k = 1; k < cs.size(); ++k) distinct += cs[k] != cs[k - 1];
-      if (distinct > best) { best = distinct; ax = a; cbest.swap(cs); }
-    }
-    std::vector<double> c(S.size());
-    for (size_t k = 0; k < S.size(); ++k) c[k] = xy[(size_t)S[k] * dim + ax];
-    double med = cbest[cbest.size() / 2];
-    std::vector<int> A, B;
-    for (size_t k = 0; k < S.size(); ++k) (c[k] <= med ? A : B).push_back(S[k]);
-    if (A.empty() || B.empty()) {
-      A.clear(); B.clear();
-      for (size_t k = 0; k < S.size(); ++k) (c[k] < med ? A : B).push_back(S[k]);
-      if (A.empty() || B.empty()) return make_leaf(S);
-    }
-    std::vector<int>().swap(S);
-    for (int v : B) mark[v] = 1;
-    std::vector<int> sep, A2;
-    for (int v : A) {
-      bool touch = false;
-      for (int p = ptr[v]; p < ptr[v + 1] && !touch; ++p) touch = mark[idx[p]] == 1;
-      (touch ? sep : A2).push_back(v);
-    }
-    for (int v : B) mark[v] = 0;
-    std::vector<int>().swap(A);
-    int c0 = A2.empty() ? -1 : rec(A2);
-    int c1 = rec(B);
-    TreeNode t;
-    t.piv.swap(sep);
-    t.child[0] = c0 >= 0 ? c0 : c1;
-    t.child[1] = c0 >= 0 ? c1 : -1;
-    nodes.push_back(std::move(t));
-    return (int)nodes.size() - 1;
-  }
-  int make_leaf(std::vector<int>& S) {
-    TreeNode t;
-    t.piv.swap(S);
-    nodes.push_back(std::move(t));
-    return (int)nodes.size() - 1;
-  }
-};
-
 template <typename F>
 float timed(cudaStream_t s, F&& f) {
   cudaEvent_t e0, e1;
@@ -603,86 +546,41 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_
   // role[i] (host, n_total entries): 0 = eliminate, 1 = keep as Schur boundary (never a pivot; the
   // root fronts end with the Schur complement on these unknowns), 2 = ignore (ghosts).
   DirectPtr D(new DirectSolver());
-  std::vector<int> elim, keep;
-  for (long long i = 0; i < n_total; ++i) {
-    if (role[i] == 0) elim.push_back((int)i);
-    else if (role[i] == 1) keep.push_back((int)i);
-  }
-  const long long n = (long long)elim.size();
-  D->n = n; D->n_total = n_total; D->n_keep = (long long)keep.size();
+  D->n_total = n_total;
   D->nnz = nnz; D->cplx = is_complex; D->nsm = nsm; D->s = s; D->launches = launches;
-  if (n == 0) throw std::string("sparse LU: nothing to eliminate");
   if (leaf < 8) leaf = 96;
   auto t0 = std::chrono::steady_clock::now();
-  // symmetrised pattern on the host, original numbering; rows of eliminated unknowns only
-  // (edges to kept unknowns are recorded on the eliminated side)
+  auto tlast = t0;
+  const bool dbg = getenv("VLFS_DEBUG") != nullptr;
+  auto lap = [&](const char* what) {
+    if (!dbg) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "[vlfs] symbolic: %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - tlast).count());
+    tlast = t;
+  };
   std::vector<int> rp(n_total + 1), ci(nnz);
   CUDA_TRY(cudaMemcpy(rp.data(), d_rowptr, (n_total + 1) * sizeof(int), cudaMemcpyDeviceToHost));
   CUDA_TRY(cudaMemcpy(ci.data(), d_colind, nnz * sizeof(int), cudaMemcpyDeviceToHost));
-  std::vector<int> sp(n_total + 1, 0), si;
-  {
-    std::vector<int> cnt(n_total, 0);
-    auto edge = [&](long long i, int j, auto&& f) {
-      if (role[i] == 2 || role[j] == 2 || (int)i == j) return;
-      if (role[i] == 0) f((int)i, j);
-      if (role[j] == 0) f(j, (int)i);
-    };
-    for (long long i = 0; i < n_total; ++i)
-      for (int p = rp[i]; p < rp[i + 1]; ++p) edge(i, ci[p], [&](int a, int) { ++cnt[a]; });
-    std::vector<long long> start(n_total + 1, 0);
-    for (long long i = 0; i < n_total; ++i) start[i + 1] = start[i] + cnt[i];
-    std::vector<int> tmp(start[n_total]);
-    std::vector<long long> fillp(start.begin(), start.end() - 1);
-    for (long long i = 0; i < n_total; ++i)
-      for (int p = rp[i]; p < rp[i + 1]; ++p) edge(i, ci[p], [&](int a, int b2) { tmp[fillp[a]++] = b2; });
-    si.reserve(start[n_total]);
-    for (long long i = 0; i < n_total; ++i) {
-      std::sort(tmp.begin() + start[i], tmp.begin() + start[i + 1]);
-      auto e = std::unique(tmp.begin() + start[i], tmp.begin() + start[i + 1]);
-      for (auto it = tmp.begin() + start[i]; it != e; ++it) si.push_back(*it);
-      sp[i + 1] = (int)si.size();
-    }
-  }
-  // nested dissection
-  NDBuilder nd{sp.data(), si.data(), coords, dim, leaf};
-  nd.mark.assign(n_total, 0);
-  std::vector<int> all(elim);
-  nd.nodes.reserve(2 * n / leaf + 16);
-  int root = nd.rec(all);
-  (void)root;
-  const int nf_ = (int)nd.nodes.size();
+  lap("pattern to host");
+  // host analysis (symbolic_host.hpp): A + A^T, geometric nested dissection, update sets
+  vlfs_sym::Analysis R;
+  vlfs_sym::analyse(n_total, rp.data(), ci.data(), role, coords, dim, leaf, R);
+  if (dbg)
+    fprintf(stderr, "[vlfs] symbolic: symmetrise %.1f ms, nested dissection %.1f ms, update sets %.1f ms (%u threads)\n",
+            R.ms_sym, R.ms_nd, R.ms_upd, vlfs_sym::host_threads());
+  const long long n = R.n;
+  D->n = n; D->n_keep = R.n_keep;
+  const int nf_ = (int)R.nodes.size();
   D->nfronts = nf_;
-  // permutation (postorder = creation order)
-  std::vector<int> pos(n_total, -1), front_of_pos(n);
-  std::vector<int> first(nf_), parent(nf_, -1);
-  {
-    int k = 0;
-    for (int f = 0; f < nf_; ++f) {
-      first[f] = k;
-      for (int v : nd.nodes[f].piv) { pos[v] = k; front_of_pos[k] = f; ++k; }
-      for (int c : nd.nodes[f].child) if (c >= 0) parent[c] = f;
-    }
-    if (k != n) throw std::string("nested dissection lost DOFs");
-    for (size_t q = 0; q < keep.size(); ++q) pos[keep[q]] = (int)(n + q);
-  }
-  // update sets bottom-up
-  std::vector<std::vector<int>> upd(nf_);
-  std::vector<int> level(nf_, 0);
-  std::vector<int> tmp;
-  for (int f = 0; f < nf_; ++f) {
-    const int last = first[f] + (int)nd.nodes[f].piv.size();
-    tmp.clear();
-    for (int v : nd.nodes[f].piv)
-      for (int p = sp[v]; p < sp[v + 1]; ++p) { int q = pos[si[p]]; if (q >= last) tmp.push_back(q); }
-    for (int c : nd.nodes[f].child)
-      if (c >= 0) {
-        for (int q : upd[c]) if (q >= last) tmp.push_back(q);
-        level[f] = std::max(level[f], level[c] + 1);
-      }
-    std::sort(tmp.begin(), tmp.end());
-    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-    upd[f] = tmp;
-  }
+  const std::vector<int>& pos = R.pos;
+  const std::vector<int>& front_of_pos = R.front_of_pos;
+  const std::vector<int>& first = R.first;
+  const std::vector<int>& parent = R.parent;
+  const std::vector<int>& level = R.level;
+  const std::vector<std::vector<int>>& upd = R.upd;
+  struct { const std::vector<vlfs_sym::TreeNode>& nodes; } nd{R.nodes};
+  std::vector<int>().swap(rp); std::vector<int>().swap(ci);
+  lap("update sets");
   // meta
   D->meta.resize(nf_);
   std::vector<int> upd_flat;
@@ -719,6 +617,7 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_
         if (c >= 0) D->level_maxnu_child[L] = std::max(D->level_maxnu_child[L], D->meta[c].nf - D->meta[c].np);
     }
   }
+  lap("front metadata");
   // upload
   D->d_meta.upload(D->meta.data(), nf_, s);
   D->d_pos.upload(pos.data(), n_total, s);
@@ -749,6 +648,7 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_
   for (int f = 0; f < nf_; ++f) if (parent[f] < 0) D->roots.push_back(f);
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
+  lap("upload + pool allocation");
   D->symbolic_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return D;
 }
