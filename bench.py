@@ -300,7 +300,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline()
+        cpu = cpu_baseline(with_solve=not args.no_cpu_solve)
 
     if rank == 0:
         out = {
@@ -480,7 +480,34 @@ def run_ours_distributed(args):
     dist.destroy_process_group()
 
 
-def cpu_baseline(sample=None):
+def cpu_solve_baseline():
+    """SpMV and sparse LU of the CPU path on a bounded sample (1/8 of Y1 in x: SuperLU needs ~40 s
+    there and grows superlinearly; UMFPACK, what Gridap's LUSolver calls, is the same algorithm class)."""
+    import numpy as np
+    import scipy.sparse.linalg as spla
+    from oracle.cases.yago import YagoCase
+    kw = dict(nx=8, ny=2, nz=3, order=4, lfactor=0.4, dfactor=4)
+    A, b = YagoCase(**kw).assemble()
+    A = A.tocsr()
+    n = A.shape[0]
+    x = np.sin(0.1 * np.arange(n)) + 1j * np.cos(0.1 * np.arange(n))
+    A @ x
+    t0 = time.time()
+    for _ in range(10):
+        A @ x
+    sp_s = (time.time() - t0) / 10
+    sp_bytes = A.nnz * 20 + 4 * (n + 1) + 2 * n * 16
+    t0 = time.time()
+    lu = spla.splu(A.tocsc())
+    xs = lu.solve(b)
+    lu_s = time.time() - t0
+    return {"sample": "Yago %s: N=%d nnz=%d" % (json.dumps(kw), n, A.nnz), "cores": 1,
+            "spmv_GBs": sp_bytes / sp_s / 1e9, "spmv_ms": sp_s * 1e3,
+            "solve_s_per_step": lu_s, "solver": "scipy.sparse.linalg.splu (SuperLU) + triangular solves",
+            "rel_residual": float(np.linalg.norm(A @ xs - b) / np.linalg.norm(b))}
+
+
+def cpu_baseline(sample=None, with_solve=False):
     """The oracle (CPU restatement of Gridap's assembly) timed on the host cores."""
     import numpy as np
     from oracle.cases.yago import YagoCase
@@ -489,7 +516,8 @@ def cpu_baseline(sample=None):
     t0 = time.time()
     A, b = case.assemble()
     dt = time.time() - t0
-    return {"value": A.nnz / dt, "unit": "nnz/s", "cores": 1, "kind": "port",
+    extra = {"spmv_solve": cpu_solve_baseline()} if with_solve else {}
+    return {**extra, "value": A.nnz / dt, "unit": "nnz/s", "cores": 1, "kind": "port",
             "note": "the reference path is single-threaded: Gridap 0.17 integrates and assembles in one Julia "
                     "thread (SURVEY.md §3); the port is vectorised NumPy + SciPy sum_duplicates on one core",
             "sample": "oracle (NumPy restatement of Gridap cell integration + sparse(I,J,V)) on Yago %s: "
@@ -504,8 +532,9 @@ def run_reference(args):
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_baseline(WORKLOADS["Y0"])
     c = None
-    for _ in range(max(1, min(args.steps, 3))):
-        c = cpu_baseline()
+    nst = max(1, min(args.steps, 3))
+    for i in range(nst):
+        c = cpu_baseline(with_solve=(i == nst - 1 and not args.no_cpu_solve))
         vals.append(c["value"])
     v = sum(vals) / len(vals)
     c["value"] = v
@@ -532,6 +561,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="Y1", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-solve", action="store_true", help="skip the CPU SpMV / sparse LU sample (~50 s)")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--dist-maxit", type=int, default=120, help="GMRES iterations of the N>1 solve")
