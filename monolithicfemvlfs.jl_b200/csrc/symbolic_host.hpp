@@ -64,15 +64,49 @@ inline double ms_since(std::chrono::steady_clock::time_point t0) {
 // pattern of A + A^T without the diagonal: row i keeps j when role[i] == 0 and role[j] != 2
 inline void symmetrise(long long n_total, const int* rp, const int* ci, const signed char* role,
                        std::vector<int>& sp, std::vector<int>& si) {
-  // transpose (rows sorted because the source rows are visited in ascending order)
-  std::vector<int> tp(n_total + 1, 0);
+  // transpose by counting sort, row ranges in parallel with one histogram per range: the entries
+  // of a transposed row come out in ascending order because range t precedes range t+1
   const long long nnz = rp[n_total];
-  for (long long p = 0; p < nnz; ++p) ++tp[ci[p] + 1];
-  for (long long i = 0; i < n_total; ++i) tp[i + 1] += tp[i];
-  std::vector<int> ti(nnz), fill(tp.begin(), tp.end() - 1);
-  for (long long i = 0; i < n_total; ++i)
-    for (int p = rp[i]; p < rp[i + 1]; ++p) ti[fill[ci[p]]++] = (int)i;
-  std::vector<int>().swap(fill);
+  unsigned nt = host_threads();
+  if (nnz < (1 << 20)) nt = 1;
+  std::vector<long long> rb(nt + 1);
+  for (unsigned t = 0; t <= nt; ++t) {            // ranges with about equal numbers of entries
+    const long long target = nnz / nt * t;
+    rb[t] = t == nt ? n_total : std::lower_bound(rp, rp + n_total + 1, (int)target) - rp;
+  }
+  rb[0] = 0;
+  std::vector<std::vector<int>> hist(nt);
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        hist[t].assign(n_total, 0);
+        for (long long i = rb[t]; i < rb[t + 1]; ++i)
+          for (int p = rp[i]; p < rp[i + 1]; ++p) ++hist[t][ci[p]];
+      });
+    for (auto& x : th) x.join();
+  }
+  std::vector<int> tp(n_total + 1, 0);
+  {
+    int acc = 0;
+    for (long long c = 0; c < n_total; ++c) {
+      tp[c] = acc;
+      for (unsigned t = 0; t < nt; ++t) { const int h = hist[t][c]; hist[t][c] = acc; acc += h; }
+    }
+    tp[n_total] = acc;
+  }
+  std::vector<int> ti(nnz);
+  {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        int* fill = hist[t].data();
+        for (long long i = rb[t]; i < rb[t + 1]; ++i)
+          for (int p = rp[i]; p < rp[i + 1]; ++p) ti[fill[ci[p]]++] = (int)i;
+      });
+    for (auto& x : th) x.join();
+  }
+  std::vector<std::vector<int>>().swap(hist);
   // merge of the two sorted rows: count, then fill
   auto merge_row = [&](long long i, int* out) -> int {
     if (role[i] != 0) return 0;
