@@ -179,6 +179,68 @@ function solve!(x::Vector, s::System, b::Vector)
   st
 end
 
+set_rhs_coef!(s, dom, term, c) = check(s, ccall((:vlfs_set_rhs_coef, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cdouble), s.ctx, dom, term, real(c), imag(c)))
+
+# DOF coordinates (row-major [ndofs][dim]) for the geometric nested dissection of the sparse LU
+set_dof_coords!(s::System, dim::Integer, xyz::Vector{Float64}) =
+  check(s, ccall((:vlfs_set_dof_coords, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), s.ctx, dim, xyz))
+
+# A = Σ c_k M_k on the union pattern (the Newmark matrix K + γ/(βΔt) C + 1/(βΔt²) M)
+function combine!(s::System, target::Integer, src::Vector{<:Integer}, coef::Vector{<:Number})
+  c = collect(Iterators.flatten((Float64(real(z)), Float64(imag(z))) for z in coef))
+  check(s, ccall((:vlfs_combine, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cint}, Ptr{Float64}),
+                 s.ctx, target, length(src), Cint.(src), c))
+end
+
+function spmv(s::System, x::Vector, mat::Integer=0)
+  y = similar(x)
+  check(s, ccall((:vlfs_spmv, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), s.ctx, mat, x, y))
+  y
+end
+
+# keep the symbolic analysis, refactorise the current values (next ω of a sweep)
+refactor!(s::System, mat::Integer=0) = check(s, ccall((:vlfs_solver_refactor, LIB), Cint, (Ptr{Cvoid}, Cint), s.ctx, mat))
+
+function solve_vec!(x::Vector, s::System, vec::Integer=0)
+  st = SolveStats()
+  rc = ccall((:vlfs_solve_vec, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ref{SolveStats}), s.ctx, vec, x, st)
+  check(s, rc; allow=(VLFS_OK, VLFS_NOT_CONVERGED))
+  st
+end
+
+# `solve(Newmark(ls,dt,γ,β),op,(x₀,v₀,a₀),t₀,tf)` on the device: u0, v0, a0 are advanced in place,
+# `out` receives the DOFs out_lo:out_hi-1 (0-based) of every out_stride-th step (row-major);
+# tcoef[nb, nsteps] are the time factors of the assembled right-hand-side vectors 0..nb-1
+function newmark_run!(s::System, u0::Vector{Float64}, v0::Vector{Float64}, a0::Vector{Float64};
+                      matK=0, matC=1, matM=2, nsteps::Integer, dt::Real, γ::Real=0.5, β::Real=0.25,
+                      tcoef::Matrix{Float64}=zeros(0, nsteps), out_lo::Integer=0, out_hi::Integer=0, out_stride::Integer=1)
+  nb = size(tcoef, 1)
+  nout = out_hi > out_lo ? cld(nsteps, out_stride) : 0
+  out = Matrix{Float64}(undef, out_hi - out_lo, nout)         # column = one recorded step
+  st = SolveStats()
+  rc = ccall((:vlfs_newmark_run, LIB), Cint,
+             (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cdouble, Cdouble, Cdouble, Cint, Ptr{Float64},
+              Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Cint, Ptr{Float64}, Ref{SolveStats}),
+             s.ctx, matK, matC, matM, nsteps, dt, γ, β, nb, nb == 0 ? C_NULL : tcoef, u0, v0, a0,
+             out_lo, out_hi, out_stride, nout == 0 ? C_NULL : out, st)
+  check(s, rc; allow=(VLFS_OK, VLFS_NOT_CONVERGED))
+  out, st
+end
+
+# ∑∫ |Σ_s scale_s OP(u_h) − f|² dμ on one domain (`∑(∫(x⋅x)dΩ)` of src/Periodic_Beam.jl:119-120)
+struct FunctionalDesc
+  op::Int32; weight_f::Int32
+  scale::NTuple{MAX_SLOTS,Float64}
+  dir::NTuple{3,Float64}
+end
+function eval_functional(s::System, dom::Integer, x::Vector{Float64}; op, slots, weight_f=-1, dir=(0.0, 0.0, 0.0))
+  f = FunctionalDesc(op, weight_f, scales(slots), Float64.(dir))
+  r = Ref{Float64}(0.0)
+  check(s, ccall((:vlfs_eval_functional, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{FunctionalDesc}, Ptr{Float64}, Ref{Float64}),
+                 s.ctx, dom, f, x, r))
+  r[]
+end
+
 # ---------------------------------------------------------------------------------------------
 # Gridap glue (needs `using Gridap`; kept in a function so that the module loads without it)
 # ---------------------------------------------------------------------------------------------
