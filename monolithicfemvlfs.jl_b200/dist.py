@@ -277,13 +277,20 @@ class GpuOps:
     def dense_solve(self, b, x):
         self.sys._check(self.lib.vlfs_dense_solve(self.ctx, self._p(b), self._p(x)))
 
-    def add_triplets(self, S, n, rows, cols, vals):
-        """S[rows, cols] += vals on the device (flat row-major n x n)."""
-        t = self.torch
-        r = t.from_numpy(np.ascontiguousarray(rows, dtype=np.int64)).to(self.device)
-        c = t.from_numpy(np.ascontiguousarray(cols, dtype=np.int64)).to(self.device)
-        v = self.from_host(np.ascontiguousarray(vals, dtype=self.d.dtype)).view(-1, self.sc)
-        S.view(n, n, self.sc).index_put_((r, c), v, accumulate=True)
+    def matrix_values(self, slots_t):
+        """Values of the local matrix at the given CSR slots (int32 device tensor), gathered on the
+        device: the interface rows never travel through the host."""
+        rp, ci, vp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.sys._check(self.lib.vlfs_device_ptrs(self.ctx, self.mat, C.byref(rp), C.byref(ci), C.byref(vp)))
+        buf = self.torch.empty(len(slots_t) * self.sc, dtype=self.torch.float64, device=self.device)
+        if len(slots_t):
+            self.sys._check(self.lib.vlfs_dev_gather(self.ctx, len(slots_t), self._p(slots_t), vp, self._p(buf)))
+        return buf
+
+    def add_triplets(self, S, n, rows_t, cols_t, vals):
+        """S[rows, cols] += vals on the device (flat row-major n x n; index tensors from long_index,
+        vals a flat device tensor)."""
+        S.view(n, n, self.sc).index_put_((rows_t, cols_t), vals.view(-1, self.sc), accumulate=True)
 
     def vec(self, n):
         return self.torch.zeros(n * self.sc, dtype=self.torch.float64, device=self.device)
@@ -618,52 +625,69 @@ class SchurSolver:
             m.ops.refactor()
         self._assemble_interface()
 
-    def _assemble_interface(self):
+    def _interface_pattern(self):
+        """Once per pattern: where the entries A[Γ_r rows, Γ columns] sit in every rank's local CSR
+        (slots) and in the interface matrix (rows, cols); sizes and positions of the kept sets."""
         F = self.fleet
-        nks = {m.rank: len(m.keep_local) for m in F.members}
-        pos = {m.rank: m.keep_pos for m in F.members}
-        agg = []
+        static = []
         for m in F.members:
-            # A[Γ_r rows, Γ columns] from the owner's complete rows (host CSR, setup only)
-            A = m.d.local.get_matrix(self.mat)[m.gamma_local]
-            cols_g = m.d.local_gids[A.indices]
+            rp, ci = m.d.local.get_pattern()
+            gl = m.gamma_local
+            cnt = (rp[gl + 1] - rp[gl]).astype(np.int64)
+            start = np.repeat(rp[gl].astype(np.int64), cnt)
+            within = np.arange(cnt.sum(), dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+            slot = start + within
+            cols_g = m.d.local_gids[ci[slot]]
             inG = np.isin(cols_g, self._gsorted)
-            rows = np.repeat(m.gamma_pos, np.diff(A.indptr))[inG]
+            m.if_slots = m.ops.index_tensor(slot[inG])
+            rows = np.repeat(m.gamma_pos, cnt)[inG]
             cols = self.position(cols_g[inG])
-            agg.append((rows, cols, A.data[inG]))
+            static.append((m.rank, len(m.keep_local), m.keep_pos, rows, cols))
         if F.dist is not None:
             meta = [None] * F.nranks
-            F.dist.all_gather_object(meta, (nks[F.members[0].rank], pos[F.members[0].rank], agg[0]))
-            nks = {r: meta[r][0] for r in range(F.nranks)}
-            pos = {r: meta[r][1] for r in range(F.nranks)}
-            agg = [meta[r][2] for r in range(F.nranks)]
-        self.nks, self.pos = nks, pos
+            F.dist.all_gather_object(meta, static[0])
+            static = meta
+        self.nks = {r: nk for r, nk, _, _, _ in static}
+        self.pos = {r: p for r, _, p, _, _ in static}
+        self.ntrip = {r: len(rows) for r, _, _, rows, _ in static}
+        self.tridiag = True
+        for r, nk, p, rows, cols in static:
+            self.tridiag &= bool(np.all(np.abs(self.block_of[rows] - self.block_of[cols]) <= 1))
+            bl = self.block_of[p]
+            self.tridiag &= bool(len(bl) == 0 or bl.max() - bl.min() <= 1)
+        if self.root is not None:
+            ops = self.root.ops
+            self.trip_t = {r: (ops.long_index(rows), ops.long_index(cols)) for r, _, _, rows, cols in static}
+            self.pos_t = {r: ops.long_index(self.pos[r]) for r in self.pos}
+            self.xg = ops.vec(self.ng)
+            self.gg = ops.vec(self.ng)
+        else:
+            self.xg = F.members[0].ops.vec(self.ng)
+
+    def _assemble_interface(self):
+        """S = A[Γ,Γ] + Σ_r Schur blocks on rank 0, then its factorisation.  Only device buffers move:
+        the interface entries of every rank (gathered from its CSR values on the device) and its
+        Schur block."""
+        F = self.fleet
+        if not hasattr(self, "nks"):
+            self._interface_pattern()
+        nks, pos = self.nks, self.pos
+        vals = self._gather([m.ops.matrix_values(m.if_slots) for m in F.members], self.ntrip)
         blocks = [m.ops.schur_block(len(m.keep_local)) for m in F.members]
-        sc = 2 if F.members[0].d.is_complex else 1
         got = self._gather(blocks, {r: nks[r] * nks[r] for r in nks})
         if self.root is not None:
             ops = self.root.ops
             S = ops.vec(self.ng * self.ng)
-            tridiag = True
-            for rows, cols, vals in agg:
-                ops.add_triplets(S, self.ng, rows, cols, vals)
-                tridiag &= bool(np.all(np.abs(self.block_of[rows] - self.block_of[cols]) <= 1))
+            for r, v in vals.items():
+                ops.add_triplets(S, self.ng, self.trip_t[r][0], self.trip_t[r][1], v)
             for r, blk in got.items():
                 ops.add_block(S, self.ng, pos[r], blk, nks[r])
-                bl = self.block_of[pos[r]]
-                tridiag &= bool(len(bl) == 0 or bl.max() - bl.min() <= 1)
-            if tridiag and len(self.block_sizes) > 1:
+            if self.tridiag and len(self.block_sizes) > 1:
                 ops.chain_factor(self.block_sizes, S)      # O(sum n_r^3): chain of fronts
                 self.interface_solver = "block-tridiagonal chain of %d fronts" % len(self.block_sizes)
             else:
                 ops.dense_factor(self.ng, S)
                 self.interface_solver = "dense"
-            self.xg = ops.vec(self.ng)
-            self.gg = ops.vec(self.ng)
-            self.pos_t = {r: ops.long_index(pos[r]) for r in pos}
-        else:
-            m = F.members[0]
-            self.xg = m.ops.vec(self.ng)
 
     def apply(self, rs, zs):
         """zs = A^-1 rs on distributed vectors (one device vector per local member)."""

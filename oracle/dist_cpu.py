@@ -27,6 +27,16 @@ class CpuLocalSystem(RecordingSystem):
     def get_matrix(self, mat=0):
         return self.mats[mat].tocsr()
 
+    def get_pattern(self):
+        A = self.canonical(0)
+        return A.indptr, A.indices
+
+    def canonical(self, mat):
+        """CSR with sorted column indices: the slot numbering `get_pattern` refers to."""
+        A = self.mats[mat].tocsr()
+        A.sort_indices()
+        return A
+
 
 class CpuOps:
     def __init__(self, dsys, mat=0):
@@ -122,6 +132,9 @@ class CpuOps:
     def chain_factor(self, sizes, S):
         assert sum(sizes) * sum(sizes) == len(S)
         self.dense_factor(int(sum(sizes)), S)
+
+    def matrix_values(self, slots):
+        return np.array(self.sys.canonical(0).data[slots], dtype=self.d.dtype)
 
     def add_triplets(self, S, n, rows, cols, vals):
         np.add.at(S.reshape(n, n), (rows, cols), vals)
