@@ -6,13 +6,15 @@
 // (src/Khabakhpasheva_time_domain.jl:258-259, src/Periodic_Beam.jl:107-108).  The
 // monolithic matrices are indefinite wave operators on which Jacobi/ILU0 Krylov stalls
 // (solver study), so the factorisation itself runs on the GPU:
-//   symbolic (host, once per pattern): geometric nested dissection on the DOF coordinates,
-//     separator tree -> supernodes, front index sets, level schedule;
+//   symbolic (host threads, once per pattern; symbolic_host.hpp): geometric nested dissection on
+//     the DOF coordinates, separator tree -> supernodes, front index sets, level schedule;
 //   numeric (device): dense fronts in one pool; per tree level, batched over fronts:
 //     extend-add of the children's Schur complements, then a blocked right-looking partial LU
-//     (32-column panels: diagonal-block LU in shared memory, panel triangular solves, rank-32
-//     Schur update with 64x64 register-tiled FP64 tiles);
-//   solve (device): level-scheduled forward / backward sweeps over the fronts.
+//     (32-column panels inside outer blocks of 128 pivots: diagonal-block LU in shared memory,
+//     panel triangular solves, strip updates per panel, trailing update once per outer block
+//     with 64x64 register-tiled FP64 tiles);
+//   solve (device): level-scheduled forward / backward sweeps over the fronts, one launch per
+//     panel; unknowns with role "keep" stay a Schur boundary (substructuring across GPUs).
 // No pivoting across fronts (static pivoting, verified adequate on these FE matrices); the
 // Krylov driver uses the factorisation as a right preconditioner, so the reported residual is
 // always the true one and one refinement step recovers full accuracy.

@@ -1,5 +1,5 @@
-// integrate.cu - numeric phase: cell-wise quadrature + scatter-add into the fixed CSR
-// pattern (sm_100a, FP64 throughout).
+// integrate.cu - numeric phase of the assembly into the fixed CSR pattern (sm_100a, FP64
+// throughout).
 //
 // Replaces Gridap's lazy cell-matrix evaluation and COO fill inside
 // `AffineFEOperator(a,l,X,Y)` / `assemble_matrix_and_vector`
@@ -7,16 +7,22 @@
 // src/Khabakhpasheva_freq_domain.jl:226-240, src/Khabakhpasheva_time_domain.jl:237-257,
 // src/Periodic_Beam.jl:96-104, src/Multi_geo_freq_domain.jl:125-131).
 //
-// Kernels:
-//  * integrate_cells<D>: one CTA per cell.  Stage 0 builds the Jacobian pseudo-inverse,
-//    measure and normals of every slot at every quadrature point; stage 1 evaluates the
-//    operator instances (value / gradient / directional derivative / Hessian / C:Hessian /
-//    normal contractions) of all local basis functions into shared memory; stage 2 contracts
-//    test x trial rows for every touched block and scatters through `dest`; stage 3 does
-//    the linear forms.
-//  * gather_reference: the slot-centric pass for reference-type terms on constant-Jacobian
-//    cells (∫∇u·∇v, value x value terms without coefficient field): one thread per CSR slot sums
-//    its COO entries in COO order and writes the value once (also the zero fill).
+// The numeric phase is three stages (api.cu::assemble_impl):
+//  1. class tables: cells with equal quantised Jacobians, table variants and coefficient fields
+//     share one element block.  build_class_tables tabulates the reference-type products
+//     (∫∇u·∇v, value x value on constant-Jacobian cells) and integrate_cells<D> integrates the
+//     remaining terms on ONE representative cell per class into the same contiguous tables.
+//  2. gather_compact / gather_reference: slot-centric pass - one thread per CSR slot (two slots per
+//     thread in the compact variant) sums its COO entries in COO order from the class tables and
+//     writes the value once (also the zero fill); no atomics.
+//  3. integrate_cells<D> on all cells for what stays cell-dependent (non-affine cells, fields
+//     that differ in every cell): one CTA per cell, software-pipelined over its cells.  Geometry
+//     (Jacobian pseudo-inverse, measure, normals) two cells ahead, operator tables (value /
+//     gradient / directional derivative / Laplacian / Hessian / C:Hessian / normal contractions)
+//     one cell ahead, 4x4 register-tiled contraction per (block, matrix, re|im) target,
+//     red.global.add.f64 through the tile-major `dest`.
+//  rhs_affine: linear forms on constant-Jacobian cells, warp per cell, on a side stream.
+//  functional_cells<D>: ∑∫|OP(u_h) − f|² dμ of FE functions (L2 errors, energies).
 #include "common.cuh"
 #include <cstdlib>
 #include <cuda/barrier>
@@ -767,13 +773,12 @@ __global__ void compact_gather_records(const unsigned long long* __restrict__ re
 
 struct GatherSmemDom {
   const double* geo;
-  const double* tabs;      // global tables, or (tab_smem) their copy in dynamic shared memory
+  const double* tabs;      // reference tables (global memory)
   int ncls;
   const int* cls;
   const double* ctab_m[4];
   long long ctab_off[VLFS_MAX_BLOCKS];
   int has_ctab[VLFS_MAX_BLOCKS];      // block tabulated per class (reference products or all terms)
-  int tab_smem;
   int rp_first[VLFS_MAX_BLOCKS + 1];
   int ne[VLFS_MAX_BLOCKS];
 };
@@ -786,17 +791,16 @@ __global__ void __launch_bounds__(256, 8)
 gather_reference(const uint32_t* __restrict__ run_start, const unsigned long long* __restrict__ rec,
                  const uint32_t* __restrict__ rec32, AsmPtrs ctab_all, long long nnz,
                  const GatherDom* __restrict__ doms, int ndom, int nrp_total, AsmPtrs ptrs, int nmat,
-                 int is_complex, int tabs_in_smem) {
-  // the reference tables are looked up at scattered local entries: from shared memory a warp's 32
-  // different entries cost a few bank-conflict cycles instead of 32 L1 sector accesses
-  extern __shared__ __align__(16) double stab[];
+                 int is_complex) {
+  // (staging the reference tables in shared memory was measured on B200: it halves the occupancy
+  // and is slower than reading them through L1)
   __shared__ GatherSmemDom sd[GATHER_MAX_DOM];
   __shared__ RefProd srp[GATHER_MAX_RP];
   __shared__ int srp_base[GATHER_MAX_DOM];
   if (threadIdx.x == 0) {
     int base = 0;
     for (int d = 0; d < ndom; ++d) {
-      sd[d].geo = doms[d].geo; sd[d].tabs = doms[d].tabs; sd[d].tab_smem = 0;
+      sd[d].geo = doms[d].geo; sd[d].tabs = doms[d].tabs;
       sd[d].ncls = doms[d].ncls; sd[d].cls = doms[d].cls;
       for (int m = 0; m < 4; ++m) sd[d].ctab_m[m] = doms[d].ctab_m[m];
       for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) {
@@ -812,16 +816,6 @@ gather_reference(const uint32_t* __restrict__ run_start, const unsigned long lon
     }
   }
   __syncthreads();
-  if (tabs_in_smem) {
-    int off = 0;
-    for (int d = 0; d < ndom; ++d) {
-      const int len = doms[d].tab_len;
-      for (int t = threadIdx.x; t < len; t += blockDim.x) stab[off + t] = doms[d].tabs[t];
-      if (threadIdx.x == 0) { sd[d].tabs = stab + off; sd[d].tab_smem = 1; }
-      off += len;
-    }
-    __syncthreads();
-  }
   for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < nnz;
        slot += (long long)gridDim.x * blockDim.x) {
     double are[NMAT], aim[NMAT];
@@ -1029,16 +1023,11 @@ void launch_gather_reference(const uint32_t* run_start, const unsigned long long
     throw std::string("gather_reference: too many domains / reference products");
   AsmPtrs P{}, CT{};
   for (int m = 0; m < nmat && m < 4; ++m) { P.mat[m] = mats[m]; CT.mat[m] = ctab_all[m]; }
-  const size_t smem = (size_t)tab_total * sizeof(double);
-  // (measured on B200: staging the tables in shared memory halves the occupancy and is slower)
-  const int in_smem = 0 && tab_total > 0 && smem <= 100 * 1024;
+  (void)tab_total;
   long long grid = (nnz + 255) / 256;
-  const long long cap = (long long)nsm * (in_smem ? (smem > 48 * 1024 ? 2 : 4) * 2 : 32);
-  if (grid > cap) grid = cap;
+  if (grid > (long long)nsm * 32) grid = (long long)nsm * 32;
   auto launch = [&](auto kern) {
-    if (in_smem) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, 256, in_smem ? smem : 0, s>>>(run_start, rec, rec32, CT, nnz, doms, ndom, nrp_total, P,
-                                                        nmat, is_complex, in_smem);
+    kern<<<(unsigned)grid, 256, 0, s>>>(run_start, rec, rec32, CT, nnz, doms, ndom, nrp_total, P, nmat, is_complex);
   };
   static const int kslots = getenv("VLFS_GATHER_K") ? atoi(getenv("VLFS_GATHER_K")) : 2;
   if (rec32 && kslots > 1) {

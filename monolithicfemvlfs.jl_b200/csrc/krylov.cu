@@ -4,7 +4,8 @@
 // src/Khabakhpasheva_freq_domain.jl:241, src/Multi_geo_freq_domain.jl:135) and behind
 // `Newmark(LUSolver(),Δt,γ,β)` (src/Khabakhpasheva_time_domain.jl:258-266,
 // src/Periodic_Beam.jl:107-116).  Restarted right-preconditioned GMRES with CGS2
-// orthogonalisation, BiCGStab and CG; dot products are warp-shuffle reductions batched per
+// orthogonalisation (flexible storage Z = M^-1 V and a stagnation stop when the sparse LU is the
+// preconditioner: every iteration is then a refinement step), BiCGStab and CG; dot products are warp-shuffle reductions batched per
 // iteration (one partials kernel + one finishing kernel, no atomics => deterministic).
 #include "solver.cuh"
 #include <complex>
