@@ -85,18 +85,21 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
-    def _poll(self):
+    def _sample(self):
         nv = self.nv
-        while self.run:
+        try:
+            mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
-                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    why = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.rows.append((mhz, why))
+                why = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
-                pass
+                why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            self.rows.append((mhz, why))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while self.run:
+            self._sample()
             time.sleep(0.0003)
 
     def start(self):
@@ -123,6 +126,7 @@ class ClockSampler:
 
     def stop(self):
         if self.nv is not None:
+            self._sample()          # one sample right at the end of the timed region, whatever its length
             self.run = False
             self.thread.join(timeout=1.0)
             nv = self.nv
