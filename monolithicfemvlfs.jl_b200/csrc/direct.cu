@@ -605,6 +605,18 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_
   D->pool_elems = off; D->w_elems = woff;
   D->level_lists.assign(D->nlevels, {});
   for (int f = 0; f < nf_; ++f) D->level_lists[level[f]].push_back(f);
+  {
+    // the launches are batched over the fronts of a level through gridDim.y / gridDim.z (<= 65 535):
+    // a longer level is processed as several consecutive ones (its fronts are independent)
+    int zmax = 65535;
+    if (const char* e = getenv("VLFS_LU_ZMAX")) { const int v = atoi(e); if (v >= 1 && v < zmax) zmax = v; }
+    std::vector<std::vector<int>> split;
+    for (const std::vector<int>& lst : D->level_lists)
+      for (size_t o = 0; o < lst.size(); o += (size_t)zmax)
+        split.emplace_back(lst.begin() + o, lst.begin() + std::min(lst.size(), o + (size_t)zmax));
+    D->level_lists.swap(split);
+    D->nlevels = (int)D->level_lists.size();
+  }
   D->level_maxnp.assign(D->nlevels, 0); D->level_maxnf.assign(D->nlevels, 0);
   D->level_maxnu_child.assign(D->nlevels, 0);
   std::vector<int> lists_flat;

@@ -109,3 +109,24 @@ def test_empty_triangulation_is_legal():
     assert abs(A - A.T).max() <= 1e-14 * abs(A).max()
     assert abs(A.sum() - (2.0 * 1.0 + 3.0 * 1.0)) <= 1e-12      # ∑ of all entries = 2|Ω| + 3|Γ|
     assert abs(b0.sum() - 1.0) <= 1e-13                         # ∫_Γ 1 = |Γ| = 1
+
+
+def test_levels_longer_than_the_grid_limit_are_split(prob, monkeypatch):
+    """The LU launches are batched over the fronts of a tree level through gridDim.y/z (<= 65 535);
+    longer levels are processed in consecutive pieces.  Forced here with a limit of 3 fronts (the
+    analysis is made once per context, so the second system is a fresh one)."""
+    from vlfs_b200 import _lib as L
+    from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
+    opts = dict(method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=10, maxit=20, rtol=1e-13)
+    S = prob.sys
+    S.solver_setup(0, **opts)
+    x0, st0 = S.solve(vec=0)
+    info0 = S.direct_info()
+    monkeypatch.setenv("VLFS_LU_ZMAX", "3")
+    p2 = YagoProblem(Yago_freq_domain_params(**KW), device=0)
+    p2.assemble()
+    p2.sys.solver_setup(0, **opts)
+    x1, st1 = p2.sys.solve(vec=0)
+    info1 = p2.sys.direct_info()
+    assert info1["nfronts"] == info0["nfronts"] and info1["nlevels"] > info0["nlevels"]
+    assert np.linalg.norm(x1 - x0) <= 1e-11 * np.linalg.norm(x0)
