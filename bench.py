@@ -240,7 +240,8 @@ def run_ours(args):
     sp_ms = maxms(S.spmv_device_ms(reps=max(args.steps, 10)))
     barrier()
     sp_bytes = nnz * (sT + 4) + 4 * (N + 1) + 2 * N * sT
-    spmv = {"ms": sp_ms, "GBs": world * sp_bytes / (sp_ms * 1e-3) / 1e9, "bytes": sp_bytes}
+    spmv = {"ms": sp_ms, "GBs": world * sp_bytes / (sp_ms * 1e-3) / 1e9, "bytes": sp_bytes,
+            "traffic": ncu_traffic("csr_spmv") if args.workload == "Y1" else None}
     spmv["frac"] = spmv["GBs"] / world / peak
 
     # solve: sparse LU factorisation + GMRES(1-2 its) per frequency
