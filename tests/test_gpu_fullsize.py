@@ -4,6 +4,7 @@ take minutes: size-independent properties instead of entry-by-entry oracle parit
 
   * the sizes SURVEY.md §8 derives from the reference parameters;
   * the pattern is a valid CSR (sorted, duplicate-free rows) and its CSC view is its transpose;
+  * the matrix and right-hand side equal the compiled CPU restatement entry by entry (<= 1e-12);
   * two independent code paths of the library agree entry by entry: element-block classes +
     slot-centric gather (the default on constant-Jacobian meshes) against per-point general
     quadrature + scattered reductions (`affine=False`);
@@ -75,6 +76,30 @@ def test_class_gather_path_equals_general_quadrature_path(y1):
             if m.any() and np.abs(v2[m]).max() > 0:
                 assert np.abs(v[m] - v2[m]).max() <= 1e-12 * np.abs(v2[m]).max(), (fi, fj)
     assert np.abs(b1 - b2).max() <= 1e-12 * np.abs(b2).max()
+
+
+def test_matches_compiled_cpu_restatement_entry_by_entry(y1):
+    """Full-size parity against an independent implementation: the compiled CPU restatement of the
+    assembly (oracle/c/asm_cpu.cpp, tied to the NumPy oracle at small sizes by tests/test_oracle_c.py)
+    integrates every one of the 113 M COO contributions cell by cell on the host."""
+    prob, rp, ci, v = y1
+    from oracle.c_assembly import CSystem
+    from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
+    ref = YagoProblem(Yago_freq_domain_params(**KW), system_cls=CSystem)
+    mats, vecs = ref.sys.assemble()
+    A = mats[0]
+    assert ref.sys.ncoo == prob.sys.ncoo
+    assert np.array_equal(rp, A.indptr) and np.array_equal(ci, A.indices)          # pattern bit-exact
+    o = prob.X.offsets
+    rows = np.repeat(np.arange(prob.X.ndofs, dtype=np.int32), np.diff(rp))
+    for fi in range(3):
+        rm = (rows >= o[fi]) & (rows < o[fi + 1])
+        for fj in range(3):
+            m = rm & (ci >= o[fj]) & (ci < o[fj + 1])
+            if m.any() and np.abs(A.data[m]).max() > 0:
+                assert np.abs(v[m] - A.data[m]).max() <= 1e-12 * np.abs(A.data[m]).max(), (fi, fj)
+    b = prob.sys.get_vector(0)
+    assert np.abs(b - vecs[0]).max() <= 1e-12 * np.abs(vecs[0]).max()
 
 
 def test_assembly_is_bitwise_repeatable(y1):
