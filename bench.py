@@ -313,7 +313,10 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(kw, with_solve=not args.no_cpu_solve)
+        try:
+            cpu = cpu_baseline(kw, with_solve=not args.no_cpu_solve)
+        except Exception as e:              # the CPU leg must not take the GPU numbers down with it
+            cpu = {"error": repr(e), "kind": "port"}
 
     if rank == 0:
         out = {
@@ -547,9 +550,24 @@ def cpu_baseline(sample=None, with_solve=False, threads=0):
     dt = ms["total"] * 1e-3
     nnz, n = prob.sys.nnz, prob.X.ndofs
     cores = threads if threads >= 1 else (os.cpu_count() or 1)
-    prob.sys.mats = prob.sys.vecs = None                     # 1.2 GB of results: not needed here
-    extra = {"spmv_solve": cpu_solve_baseline()} if with_solve else {}
-    return {**extra, "value": nnz / dt, "unit": "nnz/s", "cores": cores, "kind": "port",
+    spmv = None
+    try:                                                     # threaded CSR SpMV on the matrix just assembled
+        from oracle.c_assembly import spmv_ms
+        A = prob.sys.mats[0]
+        x = np.sin(0.1 * np.arange(n)) + 1j * np.cos(0.1 * np.arange(n))
+        sp_ms, _ = spmv_ms(A, x, reps=5, threads=threads)
+        sp_bytes = nnz * 20 + 4 * (n + 1) + 2 * n * 16
+        spmv = {"ms": sp_ms, "GBs": sp_bytes / (sp_ms * 1e-3) / 1e9, "cores": cores}
+    except Exception as e:                                   # never let a CPU leg break the bench line
+        spmv = {"error": repr(e)}
+    prob.sys.mats = prob.sys.vecs = None                     # 1.2 GB of results: not needed any more
+    extra = {}
+    if with_solve:
+        try:
+            extra = {"spmv_solve": cpu_solve_baseline()}
+        except Exception as e:
+            extra = {"spmv_solve": {"error": repr(e)}}
+    return {**extra, "spmv": spmv, "value": nnz / dt, "unit": "nnz/s", "cores": cores, "kind": "port",
             "note": "compiled restatement (C++, host threads) of the Gridap algorithm class; Gridap 0.17 itself "
                     "integrates and assembles in ONE Julia thread (SURVEY.md §3) - the NumPy literal-form oracle "
                     "on one core does 0.9 M nnz/s",

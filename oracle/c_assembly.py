@@ -43,6 +43,8 @@ def load(build=True):
     lib.oracle_assemble.argtypes = [C.c_int32, C.POINTER(OracleDomain), C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(ip),
                                     C.POINTER(ip), C.POINTER(dp), dp, dp]
+    lib.oracle_spmv.restype = C.c_double
+    lib.oracle_spmv.argtypes = [C.c_int64, ip, ip, dp, C.c_int32, dp, dp, C.c_int32, C.c_int32]
     lib.oracle_free.argtypes = [C.c_void_p]
     lib.oracle_free.restype = None
     _lib = lib
@@ -133,3 +135,21 @@ class CSystem(RecordingSystem):
         self.nnz, self.ncoo = n, ncoo.value
         self.ms = dict(integrate_and_fill=ms[0], compress=ms[1], total=ms[2])
         return self.mats, self.vecs
+
+
+def spmv_ms(A, x, reps=10, threads=0):
+    """Mean milliseconds of y = A x (SciPy CSR, real or complex) on the host threads, and y."""
+    lib = load()
+    A = A.tocsr()
+    cplx = np.iscomplexobj(A.data)
+    dt = np.complex128 if cplx else np.float64
+    vals = np.ascontiguousarray(A.data, dtype=dt)
+    xv = np.ascontiguousarray(x, dtype=dt)
+    y = np.zeros(A.shape[0], dtype=dt)
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+    ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    ms = lib.oracle_spmv(A.shape[0], rp.ctypes.data_as(ip), ci.ctypes.data_as(ip), vals.view(np.float64).ctypes.data_as(dp),
+                         int(cplx), xv.view(np.float64).ctypes.data_as(dp), y.view(np.float64).ctypes.data_as(dp),
+                         int(reps), int(threads))
+    return float(ms), y

@@ -61,3 +61,17 @@ def test_result_does_not_depend_on_the_number_of_threads():
         out.append((mats[0].indptr.copy(), mats[0].indices.copy(), mats[0].data.copy(), vecs[0].copy()))
     for a, b in zip(*out):
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def test_threaded_spmv_equals_scipy():
+    from oracle.c_assembly import spmv_ms
+    c = _yago(CSystem)
+    mats, _ = c.sys.assemble()
+    A = mats[0]
+    n = A.shape[0]
+    x = np.sin(0.1 * np.arange(n)) + 1j * np.cos(0.1 * np.arange(n))
+    ms, y = spmv_ms(A, x, reps=2, threads=3)
+    ref = A @ x
+    assert ms > 0 and np.abs(y - ref).max() <= 1e-13 * np.abs(ref).max()
+    ms, y = spmv_ms(A.real.tocsr(), x.real, reps=1, threads=2)
+    assert np.abs(y - A.real @ x.real).max() <= 1e-13 * np.abs(ref).max()
