@@ -4,7 +4,7 @@ libvlfs_b200 on the GPU."""
 from dataclasses import dataclass
 import numpy as np
 from .. import _lib as L
-from ..geometry import DiscreteModelFromFile, Interior, Boundary, Skeleton
+from ..geometry import DiscreteModelFromFile, Interior, Boundary, Skeleton, refine_uniform
 from ..fe import ReferenceFE, TestFESpace, TrialFESpace, MultiFieldFESpace, Measure, lagrangian
 from ..assembler import B200System
 
@@ -16,6 +16,7 @@ class MultiGeo_freq_domain_params:      # src/Multi_geo_freq_domain.jl:11-17
     order: int = 4
     dfactor: float = 3
     vtk_output: bool = False
+    refine: int = 0                     # (not in the reference) levels of uniform refinement: synthetic M2 meshes
 
 
 class MultiGeoProblem:
@@ -44,7 +45,10 @@ class MultiGeoProblem:
         ah = -1j * om / g * (1 - bh) / bh
         self.c = c = dict(g=g, rho=rho, D=D_, d0=d0, H=H, k=k, om=om, eta0=0.01, bh=bh, ah=ah,
                           mu0=2.5, Ld=3, Ld0=3, xd=10, xd0=-1)
-        self.model = model = model if model is not None else DiscreteModelFromFile(p.mesh_file)
+        model = model if model is not None else DiscreteModelFromFile(p.mesh_file)
+        for _ in range(int(p.refine)):
+            model = refine_uniform(model)
+        self.model = model
         Om = Interior(model)
         Gin = Boundary(model, tags="inlet")
         Gb = Boundary(model, tags="plate")

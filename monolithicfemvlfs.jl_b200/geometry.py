@@ -433,3 +433,77 @@ class Skeleton:
         a = np.take_along_axis(X, lv[:, 0][:, None, None].repeat(X.shape[2], 2), axis=1)[:, 0]
         b = np.take_along_axis(X, lv[:, 1][:, None, None].repeat(X.shape[2], 2), axis=1)[:, 0]
         return np.linalg.norm(b - a, axis=1)
+
+
+# ---------------------------------------------------------------------------------------
+# Uniform (red) refinement of simplicial models - synthetic scaling meshes (SURVEY.md §8d "M2":
+# the MultiGeo tetrahedral mesh refined 1-3 levels; every level multiplies the cells by 2^D)
+# ---------------------------------------------------------------------------------------
+def refine_uniform(model):
+    """One level of regular refinement of a triangular / tetrahedral model: every edge is split at
+    its midpoint, a triangle becomes 4 triangles, a tetrahedron 4 corner tetrahedra + 4 from the
+    inner octahedron (cut along the midpoint diagonal m02-m13).  Vertices 0..nv-1 are kept, the
+    midpoint of edge k becomes vertex nv+k; every new face inherits the entity of the smallest
+    face of the parent model that contains it, so `Boundary(model,tags=...)`, `Skeleton`, FE
+    spaces and the case modules work unchanged on the refined model."""
+    if not model.poly.is_simplex or model.D not in (2, 3):
+        raise ValueError("refine_uniform: triangular or tetrahedral models only")
+    if not np.array_equal(model.cell_nodes, model.cell_vertices):
+        raise ValueError("refine_uniform: periodic models are not supported")
+    D, nv = model.D, model.nvertices
+    ev = model.face_vertices[1]                                   # (nedges, 2)
+    coords = np.concatenate([model.node_coords, 0.5 * (model.node_coords[ev[:, 0]] + model.node_coords[ev[:, 1]])])
+    cv = model.cell_vertices
+    ce = model.cell_faces[1]                                      # local edge k of a cell = poly.lfaces(1)[k]
+    le = [tuple(r) for r in model.poly.lfaces(1)]
+    mid = {e: nv + ce[:, k] for k, e in enumerate(le)}            # midpoint vertex of local edge (a,b), a<b
+    m = lambda a, b: mid[(a, b) if a < b else (b, a)]
+    v = lambda a: cv[:, a]
+    if D == 2:
+        kids = [(v(0), m(0, 1), m(0, 2)), (m(0, 1), v(1), m(1, 2)), (m(0, 2), m(1, 2), v(2)),
+                (m(0, 1), m(1, 2), m(0, 2))]
+    else:
+        kids = [(v(0), m(0, 1), m(0, 2), m(0, 3)), (m(0, 1), v(1), m(1, 2), m(1, 3)),
+                (m(0, 2), m(1, 2), v(2), m(2, 3)), (m(0, 3), m(1, 3), m(2, 3), v(3)),
+                # inner octahedron around the diagonal m02-m13
+                (m(0, 2), m(1, 3), m(0, 1), m(0, 3)), (m(0, 2), m(1, 3), m(0, 3), m(2, 3)),
+                (m(0, 2), m(1, 3), m(2, 3), m(1, 2)), (m(0, 2), m(1, 3), m(1, 2), m(0, 1))]
+    cells = np.stack([np.stack(k, axis=1) for k in kids], axis=1).reshape(-1, D + 1)    # children of a cell together
+    parent_cell = np.repeat(np.arange(model.ncells), len(kids))
+    # GridapGmsh convention of the reference's models: simplex vertex ids ascending
+    cells = np.sort(cells, axis=1)
+    fine = DiscreteModel(model.poly, coords, cells, cells, len(coords)).build_topology()
+    # support of every new vertex in the parent model: the old vertices it is a combination of
+    sup = np.full((len(coords), 2), -1, dtype=np.int64)
+    sup[:nv, 0] = np.arange(nv)
+    sup[nv:] = ev
+    first_cell = {}
+    for d in range(1, D + 1):                                     # a fine cell that contains each fine d-face
+        c2f = fine.cell_faces[d]
+        fc = np.full(fine.nfaces(d), -1, dtype=np.int64)
+        fc[c2f[::-1].reshape(-1)] = np.repeat(np.arange(fine.ncells)[::-1], c2f.shape[1])
+        first_cell[d] = fc
+    fine.face_entity[0] = np.concatenate([model.face_entity[0], model.face_entity[1]])
+    for d in range(1, D + 1):
+        fv = fine.face_vertices[d]
+        s = sup[fv].reshape(len(fv), -1)                          # old vertices spanned (with -1 padding)
+        s = np.sort(s, axis=1)[:, ::-1]                           # descending: real ids first
+        ent = np.zeros(len(fv), dtype=np.int64)
+        nuniq = np.array([len(np.unique(r[r >= 0])) for r in s]) if len(s) < 200000 else None
+        if nuniq is None:                                         # vectorised count of distinct ids
+            ss = np.sort(s, axis=1)
+            nuniq = (ss >= 0).sum(axis=1) - ((ss[:, 1:] == ss[:, :-1]) & (ss[:, 1:] >= 0)).sum(axis=1)
+        for k in range(1, D + 2):                                 # k distinct old vertices -> old (k-1)-face
+            sel = np.nonzero(nuniq == k)[0]
+            if len(sel) == 0:
+                continue
+            rows = np.array([np.unique(r[r >= 0]) for r in s[sel]]).reshape(len(sel), k)
+            if k - 1 == D:
+                ent[sel] = model.face_entity[D][parent_cell[first_cell[d][sel]]]
+            elif k == 1:
+                ent[sel] = model.face_entity[0][rows[:, 0]]
+            else:
+                ent[sel] = model.face_entity[k - 1][model.face_ids(k - 1, rows)]
+        fine.face_entity[d] = ent
+    fine.tags = {name: list(ents) for name, ents in model.tags.items()}
+    return fine
