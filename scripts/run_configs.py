@@ -103,3 +103,20 @@ emit(config="5-1-4", n=64, order=4, N=prob.X.ndofs, nnz=prob.nnz, host_setup_s=t
      newmark_steps=int(states.shape[0]), newmark_s=tsolve, ms_per_step=st["solve_ms"] / max(states.shape[0], 1),
      e_phi=float(out[0][-1]), e_eta=float(out[1][-1]), E_kin_f_rel=float(out[2][-1] / out[6]),
      E_pot_f_rel=float(out[3][-1] / out[8]), run_periodic_beam_FS_s=tall)
+
+# M2: the fine MultiGeo mesh refined uniformly, order 4 - 305 016 tets, N = 736 382
+# (skipped unless RUN_M2=1: the factorisation of this 3-D mesh needs tens of GB)
+if os.environ.get("RUN_M2") == "1" and os.path.exists(os.path.join(ROOT, "tests/golden/multi_geo.msh")):
+    prob, ts = t(lambda: MultiGeoProblem(MultiGeo_freq_domain_params(
+        mesh_file=os.path.join(ROOT, "tests/golden/multi_geo.msh"), order=4, refine=1)))
+    _, ta = t(prob.assemble)
+    _, ta2 = t(prob.assemble)
+    rec = dict(config="M2", mesh="multi_geo.msh refined once", order=4, N=prob.X.ndofs, nnz=prob.nnz, host_setup_s=ts,
+               assemble_first_s=ta, assemble_s=ta2)
+    try:
+        _, tf = t(lambda: prob.sys.solver_setup(0, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=30, maxit=60, rtol=1e-10))
+        (x, st), tsol = t(lambda: prob.sys.solve(vec=0))
+        rec.update(factor_s=tf, solve_s=tsol, iterations=st["iterations"], rel_residual=st["rel_residual"])
+    except Exception as e:
+        rec.update(solve_error=repr(e))
+    emit(**rec)
