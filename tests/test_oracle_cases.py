@@ -156,3 +156,15 @@ def test_periodic_beam_fs_energies_near_analytic_constants():
     tot = E.sum(axis=1)
     assert np.abs(tot / tot[0] - 1).max() < 5e-3
     assert r["e_phi"][-1] < 5e-4 and r["e_eta"][-1] < 5e-3
+
+
+def test_periodic_beam_time_convergence():
+    """5-1-2 (scripts/5-1-2-periodic-beam-time-convergence.jl:44-63, on a coarser mesh): the L2 errors
+    at tf = 1 against the analytic wave converge with the second order of Newmark(γ=½, β=¼) in Δt."""
+    errs = []
+    for i in range(2, 6):
+        r = PeriodicBeamCase(n=16, dt=2.0 ** (-i), tf=1.0, orderphi=4, ordereta=4, k=1).run()
+        errs.append((r["e_phi"][-1], r["e_eta"][-1]))
+    e = np.array(errs)
+    slopes = np.log2(e[:-1] / e[1:])
+    assert np.all(np.abs(slopes[-2:] - 2.0) < 0.03), slopes
