@@ -12,6 +12,7 @@
 // not depend on their number.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -160,10 +161,21 @@ inline void rank_transform(long long n_total, const double* xy, int dim, std::ve
 
 struct NDBuilder {
   const int* ptr; const int* idx; const int* plane; int dim; int leaf;
-  std::vector<int> mark;           // stamp of the split that last put the vertex on its B side
-  int stamp = 0;
+  int* mark;                       // shared: stamp of the split that last put the vertex on its B side
+  std::atomic<int>* stamp;         // shared source of unique stamps (their values never matter)
+  int par_depth;                   // the two sides of a split are dissected by two threads above this depth
   std::vector<int> hist;           // scratch histogram over plane ids
-  std::vector<TreeNode> nodes;
+  std::vector<TreeNode> nodes;     // subtree in postorder, child indices local to this builder
+
+  // appends the nodes of a finished sub-builder (children before parents is preserved)
+  int adopt(NDBuilder& sub, int root_local) {
+    const int off = (int)nodes.size();
+    for (TreeNode& t : sub.nodes) {
+      for (int& c : t.child) if (c >= 0) c += off;
+      nodes.push_back(std::move(t));
+    }
+    return off + root_local;
+  }
 
   int make_leaf(std::vector<int>& S) {
     TreeNode t;
@@ -171,7 +183,7 @@ struct NDBuilder {
     nodes.push_back(std::move(t));
     return (int)nodes.size() - 1;
   }
-  int rec(std::vector<int>& S) {
+  int rec(std::vector<int>& S, int depth = 0) {
     if ((int)S.size() <= leaf) return make_leaf(S);
     // split axis = the one with the most distinct coordinate planes (the best-resolved direction:
     // its separators are the smallest; the longest geometric extent is a poor guide on strongly
@@ -203,7 +215,7 @@ struct NDBuilder {
       if (A.empty() || B.empty()) return make_leaf(S);
     }
     std::vector<int>().swap(S);
-    const int st = ++stamp;
+    const int st = stamp->fetch_add(1) + 1;
     for (int v : B) mark[v] = st;
     std::vector<int> sep, A2;
     for (int v : A) {
@@ -212,8 +224,23 @@ struct NDBuilder {
       (touch ? sep : A2).push_back(v);
     }
     std::vector<int>().swap(A);
-    int c0 = A2.empty() ? -1 : rec(A2);
-    int c1 = rec(B);
+    int c0, c1;
+    if (depth < par_depth && A2.size() > 4096 && B.size() > 4096) {
+      // no edge joins A2 and B (that is what the separator is for), so the two dissections only
+      // share `mark` entries that neither of them writes; the node order below is the one the
+      // sequential recursion produces (left subtree, right subtree, parent)
+      NDBuilder left{ptr, idx, plane, dim, leaf, mark, stamp, par_depth};
+      NDBuilder right{ptr, idx, plane, dim, leaf, mark, stamp, par_depth};
+      int l0 = -1, r0 = -1;
+      std::thread th([&]() { l0 = left.rec(A2, depth + 1); });
+      r0 = right.rec(B, depth + 1);
+      th.join();
+      c0 = adopt(left, l0);
+      c1 = adopt(right, r0);
+    } else {
+      c0 = A2.empty() ? -1 : rec(A2, depth + 1);
+      c1 = rec(B, depth + 1);
+    }
     TreeNode t;
     t.piv.swap(sep);
     t.child[0] = c0 >= 0 ? c0 : c1;
@@ -240,8 +267,11 @@ inline void analyse(long long n_total, const int* rp, const int* ci, const signe
   t0 = std::chrono::steady_clock::now();
   std::vector<int> plane, nplanes;
   rank_transform(n_total, coords, dim, plane, nplanes);
-  NDBuilder nd{R.sp.data(), R.si.data(), plane.data(), dim, leaf};
-  nd.mark.assign(n_total, 0);
+  std::vector<int> mark(n_total, 0);
+  std::atomic<int> stamp{0};
+  int par_depth = 0;
+  for (unsigned t = host_threads(); t > 1; t >>= 1) ++par_depth;
+  NDBuilder nd{R.sp.data(), R.si.data(), plane.data(), dim, leaf, mark.data(), &stamp, par_depth};
   nd.nodes.reserve(2 * n / leaf + 16);
   nd.rec(elim);
   R.nodes.swap(nd.nodes);
