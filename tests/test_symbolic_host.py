@@ -67,3 +67,29 @@ def test_analysis_with_schur_boundary_and_ghosts(bench, tmp_path):
     _write(f, A, xy, role, leaf=32)
     r = _run(bench, f, 3)
     assert r["valid"] and r["n_keep"] == int((role == 1).sum()) and r["n"] == int((role == 0).sum())
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_analysis_on_random_graphs_and_degenerate_coordinates(bench, tmp_path, seed):
+    """Not meshes: random sparse (unsymmetric) patterns, random roles, coordinates with many ties or all
+    equal, isolated unknowns - the elimination tree must still be valid."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(300, 3000))
+    A = sp.random(n, n, density=float(rng.uniform(0.002, 0.02)), random_state=int(seed), format="csr")
+    A = (A + sp.eye(n, format="csr")).tocsr()
+    dim = int(rng.integers(1, 4))
+    if seed == 0:
+        xy = np.zeros((n, dim))                                   # every coordinate equal: one big leaf
+    elif seed == 1:
+        xy = rng.integers(0, 3, size=(n, dim)).astype(float)      # three planes per axis: massive ties
+    else:
+        xy = rng.random((n, dim))
+    role = rng.choice([0, 0, 0, 0, 1, 2], size=n).astype(np.int8)
+    role[:5] = 0
+    f = str(tmp_path / "r.bin")
+    _write(f, A, xy, role, leaf=int(rng.integers(8, 64)))
+    r1, r3 = _run(bench, f, 1), _run(bench, f, 3)
+    assert r1["valid"] and r3["valid"]
+    assert r1["n"] == int((role == 0).sum()) and r1["n_keep"] == int((role == 1).sum())
+    assert r1["pos_digest"] == r3["pos_digest"] and r1["fronts"] == r3["fronts"]
