@@ -568,6 +568,7 @@ def cpu_baseline(sample=None, with_solve=False, threads=0):
         except Exception as e:
             extra = {"spmv_solve": {"error": repr(e)}}
     return {**extra, "spmv": spmv, "value": nnz / dt, "unit": "nnz/s", "cores": cores, "kind": "port",
+            "N": n, "nnz": nnz, "ncoo": prob.sys.ncoo,
             "note": "compiled restatement (C++, host threads) of the Gridap algorithm class; Gridap 0.17 itself "
                     "integrates and assembles in ONE Julia thread (SURVEY.md §3) - the NumPy literal-form oracle "
                     "on one core does 0.9 M nnz/s",
@@ -596,7 +597,9 @@ def run_reference(args):
            "value": v, "unit": "nnz/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(vals),
            "warmup": 1, "ms_per_step": c["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64 (complex128 matrix)", "data": "synthetic",
-           "config": {"workload": "%s: CPU restatement on %d host threads, %s" % (args.workload, c["cores"], c["sample"])},
+           "config": {"workload": "%s: Yago 5-4-1 %s, N=%d, nnz=%d, ncoo=%d; CPU restatement on %d host threads, %s"
+                                  % (args.workload, json.dumps(kw), c["N"], c["nnz"], c["ncoo"], c["cores"], c["sample"]),
+                      "parallelism": "host threads"},
            "cpu_baseline": c,
            "e2e": {"value": v, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
