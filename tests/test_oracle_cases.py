@@ -168,3 +168,21 @@ def test_periodic_beam_time_convergence():
     e = np.array(errs)
     slopes = np.log2(e[:-1] / e[1:])
     assert np.all(np.abs(slopes[-2:] - 2.0) < 0.03), slopes
+
+
+@pytest.mark.skipif(not os.environ.get("VLFS_SLOW"), reason="2-3 minutes of SuperLU: set VLFS_SLOW=1")
+def test_yago_rao_against_literature_curves(golden_dir):
+    """5-4-1 at `nx=8, ny=2, nz=3` (N = 128 896) against the curves the reference plots the RAO with
+    (scripts/5-4-1-Yago.jl:73-127): Fu et al. within 0.1 (measured: max 0.046 / 0.085 / 0.050)."""
+    from oracle.c_assembly import CSystem
+    from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
+    for lf, fu in ((0.4, "L_04"), (0.6, "L_06"), (0.8, "L_08")):
+        p = YagoProblem(Yago_freq_domain_params(nx=8, ny=2, nz=3, order=4, lfactor=lf, dfactor=4), system_cls=CSystem)
+        mats, vecs = p.sys.assemble()
+        x = spla.splu(mats[0].tocsc()).solve(vecs[0])
+        xs, rao = p.rao(x)
+        o = np.argsort(xs)
+        xu, iu = np.unique(xs[o], return_index=True)
+        F = np.loadtxt(os.path.join(golden_dir, "Fu_%s.csv" % fu), delimiter=",")
+        d = np.abs(np.interp(-2.0 * (F[:, 0] - 0.5), xu, rao[o][iu]) - F[:, 1])
+        assert d.max() < 0.1 and d.mean() < 0.04, (lf, d.max(), d.mean())
