@@ -38,6 +38,12 @@ extern "C" {
 #define VLFS_ERR_CUDA 1
 #define VLFS_ERR_NCCL 2
 #define VLFS_NOT_CONVERGED 3
+#define VLFS_PIVOT_PERTURBED 4 /* status of a factorisation: finished and usable, but some pivots were
+                                  tiny and replaced by a static perturbation (vlfs_direct_status);
+                                  refinement in vlfs_solve recovers the accuracy or reports
+                                  VLFS_NOT_CONVERGED */
+#define VLFS_ERR_SINGULAR 5    /* a pivot was Inf/NaN: the factorisation is unusable (UMFPACK would
+                                  raise SingularException, src/Periodic_Beam.jl:107 `LUSolver()`) */
 
 #define VLFS_MAX_SLOTS 2
 
@@ -177,19 +183,31 @@ int vlfs_assemble_matrices(vlfs_ctx* ctx);
 int vlfs_assemble_vectors(vlfs_ctx* ctx);
 int vlfs_get_values(vlfs_ctx* ctx, int mat, void* values);   /* [nnz] real or complex    */
 int vlfs_get_vector(vlfs_ctx* ctx, int vec, void* values);   /* [ndofs]                  */
+/* A matrix the host already holds (Gridap's `numerical_setup(ss, A)` hands the LinearSolver an
+ * assembled SparseMatrixCSC/CSR: src/Periodic_Beam.jl:107 `Newmark(LUSolver(),...)`): 0-based CSR
+ * pattern shared by nmat value arrays; replaces vlfs_system_init + domains + vlfs_build_pattern.
+ * vlfs_set_values / vlfs_set_vector overwrite the device copy of a value array / a rhs vector. */
+int vlfs_import_csr(vlfs_ctx* ctx, int64_t ndofs, int is_complex, int nmat, const int32_t* rowptr,
+                    const int32_t* colind);
+int vlfs_set_values(vlfs_ctx* ctx, int mat, const void* values);
+int vlfs_set_vector(vlfs_ctx* ctx, int vec, const void* values);
 /* mat[target] = sum_k coef[k] * mat[src[k]]   (Newmark: K + γ/(βΔt) C + 1/(βΔt²) M)       */
 int vlfs_combine(vlfs_ctx* ctx, int target, int n, const int* src, const double* coef_re_im);
 
 /* ---- algebra -------------------------------------------------------------------- */
 int vlfs_spmv(vlfs_ctx* ctx, int mat, const void* x, void* y);         /* host in/out   */
 /* DOF node coordinates [ndofs][dim] (Gridap: get_cell_points(get_fe_dof_basis(V))); drives the
- * geometric nested dissection of VLFS_PRECOND_SPARSE_LU. */
+ * geometric nested dissection of VLFS_PRECOND_SPARSE_LU.  Optional: without them graph distances
+ * from three far-apart unknowns are used instead (level-structure dissection). */
 int vlfs_set_dof_coords(vlfs_ctx* ctx, int dim, const double* coords);
 int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts);
 /* refactorise the current values of `mat` keeping the symbolic analysis (ω sweeps) */
 int vlfs_solver_refactor(vlfs_ctx* ctx, int mat);
 /* {nfronts, nlevels, maxfront, fill entries, flops, pool bytes, symbolic ms, numeric ms} */
 int vlfs_direct_info(vlfs_ctx* ctx, double* out8);
+/* pivot statistics of the last (re)factorisation: pivots replaced by the static perturbation
+ * after the in-block threshold partial pivoting, and non-finite pivots */
+int vlfs_direct_status(vlfs_ctx* ctx, int64_t* perturbed, int64_t* nonfinite);
 int vlfs_solve(vlfs_ctx* ctx, const void* b, void* x, vlfs_solve_stats* stats);   /* host */
 int vlfs_solve_vec(vlfs_ctx* ctx, int vec, void* x, vlfs_solve_stats* stats); /* assembled rhs */
 

@@ -13,7 +13,7 @@ OP_VAL, OP_GRAD, OP_DDIR, OP_LAPL, OP_HESS, OP_CHESS, OP_GRAD_NOWN, OP_CHESS_NPL
 MEASURE_CELL, MEASURE_FACET = 0, 1
 SOLVER_GMRES, SOLVER_BICGSTAB, SOLVER_CG = 0, 1, 2
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_BLOCK_ILU0, PRECOND_SPARSE_LU = 0, 1, 2, 3
-OK, NOT_CONVERGED = 0, 3
+OK, NOT_CONVERGED, PIVOT_PERTURBED, ERR_SINGULAR = 0, 3, 4, 5
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -76,6 +76,7 @@ EXPORTS = [
     "vlfs_dev_gemv_sub", "vlfs_dev_axpby", "vlfs_dev_gather", "vlfs_get_vector_device",
     "vlfs_eval_functional", "vlfs_set_roles", "vlfs_schur_size", "vlfs_schur_get", "vlfs_schur_forward",
     "vlfs_schur_backward", "vlfs_dense_factor", "vlfs_chain_factor", "vlfs_dense_solve",
+    "vlfs_direct_status", "vlfs_import_csr", "vlfs_set_values", "vlfs_set_vector",
 ]
 
 _lib = None
@@ -150,6 +151,10 @@ def load():
     lib.vlfs_dense_factor.argtypes = [vp, C.c_int64, vp]
     lib.vlfs_chain_factor.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), vp]
     lib.vlfs_dense_solve.argtypes = [vp, vp, vp]
+    lib.vlfs_direct_status.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.vlfs_import_csr.argtypes = [vp, C.c_int64, C.c_int, C.c_int, _ip, _ip]
+    lib.vlfs_set_values.argtypes = [vp, C.c_int, vp]
+    lib.vlfs_set_vector.argtypes = [vp, C.c_int, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

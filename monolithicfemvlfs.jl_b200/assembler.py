@@ -268,7 +268,46 @@ class B200System:
         self.n_owned = int(n_owned)
 
     def refactor(self, mat=0):
-        self._check(self.lib.vlfs_solver_refactor(self.ctx, mat))
+        self.factor_status = self._check(self.lib.vlfs_solver_refactor(self.ctx, mat), allow=(0, L.PIVOT_PERTURBED))
+
+    def direct_status(self):
+        """(pivots replaced by the static perturbation, non-finite pivots) of the last factorisation."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.vlfs_direct_status(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @classmethod
+    def from_csr(cls, A, nmat=1, device=0):
+        """The `LUSolver()` drop-in on a matrix the host already assembled (Gridap's
+        `numerical_setup(ss, A)`): imports the CSR pattern and the values of a SciPy matrix."""
+        A = sp.csr_matrix(A)
+        A.sort_indices()
+        is_complex = np.iscomplexobj(A.data)
+        self = cls.__new__(cls)
+        self.lib = L.load()
+        self.ctx = C.c_void_p()
+        rc = self.lib.vlfs_create(C.byref(self.ctx), device)
+        if rc != 0:
+            raise L.VlfsError("vlfs_create failed (status %d): no usable sm_100 GPU; the B200 "
+                              "path has no CPU fallback" % rc)
+        self.ndofs, self.is_complex, self.nmat, self.nvec = A.shape[0], bool(is_complex), nmat, 1
+        self.dtype = np.complex128 if is_complex else np.float64
+        rp, ci = L.i32(A.indptr), L.i32(A.indices)
+        self._check(self.lib.vlfs_import_csr(self.ctx, self.ndofs, int(is_complex), nmat, L.iptr(rp), L.iptr(ci)))
+        self.nnz = self.ncoo = int(rp[-1])
+        self.domains, self._pattern = [], (rp, ci)
+        self.set_values(A.data, 0)
+        return self
+
+    def set_values(self, values, mat=0):
+        v = np.ascontiguousarray(values, dtype=self.dtype)
+        assert v.shape == (self.nnz,)
+        self._check(self.lib.vlfs_set_values(self.ctx, mat, v.ctypes.data_as(C.c_void_p)))
+
+    def set_vector(self, values, vec=0):
+        v = np.ascontiguousarray(values, dtype=self.dtype)
+        assert v.shape == (self.ndofs,)
+        self._check(self.lib.vlfs_set_vector(self.ctx, vec, v.ctypes.data_as(C.c_void_p)))
 
     def direct_info(self):
         out = np.zeros(8)
@@ -279,7 +318,9 @@ class B200System:
     def solver_setup(self, mat=0, method=L.SOLVER_GMRES, precond=L.PRECOND_JACOBI, restart=100,
                      maxit=5000, rtol=1e-10, block_size_hint=0, sweeps=0):
         o = L.SolverOpts(method, precond, restart, maxit, rtol, block_size_hint, sweeps)
-        self._check(self.lib.vlfs_solver_setup(self.ctx, mat, C.byref(o)))
+        # VLFS_PIVOT_PERTURBED is a status: the factorisation is usable, refinement decides
+        self.factor_status = self._check(self.lib.vlfs_solver_setup(self.ctx, mat, C.byref(o)),
+                                         allow=(0, L.PIVOT_PERTURBED))
 
     def solve(self, b=None, vec=0, x0=None):
         x = np.zeros(self.ndofs, dtype=self.dtype) if x0 is None else np.ascontiguousarray(x0, dtype=self.dtype).copy()

@@ -3,6 +3,7 @@
 // the kernels of integrate.cu / pattern.cu / spmv.cu / krylov.cu.
 #include "common.cuh"
 #include "solver.cuh"
+#include "symbolic_host.hpp"
 #include <cstring>
 #include <cstdlib>
 #include <memory>
@@ -126,6 +127,7 @@ struct vlfs_ctx {
   int is_complex = 0, nmat = 0, nvec = 0;
   std::vector<std::unique_ptr<Domain>> doms;
   bool pattern_built = false;
+  bool imported = false;                // pattern given by vlfs_import_csr: no domains, nothing to assemble
   long long nnz = 0, ncoo = 0;
   DevBuf<int> rowptr, colind, rowind, dest_all;
   DevBuf<uint32_t> perm, run_start;     // sorted COO order and first sorted entry of every slot
@@ -641,6 +643,7 @@ void rebuild_compact_records(vlfs_ctx* ctx) {
 
 void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   if (!ctx->pattern_built) throw std::string("vlfs_build_pattern must be called first");
+  if (ctx->imported) throw std::string("the matrix was imported (vlfs_import_csr): nothing to assemble");
   cudaStream_t s = ctx->stream;
   std::vector<double*> mp, vp;
   for (auto& m : ctx->mats) mp.push_back(m.p);
@@ -757,6 +760,22 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   if (vec_aside && !vec_join_early) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_vec_join, 0));
 }
 
+// status of the factorisation behind ctx->direct (after direct_numeric)
+int pivot_status(vlfs_ctx* ctx) {
+  long long pert = 0, bad = 0;
+  direct_pivot_status(*ctx->direct, &pert, &bad);
+  char buf[160];
+  if (bad > 0) {
+    snprintf(buf, sizeof buf, "sparse LU: %lld non-finite pivots (singular or overflowing matrix)", bad);
+    return fail(ctx, VLFS_ERR_SINGULAR, buf);
+  }
+  if (pert > 0) {
+    snprintf(buf, sizeof buf, "sparse LU: %lld tiny pivots replaced by a static perturbation", pert);
+    return fail(ctx, VLFS_PIVOT_PERTURBED, buf);
+  }
+  return VLFS_OK;
+}
+
 template <typename T>
 void upload_opt(DevBuf<T>& b, const T* h, size_t n, cudaStream_t s) {
   if (h && n) b.upload(h, n, s);
@@ -831,7 +850,8 @@ int vlfs_system_init(vlfs_ctx* ctx, int64_t ndofs, int is_complex, int nmat, int
     ctx->ndofs = ndofs; ctx->is_complex = is_complex ? 1 : 0; ctx->nmat = nmat; ctx->nvec = nvec;
     ctx->nowned = ndofs;
     ctx->doms.clear(); ctx->mats.clear(); ctx->vecs.clear();
-    ctx->pattern_built = false; ctx->solver.reset(); ctx->direct.reset(); ctx->dof_coords.clear();
+    ctx->pattern_built = false; ctx->imported = false; ctx->solver.reset(); ctx->direct.reset(); ctx->dense.reset();
+    ctx->dof_coords.clear(); ctx->coord_dim = 0; ctx->roles.clear(); ctx->solver_mat = -1;
     ctx->vecs.resize(nvec);
     for (auto& v : ctx->vecs) { v.alloc((size_t)ndofs * ctx->scalar()); v.zero(ctx->stream); }
     return VLFS_OK;
@@ -989,6 +1009,9 @@ int vlfs_set_weights(vlfs_ctx* ctx, int domain_id, int weight, const double* val
 int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
   return guarded(ctx, [&]() {
     if (ctx->doms.empty()) return fail(ctx, VLFS_ERR_STATE, "no domains");
+    // solver, LU and interface objects hold raw pointers into the pattern and value arrays: a
+    // second build would leave them dangling, so it is refused (vlfs_system_init starts over)
+    if (ctx->pattern_built) return fail(ctx, VLFS_ERR_STATE, "pattern already built (vlfs_system_init starts a new system)");
     std::vector<DomainDev> devs;
     for (auto& d : ctx->doms) { finalize_domain(ctx, *d); devs.push_back(d->dev); }
     long long n1 = 0, n2 = 0;
@@ -1022,6 +1045,57 @@ int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
     ctx->pattern_built = true;
     if (nnz) *nnz = n1;
     if (ncoo) *ncoo = n2;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_import_csr(vlfs_ctx* ctx, int64_t ndofs, int is_complex, int nmat, const int32_t* rowptr,
+                    const int32_t* colind) {
+  return guarded(ctx, [&]() {
+    if (!rowptr || !colind || ndofs <= 0 || ndofs >= (1ll << 31) || nmat < 1 || nmat > 4 || rowptr[0] != 0)
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_import_csr: bad arguments (0-based CSR, 1<=nmat<=4)");
+    const long long nnz = rowptr[ndofs];
+    if (nnz <= 0) return fail(ctx, VLFS_ERR_ARG, "vlfs_import_csr: empty matrix");
+    std::vector<int> rowind((size_t)nnz);
+    for (long long i = 0; i < ndofs; ++i) {
+      if (rowptr[i + 1] < rowptr[i]) return fail(ctx, VLFS_ERR_ARG, "vlfs_import_csr: rowptr not monotone");
+      for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+        if (colind[p] < 0 || colind[p] >= ndofs) return fail(ctx, VLFS_ERR_ARG, "vlfs_import_csr: column index out of range");
+        if (p > rowptr[i] && colind[p] <= colind[p - 1])
+          return fail(ctx, VLFS_ERR_ARG, "vlfs_import_csr: column indices must ascend strictly inside a row");
+        rowind[p] = (int)i;
+      }
+    }
+    int rc = vlfs_system_init(ctx, ndofs, is_complex, nmat, 1);
+    if (rc != VLFS_OK) return rc;
+    ctx->rowptr.upload(rowptr, (size_t)ndofs + 1, ctx->stream);
+    ctx->colind.upload(colind, (size_t)nnz, ctx->stream);
+    ctx->rowind.upload(rowind.data(), (size_t)nnz, ctx->stream);
+    ctx->nnz = nnz; ctx->ncoo = nnz;
+    ctx->mats.clear();
+    ctx->mats.resize(nmat);
+    for (auto& m : ctx->mats) { m.alloc((size_t)nnz * ctx->scalar()); m.zero(ctx->stream); }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->pattern_built = true;
+    ctx->imported = true;
+    return VLFS_OK;
+  });
+}
+
+int vlfs_set_values(vlfs_ctx* ctx, int mat, const void* values) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !values) return fail(ctx, VLFS_ERR_ARG, "bad matrix");
+    CUDA_TRY(cudaMemcpyAsync(ctx->mats[mat].p, values, ctx->nnz * ctx->scalar() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VLFS_OK;
+  });
+}
+
+int vlfs_set_vector(vlfs_ctx* ctx, int vec, const void* values) {
+  return guarded(ctx, [&]() {
+    if (vec < 0 || vec >= ctx->nvec || !values) return fail(ctx, VLFS_ERR_ARG, "bad vector");
+    CUDA_TRY(cudaMemcpyAsync(ctx->vecs[vec].p, values, ctx->ndofs * ctx->scalar() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return VLFS_OK;
   });
 }
@@ -1210,8 +1284,15 @@ int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
     if (o2.precond == VLFS_PRECOND_BLOCK_ILU0) o2.precond = VLFS_PRECOND_SPARSE_LU;
     opts = &o2;
     if (opts->precond == VLFS_PRECOND_SPARSE_LU) {
-      if (ctx->dof_coords.empty()) return fail(ctx, VLFS_ERR_STATE, "vlfs_set_dof_coords first (sparse LU ordering)");
       if (!ctx->direct) {
+        if (ctx->dof_coords.empty()) {
+          // no DOF coordinates (an imported matrix): graph distances stand in for them
+          std::vector<int> rp((size_t)ctx->ndofs + 1), ci((size_t)ctx->nnz);
+          CUDA_TRY(cudaMemcpy(rp.data(), ctx->rowptr.p, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+          CUDA_TRY(cudaMemcpy(ci.data(), ctx->colind.p, ci.size() * sizeof(int), cudaMemcpyDeviceToHost));
+          vlfs_sym::pseudo_coords(ctx->ndofs, rp.data(), ci.data(), ctx->dof_coords);
+          ctx->coord_dim = 3;
+        }
         std::vector<signed char> role = ctx->roles;
         if (role.empty()) {
           role.assign((size_t)ctx->ndofs, 2);
@@ -1227,7 +1308,7 @@ int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
                                 ctx->is_complex, *opts, ctx->nsm, ctx->stream, &ctx->launches,
                                 ctx->direct.get());
     ctx->solver_mat = mat;
-    return VLFS_OK;
+    return opts->precond == VLFS_PRECOND_SPARSE_LU ? pivot_status(ctx) : VLFS_OK;
   });
 }
 
@@ -1246,8 +1327,20 @@ int vlfs_solver_refactor(vlfs_ctx* ctx, int mat) {
     if (!ctx->solver || !ctx->direct || mat < 0 || mat >= ctx->nmat)
       return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup with VLFS_PRECOND_SPARSE_LU first");
     direct_numeric(*ctx->direct, ctx->rowind.p, ctx->colind.p, ctx->mats[mat].p);
-    return VLFS_OK;
+    // the Krylov residual must use the matrix that was just factorised
+    solver_set_matrix(*ctx->solver, ctx->mats[mat].p);
+    ctx->solver_mat = mat;
+    return pivot_status(ctx);
   });
+}
+
+int vlfs_direct_status(vlfs_ctx* ctx, int64_t* perturbed, int64_t* nonfinite) {
+  if (!ctx || !ctx->direct) return VLFS_ERR_ARG;
+  long long a = 0, b = 0;
+  direct_pivot_status(*ctx->direct, &a, &b);
+  if (perturbed) *perturbed = a;
+  if (nonfinite) *nonfinite = b;
+  return VLFS_OK;
 }
 
 int vlfs_direct_info(vlfs_ctx* ctx, double* out8) {
@@ -1300,7 +1393,7 @@ int vlfs_newmark_run(vlfs_ctx* ctx, int matK, int matC, int matM, int nsteps, do
       return fail(ctx, VLFS_ERR_ARG, "vlfs_newmark_run: bad arguments");
     std::vector<double*> bv;
     for (int k = 0; k < nb; ++k) bv.push_back(ctx->vecs[k].p);
-    return newmark_run(*ctx->solver, ctx->rowptr.p, ctx->colind.p, ctx->mats[matC].p, ctx->mats[matM].p,
+    return newmark_run(*ctx->solver, ctx->rowptr.p, ctx->colind.p, ctx->mats[matK].p, ctx->mats[matC].p, ctx->mats[matM].p,
                        ctx->ndofs, ctx->nnz, nsteps, dt, gamma, beta, nb, bv.data(), tcoef, u0, v0, a0,
                        out_lo, out_hi, out_stride, out, stats, ctx->nsm, ctx->stream, &ctx->launches);
   });
@@ -1429,9 +1522,9 @@ int vlfs_eval_functional(vlfs_ctx* ctx, int domain_id, const vlfs_functional_des
     }
     DevBuf<double> dx, res;
     dx.upload((const double*)x_host, (size_t)ctx->ndofs, ctx->stream);
-    res.alloc(1); res.zero(ctx->stream);
+    res.alloc((size_t)ctx->nsm * 8 + 1); res.zero(ctx->stream);   // [0] the value, then one partial per CTA
     launch_functional(dev, O[0], O[1], sc[0], sc[1], f->weight_f, dx.p, res.p, ctx->nsm, ctx->stream);
-    ++ctx->launches;
+    ctx->launches += 2;
     CUDA_TRY(cudaMemcpyAsync(value, res.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return VLFS_OK;

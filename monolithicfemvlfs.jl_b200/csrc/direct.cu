@@ -15,9 +15,12 @@
 //     with 64x64 register-tiled FP64 tiles);
 //   solve (device): level-scheduled forward / backward sweeps over the fronts, one launch per
 //     panel; unknowns with role "keep" stay a Schur boundary (substructuring across GPUs).
-// No pivoting across fronts (static pivoting, verified adequate on these FE matrices); the
-// Krylov driver uses the factorisation as a right preconditioner, so the reported residual is
-// always the true one and one refinement step recovers full accuracy.
+// Pivoting: the elimination order of the fronts is static; inside every 32-row pivot block rows are
+// interchanged by threshold partial pivoting (diag_lu), pivots that stay tiny are perturbed and
+// counted, non-finite pivots are counted (direct_pivot_status -> VLFS_PIVOT_PERTURBED /
+// VLFS_ERR_SINGULAR at the C ABI).  The Krylov driver uses the factorisation as a right
+// preconditioner, so the reported residual is always the true one and refinement recovers the
+// accuracy a perturbed pivot costs.
 #include "common.cuh"
 #include "direct.cuh"
 #include "symbolic_host.hpp"
@@ -150,28 +153,83 @@ extend_add(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int
   }
 }
 
-// LU without pivoting of the diagonal block of panel k (in place)
+// |re| + |im| (LAPACK cabs1): cheap magnitude for pivot comparisons
+__device__ __forceinline__ double abs1(double a) { return fabs(a); }
+__device__ __forceinline__ double abs1(double2 a) { return fabs(a.x) + fabs(a.y); }
+__device__ __forceinline__ bool finite1(double a) { return isfinite(a); }
+__device__ __forceinline__ bool finite1(double2 a) { return isfinite(a.x) && isfinite(a.y); }
+__device__ __forceinline__ double perturbed(double a, double tau) { return a < 0.0 ? -tau : tau; }
+__device__ __forceinline__ double2 perturbed(double2 a, double tau) {
+  const double m = fabs(a.x) + fabs(a.y);
+  return m > 0.0 ? make_double2(a.x / m * tau, a.y / m * tau) : make_double2(tau, 0.0);
+}
+
+// LU of the diagonal block of panel k (in place) with THRESHOLD PARTIAL PIVOTING INSIDE THE BLOCK:
+// the diagonal entry stays the pivot while |a_jj| >= 0.1 max_r |a_rj|, otherwise the largest entry
+// of the column inside the block is swapped in (UMFPACK's strategy, restricted to the 32 rows of
+// the block so that the front structure is static).  perm[first + k0 + r] = row of the block that
+// ends up at position r; panel_trsm (U part) and the forward sweep apply it to the rows k0..k1 of
+// the front / the work vector.  A pivot that is still tiny against the block (< 2^-43 of its
+// largest entry) or not finite is counted in info[0] / info[1]; tiny pivots are replaced by
+// +-tau (static perturbation, as SuperLU_DIST does) so that no Inf/NaN spreads silently.
 template <bool C>
 __global__ void __launch_bounds__(NB * NB)
 diag_lu(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
-        typename Num<C>::T* __restrict__ pool) {
+        typename Num<C>::T* __restrict__ pool, int* __restrict__ perm, int* __restrict__ info) {
   using N = Num<C>;
   __shared__ typename N::T sm[NB][NB + 1];
+  __shared__ double smax[NB];
+  __shared__ int s_p, s_perm[NB];
   const FrontMeta F = meta[list[blockIdx.x]];
   const int k0 = k * NB;
   if (k0 >= F.np) return;
   const int kb = min(NB, F.np - k0);
-  const int r = threadIdx.y, c = threadIdx.x;
+  const int r = threadIdx.y, c = threadIdx.x;      // warp = row r
   typename N::T* D = pool + F.off + (long long)k0 * F.nf + k0;
-  if (r < kb && c < kb) sm[r][c] = D[(long long)r * F.nf + c];
+  double mine = 0.0;
+  if (r < kb && c < kb) { sm[r][c] = D[(long long)r * F.nf + c]; mine = abs1(sm[r][c]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine = fmax(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+  if (c == 0) { smax[r] = mine; s_perm[r] = r; }
   __syncthreads();
+  double scale = 0.0;
+  for (int q = 0; q < NB; ++q) scale = fmax(scale, smax[q]);
+  const double tau = scale * 1.1368683772161603e-13;       // 2^-43
   for (int j = 0; j < kb; ++j) {
+    if (r == 0) {                                           // warp 0: pivot search in column j
+      double a = (c >= j && c < kb) ? abs1(sm[c][j]) : -1.0;
+      const double ajj = __shfl_sync(0xffffffffu, a, j);
+      int p = c;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double a2 = __shfl_xor_sync(0xffffffffu, a, o);
+        const int p2 = __shfl_xor_sync(0xffffffffu, p, o);
+        if (a2 > a || (a2 == a && p2 < p)) { a = a2; p = p2; }
+      }
+      if (c == 0) s_p = (ajj >= 0.1 * a) ? j : p;           // NaNs compare false: keeps the search result
+    }
+    __syncthreads();
+    const int p = s_p;
+    if (r == j) {                                           // warp j: swap rows j and p of the block
+      if (p != j && c < kb) { typename N::T t = sm[j][c]; sm[j][c] = sm[p][c]; sm[p][c] = t; }
+      if (c == j) {
+        if (p != j) { const int t = s_perm[j]; s_perm[j] = s_perm[p]; s_perm[p] = t; }
+        const typename N::T pv = sm[j][j];
+        if (!finite1(pv)) atomicAdd(info + 1, 1);
+        else if (abs1(pv) < tau || abs1(pv) == 0.0) {
+          sm[j][j] = perturbed(pv, tau > 0.0 ? tau : 1.0);
+          atomicAdd(info, 1);
+        }
+      }
+    }
+    __syncthreads();
     if (c == j && r > j && r < kb) sm[r][j] = N::div(sm[r][j], sm[j][j]);
     __syncthreads();
     if (r > j && c > j && r < kb && c < kb) sm[r][c] = N::fnma(sm[r][j], sm[j][c], sm[r][c]);
     __syncthreads();
   }
   if (r < kb && c < kb) D[(long long)r * F.nf + c] = sm[r][c];
+  if (r == 0 && c < kb) perm[F.first + k0 + c] = s_perm[c];
 }
 
 // L-panel: rows below the diagonal block times U11^{-1};  U-panel: L11^{-1} times the columns
@@ -179,9 +237,10 @@ diag_lu(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
 template <bool C>
 __global__ void __launch_bounds__(128)
 panel_trsm(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
-           typename Num<C>::T* __restrict__ pool) {
+           typename Num<C>::T* __restrict__ pool, const int* __restrict__ perm) {
   using N = Num<C>;
   __shared__ typename N::T sD[NB][NB + 1];
+  __shared__ int sperm[NB];
   const FrontMeta F = meta[list[blockIdx.z]];
   const int k0 = k * NB;
   if (k0 >= F.np) return;
@@ -192,6 +251,7 @@ panel_trsm(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int
   typename N::T* Fp = pool + F.off;
   for (int t = threadIdx.x; t < kb * kb; t += 128)
     sD[t / kb][t % kb] = Fp[(long long)(k0 + t / kb) * F.nf + k0 + t % kb];
+  if (threadIdx.x < NB) sperm[threadIdx.x] = threadIdx.x < kb ? perm[F.first + k0 + threadIdx.x] : 0;
   __syncthreads();
   if (idx >= F.nf) return;
   typename N::T x[NB];
@@ -213,7 +273,7 @@ panel_trsm(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int
   } else {
     typename N::T* col = Fp + (long long)k0 * F.nf + idx;
 #pragma unroll
-    for (int r = 0; r < NB; ++r) x[r] = r < kb ? col[(long long)r * F.nf] : N::zero();
+    for (int r = 0; r < NB; ++r) x[r] = r < kb ? col[(long long)sperm[r] * F.nf] : N::zero();   // rows as pivoted
 #pragma unroll
     for (int r = 0; r < NB; ++r) {
       if (r < kb) {
@@ -390,7 +450,7 @@ template <bool C>
 __global__ void __launch_bounds__(256)
 fwd_panel(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int k,
           const typename Num<C>::T* __restrict__ pool, typename Num<C>::T* __restrict__ w,
-          typename Num<C>::T* __restrict__ bp) {
+          typename Num<C>::T* __restrict__ bp, const int* __restrict__ perm) {
   using N = Num<C>;
   __shared__ typename N::T sx[NB];
   __shared__ typename N::T sD[NB][NB + 1];
@@ -409,7 +469,7 @@ fwd_panel(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int 
   __syncthreads();
   if (threadIdx.x < 32) {
     const int r = threadIdx.x;
-    typename N::T x = r < kb ? wf[k0 + r] : N::zero();
+    typename N::T x = r < kb ? wf[k0 + perm[F.first + k0 + r]] : N::zero();   // row interchanges of the block
     for (int c = 0; c < kb; ++c) {
       typename N::T xc = N::shfl(x, c);
       if (r > c && r < kb) x = N::fnma(sD[r][c], xc, x);
@@ -519,7 +579,14 @@ struct DirectSolver {
   DevBuf<int> d_pos, d_front_of_pos, d_upd, d_cmap, d_lists;
   std::vector<int> list_off;
   DevBuf<double> pool, w, bp, xp;
+  DevBuf<int> d_perm;                // row interchanges inside the 32-row pivot blocks (diag_lu)
+  DevBuf<int> d_info;                // {perturbed pivots, non-finite pivots} of the last factorisation
+  long long n_perturbed = 0, n_nonfinite = 0;
   double symbolic_ms = 0, numeric_ms = 0;
+  void alloc_pivot_state() {
+    d_perm.alloc((size_t)std::max<long long>(n, 1));
+    d_info.alloc(2);
+  }
 };
 
 namespace {
@@ -659,6 +726,7 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_
   D->bp.alloc((size_t)(n + D->n_keep) * sc);
   D->xp.alloc((size_t)(n + D->n_keep) * sc);
   D->xp.zero(s);
+  D->alloc_pivot_state();
   for (int f = 0; f < nf_; ++f) if (parent[f] < 0) D->roots.push_back(f);
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
@@ -676,6 +744,7 @@ static void factor_levels(DirectSolver& D) {
   CUDA_TRY(cudaFuncSetAttribute(schur_update<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const int outer_env = getenv("VLFS_LU_OUTER") ? atoi(getenv("VLFS_LU_OUTER")) : 4;
   const int outer = outer_env < 1 ? 1 : outer_env;   // panels per outer block (4 = 128 pivots)
+  D.d_info.zero(s);
   for (int L = 0; L < D.nlevels; ++L) {
     const int nfr = (int)D.level_lists[L].size();
     const int* list = D.d_lists.p + D.list_off[L];
@@ -692,12 +761,12 @@ static void factor_levels(DirectSolver& D) {
     for (int K0 = 0; K0 < npan; K0 += outer) {
       const int K1 = std::min(K0 + outer, npan);          // outer block = panels [K0, K1)
       for (int k = K0; k < K1; ++k) {
-        diag_lu<C><<<nfr, dim3(NB, NB), 0, s>>>(D.d_meta.p, list, k, pool);
+        diag_lu<C><<<nfr, dim3(NB, NB), 0, s>>>(D.d_meta.p, list, k, pool, D.d_perm.p, D.d_info.p);
         ++*D.launches;
         const int rem = maxnf - k * NB;                   // upper bound of the rows/columns from panel k on
         if (rem <= 0) continue;
         dim3 g2((rem + 127) / 128, 2, nfr);
-        panel_trsm<C><<<g2, 128, 0, s>>>(D.d_meta.p, list, k, pool);
+        panel_trsm<C><<<g2, 128, 0, s>>>(D.d_meta.p, list, k, pool, D.d_perm.p);
         ++*D.launches;
         const int strip = (K1 - k - 1) * NB;              // rest of the outer block after panel k
         if (strip > 0) {
@@ -717,6 +786,14 @@ static void factor_levels(DirectSolver& D) {
     }
   }
   CUDA_TRY(cudaGetLastError());
+}
+
+// pivot statistics of the factorisation just enqueued (synchronises the stream)
+static void read_pivot_info(DirectSolver& D) {
+  int h[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(h, D.d_info.p, sizeof h, cudaMemcpyDeviceToHost, D.s));
+  CUDA_TRY(cudaStreamSynchronize(D.s));
+  D.n_perturbed = h[0]; D.n_nonfinite = h[1];
 }
 
 template <bool C>
@@ -740,6 +817,12 @@ void direct_numeric(DirectSolver& D, const int* rowind, const int* colind, const
     if (D.cplx) numeric_impl<true>(D, rowind, colind, vals);
     else numeric_impl<false>(D, rowind, colind, vals);
   });
+  read_pivot_info(D);
+}
+
+void direct_pivot_status(const DirectSolver& D, long long* perturbed, long long* nonfinite) {
+  if (perturbed) *perturbed = D.n_perturbed;
+  if (nonfinite) *nonfinite = D.n_nonfinite;
 }
 
 // forward sweep: y = L^-1 b on the eliminated unknowns; g_keep (optional, accumulated into) receives
@@ -763,7 +846,7 @@ static void forward_impl(DirectSolver& D, const double* b, double* g_keep) {
     for (int k = 0; k < npan; ++k) {
       const int rem = D.level_maxnf[L] - k * NB;
       dim3 g((std::max(rem, 1) + 255) / 256, nfr);
-      fwd_panel<C><<<g, 256, 0, s>>>(D.d_meta.p, list, k, pool, w, bp);
+      fwd_panel<C><<<g, 256, 0, s>>>(D.d_meta.p, list, k, pool, w, bp, D.d_perm.p);
       ++*D.launches;
     }
   }
@@ -865,6 +948,7 @@ DirectPtr direct_dense(long long n, int is_complex, int nsm, cudaStream_t s, lon
   const size_t sc = is_complex ? 2 : 1;
   D->pool.alloc((size_t)n * n * sc);
   D->w.alloc((size_t)n * sc); D->bp.alloc((size_t)n * sc); D->xp.alloc((size_t)n * sc);
+  D->alloc_pivot_state();
   CUDA_TRY(cudaStreamSynchronize(s));
   return D;
 }
@@ -916,6 +1000,7 @@ DirectPtr direct_chain(int nblocks, const long long* sizes, int is_complex, int 
   const size_t sc = is_complex ? 2 : 1;
   D->pool.alloc((size_t)off * sc);
   D->w.alloc((size_t)woff * sc); D->bp.alloc((size_t)n * sc); D->xp.alloc((size_t)n * sc);
+  D->alloc_pivot_state();
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaGetLastError());
   return D;
@@ -932,6 +1017,7 @@ void direct_chain_factor(DirectSolver& D, const double* S_dev) {
     }
     if (D.cplx) factor_levels<true>(D); else factor_levels<false>(D);
   });
+  read_pivot_info(D);
 }
 
 void direct_dense_factor(DirectSolver& D, const double* S_dev) {
@@ -940,6 +1026,7 @@ void direct_dense_factor(DirectSolver& D, const double* S_dev) {
     CUDA_TRY(cudaMemcpyAsync(D.pool.p, S_dev, (size_t)D.n * D.n * sc * sizeof(double), cudaMemcpyDeviceToDevice, D.s));
     if (D.cplx) factor_levels<true>(D); else factor_levels<false>(D);
   });
+  read_pivot_info(D);
 }
 
 void direct_info(const DirectSolver& D, double* out8) {

@@ -13,6 +13,8 @@ DirectPtr direct_symbolic(const int* d_rowptr, const int* d_colind, long long n_
                           const signed char* role, long long nnz, const double* coords, int dim, int leaf,
                           int is_complex, int nsm, cudaStream_t s, long long* launches);
 void direct_numeric(DirectSolver& D, const int* d_rowind, const int* d_colind, const double* d_vals);
+// {pivots replaced by the static perturbation, non-finite pivots} of the last factorisation
+void direct_pivot_status(const DirectSolver& D, long long* perturbed, long long* nonfinite);
 void direct_solve(DirectSolver& D, const double* b_dev, double* x_dev);
 // split solve for substructuring: forward accumulates -A_KE A_EE^-1 b_E into g_keep; backward takes
 // the kept values and writes eliminated + kept entries of x (original numbering)

@@ -544,8 +544,23 @@ functional_cells(DomainDev dom, OpInst O0, OpInst O1, double sc0, double sc1, in
   if (tid == 0) {
     double t = 0;
     for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
-    if (t != 0.0) atomicAdd(result, t);
+    result[1 + blockIdx.x] = t;          // per-CTA partial; functional_finish adds them in a fixed order
   }
+}
+
+// result[0] = sum of the nblk per-CTA partials result[1..nblk], in an order that does not depend on
+// the schedule (no atomics: the value is bitwise repeatable)
+__global__ void __launch_bounds__(256) functional_finish(double* __restrict__ result, int nblk) {
+  __shared__ double sh[256];
+  double t = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += 256) t += result[1 + b];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) result[0] = sh[0];
 }
 
 // ---- fast path: ∫ ∇u·∇v on constant-Jacobian cells --------------------------------
@@ -1125,6 +1140,7 @@ void launch_functional(const DomainDev& dom_in, const OpInst& O0, const OpInst& 
   if (dom.D == 1) launch(functional_cells<1>);
   else if (dom.D == 2) launch(functional_cells<2>);
   else launch(functional_cells<3>);
+  functional_finish<<<1, 256, 0, s>>>(result, (int)grid);
   CUDA_TRY(cudaGetLastError());
 }
 

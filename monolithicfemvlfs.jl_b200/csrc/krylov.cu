@@ -10,6 +10,8 @@
 #include "solver.cuh"
 #include <complex>
 #include <cmath>
+#include <cstring>
+#include <limits>
 
 void launch_spmv(const int* rowptr, const int* colind, const void* vals, const void* x, void* y,
                  long long nrows, long long nnz, int is_complex, const double* alpha,
@@ -223,6 +225,38 @@ __global__ void newmark_correct(double* __restrict__ u, double* __restrict__ v, 
   }
 }
 __global__ void bump_counter(int* step) { ++*step; }
+// worst relative residual over the steps of a replayed graph: track[0] = max |r|^2/|b|^2 (finite
+// values), track[1] counts steps whose residual is not finite; rr/bb are the two dot products of
+// the step (device memory)
+__global__ void newmark_track(const double* __restrict__ rr, const double* __restrict__ bb, double* __restrict__ track) {
+  const double r2 = *rr, b2 = *bb;
+  if (!isfinite(r2) || !isfinite(b2)) { track[1] += 1.0; return; }
+  const double rel2 = b2 > 0.0 ? r2 / b2 : (r2 > 0.0 ? 1e300 : 0.0);
+  if (rel2 > track[0]) track[0] = rel2;
+}
+// stats[0] = max |A - (K + cu C + cuu M)|, stats[1] = max |A| as bit patterns of non-negative
+// doubles (their integer order is their numeric order)
+__global__ void newmark_check_operator(const double* __restrict__ A, const double* __restrict__ K,
+                                       const double* __restrict__ Cm, const double* __restrict__ M, long long nnz,
+                                       double cu, double cuu, unsigned long long* __restrict__ stats) {
+  double d = 0.0, a = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nnz; i += (long long)gridDim.x * blockDim.x) {
+    const double ref = fma(cuu, M[i], fma(cu, Cm[i], K[i]));
+    const double e = fabs(A[i] - ref);
+    d = e > d || e != e ? e : d;
+    a = fmax(a, fabs(A[i]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double d2 = __shfl_xor_sync(0xffffffffu, d, o);
+    d = (d2 > d || d2 != d2) ? d2 : d;
+    a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(stats, d != d ? 0x7ff0000000000000ull : (unsigned long long)__double_as_longlong(d));
+    atomicMax(stats + 1, (unsigned long long)__double_as_longlong(a));
+  }
+}
 
 // dst[k] = src[idx[k]]  (halo pack)
 template <bool C>
@@ -373,6 +407,7 @@ SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals
 void SolverDeleter::operator()(SolverState* p) const { delete p; }
 
 void solver_precond(SolverState& S, const double* r_dev, double* z_dev) { S.precond(r_dev, z_dev); }
+void solver_set_matrix(SolverState& S, const double* vals) { S.vals = vals; }
 
 namespace {
 
@@ -581,7 +616,7 @@ int solver_solve(SolverState& S, const double* b, double* x, vlfs_solve_stats* s
   return rc;
 }
 
-int newmark_run(SolverState& S, const int* rowptr, const int* colind, const double* Cvals,
+int newmark_run(SolverState& S, const int* rowptr, const int* colind, const double* Kvals, const double* Cvals,
                 const double* Mvals, long long n, long long nnz, int nsteps, double dt, double gamma,
                 double beta, int nb, double* const* bvecs, const double* tcoef, double* u0, double* v0,
                 double* a0, long long out_lo, long long out_hi, int out_stride, double* out,
@@ -591,6 +626,21 @@ int newmark_run(SolverState& S, const int* rowptr, const int* colind, const doub
   u1.alloc(n); rhs.alloc(n); vs.alloc(n); as.alloc(n);
   const double c_u = gamma / (beta * dt), c_uu = 1.0 / (beta * dt * dt);
   const double one[2] = {1, 0}, mone[2] = {-1, 0};
+  {
+    // the solver must have been set up on K + γ/(βΔt) C + 1/(βΔt²) M for THIS Δt, γ, β
+    DevBuf<unsigned long long> chk;
+    chk.alloc(2); chk.zero(s);
+    newmark_check_operator<<<vgrid(nnz, nsm), 256, 0, s>>>(S.vals, Kvals, Cvals, Mvals, nnz, c_u, c_uu, chk.p);
+    ++*launches;
+    unsigned long long h[2];
+    CUDA_TRY(cudaMemcpyAsync(h, chk.p, sizeof h, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    double diff, amax;
+    memcpy(&diff, &h[0], 8); memcpy(&amax, &h[1], 8);
+    if (!(diff <= 1e-10 * amax))
+      throw std::string("vlfs_newmark_run: the solver's matrix is not K + gamma/(beta dt) C + 1/(beta dt^2) M "
+                        "for these dt, gamma, beta (vlfs_combine + vlfs_solver_setup/refactor first)");
+  }
   if (S.opts.precond == VLFS_PRECOND_SPARSE_LU && S.direct) {
     // Constant operator + sparse LU: a step is a fixed kernel sequence (predictor, right-hand side,
     // two SpMVs, LU solve, one refinement solve, corrector).  It is captured ONCE in a CUDA graph -
@@ -598,10 +648,11 @@ int newmark_run(SolverState& S, const int* rowptr, const int* colind, const doub
     // small time-domain cases are launch-latency bound (N = 35 224: ~300 launches per step).
     const long long nout = out_hi - out_lo;
     const long long nrec = nout > 0 ? nsteps / out_stride : 0;
-    DevBuf<double> dx, r, tc, hist;
+    DevBuf<double> dx, r, tc, hist, track;
     DevBuf<const double*> bptr;
     DevBuf<int> counter;
     dx.alloc(n); r.alloc(n);
+    track.alloc(2); track.zero(s);
     if (nb) {
       tc.upload(tcoef, (size_t)nsteps * nb, s);
       std::vector<const double*> hb(bvecs, bvecs + nb);
@@ -627,21 +678,26 @@ int newmark_run(SolverState& S, const int* rowptr, const int* colind, const doub
     };
     // number of refinement steps: measured once on the first step's system (no state update),
     // the smallest count that reaches the tolerance or the attainable accuracy, at most 4
+    // A zero first right-hand side says nothing about the accuracy of one sweep: two refinements then.
     int nref = 0;
+    double nref_floor = 0.0;              // relative residual the probe ended with (attainable accuracy)
     {
       build_rhs();
       direct_solve(*S.direct, rhs.p, u1.p);
       const double bn = S.nrm2(rhs.p);
       double prev = 1e300;
-      for (; nref < 4; ++nref) {
-        S.copy(rhs.p, r.p);
-        S.spmv(u1.p, r.p, -1.0, 1.0);
-        const double rel = bn > 0 ? S.nrm2(r.p) / bn : 0.0;
-        if (rel <= S.opts.rtol || rel > 0.25 * prev) break;
-        prev = rel;
-        direct_solve(*S.direct, r.p, dx.p);
-        S.axpby_(cd(1, 0), dx.p, cd(1, 0), u1.p);
-      }
+      if (!(bn > 0.0)) nref = 2;
+      else
+        for (; nref < 4; ++nref) {
+          S.copy(rhs.p, r.p);
+          S.spmv(u1.p, r.p, -1.0, 1.0);
+          const double rel = S.nrm2(r.p) / bn;
+          nref_floor = rel;
+          if (rel <= S.opts.rtol || rel > 0.25 * prev) break;
+          prev = rel;
+          direct_solve(*S.direct, r.p, dx.p);
+          S.axpby_(cd(1, 0), dx.p, cd(1, 0), u1.p);
+        }
       if (nref < 1) nref = 1;
     }
     const long long launches_before2 = *launches;
@@ -649,6 +705,15 @@ int newmark_run(SolverState& S, const int* rowptr, const int* colind, const doub
       build_rhs();
       direct_solve(*S.direct, rhs.p, u1.p);                 // x = A^-1 rhs
       for (int k = 0; k < nref; ++k) refine();
+      // true residual of this step's system, folded into a device-side maximum (no host round trip)
+      S.copy(rhs.p, r.p);
+      S.spmv(u1.p, r.p, -1.0, 1.0);
+      multidot_partial<false><<<dim3(S.nred, 1), RED_THREADS, 0, s>>>(r.p, (size_t)n, r.p, n, S.partial.p);
+      multidot_finish<false><<<1, RED_THREADS, 0, s>>>(S.partial.p, S.nred, S.hdev.p);
+      multidot_partial<false><<<dim3(S.nred, 1), RED_THREADS, 0, s>>>(rhs.p, (size_t)n, rhs.p, n, S.partial.p + S.nred);
+      multidot_finish<false><<<1, RED_THREADS, 0, s>>>(S.partial.p + S.nred, S.nred, S.hdev.p + 1);
+      newmark_track<<<1, 1, 0, s>>>(S.hdev.p, S.hdev.p + 1, track.p);
+      *launches += 5;
       newmark_correct<<<g, 256, 0, s>>>(u.p, v.p, a.p, u1.p, vs.p, as.p, n, c_u, c_uu,
                                         nrec > 0 ? hist.p : nullptr, out_lo, out_hi, out_stride, counter.p);
       bump_counter<<<1, 1, 0, s>>>(counter.p);
@@ -660,7 +725,14 @@ int newmark_run(SolverState& S, const int* rowptr, const int* colind, const doub
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    one_step();
+    try {
+      one_step();
+    } catch (...) {                       // never leave the context's stream in capture state
+      cudaStreamEndCapture(s, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      throw;
+    }
     CUDA_TRY(cudaStreamEndCapture(s, &graph));
     CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
     const long long per_step = *launches - launches_before2;
@@ -673,12 +745,16 @@ int newmark_run(SolverState& S, const int* rowptr, const int* colind, const doub
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
-    // true residual of the last step's system (one host round trip, after the timed region)
-    S.copy(rhs.p, r.p);
-    S.spmv(u.p, r.p, -1.0, 1.0);
-    const double bn = S.nrm2(rhs.p), rn = S.nrm2(r.p);
+    // worst true relative residual over ALL steps (tracked on the device inside the graph)
+    double htrack[2] = {0.0, 0.0};
+    CUDA_TRY(cudaMemcpyAsync(htrack, track.p, sizeof htrack, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     vlfs_solve_stats tot{};
-    tot.iterations = (1 + nref) * nsteps; tot.converged = 1; tot.rel_residual = bn > 0 ? rn / bn : 0.0;
+    tot.iterations = (1 + nref) * nsteps;
+    tot.rel_residual = htrack[1] > 0.0 ? std::numeric_limits<double>::quiet_NaN() : std::sqrt(htrack[0]);
+    // the refinement stops at the attainable accuracy: accept a few times the requested tolerance
+    // there, never a non-finite or stagnating step
+    tot.converged = htrack[1] == 0.0 && tot.rel_residual <= std::max(S.opts.rtol, nref_floor * 4.0);
     tot.solve_ms = ms; tot.setup_ms = S.setup_ms;
     if (nrec > 0) CUDA_TRY(cudaMemcpyAsync(out, hist.p, (size_t)nrec * nout * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(u0, u.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -686,7 +762,7 @@ int newmark_run(SolverState& S, const int* rowptr, const int* colind, const doub
     CUDA_TRY(cudaMemcpyAsync(a0, a.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (stats) *stats = tot;
-    return VLFS_OK;
+    return tot.converged ? VLFS_OK : VLFS_NOT_CONVERGED;
   }
   vlfs_solve_stats tot{};
   tot.converged = 1;

@@ -13,8 +13,9 @@ SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals
                         long long n, long long nnz, int is_complex,
                                            const vlfs_solver_opts& opts, int nsm, cudaStream_t s,
                                            long long* launches, DirectSolver* direct);
+void solver_set_matrix(SolverState& S, const double* vals);   // after a refactorisation of another matrix
 int solver_solve(SolverState& S, const double* b_dev, double* x_dev, vlfs_solve_stats* stats);
-int newmark_run(SolverState& S, const int* rowptr, const int* colind, const double* Cvals,
+int newmark_run(SolverState& S, const int* rowptr, const int* colind, const double* Kvals, const double* Cvals,
                 const double* Mvals, long long n, long long nnz, int nsteps, double dt, double gamma,
                 double beta, int nb, double* const* bvecs, const double* tcoef, double* u0, double* v0,
                 double* a0, long long out_lo, long long out_hi, int out_stride, double* out,

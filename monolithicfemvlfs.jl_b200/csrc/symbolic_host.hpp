@@ -159,6 +159,54 @@ inline void rank_transform(long long n_total, const double* xy, int dim, std::ve
   for (auto& x : th) x.join();
 }
 
+// Coordinate-free fallback of the geometric dissection: graph distances from three far-apart
+// vertices serve as "coordinates" (a level set of a breadth-first search is a separator, George's
+// level-structure dissection).  Used when the host gives a matrix without DOF coordinates
+// (`LUSolver()` drop-in on a matrix Gridap assembled: numerical_setup(ss, A)).
+inline void pseudo_coords(long long n, const int* rp, const int* ci, std::vector<double>& xyz) {
+  const int dim = 3;
+  xyz.assign((size_t)n * dim, 0.0);
+  // symmetric adjacency (pattern + transpose) so that distances are well defined
+  std::vector<int> deg(n + 1, 0);
+  for (long long i = 0; i < n; ++i)
+    for (int p = rp[i]; p < rp[i + 1]; ++p) if (ci[p] != i) { ++deg[i + 1]; ++deg[ci[p] + 1]; }
+  for (long long i = 0; i < n; ++i) deg[i + 1] += deg[i];
+  std::vector<int> adj(deg[n]), fill(deg.begin(), deg.end() - 1);
+  for (long long i = 0; i < n; ++i)
+    for (int p = rp[i]; p < rp[i + 1]; ++p) if (ci[p] != i) { adj[fill[i]++] = ci[p]; adj[fill[ci[p]]++] = (int)i; }
+  std::vector<int> dist(n), queue(n);
+  auto bfs = [&](int src) -> int {           // returns the last vertex reached (farthest)
+    std::fill(dist.begin(), dist.end(), -1);
+    long long head = 0, tail = 0;
+    int last = src, far = 0;
+    auto run = [&](int s0) {
+      dist[s0] = far; queue[tail++] = s0;
+      while (head < tail) {
+        const int v = queue[head++];
+        last = v;
+        for (int p = deg[v]; p < deg[v + 1]; ++p) { const int w = adj[p]; if (dist[w] < 0) { dist[w] = dist[v] + 1; queue[tail++] = w; } }
+      }
+      far = dist[last] + 1;
+    };
+    run(src);
+    for (long long v = 0; v < n; ++v) if (dist[v] < 0) run((int)v);   // further components continue the numbering
+    return last;
+  };
+  int a = bfs(0);
+  a = bfs(a);                                 // pseudo-peripheral vertex
+  int b = bfs(a);
+  for (long long v = 0; v < n; ++v) xyz[(size_t)v * dim + 0] = dist[v];
+  bfs(b);
+  int c = 0; long long best = -1;
+  for (long long v = 0; v < n; ++v) {
+    xyz[(size_t)v * dim + 1] = dist[v];
+    const long long m = std::min<long long>((long long)xyz[(size_t)v * dim], dist[v]);   // far from both a and b
+    if (m > best) { best = m; c = (int)v; }
+  }
+  bfs(c);
+  for (long long v = 0; v < n; ++v) xyz[(size_t)v * dim + 2] = dist[v];
+}
+
 struct NDBuilder {
   const int* ptr; const int* idx; const int* plane; int dim; int leaf;
   int* mark;                       // shared: stamp of the split that last put the vertex on its B side
