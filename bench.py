@@ -219,8 +219,13 @@ def run_ours(args):
     # per-kernel times (CUDA events on the launching stream) for the roofline of the dominant kernel
     prof = S.assemble_profile(reps=3)
     dom_name, dom_ms = max(prof, key=lambda kv: kv[1])
-    ent_gf = prob.Gf.ncells * (27 + prob.V_Gk.reffe.ndofs) ** 2
-    if dom_name.startswith("gather_reference"):
+    rows_ms = sum(t for n, t in prof if n.startswith("assemble_rows"))
+    if rows_ms > 0:
+        # row-centric pass (one kernel, launched for the early and the late rows): every CSR value
+        # written once + the COO->slot permutation read once = SURVEY.md §8(d)'s per-unit figure
+        dom_name, dom_ms = "assemble_rows", rows_ms
+        kbytes = nnz * sT + 4 * ncoo
+    elif dom_name.startswith("gather_reference"):
         # slot-centric pass: every value written once, one index per COO entry, one run pointer per slot
         kbytes = nnz * sT + 4 * ncoo + 4 * nnz
     else:

@@ -33,6 +33,15 @@ void launch_compact_gather_records(const unsigned long long* rec, long long ncoo
 void launch_gather_reference(const uint32_t* run_start, const unsigned long long* rec, const uint32_t* rec32,
                              double* const* ctab_all, long long nnz, const GatherDom* doms, int ndom, int nrp_total, long long tab_total,
                              double* const* mats, int nmat, int is_complex, int nsm, cudaStream_t s);
+void build_row_incidence(const std::vector<DomainDev>& doms, long long ndofs, DevBuf<int>& incptr,
+                         DevBuf<unsigned long long>& inc_src, long long* nrec_out, cudaStream_t s,
+                         long long* launches);
+void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, long long nrows,
+                               const GatherDom* doms, const int* dom_late, RowInc* out, unsigned char* late,
+                               cudaStream_t s);
+bool launch_assemble_rows(const int* rowptr, const int* incptr, const RowInc* inc, const int* dest,
+                          double* const* ctab_all, long long nrows, double* const* mats, int nmat, int is_complex,
+                          int maxrow, const unsigned char* late, int phase, int nsm, cudaStream_t s);
 void build_csc_device(const int* rowind, const int* colind, long long nnz, long long ndofs,
                       DevBuf<int>& colptr, DevBuf<int>& rowval, DevBuf<int>& csr_slot,
                       cudaStream_t s, long long* launches);
@@ -135,6 +144,14 @@ struct vlfs_ctx {
   DevBuf<uint32_t> gather_rec32;           // index of the entry's class-table value (all domains tabulated)
   DevBuf<double> ctab_all[4];              // per matrix: the class tables of all domains, contiguous
   bool rec32_valid = false;
+  // row-centric numeric pass: incidence records of every row (pattern.cu: build_row_incidence)
+  DevBuf<int> incptr, dom_late;
+  DevBuf<unsigned long long> inc_src;
+  DevBuf<RowInc> inc;
+  DevBuf<unsigned char> row_late;
+  long long ninc = 0;
+  int maxrow = 0;
+  bool rows_valid = false, rows_two_phase = false;
   int nrp_total = 0;
   long long tab_total = 0;
   DevBuf<GatherDom> gather_doms;
@@ -641,6 +658,47 @@ void rebuild_compact_records(vlfs_ctx* ctx) {
   ctx->rec32_valid = true;
 }
 
+// slot-centric fallback records, built on demand from the sorted COO order
+void ensure_gather_records(vlfs_ctx* ctx) {
+  if (ctx->gather_rec.n == (size_t)ctx->ncoo || ctx->ncoo == 0) return;
+  if (ctx->perm.n != (size_t)ctx->ncoo) throw std::string("internal: sorted COO order no longer available");
+  ctx->gather_rec.alloc((size_t)ctx->ncoo);
+  launch_pack_gather_records(ctx->perm.p, ctx->ncoo, ctx->gather_doms.p, (int)ctx->doms.size(), ctx->gather_rec.p, ctx->stream);
+  ++ctx->launches;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+}
+
+// RowInc records of the row-centric pass: possible when every domain that owns COO entries is
+// class-tabulated (same condition as the 32-bit gather records)
+void rebuild_row_records(vlfs_ctx* ctx) {
+  ctx->rows_valid = false;
+  static const bool enabled = !(getenv("VLFS_ASM_ROWS") && atoi(getenv("VLFS_ASM_ROWS")) == 0);
+  if (!enabled || ctx->ninc == 0 || ctx->maxrow == 0) return;
+  if ((size_t)ctx->nmat * ctx->maxrow * ctx->scalar() * sizeof(double) > 200 * 1024) return;   // row segment > shared memory
+  long long total = 0;
+  std::vector<int> late(ctx->doms.size(), 0);
+  bool any_late = false, any_early = false;
+  for (size_t di = 0; di < ctx->doms.size(); ++di) {
+    Domain& d = *ctx->doms[di];
+    if (d.dev.ncells * (long long)d.dev.entries_per_cell == 0) continue;
+    if (d.ncls == 0) return;
+    if (!d.terms_host.empty() && !d.cls_full) return;      // cell-centric terms left: they need the zero fill first
+    total += d.ctab_entries;
+    late[di] = d.cls_full ? 1 : 0;
+    (d.cls_full ? any_late : any_early) = true;
+  }
+  if (total >= 0xffffffffll) return;
+  ctx->dom_late.upload(late.data(), late.size(), ctx->stream);
+  if (ctx->inc.n != (size_t)ctx->ninc) ctx->inc.alloc((size_t)ctx->ninc);
+  if (ctx->row_late.n != (size_t)ctx->ndofs) ctx->row_late.alloc((size_t)ctx->ndofs);
+  launch_fill_row_incidence(ctx->inc_src.p, ctx->incptr.p, ctx->ndofs, ctx->gather_doms.p, ctx->dom_late.p,
+                            ctx->inc.p, ctx->row_late.p, ctx->stream);
+  ++ctx->launches;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->rows_two_phase = any_late && any_early;
+  ctx->rows_valid = true;
+}
+
 void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   if (!ctx->pattern_built) throw std::string("vlfs_build_pattern must be called first");
   if (ctx->imported) throw std::string("the matrix was imported (vlfs_import_csr): nothing to assemble");
@@ -653,8 +711,13 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     bool reclass = false;
     for (auto& dp : ctx->doms)
       if (dp->cls_dirty) { classify_domain(ctx, *dp); reclass = true; }
-    if (reclass) { upload_gather_doms(ctx); rebuild_compact_records(ctx); }
+    if (reclass) {
+      upload_gather_doms(ctx);
+      rebuild_row_records(ctx);
+      if (!ctx->rows_valid) { ensure_gather_records(ctx); rebuild_compact_records(ctx); }
+    }
   }
+  const bool use_rows = do_mat && ctx->rows_valid;
   // linear forms of constant-Jacobian domains touch only the vectors: they run on their own stream
   // beside the matrix passes (when both are assembled and nobody is timing kernels one by one)
   const bool vec_aside = do_vec && do_mat && !ctx->profile;
@@ -681,6 +744,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     for (auto& dp : ctx->doms) if (!dp->rhs_host.empty() && !dp->rhs_fast) vec_join_early = true;
     if (vec_join_early) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_vec_join, 0));
   }
+  bool used[3] = {false, false, false};
   if (do_mat) {
     // per-class element blocks: reference products tabulated directly, general (quadrature) terms
     // integrated on the class representatives only, reduced into the class tables.  These are
@@ -694,14 +758,15 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
       }
     }
     CUDA_TRY(cudaEventRecord(ctx->ev_fork, s));
-    bool used[3] = {false, false, false};
     int k = 0;
     for (size_t di = 0; di < ctx->doms.size(); ++di) {
       Domain& d = *ctx->doms[di];
       if (d.ncls == 0) continue;
-      cudaStream_t a = ctx->aux[k % 3];
-      if (!used[k % 3]) { CUDA_TRY(cudaStreamWaitEvent(a, ctx->ev_fork, 0)); used[k % 3] = true; }
-      ++k;
+      // row-centric pass in two phases: the directly tabulated domains share stream 0 (their tables
+      // are ready first), the quadrature-tabulated ones alternate between streams 1 and 2
+      const int q = (use_rows && ctx->rows_two_phase) ? (d.cls_full ? 1 + (k++ & 1) : 0) : (k++ % 3);
+      cudaStream_t a = ctx->aux[q];
+      if (!used[q]) { CUDA_TRY(cudaStreamWaitEvent(a, ctx->ev_fork, 0)); used[q] = true; }
       launch_build_class_tables(ctx->gather_doms.p, (int)di, d.ctab_work, ctx->nmat, ctx->is_complex, a);
       ++ctx->launches;
       if (d.cls_full) {
@@ -714,14 +779,35 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     for (int q = 0; q < 3; ++q)
       if (used[q]) {
         CUDA_TRY(cudaEventRecord(ctx->ev_join[q], ctx->aux[q]));
-        CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
+        if (!(use_rows && ctx->rows_two_phase && q > 0)) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
       }
+  }
+  if (use_rows) {
+    {
+      double* ca[4] = {ctx->ctab_all[0].p, ctx->ctab_all[1].p, ctx->ctab_all[2].p, ctx->ctab_all[3].p};
+      auto rows = [&](int phase) {
+        if (!launch_assemble_rows(ctx->rowptr.p, ctx->incptr.p, ctx->inc.p, ctx->dest_all.p, ca, ctx->ndofs, mp.data(),
+                                  (int)mp.size(), ctx->is_complex, ctx->maxrow, ctx->row_late.p, phase, ctx->nsm, s))
+          throw std::string("row-centric pass: a matrix row does not fit the shared memory");
+        ++ctx->launches;
+      };
+      if (ctx->rows_two_phase) {
+        { ProfScope p1(ctx, "assemble_rows:early"); rows(1); }
+        {
+          ProfScope pw(ctx, "class_tables:quadrature_wait");
+          for (int q = 1; q < 3; ++q) if (used[q]) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
+        }
+        { ProfScope p2(ctx, "assemble_rows:late"); rows(2); }
+      } else {
+        ProfScope p0(ctx, "assemble_rows"); rows(0);
+      }
+    }
   }
   {
     // slot-centric pass: writes every CSR value (zero fill included) with the tabulated /
     // reference-type contributions summed in COO order; the cell-centric kernels then add the rest
-    ProfScope ps(ctx, "gather_reference");
-    if (do_mat) {
+    ProfScope ps(ctx, use_rows ? "vector_zero" : "gather_reference");
+    if (do_mat && !use_rows) {
       double* ca[4] = {ctx->ctab_all[0].p, ctx->ctab_all[1].p, ctx->ctab_all[2].p, ctx->ctab_all[3].p};
       launch_gather_reference(ctx->run_start.p, ctx->gather_rec.p,
                               ctx->rec32_valid ? ctx->gather_rec32.p : nullptr, ca, ctx->nnz, ctx->gather_doms.p,
@@ -1017,6 +1103,7 @@ int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
     long long n1 = 0, n2 = 0;
     build_pattern_device(devs, ctx->ndofs, ctx->rowptr, ctx->colind, ctx->rowind, ctx->dest_all,
                          ctx->dest_off, ctx->perm, ctx->run_start, &n1, &n2, ctx->stream, &ctx->launches);
+    ctx->nnz = n1; ctx->ncoo = n2;
     {
       for (auto& d : ctx->doms) classify_domain(ctx, *d);
       upload_gather_doms(ctx);
@@ -1024,12 +1111,19 @@ int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
       ctx->tab_total = 0;
       for (auto& d : ctx->doms) { ctx->nrp_total += (int)d->refprods_host.size(); ctx->tab_total += (long long)d->reftabs.n; }
       if ((int)ctx->doms.size() > 16) throw std::string("more than 16 integration domains");
-      ctx->gather_rec.alloc((size_t)n2);
-      launch_pack_gather_records(ctx->perm.p, n2, ctx->gather_doms.p, (int)ctx->doms.size(), ctx->gather_rec.p, ctx->stream);
-      ++ctx->launches;
-      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-      ctx->perm.release();
-      rebuild_compact_records(ctx);
+      // row-centric numeric pass: incidence lists of every row, longest row (its shared-memory segment)
+      build_row_incidence(devs, ctx->ndofs, ctx->incptr, ctx->inc_src, &ctx->ninc, ctx->stream, &ctx->launches);
+      {
+        std::vector<int> rp((size_t)ctx->ndofs + 1);
+        CUDA_TRY(cudaMemcpy(rp.data(), ctx->rowptr.p, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        int mx = 0;
+        for (long long i = 0; i < ctx->ndofs; ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
+        ctx->maxrow = mx;
+      }
+      rebuild_row_records(ctx);
+      // the slot-centric records (0.9 GB on the paper-size Yago mesh) are only built when the
+      // row-centric pass cannot run; the sorted COO order stays for a later fallback
+      if (!ctx->rows_valid) { ensure_gather_records(ctx); rebuild_compact_records(ctx); }
     }
     ctx->nnz = n1; ctx->ncoo = n2;
     for (size_t di = 0; di < ctx->doms.size(); ++di) {

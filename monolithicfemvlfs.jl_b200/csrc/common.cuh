@@ -173,6 +173,12 @@ struct GatherDom {
   long long ctab_off[VLFS_MAX_BLOCKS];   // entry offset of every block inside a class table
 };
 
+// ---- row-centric numeric pass (integrate.cu: assemble_rows) --------------------------------------
+// One record per (cell, touched block, local test row) contributing to a CSR row: the nc COO
+// entries coo..coo+nc-1 (their CSR slots are dest[coo+j]) take the class-table values tab..tab+nc-1.
+// tab = 0xffffffff: the block has no class table (its terms are added by the cell-centric kernel).
+struct RowInc { uint32_t coo, tab, nc; };
+
 // ---- primitives -------------------------------------------------------------------
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev,
                         cudaStream_t s);

@@ -955,7 +955,169 @@ gather_compact(const uint32_t* __restrict__ run_start, const uint32_t* __restric
   }
 }
 
+// packed (domain, block, local row, cell) sources -> RowInc records; once per pattern and again when
+// the element-block classes change.  late[row] = 1 when a contributing domain's class tables come
+// out of the quadrature kernel (they are ready later than the directly tabulated ones).
+__global__ void fill_row_incidence(const unsigned long long* __restrict__ src, const int* __restrict__ incptr,
+                                   long long nrows, const GatherDom* __restrict__ doms, const int* __restrict__ dom_late,
+                                   RowInc* __restrict__ out, unsigned char* __restrict__ late) {
+  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < nrows;
+       row += (long long)gridDim.x * blockDim.x) {
+    unsigned char l = 0;
+    for (int k = incptr[row]; k < incptr[row + 1]; ++k) {
+      const unsigned long long r = src[k];
+      const unsigned d = (unsigned)(r >> 60), b = (unsigned)((r >> 58) & 3u), a = (unsigned)((r >> 32) & 0x3fffu);
+      const unsigned e = (unsigned)(r & 0xffffffffull);
+      const GatherDom& G = doms[d];
+      const int nc = G.blk[b].nc;
+      RowInc R;
+      R.coo = (uint32_t)(G.coo_lo + (long long)e * G.epc + G.blk[b].off + (long long)a * nc);
+      R.nc = (uint32_t)nc;
+      R.tab = (G.ncls > 0 && G.ctab_off[b] >= 0)
+                  ? (uint32_t)(G.ctab_base + G.ctab_off[b] + (long long)G.cls[e] * (G.blk[b].nr * nc) + (long long)a * nc)
+                  : 0xffffffffu;
+      out[k] = R;
+      l |= (unsigned char)dom_late[d];
+    }
+    late[row] = l;
+  }
+}
+
+// Row-centric numeric pass (every domain class-tabulated): one warp per CSR row.  The row's value
+// segment lives in shared memory; for every incidence record the lanes read the nc consecutive
+// `dest` entries and the nc consecutive class-table values of that element-matrix row (both
+// coalesced), add into the segment - records in COO order, one record at a time, so the sum order is
+// the one of Julia's sparse(I,J,V) and bitwise repeatable - and the finished segment is written to
+// the CSR values with one coalesced pass: every value is written exactly once (this is also the
+// zero fill), every `dest` entry is read exactly once, nothing else streams from HBM.
+// phase: 0 all rows, 1 rows whose tables are ready early (late[row] == 0), 2 the others.
+template <int NMAT, bool CPLX>
+__global__ void __launch_bounds__(256)
+assemble_rows(const int* __restrict__ rowptr, const int* __restrict__ incptr, const RowInc* __restrict__ inc,
+              const int* __restrict__ dest, AsmPtrs ctab_all, long long nrows, AsmPtrs ptrs, int maxrow,
+              const unsigned char* __restrict__ late, int phase) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  extern __shared__ __align__(16) double seg_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  T* seg = reinterpret_cast<T*>(seg_raw) + (size_t)wib * NMAT * maxrow;
+  const long long nwarps = (long long)gridDim.x * wpb;
+  for (long long row = (long long)blockIdx.x * wpb + wib; row < nrows; row += nwarps) {
+    if (phase != 0 && (late[row] != 0) != (phase == 2)) continue;
+    const int r0 = __ldg(rowptr + row), L = __ldg(rowptr + row + 1) - r0;
+    for (int sidx = lane; sidx < L; sidx += 32) {
+#pragma unroll
+      for (int m = 0; m < NMAT; ++m) seg[m * maxrow + sidx] = T{};
+    }
+    __syncwarp();
+    const int k0 = __ldg(incptr + row), k1 = __ldg(incptr + row + 1);
+    for (int kb = k0; kb < k1; kb += 32) {
+      RowInc mine{0u, 0xffffffffu, 0u};
+      if (kb + lane < k1) mine = inc[kb + lane];
+      const int cnt = min(32, k1 - kb);
+      // software pipeline: the loads of record g+1 are in flight while record g is added
+      int dn = -1;
+      T vn[NMAT];
+      auto fetch = [&](int g) {
+        const uint32_t coo = __shfl_sync(0xffffffffu, mine.coo, g);
+        const uint32_t tab = __shfl_sync(0xffffffffu, mine.tab, g);
+        const int nc = (int)__shfl_sync(0xffffffffu, mine.nc, g);
+        dn = -1;
+        if (lane < nc && tab != 0xffffffffu) {
+          dn = __ldg(dest + coo + lane) - r0;
+#pragma unroll
+          for (int m = 0; m < NMAT; ++m) vn[m] = __ldg(reinterpret_cast<const T*>(ctab_all.mat[m]) + tab + lane);
+        }
+        return nc;
+      };
+      int nc = fetch(0);
+      for (int g = 0; g < cnt; ++g) {
+        const int d = dn;
+        T v[NMAT];
+#pragma unroll
+        for (int m = 0; m < NMAT; ++m) v[m] = vn[m];
+        const int nc_cur = nc;
+        const uint32_t coo_cur = __shfl_sync(0xffffffffu, mine.coo, g);
+        const uint32_t tab_cur = __shfl_sync(0xffffffffu, mine.tab, g);
+        if (g + 1 < cnt) nc = fetch(g + 1);
+        if (d >= 0) {
+#pragma unroll
+          for (int m = 0; m < NMAT; ++m) {
+            T* p = seg + m * maxrow + d;
+            if constexpr (CPLX) { T o = *p; o.x += v[m].x; o.y += v[m].y; *p = o; }
+            else *p += v[m];
+          }
+        }
+        // element rows wider than a warp (P4 tetrahedra: 35 columns): the rest, unpipelined
+        if (nc_cur > 32 && tab_cur != 0xffffffffu)
+          for (int j = 32 + lane; j < nc_cur; j += 32) {
+            const int d2 = __ldg(dest + coo_cur + j) - r0;
+#pragma unroll
+            for (int m = 0; m < NMAT; ++m) {
+              const T v2 = __ldg(reinterpret_cast<const T*>(ctab_all.mat[m]) + tab_cur + j);
+              T* p = seg + m * maxrow + d2;
+              if constexpr (CPLX) { T o = *p; o.x += v2.x; o.y += v2.y; *p = o; }
+              else *p += v2;
+            }
+          }
+        __syncwarp();            // the next record may hit the same slots from other lanes
+      }
+    }
+    for (int sidx = lane; sidx < L; sidx += 32) {
+#pragma unroll
+      for (int m = 0; m < NMAT; ++m) reinterpret_cast<T*>(ptrs.mat[m])[r0 + sidx] = seg[m * maxrow + sidx];
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
+
+void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, long long nrows,
+                               const GatherDom* doms, const int* dom_late, RowInc* out, unsigned char* late,
+                               cudaStream_t s) {
+  if (nrows == 0) return;
+  long long grid = (nrows + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  fill_row_incidence<<<(unsigned)grid, 256, 0, s>>>(src, incptr, nrows, doms, dom_late, out, late);
+  CUDA_TRY(cudaGetLastError());
+}
+
+// returns false when a row segment does not fit the shared memory of a CTA (the caller then uses
+// the slot-centric gather)
+bool launch_assemble_rows(const int* rowptr, const int* incptr, const RowInc* inc, const int* dest,
+                          double* const* ctab_all, long long nrows, double* const* mats, int nmat, int is_complex,
+                          int maxrow, const unsigned char* late, int phase, int nsm, cudaStream_t s) {
+  if (nrows == 0) return true;
+  AsmPtrs P{}, CT{};
+  for (int m = 0; m < nmat && m < 4; ++m) { P.mat[m] = mats[m]; CT.mat[m] = ctab_all[m]; }
+  const size_t per_warp = (size_t)nmat * maxrow * (is_complex ? 16 : 8);
+  int wpb = 8;
+  while (wpb > 1 && per_warp * wpb > 64 * 1024) wpb >>= 1;      // keep several CTAs per SM
+  const size_t smem = per_warp * wpb;
+  if (smem > 200 * 1024) return false;
+  static const int cta_per_sm = getenv("VLFS_ROWS_CTAS") ? atoi(getenv("VLFS_ROWS_CTAS")) : 0;
+  int per_sm = cta_per_sm > 0 ? cta_per_sm : (int)std::min<size_t>(2048 / (32 * wpb), (220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)nsm * per_sm;
+  const long long need = (nrows + wpb - 1) / wpb;
+  if (grid > need) grid = need;
+  auto go = [&](auto kern) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, 32 * wpb, smem, s>>>(rowptr, incptr, inc, dest, CT, nrows, P, maxrow, late, phase);
+  };
+  switch (nmat * 2 + (is_complex ? 1 : 0)) {
+    case 2: go(assemble_rows<1, false>); break;
+    case 3: go(assemble_rows<1, true>); break;
+    case 4: go(assemble_rows<2, false>); break;
+    case 5: go(assemble_rows<2, true>); break;
+    case 6: go(assemble_rows<3, false>); break;
+    case 7: go(assemble_rows<3, true>); break;
+    case 8: go(assemble_rows<4, false>); break;
+    default: go(assemble_rows<4, true>); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return true;
+}
 
 void launch_cell_geometry(const DomainDev& dom, int want_gradgrad, double* out, cudaStream_t s) {
   if (dom.ncells == 0) return;
