@@ -228,6 +228,9 @@ int vlfs_assemble_timed(vlfs_ctx* ctx, int reps, float* ms_total);
 /* per-kernel CUDA-event times of one assembly pass (averaged over reps); names ';'-joined */
 int vlfs_assemble_profile(vlfs_ctx* ctx, int reps, char* names, int names_cap, float* ms, int ms_cap, int* nrec);
 int vlfs_last_kernel_launches(vlfs_ctx* ctx, int64_t* n);
+/* measured FP64 FMA rate of the device (TFLOP/s, dependent-free DFMA chains on every SM): the roofline
+ * denominator of the general-quadrature kernel and of the LU's Schur updates */
+int vlfs_measure_fp64_peak(vlfs_ctx* ctx, double* tflops);
 int vlfs_device_ptrs(vlfs_ctx* ctx, int mat, void** rowptr, void** colind, void** values);
 
 /* ---- functionals of FE functions (the integrals the reference evaluates after each step:
@@ -249,7 +252,8 @@ int vlfs_eval_functional(vlfs_ctx* ctx, int domain_id, const vlfs_functional_des
  * [0,n_owned) of the local CSR are then complete.  The entry points below take DEVICE pointers
  * (vectors of the local length, scalars interleaved as elsewhere) and run on the stream given to
  * vlfs_set_stream (e.g. the caller's torch / CUDA.jl stream); halo exchange and the all-reduce of
- * the dot products are the caller's (NCCL through torch.distributed in the Python mirror).
+ * the dot products are the caller's with these low-level calls (see the multi-GPU section below
+ * for the path in which the library does both itself).
  * Replaces nothing in the (serial) reference: SURVEY.md §8(e). */
 int vlfs_set_stream(vlfs_ctx* ctx, void* cuda_stream);          /* before vlfs_solver_setup     */
 int vlfs_set_owned_rows(vlfs_ctx* ctx, int64_t n_owned);
@@ -265,6 +269,42 @@ int vlfs_dev_axpby(vlfs_ctx* ctx, double a_re, double a_im, const void* x_dev, d
 int vlfs_dev_gather(vlfs_ctx* ctx, int64_t n, const int32_t* idx_dev, const void* src_dev,
                     void* dst_dev);                                           /* halo pack       */
 int vlfs_get_vector_device(vlfs_ctx* ctx, int vec, void** ptr);
+
+/* ---- multi-GPU systems: the library owns the communicator and the whole data plane ------------
+ * Every rank (one context per GPU) holds the rows of the DOFs it owns, with LOCAL ids [owned | ghosts
+ * grouped by owner]; it registers the cells that touch an owned DOF, so that assembly needs no
+ * communication.  Ranks are threads of ONE process (vlfs_multi_create: ncclCommInitAll; what the Julia
+ * shim uses) or one process each (vlfs_dist_unique_id on rank 0, the host hands the 128 bytes to every
+ * rank, vlfs_dist_init).  After vlfs_dist_set_halo the ordinary entry points become collective:
+ *   vlfs_spmv / vlfs_dev_spmv / vlfs_spmv_device : pack + grouped ncclSend/ncclRecv of the ghost values
+ *       on a side stream while the rows without ghost columns are multiplied, then the others;
+ *   vlfs_solver_setup(VLFS_PRECOND_SPARSE_LU) / vlfs_solver_refactor : local multifrontal LU with the
+ *       rank's own cut and the next rank's cut kept, then the rank's link of the block-tridiagonal
+ *       interface chain (corner relayed from rank-1, own corner passed to rank+1) - requires that the
+ *       cuts form a chain (slab-like partitions; VLFS_ERR_STATE otherwise);
+ *   vlfs_solve / vlfs_solve_vec : GMRES whose dot products are ONE ncclAllReduce per iteration, with
+ *       the substructuring solve as exact preconditioner (x: n_local entries, owned part meaningful).
+ * Ranks that share one device (tests on a 1-GPU box) use an in-process transport instead of NCCL.
+ * The vlfs_multi_* calls run the per-rank call on one host thread per rank (collectives block on each
+ * other); arrays of per-rank results are indexed by rank.  Replaces nothing in the serial reference:
+ * SURVEY.md §8(e). */
+int vlfs_dist_unique_id(void* id128);
+int vlfs_dist_init(vlfs_ctx* ctx, int rank, int nranks, const void* id128);
+int vlfs_multi_create(vlfs_ctx** ctxs, int ngpu, const int* devices);
+/* peers[p]: rank exchanged with; send_idx[send_ptr[p]..send_ptr[p+1]) owned local ids peer p needs, in
+ * the order of its ghost block; recv_ptr[p]..recv_ptr[p+1]: range of this rank's ghost block owned by
+ * peer p (the ranges cover the ghost block).  After vlfs_build_pattern. */
+int vlfs_dist_set_halo(vlfs_ctx* ctx, int64_t n_owned, int npeers, const int32_t* peers,
+                       const int64_t* send_ptr, const int32_t* send_idx, const int64_t* recv_ptr);
+/* {own cut size, next cut size, interface-chain factorisation ms (incl. waiting for rank-1), rows with ghost columns} */
+int vlfs_dist_info(vlfs_ctx* ctx, double* out4);
+int vlfs_multi_build_pattern(vlfs_ctx** ctxs, int n, int64_t* nnz, int64_t* ncoo);
+int vlfs_multi_assemble(vlfs_ctx** ctxs, int n);
+int vlfs_multi_solver_setup(vlfs_ctx** ctxs, int n, int mat, const vlfs_solver_opts* opts);
+int vlfs_multi_solver_refactor(vlfs_ctx** ctxs, int n, int mat);
+int vlfs_multi_solve_vec(vlfs_ctx** ctxs, int n, int vec, void** x_hosts, vlfs_solve_stats* stats);
+int vlfs_multi_spmv(vlfs_ctx** ctxs, int n, int mat, const void* const* x_hosts, void** y_hosts);
+int vlfs_multi_spmv_device(vlfs_ctx** ctxs, int n, int mat, int reps, float* ms_total);
 
 /* Substructuring (exact distributed solve).  role[i]: 0 eliminate, 1 keep (interface unknown,
  * never a pivot), 2 ignore.  After vlfs_solver_setup(VLFS_PRECOND_SPARSE_LU) the factorisation is

@@ -77,6 +77,9 @@ EXPORTS = [
     "vlfs_eval_functional", "vlfs_set_roles", "vlfs_schur_size", "vlfs_schur_get", "vlfs_schur_forward",
     "vlfs_schur_backward", "vlfs_dense_factor", "vlfs_chain_factor", "vlfs_dense_solve",
     "vlfs_direct_status", "vlfs_import_csr", "vlfs_set_values", "vlfs_set_vector",
+    "vlfs_dist_unique_id", "vlfs_dist_init", "vlfs_multi_create", "vlfs_dist_set_halo", "vlfs_dist_info",
+    "vlfs_multi_build_pattern", "vlfs_multi_assemble", "vlfs_multi_solver_setup", "vlfs_multi_solver_refactor",
+    "vlfs_multi_solve_vec", "vlfs_multi_spmv", "vlfs_multi_spmv_device", "vlfs_measure_fp64_peak",
 ]
 
 _lib = None
@@ -151,6 +154,20 @@ def load():
     lib.vlfs_dense_factor.argtypes = [vp, C.c_int64, vp]
     lib.vlfs_chain_factor.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), vp]
     lib.vlfs_dense_solve.argtypes = [vp, vp, vp]
+    i64p = C.POINTER(C.c_int64)
+    lib.vlfs_dist_unique_id.argtypes = [vp]
+    lib.vlfs_dist_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.vlfs_multi_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_int)]
+    lib.vlfs_dist_set_halo.argtypes = [vp, C.c_int64, C.c_int, _ip, i64p, _ip, i64p]
+    lib.vlfs_dist_info.argtypes = [vp, _dp]
+    lib.vlfs_multi_build_pattern.argtypes = [C.POINTER(vp), C.c_int, i64p, i64p]
+    lib.vlfs_multi_assemble.argtypes = [C.POINTER(vp), C.c_int]
+    lib.vlfs_multi_solver_setup.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(SolverOpts)]
+    lib.vlfs_multi_solver_refactor.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    lib.vlfs_multi_solve_vec.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(vp), C.POINTER(SolveStats)]
+    lib.vlfs_multi_spmv.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+    lib.vlfs_multi_spmv_device.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    lib.vlfs_measure_fp64_peak.argtypes = [vp, _dp]
     lib.vlfs_direct_status.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.vlfs_import_csr.argtypes = [vp, C.c_int64, C.c_int, C.c_int, _ip, _ip]
     lib.vlfs_set_values.argtypes = [vp, C.c_int, vp]

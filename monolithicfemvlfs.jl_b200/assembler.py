@@ -130,7 +130,24 @@ class B200System:
         self.domains = []
         self._pattern = None
 
+    @classmethod
+    def adopt(cls, ctx, ndofs, is_complex, nmat=1, nvec=1):
+        """A system on a context somebody else created (the ranks of `vlfs_multi_create`)."""
+        self = cls.__new__(cls)
+        self.lib = L.load()
+        self.ctx = ctx
+        self.owns_ctx = False
+        self.ndofs, self.is_complex, self.nmat, self.nvec = int(ndofs), bool(is_complex), nmat, nvec
+        self.dtype = np.complex128 if is_complex else np.float64
+        self._check(self.lib.vlfs_system_init(self.ctx, self.ndofs, int(self.is_complex), nmat, nvec))
+        self.nnz = self.ncoo = None
+        self.domains, self._pattern = [], None
+        return self
+
     def close(self):
+        if not getattr(self, "owns_ctx", True):
+            self.ctx = C.c_void_p()
+            return
         if self.ctx:
             self.lib.vlfs_destroy(self.ctx)
             self.ctx = C.c_void_p()
@@ -369,6 +386,12 @@ class B200System:
         self._check(self.lib.vlfs_assemble_profile(self.ctx, reps, names, 4096, ms, 64, C.byref(n)))
         nm = names.value.decode().split(";")[:n.value]
         return [(nm[k], float(ms[k])) for k in range(n.value)]
+
+    def fp64_peak_tflops(self):
+        """Measured FP64 FMA rate of this device (roofline denominator of the FP64-bound kernels)."""
+        v = C.c_double(0.0)
+        self._check(self.lib.vlfs_measure_fp64_peak(self.ctx, C.byref(v)))
+        return v.value
 
     def launches(self):
         n = C.c_int64(0)

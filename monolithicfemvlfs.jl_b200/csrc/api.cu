@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "solver.cuh"
 #include "symbolic_host.hpp"
+#include "dist.cuh"
+#include <thread>
 #include <cstring>
 #include <cstdlib>
 #include <memory>
@@ -36,12 +38,15 @@ void launch_gather_reference(const uint32_t* run_start, const unsigned long long
 void build_row_incidence(const std::vector<DomainDev>& doms, long long ndofs, DevBuf<int>& incptr,
                          DevBuf<unsigned long long>& inc_src, long long* nrec_out, cudaStream_t s,
                          long long* launches);
-void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, long long nrows,
-                               const GatherDom* doms, const int* dom_late, RowInc* out, unsigned char* late,
-                               cudaStream_t s);
-bool launch_assemble_rows(const int* rowptr, const int* incptr, const RowInc* inc, const int* dest,
+void launch_count_row_entries(const unsigned long long* src, const int* incptr, long long nrows,
+                              const GatherDom* doms, uint32_t* cnt, cudaStream_t s);
+void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, const uint32_t* rowstart,
+                               long long nrows, const GatherDom* doms, const int* dom_late, RowInc* out,
+                               unsigned char* late, const int* dest, int* dest_rows, cudaStream_t s);
+bool launch_assemble_rows(const int* rowptr, const int* incptr, const RowInc* inc, const int* dest_rows,
                           double* const* ctab_all, long long nrows, double* const* mats, int nmat, int is_complex,
                           int maxrow, const unsigned char* late, int phase, int nsm, cudaStream_t s);
+double measure_fp64_fma_tflops(int nsm, int reps, cudaStream_t s);
 void build_csc_device(const int* rowind, const int* colind, long long nnz, long long ndofs,
                       DevBuf<int>& colptr, DevBuf<int>& rowval, DevBuf<int>& csr_slot,
                       cudaStream_t s, long long* launches);
@@ -145,7 +150,8 @@ struct vlfs_ctx {
   DevBuf<double> ctab_all[4];              // per matrix: the class tables of all domains, contiguous
   bool rec32_valid = false;
   // row-centric numeric pass: incidence records of every row (pattern.cu: build_row_incidence)
-  DevBuf<int> incptr, dom_late;
+  DevBuf<int> incptr, dom_late, dest_rows;   // dest_rows: the COO->slot permutation re-laid row by row
+  DevBuf<uint32_t> rowstart;                 // first entry of every row's run in dest_rows
   DevBuf<unsigned long long> inc_src;
   DevBuf<RowInc> inc;
   DevBuf<unsigned char> row_late;
@@ -170,6 +176,8 @@ struct vlfs_ctx {
   DirectPtr dense;                  // dense LU of an interface system (substructuring)
   bool own_stream = true;
   DevBuf<double> dev_partial, dev_h;  // scratch of the vlfs_dev_* reductions
+  DistPtr dist;                       // rank of a multi-GPU system (dist.cu); null: single GPU
+  bool dist_active() const { return dist && dist_has_halo(*dist); }
   size_t scalar() const { return is_complex ? 2 : 1; }
 };
 
@@ -193,6 +201,8 @@ int guarded(vlfs_ctx* ctx, F&& f) {
              ce.file, ce.line);
     cudaGetLastError();
     return fail(ctx, VLFS_ERR_CUDA, buf);
+  } catch (const NcclError& ne) {
+    return fail(ctx, VLFS_ERR_NCCL, ne.msg);
   } catch (const std::string& s) {
     return fail(ctx, VLFS_ERR_STATE, s);
   } catch (const std::bad_alloc&) {
@@ -691,8 +701,20 @@ void rebuild_row_records(vlfs_ctx* ctx) {
   ctx->dom_late.upload(late.data(), late.size(), ctx->stream);
   if (ctx->inc.n != (size_t)ctx->ninc) ctx->inc.alloc((size_t)ctx->ninc);
   if (ctx->row_late.n != (size_t)ctx->ndofs) ctx->row_late.alloc((size_t)ctx->ndofs);
-  launch_fill_row_incidence(ctx->inc_src.p, ctx->incptr.p, ctx->ndofs, ctx->gather_doms.p, ctx->dom_late.p,
-                            ctx->inc.p, ctx->row_late.p, ctx->stream);
+  const bool first = ctx->dest_rows.n != (size_t)ctx->ncoo;
+  if (first) {                                // once per pattern: row-major copy of the slot permutation
+    DevBuf<uint32_t> cnt, total;
+    cnt.alloc((size_t)ctx->ndofs); total.alloc(1);
+    ctx->rowstart.alloc((size_t)ctx->ndofs);
+    launch_count_row_entries(ctx->inc_src.p, ctx->incptr.p, ctx->ndofs, ctx->gather_doms.p, cnt.p, ctx->stream);
+    exclusive_scan_u32(cnt.p, ctx->rowstart.p, (size_t)ctx->ndofs, total.p, ctx->stream);
+    ctx->dest_rows.alloc((size_t)ctx->ncoo);
+    ctx->launches += 3;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  launch_fill_row_incidence(ctx->inc_src.p, ctx->incptr.p, ctx->rowstart.p, ctx->ndofs, ctx->gather_doms.p,
+                            ctx->dom_late.p, ctx->inc.p, ctx->row_late.p, ctx->dest_all.p,
+                            first ? ctx->dest_rows.p : nullptr, ctx->stream);
   ++ctx->launches;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   ctx->rows_two_phase = any_late && any_early;
@@ -786,7 +808,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     {
       double* ca[4] = {ctx->ctab_all[0].p, ctx->ctab_all[1].p, ctx->ctab_all[2].p, ctx->ctab_all[3].p};
       auto rows = [&](int phase) {
-        if (!launch_assemble_rows(ctx->rowptr.p, ctx->incptr.p, ctx->inc.p, ctx->dest_all.p, ca, ctx->ndofs, mp.data(),
+        if (!launch_assemble_rows(ctx->rowptr.p, ctx->incptr.p, ctx->inc.p, ctx->dest_rows.p, ca, ctx->ndofs, mp.data(),
                                   (int)mp.size(), ctx->is_complex, ctx->maxrow, ctx->row_late.p, phase, ctx->nsm, s))
           throw std::string("row-centric pass: a matrix row does not fit the shared memory");
         ++ctx->launches;
@@ -869,6 +891,22 @@ void upload_opt(DevBuf<T>& b, const T* h, size_t n, cudaStream_t s) {
 
 }  // namespace
 
+namespace {
+// one host thread per rank: the collective entry points block on each other through NCCL
+template <typename F>
+int run_ranks(int n, vlfs_ctx** ctxs, F&& f) {
+  if (!ctxs || n < 1) return VLFS_ERR_ARG;
+  std::vector<int> rc(n, VLFS_OK);
+  std::vector<std::thread> th;
+  for (int r = 0; r < n; ++r) th.emplace_back([&, r]() { rc[r] = f(r, ctxs[r]); });
+  for (auto& t : th) t.join();
+  int worst = VLFS_OK;
+  for (int r = 0; r < n; ++r)
+    if (rc[r] != VLFS_OK && (worst == VLFS_OK || worst == VLFS_NOT_CONVERGED || worst == VLFS_PIVOT_PERTURBED)) worst = rc[r];
+  return worst;
+}
+}  // namespace
+
 extern "C" {
 
 int vlfs_version(void) { return 100; }
@@ -909,6 +947,7 @@ int vlfs_destroy(vlfs_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->solver.reset();
+  ctx->dist.reset();
   ctx->direct.reset();
   ctx->dense.reset();
   ctx->doms.clear();
@@ -1264,10 +1303,11 @@ int vlfs_spmv(vlfs_ctx* ctx, int mat, const void* x, void* y) {
     size_t nb = (size_t)ctx->ndofs * ctx->scalar();
     DevBuf<double> dx, dy;
     dx.upload((const double*)x, nb, ctx->stream);
-    dy.alloc(nb);
+    dy.alloc(nb); dy.zero(ctx->stream);
     const double one[2] = {1, 0}, zero[2] = {0, 0};
-    launch_spmv(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, dx.p, dy.p, ctx->ndofs, ctx->nnz,
-                ctx->is_complex, one, zero, ctx->nsm, ctx->stream);
+    if (ctx->dist_active()) dist_hooks(*ctx->dist)->spmv(ctx->mats[mat].p, dx.p, dy.p, one, zero);   // owned rows, halo first
+    else launch_spmv(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, dx.p, dy.p, ctx->ndofs, ctx->nnz,
+                     ctx->is_complex, one, zero, ctx->nsm, ctx->stream);
     ++ctx->launches;
     CUDA_TRY(cudaMemcpyAsync(y, dy.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1291,9 +1331,11 @@ int vlfs_spmv_device(vlfs_ctx* ctx, int mat, int reps, float* ms_total) {
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, ctx->stream));
-    for (int r = 0; r < reps; ++r)
-      launch_spmv(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, dx.p, dy.p, ctx->ndofs, ctx->nnz,
-                  ctx->is_complex, one, zero, ctx->nsm, ctx->stream);
+    for (int r = 0; r < reps; ++r) {
+      if (ctx->dist_active()) dist_hooks(*ctx->dist)->spmv(ctx->mats[mat].p, dx.p, dy.p, one, zero);
+      else launch_spmv(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, dx.p, dy.p, ctx->ndofs, ctx->nnz,
+                       ctx->is_complex, one, zero, ctx->nsm, ctx->stream);
+    }
     CUDA_TRY(cudaEventRecord(e1, ctx->stream));
     CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0;
@@ -1355,6 +1397,15 @@ int vlfs_assemble_profile(vlfs_ctx* ctx, int reps, char* names, int names_cap, f
   });
 }
 
+int vlfs_measure_fp64_peak(vlfs_ctx* ctx, double* tflops) {
+  return guarded(ctx, [&]() {
+    if (!tflops) return fail(ctx, VLFS_ERR_ARG, "null argument");
+    *tflops = measure_fp64_fma_tflops(ctx->nsm, 5, ctx->stream);
+    ctx->launches += 7;
+    return VLFS_OK;
+  });
+}
+
 int vlfs_last_kernel_launches(vlfs_ctx* ctx, int64_t* n) {
   if (!ctx || !n) return VLFS_ERR_ARG;
   *n = ctx->launches;
@@ -1378,6 +1429,8 @@ int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
     if (o2.precond == VLFS_PRECOND_BLOCK_ILU0) o2.precond = VLFS_PRECOND_SPARSE_LU;
     opts = &o2;
     if (opts->precond == VLFS_PRECOND_SPARSE_LU) {
+      const bool chain = ctx->dist_active() && dist_nranks(*ctx->dist) > 1;
+      if (chain && !ctx->direct) dist_roles(*ctx->dist, ctx->roles);     // cuts kept, lower ghosts ignored
       if (!ctx->direct) {
         if (ctx->dof_coords.empty()) {
           // no DOF coordinates (an imported matrix): graph distances stand in for them
@@ -1397,10 +1450,11 @@ int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
                                       ctx->stream, &ctx->launches);
       }
       direct_numeric(*ctx->direct, ctx->rowind.p, ctx->colind.p, ctx->mats[mat].p);
+      if (chain) dist_schur_factor(*ctx->dist, *ctx->direct, ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p);
     }
     ctx->solver = solver_create(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, ctx->nowned, ctx->nnz,
                                 ctx->is_complex, *opts, ctx->nsm, ctx->stream, &ctx->launches,
-                                ctx->direct.get());
+                                ctx->direct.get(), ctx->dist_active() ? dist_hooks(*ctx->dist) : nullptr);
     ctx->solver_mat = mat;
     return opts->precond == VLFS_PRECOND_SPARSE_LU ? pivot_status(ctx) : VLFS_OK;
   });
@@ -1421,6 +1475,8 @@ int vlfs_solver_refactor(vlfs_ctx* ctx, int mat) {
     if (!ctx->solver || !ctx->direct || mat < 0 || mat >= ctx->nmat)
       return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup with VLFS_PRECOND_SPARSE_LU first");
     direct_numeric(*ctx->direct, ctx->rowind.p, ctx->colind.p, ctx->mats[mat].p);
+    if (ctx->dist_active() && dist_nranks(*ctx->dist) > 1)
+      dist_schur_factor(*ctx->dist, *ctx->direct, ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p);
     // the Krylov residual must use the matrix that was just factorised
     solver_set_matrix(*ctx->solver, ctx->mats[mat].p);
     ctx->solver_mat = mat;
@@ -1518,8 +1574,9 @@ int vlfs_dev_spmv(vlfs_ctx* ctx, int mat, const void* x_dev, void* y_dev) {
   return guarded(ctx, [&]() {
     if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !x_dev || !y_dev) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
     const double one[2] = {1, 0}, zero[2] = {0, 0};
-    launch_spmv(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, x_dev, y_dev, ctx->nowned, ctx->nnz,
-                ctx->is_complex, one, zero, ctx->nsm, ctx->stream);
+    if (ctx->dist_active()) dist_hooks(*ctx->dist)->spmv(ctx->mats[mat].p, (double*)const_cast<void*>(x_dev), (double*)y_dev, one, zero);
+    else launch_spmv(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, x_dev, y_dev, ctx->nowned, ctx->nnz,
+                     ctx->is_complex, one, zero, ctx->nsm, ctx->stream);
     ++ctx->launches;
     return VLFS_OK;
   });
@@ -1685,6 +1742,89 @@ int vlfs_chain_factor(vlfs_ctx* ctx, int nblocks, const int64_t* sizes, const vo
     direct_chain_factor(*ctx->dense, (const double*)S_dev);
     return VLFS_OK;
   });
+}
+
+/* ---- multi-GPU: communicator, halo plan, collective calls ------------------------------------ */
+int vlfs_dist_unique_id(void* id128) {
+  if (!id128) return VLFS_ERR_ARG;
+  try { dist_unique_id(id128); } catch (...) { return VLFS_ERR_NCCL; }
+  return VLFS_OK;
+}
+
+int vlfs_dist_init(vlfs_ctx* ctx, int rank, int nranks, const void* id128) {
+  return guarded(ctx, [&]() {
+    if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !id128)) return fail(ctx, VLFS_ERR_ARG, "vlfs_dist_init: bad rank / id");
+    if (ctx->solver || ctx->direct) return fail(ctx, VLFS_ERR_STATE, "vlfs_dist_init before vlfs_solver_setup");
+    ctx->dist = dist_init_rank(rank, nranks, id128, ctx->device);
+    dist_bind(*ctx->dist, ctx->stream, ctx->is_complex, ctx->nsm, &ctx->launches);
+    return VLFS_OK;
+  });
+}
+
+int vlfs_multi_create(vlfs_ctx** ctxs, int ngpu, const int* devices) {
+  if (!ctxs || ngpu < 1 || ngpu > 64 || !devices) return VLFS_ERR_ARG;
+  for (int r = 0; r < ngpu; ++r) ctxs[r] = nullptr;
+  int rc = VLFS_OK;
+  for (int r = 0; r < ngpu && rc == VLFS_OK; ++r) rc = vlfs_create(&ctxs[r], devices[r]);
+  if (rc == VLFS_OK) {
+    try {
+      std::vector<DistPtr> d;
+      dist_init_all(ngpu, devices, d);
+      for (int r = 0; r < ngpu; ++r) ctxs[r]->dist = std::move(d[r]);
+    } catch (const NcclError& e) { ctxs[0]->err = e.msg; rc = VLFS_ERR_NCCL; }
+    catch (...) { rc = VLFS_ERR_NCCL; }
+  }
+  if (rc != VLFS_OK) for (int r = 0; r < ngpu; ++r) if (ctxs[r]) { vlfs_destroy(ctxs[r]); ctxs[r] = nullptr; }
+  return rc;
+}
+
+int vlfs_dist_set_halo(vlfs_ctx* ctx, int64_t n_owned, int npeers, const int32_t* peers, const int64_t* send_ptr,
+                       const int32_t* send_idx, const int64_t* recv_ptr) {
+  return guarded(ctx, [&]() {
+    if (!ctx->dist) return fail(ctx, VLFS_ERR_STATE, "vlfs_dist_init / vlfs_multi_create first");
+    if (!ctx->pattern_built) return fail(ctx, VLFS_ERR_STATE, "vlfs_build_pattern first");
+    if (n_owned < 1 || n_owned > ctx->ndofs || npeers < 0 || (npeers && (!peers || !send_ptr || !recv_ptr)))
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_dist_set_halo: bad arguments");
+    ctx->nowned = n_owned;
+    ctx->solver.reset(); ctx->direct.reset(); ctx->roles.clear();
+    dist_bind(*ctx->dist, ctx->stream, ctx->is_complex, ctx->nsm, &ctx->launches);
+    std::vector<long long> sp(npeers + 1, 0), rp(npeers + 1, 0);
+    for (int p = 0; p <= npeers && npeers > 0; ++p) { sp[p] = send_ptr[p]; rp[p] = recv_ptr[p]; }
+    dist_set_halo(*ctx->dist, n_owned, ctx->ndofs, npeers, peers, sp.data(), send_idx, rp.data(),
+                  ctx->rowptr.p, ctx->colind.p, ctx->nnz);
+    return VLFS_OK;
+  });
+}
+
+int vlfs_dist_info(vlfs_ctx* ctx, double* out4) {
+  if (!ctx || !ctx->dist || !out4) return VLFS_ERR_ARG;
+  dist_schur_info(*ctx->dist, out4);
+  return VLFS_OK;
+}
+
+
+int vlfs_multi_build_pattern(vlfs_ctx** ctxs, int n, int64_t* nnz, int64_t* ncoo) {
+  return run_ranks(n, ctxs, [&](int r, vlfs_ctx* c) { return vlfs_build_pattern(c, nnz ? nnz + r : nullptr, ncoo ? ncoo + r : nullptr); });
+}
+int vlfs_multi_assemble(vlfs_ctx** ctxs, int n) {
+  return run_ranks(n, ctxs, [&](int, vlfs_ctx* c) { return vlfs_assemble(c); });
+}
+int vlfs_multi_solver_setup(vlfs_ctx** ctxs, int n, int mat, const vlfs_solver_opts* opts) {
+  return run_ranks(n, ctxs, [&](int, vlfs_ctx* c) { return vlfs_solver_setup(c, mat, opts); });
+}
+int vlfs_multi_solver_refactor(vlfs_ctx** ctxs, int n, int mat) {
+  return run_ranks(n, ctxs, [&](int, vlfs_ctx* c) { return vlfs_solver_refactor(c, mat); });
+}
+int vlfs_multi_solve_vec(vlfs_ctx** ctxs, int n, int vec, void** x_hosts, vlfs_solve_stats* stats) {
+  if (!x_hosts) return VLFS_ERR_ARG;
+  return run_ranks(n, ctxs, [&](int r, vlfs_ctx* c) { return vlfs_solve_vec(c, vec, x_hosts[r], stats ? stats + r : nullptr); });
+}
+int vlfs_multi_spmv(vlfs_ctx** ctxs, int n, int mat, const void* const* x_hosts, void** y_hosts) {
+  if (!x_hosts || !y_hosts) return VLFS_ERR_ARG;
+  return run_ranks(n, ctxs, [&](int r, vlfs_ctx* c) { return vlfs_spmv(c, mat, x_hosts[r], y_hosts[r]); });
+}
+int vlfs_multi_spmv_device(vlfs_ctx** ctxs, int n, int mat, int reps, float* ms_total) {
+  return run_ranks(n, ctxs, [&](int r, vlfs_ctx* c) { return vlfs_spmv_device(c, mat, reps, ms_total ? ms_total + r : nullptr); });
 }
 
 int vlfs_dense_solve(vlfs_ctx* ctx, const void* b_dev, void* x_dev) {

@@ -17,6 +17,7 @@
 #define VLFS_DEST_PAD (-1)
 
 struct CudaError { cudaError_t e; const char* file; int line; };
+struct NcclError { std::string msg; };
 
 #define CUDA_TRY(x)                                              \
   do {                                                           \
@@ -174,10 +175,12 @@ struct GatherDom {
 };
 
 // ---- row-centric numeric pass (integrate.cu: assemble_rows) --------------------------------------
-// One record per (cell, touched block, local test row) contributing to a CSR row: the nc COO
-// entries coo..coo+nc-1 (their CSR slots are dest[coo+j]) take the class-table values tab..tab+nc-1.
-// tab = 0xffffffff: the block has no class table (its terms are added by the cell-centric kernel).
-struct RowInc { uint32_t coo, tab, nc; };
+// One record per (cell, touched block, local test row) contributing to a CSR row: nc entries whose
+// CSR slots are dest_rows[start .. start+nc) - the COO->slot permutation re-laid row by row, so
+// that a row's slots are ONE contiguous run - and whose values are the class-table entries
+// tab .. tab+nc-1.  tab = 0xffffffff: the block has no class table (its terms are added by the
+// cell-centric kernel).
+struct RowInc { uint32_t start, tab, nc; };
 
 // ---- primitives -------------------------------------------------------------------
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev,

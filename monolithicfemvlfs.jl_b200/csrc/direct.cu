@@ -953,6 +953,51 @@ DirectPtr direct_dense(long long n, int is_complex, int nsm, cudaStream_t s, lon
   return D;
 }
 
+// ---- one partial front: np pivots, nf - np kept unknowns (a rank's link of the distributed interface
+// chain: own cut = pivots, next cut = update set).  Same kernels; np = 0 is legal (nothing to do).
+DirectPtr direct_front(long long np, long long nf, int is_complex, int nsm, cudaStream_t s, long long* launches) {
+  DirectPtr D(new DirectSolver());
+  D->n = np; D->n_total = nf; D->n_keep = nf - np; D->nnz = 0; D->cplx = is_complex; D->nsm = nsm; D->s = s;
+  D->launches = launches; D->dense = true;
+  D->nfronts = 1; D->nlevels = 1; D->maxnf = (int)nf;
+  FrontMeta M{};
+  M.off = 0; M.woff = 0; M.first = 0; M.np = (int)np; M.nf = (int)nf; M.upd_ptr = 0; M.child[0] = M.child[1] = -1;
+  M.cmap_ptr = 0; M.parent = -1;
+  D->meta.assign(1, M);
+  D->level_lists.assign(1, std::vector<int>{0});
+  D->level_maxnp.assign(1, (int)np); D->level_maxnf.assign(1, (int)nf); D->level_maxnu_child.assign(1, 0);
+  D->list_off.assign(1, 0);
+  D->roots.assign(1, 0);
+  D->pool_elems = nf * nf; D->w_elems = nf;
+  const double p = (double)np, u = (double)(nf - np);
+  D->fill = (long long)(p * p + 2 * p * u); D->flops = (2.0 / 3.0) * p * p * p + 2 * p * p * u + 2 * p * u * u;
+  std::vector<int> pos(nf), upd, zero1(1, 0);
+  std::iota(pos.begin(), pos.end(), 0);
+  for (long long k = np; k < nf; ++k) upd.push_back((int)k);
+  if (upd.empty()) upd.push_back(0);
+  D->d_meta.upload(D->meta.data(), 1, s);
+  D->d_pos.upload(pos.data(), nf, s);
+  D->d_front_of_pos.alloc(1);
+  D->d_upd.upload(upd.data(), upd.size(), s);
+  D->d_cmap.alloc(1);
+  D->d_lists.upload(zero1.data(), 1, s);
+  const size_t sc = is_complex ? 2 : 1;
+  D->pool.alloc((size_t)nf * nf * sc);
+  D->w.alloc((size_t)nf * sc); D->bp.alloc((size_t)nf * sc); D->xp.alloc((size_t)nf * sc);
+  D->xp.zero(s);
+  D->alloc_pivot_state();
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return D;
+}
+double* direct_pool(DirectSolver& D) { return D.pool.p; }
+// factorises the np pivots of the front whose nf x nf entries the caller wrote into direct_pool();
+// asynchronous (no host synchronisation: the chain of ranks is ordered by the stream and NCCL)
+void direct_front_factor_async(DirectSolver& D) {
+  if (D.n == 0) return;
+  if (D.cplx) factor_levels<true>(D); else factor_levels<false>(D);
+}
+void direct_front_read_status(DirectSolver& D) { read_pivot_info(D); }
+
 // ---- block-tridiagonal interface system (slab cuts in rank order): a chain of fronts, front r has
 // the unknowns of cut r as pivots and those of cut r+1 as update set - the same kernels, O(sum n_r^3)
 DirectPtr direct_chain(int nblocks, const long long* sizes, int is_complex, int nsm, cudaStream_t s,

@@ -25,6 +25,11 @@ long long direct_nkeep(const DirectSolver& D);
 // dense n x n LU with the same front kernels (interface system)
 DirectPtr direct_dense(long long n, int is_complex, int nsm, cudaStream_t s, long long* launches);
 void direct_dense_factor(DirectSolver& D, const double* S_dev);
+// one partial front (np pivots, nf - np kept): link of the distributed interface chain (dist.cu)
+DirectPtr direct_front(long long np, long long nf, int is_complex, int nsm, cudaStream_t s, long long* launches);
+double* direct_pool(DirectSolver& D);                 // nf x nf row-major entries of that front
+void direct_front_factor_async(DirectSolver& D);      // no host synchronisation
+void direct_front_read_status(DirectSolver& D);       // pivot statistics (synchronises)
 // block-tridiagonal n x n system (blocks of the given sizes, dense row-major S): chain of fronts
 DirectPtr direct_chain(int nblocks, const long long* sizes, int is_complex, int nsm, cudaStream_t s,
                        long long* launches);

@@ -958,12 +958,16 @@ gather_compact(const uint32_t* __restrict__ run_start, const uint32_t* __restric
 // packed (domain, block, local row, cell) sources -> RowInc records; once per pattern and again when
 // the element-block classes change.  late[row] = 1 when a contributing domain's class tables come
 // out of the quadrature kernel (they are ready later than the directly tabulated ones).
+// dest_rows (optional, once per pattern): the records' dest entries copied into row-major order.
 __global__ void fill_row_incidence(const unsigned long long* __restrict__ src, const int* __restrict__ incptr,
-                                   long long nrows, const GatherDom* __restrict__ doms, const int* __restrict__ dom_late,
-                                   RowInc* __restrict__ out, unsigned char* __restrict__ late) {
+                                   const uint32_t* __restrict__ rowstart, long long nrows,
+                                   const GatherDom* __restrict__ doms, const int* __restrict__ dom_late,
+                                   RowInc* __restrict__ out, unsigned char* __restrict__ late,
+                                   const int* __restrict__ dest, int* __restrict__ dest_rows) {
   for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < nrows;
        row += (long long)gridDim.x * blockDim.x) {
     unsigned char l = 0;
+    uint32_t pos = rowstart[row];
     for (int k = incptr[row]; k < incptr[row + 1]; ++k) {
       const unsigned long long r = src[k];
       const unsigned d = (unsigned)(r >> 60), b = (unsigned)((r >> 58) & 3u), a = (unsigned)((r >> 32) & 0x3fffu);
@@ -971,120 +975,183 @@ __global__ void fill_row_incidence(const unsigned long long* __restrict__ src, c
       const GatherDom& G = doms[d];
       const int nc = G.blk[b].nc;
       RowInc R;
-      R.coo = (uint32_t)(G.coo_lo + (long long)e * G.epc + G.blk[b].off + (long long)a * nc);
+      R.start = pos;
       R.nc = (uint32_t)nc;
       R.tab = (G.ncls > 0 && G.ctab_off[b] >= 0)
                   ? (uint32_t)(G.ctab_base + G.ctab_off[b] + (long long)G.cls[e] * (G.blk[b].nr * nc) + (long long)a * nc)
                   : 0xffffffffu;
       out[k] = R;
+      if (dest_rows) {
+        const long long coo = G.coo_lo + (long long)e * G.epc + G.blk[b].off + (long long)a * nc;
+        for (int j = 0; j < nc; ++j) dest_rows[pos + j] = dest[coo + j];
+      }
+      pos += nc;
       l |= (unsigned char)dom_late[d];
     }
     late[row] = l;
   }
 }
 
+// contributions (COO entries) per row -> cnt[row]  (scanned into rowstart by the caller)
+__global__ void count_row_entries(const unsigned long long* __restrict__ src, const int* __restrict__ incptr,
+                                  long long nrows, const GatherDom* __restrict__ doms, uint32_t* __restrict__ cnt) {
+  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < nrows;
+       row += (long long)gridDim.x * blockDim.x) {
+    uint32_t c = 0;
+    for (int k = incptr[row]; k < incptr[row + 1]; ++k) {
+      const unsigned long long r = src[k];
+      c += (uint32_t)doms[(unsigned)(r >> 60)].blk[(unsigned)((r >> 58) & 3u)].nc;
+    }
+    cnt[row] = c;
+  }
+}
+
 // Row-centric numeric pass (every domain class-tabulated): one warp per CSR row.  The row's value
-// segment lives in shared memory; for every incidence record the lanes read the nc consecutive
-// `dest` entries and the nc consecutive class-table values of that element-matrix row (both
-// coalesced), add into the segment - records in COO order, one record at a time, so the sum order is
-// the one of Julia's sparse(I,J,V) and bitwise repeatable - and the finished segment is written to
-// the CSR values with one coalesced pass: every value is written exactly once (this is also the
-// zero fill), every `dest` entry is read exactly once, nothing else streams from HBM.
-// phase: 0 all rows, 1 rows whose tables are ready early (late[row] == 0), 2 the others.
+// segment lives in shared memory.  The row's contributions are ONE contiguous run of dest_rows
+// (slots) described by its incidence records (class-table position of every element-matrix row):
+// the lanes stream the run with coalesced loads (4 windows of 32 entries in flight), look up the
+// record of their entry with shuffles, read the class-table value (contiguous inside a record, L2
+// resident) and add into the segment - record by record, i.e. in COO order, the order in which
+// Julia's sparse(I,J,V) adds duplicates, so the result is bitwise repeatable without atomics.  The
+// finished segment is written to the CSR values in one coalesced pass: every value is written exactly
+// once (this is also the zero fill), every dest entry is read exactly once, nothing else streams
+// from HBM.  phase: 0 all rows, 1 rows whose tables are ready early (late[row] == 0), 2 the others.
 template <int NMAT, bool CPLX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NMAT == 1 ? 4 : (NMAT == 2 ? 3 : 2))
 assemble_rows(const int* __restrict__ rowptr, const int* __restrict__ incptr, const RowInc* __restrict__ inc,
-              const int* __restrict__ dest, AsmPtrs ctab_all, long long nrows, AsmPtrs ptrs, int maxrow,
+              const int* __restrict__ dest_rows, AsmPtrs ctab_all, long long nrows, AsmPtrs ptrs, int maxrow,
               const unsigned char* __restrict__ late, int phase) {
   using T = typename std::conditional<CPLX, double2, double>::type;
+  constexpr int W = 4;                 // windows of 32 entries in flight
   extern __shared__ __align__(16) double seg_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   T* seg = reinterpret_cast<T*>(seg_raw) + (size_t)wib * NMAT * maxrow;
   const long long nwarps = (long long)gridDim.x * wpb;
-  for (long long row = (long long)blockIdx.x * wpb + wib; row < nrows; row += nwarps) {
-    if (phase != 0 && (late[row] != 0) != (phase == 2)) continue;
-    const int r0 = __ldg(rowptr + row), L = __ldg(rowptr + row + 1) - r0;
+  auto next_row = [&](long long r) {    // next row of this warp that belongs to the phase
+    while (r < nrows && phase != 0 && (__ldg(late + r) != 0) != (phase == 2)) r += nwarps;
+    return r;
+  };
+  const RowInc none{0u, 0xffffffffu, 0u};
+  long long row = next_row((long long)blockIdx.x * wpb + wib);
+  int r0 = 0, r1 = 0, k0 = 0, k1 = 0;
+  RowInc mine = none;
+  if (row < nrows) {
+    r0 = __ldg(rowptr + row); r1 = __ldg(rowptr + row + 1);
+    k0 = __ldg(incptr + row); k1 = __ldg(incptr + row + 1);
+    if (k0 + lane < k1) mine = inc[k0 + lane];
+  }
+  while (row < nrows) {
+    // the next row's pointers and first records travel while this row is summed
+    const long long nrow = next_row(row + nwarps);
+    int nr0 = 0, nr1 = 0, nk0 = 0, nk1 = 0;
+    if (nrow < nrows) {
+      nr0 = __ldg(rowptr + nrow); nr1 = __ldg(rowptr + nrow + 1);
+      nk0 = __ldg(incptr + nrow); nk1 = __ldg(incptr + nrow + 1);
+    }
+    RowInc nmine = none;
+    bool nfetched = false;
+    const int L = r1 - r0;
     for (int sidx = lane; sidx < L; sidx += 32) {
 #pragma unroll
       for (int m = 0; m < NMAT; ++m) seg[m * maxrow + sidx] = T{};
     }
     __syncwarp();
-    const int k0 = __ldg(incptr + row), k1 = __ldg(incptr + row + 1);
     for (int kb = k0; kb < k1; kb += 32) {
-      RowInc mine{0u, 0xffffffffu, 0u};
-      if (kb + lane < k1) mine = inc[kb + lane];
+      if (kb > k0) { mine = none; if (kb + lane < k1) mine = inc[kb + lane]; }
       const int cnt = min(32, k1 - kb);
-      // software pipeline: the loads of record g+1 are in flight while record g is added
-      int dn = -1;
-      T vn[NMAT];
-      auto fetch = [&](int g) {
-        const uint32_t coo = __shfl_sync(0xffffffffu, mine.coo, g);
-        const uint32_t tab = __shfl_sync(0xffffffffu, mine.tab, g);
-        const int nc = (int)__shfl_sync(0xffffffffu, mine.nc, g);
-        dn = -1;
-        if (lane < nc && tab != 0xffffffffu) {
-          dn = __ldg(dest + coo + lane) - r0;
+      const uint32_t e0 = __shfl_sync(0xffffffffu, mine.start, 0);
+      const uint32_t rs = mine.start - e0;                          // my record's first entry, relative
+      const uint32_t re = lane < cnt ? rs + mine.nc : 0xffffffffu;   // ... and one past its last
+      const int total = (int)__shfl_sync(0xffffffffu, re, cnt - 1);
+      for (int w0 = 0; w0 < total; w0 += 32 * W) {
+        int slot[W], g[W], gb[W], npass[W];
+        uint32_t tix[W];
+        T v[W][NMAT];
 #pragma unroll
-          for (int m = 0; m < NMAT; ++m) vn[m] = __ldg(reinterpret_cast<const T*>(ctab_all.mat[m]) + tab + lane);
+        for (int t = 0; t < W; ++t) {                    // W coalesced loads of the slot stream
+          const int q = w0 + 32 * t + lane;
+          slot[t] = q < total ? __ldg(dest_rows + e0 + q) - r0 : -1;
         }
-        return nc;
-      };
-      int nc = fetch(0);
-      for (int g = 0; g < cnt; ++g) {
-        const int d = dn;
-        T v[NMAT];
+        if (!nfetched) {                                 // first records of the next row
+          nfetched = true;
+          if (nrow < nrows && nk0 + lane < nk1) nmine = inc[nk0 + lane];
+        }
 #pragma unroll
-        for (int m = 0; m < NMAT; ++m) v[m] = vn[m];
-        const int nc_cur = nc;
-        const uint32_t coo_cur = __shfl_sync(0xffffffffu, mine.coo, g);
-        const uint32_t tab_cur = __shfl_sync(0xffffffffu, mine.tab, g);
-        if (g + 1 < cnt) nc = fetch(g + 1);
-        if (d >= 0) {
-#pragma unroll
-          for (int m = 0; m < NMAT; ++m) {
-            T* p = seg + m * maxrow + d;
-            if constexpr (CPLX) { T o = *p; o.x += v[m].x; o.y += v[m].y; *p = o; }
-            else *p += v[m];
+        for (int t = 0; t < W; ++t) {                    // record of every entry (shuffles only)
+          const int qf = w0 + 32 * t;
+          gb[t] = 0; npass[t] = 0; g[t] = 0; tix[t] = 0xffffffffu;
+          if (qf >= total) continue;                     // (uniform)
+          const int ql = min(qf + 31, total - 1), q = qf + lane;
+          gb[t] = __ffs(__ballot_sync(0xffffffffu, re > (uint32_t)qf)) - 1;       // first record reaching the window
+          const int gl = __ffs(__ballot_sync(0xffffffffu, re > (uint32_t)ql)) - 1; // record of its last entry
+          npass[t] = gl - gb[t] + 1;
+          int gg = gb[t];
+          for (int p = 0; p + 1 < npass[t]; ++p) {
+            const uint32_t e = __shfl_sync(0xffffffffu, re, min(gg, 31));
+            if (e <= (uint32_t)q) ++gg;
           }
+          gg = min(gg, cnt - 1);
+          g[t] = gg;
+          const uint32_t s_ = __shfl_sync(0xffffffffu, rs, gg);
+          const uint32_t tb = __shfl_sync(0xffffffffu, mine.tab, gg);
+          if (q < total && tb != 0xffffffffu) tix[t] = tb + ((uint32_t)q - s_);
         }
-        // element rows wider than a warp (P4 tetrahedra: 35 columns): the rest, unpipelined
-        if (nc_cur > 32 && tab_cur != 0xffffffffu)
-          for (int j = 32 + lane; j < nc_cur; j += 32) {
-            const int d2 = __ldg(dest + coo_cur + j) - r0;
 #pragma unroll
-            for (int m = 0; m < NMAT; ++m) {
-              const T v2 = __ldg(reinterpret_cast<const T*>(ctab_all.mat[m]) + tab_cur + j);
-              T* p = seg + m * maxrow + d2;
-              if constexpr (CPLX) { T o = *p; o.x += v2.x; o.y += v2.y; *p = o; }
-              else *p += v2;
+        for (int t = 0; t < W; ++t)                      // class-table values (L2 resident)
+          if (tix[t] != 0xffffffffu) {
+#pragma unroll
+            for (int m = 0; m < NMAT; ++m) v[t][m] = __ldg(reinterpret_cast<const T*>(ctab_all.mat[m]) + tix[t]);
+          }
+#pragma unroll
+        for (int t = 0; t < W; ++t)                      // adds, one record at a time (COO order)
+          for (int p = 0; p < npass[t]; ++p) {
+            if (g[t] == gb[t] + p && tix[t] != 0xffffffffu) {
+#pragma unroll
+              for (int m = 0; m < NMAT; ++m) {
+                T* ptr = seg + m * maxrow + slot[t];
+                if constexpr (CPLX) { T o = *ptr; o.x += v[t][m].x; o.y += v[t][m].y; *ptr = o; }
+                else *ptr += v[t][m];
+              }
             }
+            __syncwarp();        // the next record may hit the same slots from other lanes
           }
-        __syncwarp();            // the next record may hit the same slots from other lanes
       }
     }
+    if (!nfetched && nrow < nrows && nk0 + lane < nk1) nmine = inc[nk0 + lane];
+    __syncwarp();
     for (int sidx = lane; sidx < L; sidx += 32) {
 #pragma unroll
       for (int m = 0; m < NMAT; ++m) reinterpret_cast<T*>(ptrs.mat[m])[r0 + sidx] = seg[m * maxrow + sidx];
     }
     __syncwarp();
+    row = nrow; r0 = nr0; r1 = nr1; k0 = nk0; k1 = nk1; mine = nmine;
   }
 }
 
 }  // namespace
 
-void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, long long nrows,
-                               const GatherDom* doms, const int* dom_late, RowInc* out, unsigned char* late,
-                               cudaStream_t s) {
+void launch_count_row_entries(const unsigned long long* src, const int* incptr, long long nrows,
+                              const GatherDom* doms, uint32_t* cnt, cudaStream_t s) {
   if (nrows == 0) return;
   long long grid = (nrows + 255) / 256;
   if (grid > 148 * 32) grid = 148 * 32;
-  fill_row_incidence<<<(unsigned)grid, 256, 0, s>>>(src, incptr, nrows, doms, dom_late, out, late);
+  count_row_entries<<<(unsigned)grid, 256, 0, s>>>(src, incptr, nrows, doms, cnt);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, const uint32_t* rowstart,
+                               long long nrows, const GatherDom* doms, const int* dom_late, RowInc* out,
+                               unsigned char* late, const int* dest, int* dest_rows, cudaStream_t s) {
+  if (nrows == 0) return;
+  long long grid = (nrows + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  fill_row_incidence<<<(unsigned)grid, 256, 0, s>>>(src, incptr, rowstart, nrows, doms, dom_late, out, late, dest, dest_rows);
   CUDA_TRY(cudaGetLastError());
 }
 
 // returns false when a row segment does not fit the shared memory of a CTA (the caller then uses
 // the slot-centric gather)
-bool launch_assemble_rows(const int* rowptr, const int* incptr, const RowInc* inc, const int* dest,
+bool launch_assemble_rows(const int* rowptr, const int* incptr, const RowInc* inc, const int* dest_rows,
                           double* const* ctab_all, long long nrows, double* const* mats, int nmat, int is_complex,
                           int maxrow, const unsigned char* late, int phase, int nsm, cudaStream_t s) {
   if (nrows == 0) return true;
@@ -1096,14 +1163,16 @@ bool launch_assemble_rows(const int* rowptr, const int* incptr, const RowInc* in
   const size_t smem = per_warp * wpb;
   if (smem > 200 * 1024) return false;
   static const int cta_per_sm = getenv("VLFS_ROWS_CTAS") ? atoi(getenv("VLFS_ROWS_CTAS")) : 0;
-  int per_sm = cta_per_sm > 0 ? cta_per_sm : (int)std::min<size_t>(2048 / (32 * wpb), (220 * 1024) / (smem + 1024));
-  if (per_sm < 1) per_sm = 1;
-  long long grid = (long long)nsm * per_sm;
   const long long need = (nrows + wpb - 1) / wpb;
-  if (grid > need) grid = need;
   auto go = [&](auto kern) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, 32 * wpb, smem, s>>>(rowptr, incptr, inc, dest, CT, nrows, P, maxrow, late, phase);
+    int per_sm = 0;                      // resident CTAs per SM (registers and shared memory): a persistent grid
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * wpb, smem));
+    if (cta_per_sm > 0) per_sm = cta_per_sm;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)nsm * per_sm;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, 32 * wpb, smem, s>>>(rowptr, incptr, inc, dest_rows, CT, nrows, P, maxrow, late, phase);
   };
   switch (nmat * 2 + (is_complex ? 1 : 0)) {
     case 2: go(assemble_rows<1, false>); break;

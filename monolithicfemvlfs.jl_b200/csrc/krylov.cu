@@ -315,11 +315,14 @@ struct SolverState {
   DevBuf<double> dinv, V, Z, w, z, r, partial, hdev, tmp1, tmp2, tmp3, tmp4;
   double setup_ms = 0;
   DirectSolver* direct = nullptr;
+  DistHooks* dist = nullptr;    // row-partitioned system: n = owned rows, vectors have nalloc = owned + ghost entries
+  long long nalloc = 0;
 
-  double* vec(DevBuf<double>& b) { if (b.n == 0) b.alloc((size_t)n * sc); return b.p; }
+  double* vec(DevBuf<double>& b) { if (b.n == 0) { b.alloc((size_t)nalloc * sc); b.zero(s); } return b.p; }
 
   void spmv(const double* x, double* y, double are = 1.0, double bre = 0.0) {
     const double a[2] = {are, 0}, b[2] = {bre, 0};
+    if (dist) { dist->spmv(vals, const_cast<double*>(x), y, a, b); *launches += 4; return; }
     launch_spmv(rowptr, colind, vals, x, y, n, nnz, cplx, a, b, nsm, s);
     ++*launches;
   }
@@ -331,17 +334,19 @@ struct SolverState {
   void copy(const double* x, double* y) {
     CUDA_TRY(cudaMemcpyAsync(y, x, (size_t)n * sc * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
-  // out[k] = <V_k, w>, k < nv   (V rows contiguous with leading dimension n scalars)
+  // out[k] = <V_k, w>, k < nv   (V rows contiguous with leading dimension nalloc scalars); on a
+  // row-partitioned system the partial results of the ranks are summed by ONE all-reduce
   void multidot(const double* Vp, int nv, const double* wp, cd* out) {
     dim3 grid(nred, nv);
     if (cplx) {
-      multidot_partial<true><<<grid, RED_THREADS, 0, s>>>((const double2*)Vp, (size_t)n, (const double2*)wp, n, (double2*)partial.p);
+      multidot_partial<true><<<grid, RED_THREADS, 0, s>>>((const double2*)Vp, (size_t)nalloc, (const double2*)wp, n, (double2*)partial.p);
       multidot_finish<true><<<nv, RED_THREADS, 0, s>>>((const double2*)partial.p, nred, (double2*)hdev.p);
     } else {
-      multidot_partial<false><<<grid, RED_THREADS, 0, s>>>(Vp, (size_t)n, wp, n, partial.p);
+      multidot_partial<false><<<grid, RED_THREADS, 0, s>>>(Vp, (size_t)nalloc, wp, n, partial.p);
       multidot_finish<false><<<nv, RED_THREADS, 0, s>>>(partial.p, nred, hdev.p);
     }
     *launches += 2;
+    if (dist) dist->allreduce_sum(hdev.p, (int)(nv * sc));
     std::vector<double> h((size_t)nv * sc);
     CUDA_TRY(cudaMemcpyAsync(h.data(), hdev.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
@@ -354,13 +359,14 @@ struct SolverState {
     for (int k = 0; k < nv; ++k) { if (cplx) { hh[2 * k] = h[k].real(); hh[2 * k + 1] = h[k].imag(); } else hh[k] = h[k].real(); }
     CUDA_TRY(cudaMemcpyAsync(hdev.p, hh.data(), hh.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     size_t smem = (size_t)nv * sc * sizeof(double);
-    if (cplx) gemv_sub<true><<<vgrid(n, nsm), 256, smem, s>>>((const double2*)Vp, (size_t)n, (const double2*)hdev.p, nv, (double2*)wp, n);
-    else gemv_sub<false><<<vgrid(n, nsm), 256, smem, s>>>(Vp, (size_t)n, hdev.p, nv, wp, n);
+    if (cplx) gemv_sub<true><<<vgrid(n, nsm), 256, smem, s>>>((const double2*)Vp, (size_t)nalloc, (const double2*)hdev.p, nv, (double2*)wp, n);
+    else gemv_sub<false><<<vgrid(n, nsm), 256, smem, s>>>(Vp, (size_t)nalloc, hdev.p, nv, wp, n);
     ++*launches;
     CUDA_TRY(cudaStreamSynchronize(s));   // hh dies at scope exit
   }
   void precond(const double* rin, double* zout) {
     if (opts.precond == VLFS_PRECOND_NONE) { copy(rin, zout); return; }
+    if (opts.precond == VLFS_PRECOND_SPARSE_LU && dist && dist->has_exact_apply()) { dist->apply(rin, zout); return; }
     if (opts.precond == VLFS_PRECOND_SPARSE_LU) { direct_solve(*direct, rin, zout); return; }
     if (cplx) pointwise_mul<true><<<vgrid(n, nsm), 256, 0, s>>>((const double2*)dinv.p, (const double2*)rin, (double2*)zout, n);
     else pointwise_mul<false><<<vgrid(n, nsm), 256, 0, s>>>(dinv.p, rin, zout, n);
@@ -371,8 +377,10 @@ struct SolverState {
 SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals,
                                            long long n, long long nnz, int is_complex,
                                            const vlfs_solver_opts& opts, int nsm, cudaStream_t s,
-                                           long long* launches, DirectSolver* direct) {
+                                           long long* launches, DirectSolver* direct, DistHooks* dist) {
   SolverPtr S(new SolverState());
+  S->dist = dist;
+  S->nalloc = dist ? dist->n_local : n;
   S->rowptr = rowptr; S->colind = colind; S->vals = vals; S->n = n; S->nnz = nnz;
   S->cplx = is_complex; S->opts = opts; S->nsm = nsm; S->s = s; S->launches = launches;
   S->direct = direct;
@@ -393,7 +401,7 @@ SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals
     else extract_inv_diag<false><<<vgrid(n, nsm), 256, 0, s>>>(rowptr, colind, vals, S->dinv.p, n);
     ++*launches;
   }
-  if (S->opts.method == VLFS_SOLVER_GMRES) S->V.alloc((size_t)(m + 1) * n * S->sc);
+  if (S->opts.method == VLFS_SOLVER_GMRES) { S->V.alloc((size_t)(m + 1) * S->nalloc * S->sc); S->V.zero(s); }
   CUDA_TRY(cudaEventRecord(e1, s));
   CUDA_TRY(cudaEventSynchronize(e1));
   float ms = 0;
@@ -412,9 +420,14 @@ void solver_set_matrix(SolverState& S, const double* vals) { S.vals = vals; }
 namespace {
 
 int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
+  // Right-preconditioned restarted GMRES with ONE batched reduction per iteration: w = A M^-1 v_j is
+  // written into the next basis slot, <v_0..v_j, w> and <w, w> come out of one multidot (and, on a
+  // row-partitioned system, one all-reduce); the norm of the orthogonalised vector follows from
+  // Pythagoras.  When that difference cancels (less than 5 % of |w|^2 left) a second classical
+  // Gram-Schmidt pass is made (CGS2).
   const int m = S.opts.restart;
   const long long n = S.n;
-  const size_t ld = (size_t)n * S.sc;
+  const size_t ld = (size_t)S.nalloc * S.sc;
   double* w = S.vec(S.w);
   double* z = S.vec(S.z);
   double* r = S.vec(S.r);
@@ -424,14 +437,15 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
     st->iterations = 0; st->converged = 1; st->rel_residual = 0;
     return VLFS_OK;
   }
-  std::vector<cd> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), h(m + 2), h2(m + 2), y(m);
+  if (!std::isfinite(bnorm)) { st->iterations = 0; st->converged = 0; st->rel_residual = bnorm; return VLFS_NOT_CONVERGED; }
+  std::vector<cd> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), h(m + 3), h2(m + 3), y(m);
   int it = 0;
   double rel = 1.0;
-  // With the sparse LU as preconditioner every iteration is a refinement step that gains
-  // many digits; when it stops doing so the attainable accuracy eps*|A||x|/|b| is reached
-  // and further iterations are wasted.
+  // With an exact preconditioner (sparse LU, substructuring) every iteration is a refinement step
+  // that gains many digits; the loop ends when the tolerance is met or a step no longer gains a
+  // factor 4 (the attainable accuracy eps*|A||x|/|b| is reached).
   const bool direct = S.opts.precond == VLFS_PRECOND_SPARSE_LU;
-  if (direct && S.Z.n != (size_t)m * ld) S.Z.alloc((size_t)m * ld);
+  if (direct && S.Z.n != (size_t)m * ld) { S.Z.alloc((size_t)m * ld); S.Z.zero(S.s); }
   bool stagnated = false;
   double prev_cycle_rel = 1e300;
   while (true) {
@@ -440,7 +454,7 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
     S.spmv(x, r, -1.0, 1.0);
     double beta = S.nrm2(r);
     rel = beta / bnorm;
-    if (rel <= S.opts.rtol || it >= S.opts.maxit || stagnated) break;
+    if (!(rel > S.opts.rtol) || it >= S.opts.maxit || stagnated) break;     // (NaN ends the loop too)
     if (direct && rel > 0.25 * prev_cycle_rel) break;
     prev_cycle_rel = rel;
     S.axpby_(cd(1.0 / beta, 0), r, cd(0, 0), S.V.p);      // V_0
@@ -450,17 +464,26 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
     for (; j < m && it < S.opts.maxit; ++j, ++it) {
       double* vj = S.V.p + (size_t)j * ld;
       double* zj = direct ? S.Z.p + (size_t)j * ld : z;     // flexible variant: keep M^-1 v_j
+      double* wj = S.V.p + (size_t)(j + 1) * ld;            // w lives in the next basis slot
       S.precond(vj, zj);
-      S.spmv(zj, w);
-      // CGS2
-      S.multidot(S.V.p, j + 1, w, h.data());
-      S.gemv_sub_(S.V.p, j + 1, h.data(), w);
-      S.multidot(S.V.p, j + 1, w, h2.data());
-      S.gemv_sub_(S.V.p, j + 1, h2.data(), w);
-      for (int k = 0; k <= j; ++k) h[k] += h2[k];
-      double hn = S.nrm2(w);
+      S.spmv(zj, wj);
+      S.multidot(S.V.p, j + 2, wj, h.data());               // h_0..h_j and <w,w> in one reduction
+      auto tail2 = [&](const std::vector<cd>& hh) {
+        double s2 = 0.0;
+        for (int k = 0; k <= j; ++k) s2 += std::norm(hh[k]);
+        return hh[j + 1].real() - s2;
+      };
+      double hn2 = tail2(h);
+      S.gemv_sub_(S.V.p, j + 1, h.data(), wj);
+      if (!(hn2 > 0.05 * h[j + 1].real())) {                // cancellation: second Gram-Schmidt pass
+        S.multidot(S.V.p, j + 2, wj, h2.data());
+        hn2 = tail2(h2);
+        S.gemv_sub_(S.V.p, j + 1, h2.data(), wj);
+        for (int k = 0; k <= j; ++k) h[k] += h2[k];
+      }
+      const double hn = hn2 > 0.0 ? std::sqrt(hn2) : 0.0;
       h[j + 1] = hn;
-      if (hn > 0) S.axpby_(cd(1.0 / hn, 0), w, cd(0, 0), S.V.p + (size_t)(j + 1) * ld);
+      if (hn > 0) S.axpby_(cd(1.0 / hn, 0), wj, cd(0, 0), wj);
       // Givens
       for (int k = 0; k < j; ++k) {
         cd t = cs[k] * h[k] + sn[k] * h[k + 1];
@@ -482,7 +505,7 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
       for (int k = 0; k <= j; ++k) H[(size_t)k * m + j] = h[k];
       const double prev = rel;
       rel = std::abs(g[j + 1]) / bnorm;
-      if (rel <= S.opts.rtol || hn == 0.0) { ++j; ++it; break; }
+      if (!(rel > S.opts.rtol) || hn == 0.0) { ++j; ++it; break; }
       if (direct && j >= 1 && rel > 0.25 * prev) { stagnated = true; ++j; ++it; break; }
     }
     // y = H^{-1} g ; x += M^{-1} V y
@@ -494,6 +517,7 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
     CUDA_TRY(cudaMemsetAsync(w, 0, ld * sizeof(double), S.s));
     std::vector<cd> ny(j);
     for (int k = 0; k < j; ++k) ny[k] = -y[k];
+    if (j == 0) continue;
     if (direct) {                               // x += Z y: no further application of the LU sweeps
       S.gemv_sub_(S.Z.p, j, ny.data(), w);
       S.axpby_(cd(1, 0), w, cd(1, 0), x);

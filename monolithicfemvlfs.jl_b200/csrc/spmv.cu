@@ -21,11 +21,12 @@ template <int TPR>
 __global__ void __launch_bounds__(256)
 csr_spmv_real(const int* __restrict__ rowptr, const int* __restrict__ colind,
               const double* __restrict__ vals, const double* __restrict__ x,
-              double* __restrict__ y, long long nrows, double alpha, double beta) {
+              double* __restrict__ y, long long nrows, double alpha, double beta, const int* __restrict__ rows) {
   const int lane = threadIdx.x & (TPR - 1);
   const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
   const long long nrg = ((long long)gridDim.x * blockDim.x) / TPR;
-  for (long long r = gid; r < nrows; r += nrg) {
+  for (long long q = gid; q < nrows; q += nrg) {
+    const long long r = rows ? rows[q] : q;          // optional row list (interior / boundary rows of a rank)
     const int p0 = rowptr[r], p1 = rowptr[r + 1];
     double s0 = 0, s1 = 0;
     int p = p0 + lane;
@@ -47,11 +48,12 @@ template <int TPR>
 __global__ void __launch_bounds__(256)
 csr_spmv_cplx(const int* __restrict__ rowptr, const int* __restrict__ colind,
               const double2* __restrict__ vals, const double2* __restrict__ x,
-              double2* __restrict__ y, long long nrows, double2 alpha, double2 beta) {
+              double2* __restrict__ y, long long nrows, double2 alpha, double2 beta, const int* __restrict__ rows) {
   const int lane = threadIdx.x & (TPR - 1);
   const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
   const long long nrg = ((long long)gridDim.x * blockDim.x) / TPR;
-  for (long long r = gid; r < nrows; r += nrg) {
+  for (long long q = gid; q < nrows; q += nrg) {
+    const long long r = rows ? rows[q] : q;          // optional row list (interior / boundary rows of a rank)
     const int p0 = rowptr[r], p1 = rowptr[r + 1];
     double sr0 = 0, si0 = 0, sr1 = 0, si1 = 0;
     int p = p0 + lane;
@@ -93,9 +95,20 @@ csr_spmv_cplx(const int* __restrict__ rowptr, const int* __restrict__ colind,
 }  // namespace
 
 // y = alpha*A*x + beta*y ; alpha/beta given as (re,im) pairs (im ignored when real)
+void launch_spmv_rows(const int* rowptr, const int* colind, const void* vals, const void* x, void* y,
+                      const int* rows, long long nrows, long long nnz, int is_complex, const double* alpha,
+                      const double* beta, int nsm, cudaStream_t s);
+
 void launch_spmv(const int* rowptr, const int* colind, const void* vals, const void* x, void* y,
                  long long nrows, long long nnz, int is_complex, const double* alpha,
                  const double* beta, int nsm, cudaStream_t s) {
+  launch_spmv_rows(rowptr, colind, vals, x, y, nullptr, nrows, nnz, is_complex, alpha, beta, nsm, s);
+}
+
+// the same product over the rows of a list (nnz: entries of those rows, for the lanes-per-row choice)
+void launch_spmv_rows(const int* rowptr, const int* colind, const void* vals, const void* x, void* y,
+                      const int* rows, long long nrows, long long nnz, int is_complex, const double* alpha,
+                      const double* beta, int nsm, cudaStream_t s) {
   if (nrows == 0) return;
   double avg = (double)nnz / (double)nrows;
   int tpr = avg >= 48 ? 32 : avg >= 24 ? 16 : avg >= 12 ? 8 : 4;
@@ -107,10 +120,10 @@ void launch_spmv(const int* rowptr, const int* colind, const void* vals, const v
   if (is_complex)                                                                               \
     csr_spmv_cplx<T><<<(unsigned)grid, 256, 0, s>>>(rowptr, colind, (const double2*)vals,       \
         (const double2*)x, (double2*)y, nrows, make_double2(alpha[0], alpha[1]),                \
-        make_double2(beta[0], beta[1]));                                                        \
+        make_double2(beta[0], beta[1]), rows);                                                        \
   else                                                                                          \
     csr_spmv_real<T><<<(unsigned)grid, 256, 0, s>>>(rowptr, colind, (const double*)vals,        \
-        (const double*)x, (double*)y, nrows, alpha[0], beta[0]);
+        (const double*)x, (double*)y, nrows, alpha[0], beta[0], rows);
   switch (tpr) {
     case 32: VLFS_SPMV_CASE(32) break;
     case 16: VLFS_SPMV_CASE(16) break;

@@ -36,6 +36,79 @@ def slab_owner(x, nranks):
     return np.searchsorted(cuts, x, side="left").astype(np.int32)
 
 
+# ---------------------------------------------------------------------------------------------
+# cell-based partition: recursive coordinate bisection of the cell centroids
+# ---------------------------------------------------------------------------------------------
+def rcb_tree(points, nparts, axes=None):
+    """Recursive coordinate bisection of `points` (n, dim) into `nparts` parts of (nearly) equal
+    size; a split is made along the axis (among `axes`, default all) of the largest extent, the
+    part numbers grow along the split axis.  Returns the tree ("leaf", part) |
+    ("split", axis, cut, left, right); classify other points with `rcb_classify`."""
+    points = np.asarray(points, dtype=np.float64)
+    axes = list(range(points.shape[1])) if axes is None else list(axes)
+
+    def rec(idx, first, count):
+        if count == 1 or len(idx) == 0:
+            return ("leaf", first)
+        P = points[idx]
+        ext = [P[:, a].max() - P[:, a].min() for a in axes]
+        a = axes[int(np.argmax(ext))]
+        nl = count // 2
+        order = np.argsort(P[:, a], kind="stable")
+        k = (len(idx) * nl) // count
+        k = min(max(k, 1), len(idx) - 1)
+        lo, hi = P[order[k - 1], a], P[order[k], a]
+        cut = 0.5 * (lo + hi)
+        left = idx[P[:, a] <= cut] if lo < hi else idx[order[:k]]
+        right = idx[P[:, a] > cut] if lo < hi else idx[order[k:]]
+        return ("split", a, cut, rec(left, first, nl), rec(right, first + nl, count - nl))
+    return rec(np.arange(len(points)), 0, nparts)
+
+
+def rcb_classify(tree, points):
+    points = np.asarray(points, dtype=np.float64)
+    out = np.zeros(len(points), dtype=np.int32)
+
+    def rec(node, idx):
+        if node[0] == "leaf":
+            out[idx] = node[1]
+            return
+        _, a, cut, left, right = node
+        m = points[idx, a] <= cut
+        rec(left, idx[m])
+        rec(right, idx[~m])
+    rec(tree, np.arange(len(points)))
+    return out
+
+
+def _cell_centroids(slots):
+    """Centroid of every integration cell, taken from the slot with the highest reference
+    dimension (a boundary facet follows the volume cell it is glued to)."""
+    s = max(slots, key=lambda t: t["dref"])
+    return np.asarray(s["coords"], dtype=np.float64).mean(axis=1)
+
+
+def cell_partition_owner(domain_slots, ndofs, nranks, axes=None):
+    """Cell-based partition: the cells of the domain with the most cells are bisected recursively
+    by centroid (`rcb_tree`), the cells of every other domain fall where their centroid lies, and a
+    DOF belongs to the HIGHEST part among the cells that touch it.  The unknowns a lower rank then
+    holds as ghosts are exactly those on the faces between parts - the smallest interface a
+    cell partition allows.  Returns (owner[ndofs], [part of every cell, per domain])."""
+    if nranks == 1:
+        return np.zeros(ndofs, dtype=np.int32), [np.zeros(len(sl[0]["dofs"]), dtype=np.int32) for sl in domain_slots]
+    cents = [_cell_centroids(sl) for sl in domain_slots]
+    primary = int(np.argmax([len(c) for c in cents]))
+    tree = rcb_tree(cents[primary], nranks, axes)
+    parts = [rcb_classify(tree, c) for c in cents]
+    owner = np.full(ndofs, -1, dtype=np.int32)
+    for sl, part in zip(domain_slots, parts):
+        for s in sl:
+            dofs = np.asarray(s["dofs"])
+            np.maximum.at(owner, dofs.reshape(-1), np.repeat(part, dofs.shape[1]))
+    owner[owner < 0] = 0                      # DOFs no cell touches (none in the reference's cases)
+    return owner, parts
+
+
 class _DomainProxy:
     """Records what a case module registers on a domain; forwards coefficient updates to the
     rank-local domain once it exists."""
@@ -47,6 +120,27 @@ class _DomainProxy:
         self.nq = kwargs["nq"]
         self.weights = [np.asarray(w, dtype=np.float64).reshape(self.ncells, self.nq).copy()
                         for w in kwargs.get("weights", ())]
+
+    def used_slots(self):
+        """Slots some bilinear or linear term acts on (a measure-only slot, e.g. the Q1 face of the
+        inlet right-hand side, carries placeholder DOF ids that must not create couplings)."""
+        used = set()
+
+        def note(spec):
+            if isinstance(spec, dict):
+                used.update(int(k) for k, v in spec.items() if v != 0)
+            else:
+                used.add(int(spec))
+        for a, k in self.terms:          # (mat, coef, test_op, test_slots, trial_op, trial_slots, ...)
+            note(a[3]); note(a[5])
+        for a, k in self.rhs:            # (vec, coef, op, slots, ...)
+            note(a[3])
+        return sorted(used)
+
+    def touch_dofs(self):
+        """(ncells, n) global DOF ids of the used slots of every cell."""
+        sl = self.kwargs["slots"]
+        return np.concatenate([np.asarray(sl[k]["dofs"]) for k in self.used_slots()], axis=1)
 
     def add_term(self, *a, **k):
         self.terms.append((a, k))
@@ -78,12 +172,16 @@ class DistributedSystem:
     """Same surface as `B200System` for the case modules; builds the rank-local system."""
 
     def __init__(self, ndofs, is_complex, nmat=1, nvec=1, device=0, rank=0, nranks=1, axis=0,
-                 backend=None):
+                 backend=None, partition="dofs", rcb_axes=None):
+        """partition: "dofs" - slabs of equal DOF count along coordinate `axis` (slab_owner);
+        "cells" - recursive coordinate bisection of the cells, DOFs to the highest touching part
+        (cell_partition_owner; `rcb_axes` restricts the split axes, e.g. (0,) for slabs)."""
         if backend is None:
             from .assembler import B200System as backend
         self.backend, self.device = backend, device
         self.ndofs_global, self.is_complex, self.nmat, self.nvec = int(ndofs), bool(is_complex), nmat, nvec
         self.rank, self.nranks, self.axis = rank, nranks, axis
+        self.partition, self.rcb_axes = partition, rcb_axes
         self.dtype = np.complex128 if is_complex else np.float64
         self.domains, self.coords, self.local = [], None, None
 
@@ -100,17 +198,19 @@ class DistributedSystem:
         if self.coords is None:
             raise ValueError("DistributedSystem needs set_dof_coords before build_pattern")
         N = self.ndofs_global
-        self.owner = owner = slab_owner(self.coords[:, self.axis], self.nranks)
+        if self.partition == "cells":
+            self.owner, self.cell_parts = cell_partition_owner(
+                [[d.kwargs["slots"][k] for k in d.used_slots()] for d in self.domains], N, self.nranks, self.rcb_axes)
+            owner = self.owner
+        else:
+            self.owner = owner = slab_owner(self.coords[:, self.axis], self.nranks)
         mine = owner == self.rank
         self.owned = np.nonzero(mine)[0]
         touched = np.zeros(N, dtype=bool)
         for d in self.domains:
-            keep = np.zeros(d.ncells, dtype=bool)
-            for s in d.kwargs["slots"]:
-                keep |= mine[np.asarray(s["dofs"])].any(axis=1)
-            d.cells = np.nonzero(keep)[0]
-            for s in d.kwargs["slots"]:
-                touched[np.asarray(s["dofs"])[d.cells].reshape(-1)] = True
+            td = d.touch_dofs()
+            d.cells = np.nonzero(mine[td].any(axis=1))[0]
+            touched[td[d.cells].reshape(-1)] = True
         gh = np.nonzero(touched & ~mine)[0]
         # ghost block grouped by owner (then ascending id): every peer's halo is contiguous
         self.ghosts = gh[np.lexsort((gh, owner[gh]))]
@@ -127,10 +227,11 @@ class DistributedSystem:
         for d in self.domains:
             kw = dict(d.kwargs)
             slots = []
-            for s in kw.pop("slots"):
+            used = d.used_slots()
+            for ks, s in enumerate(kw.pop("slots")):
                 t = dict(s)
                 t["coords"] = np.asarray(s["coords"])[d.cells]
-                t["dofs"] = g2l[np.asarray(s["dofs"])[d.cells]]
+                t["dofs"] = g2l[np.asarray(s["dofs"])[d.cells]] if ks in used else np.zeros_like(np.asarray(s["dofs"])[d.cells])
                 if s.get("variant") is not None:
                     t["variant"] = np.asarray(s["variant"])[d.cells]
                 slots.append(t)
@@ -155,6 +256,40 @@ class DistributedSystem:
 
     def scatter_owned(self, xl, out):
         out[self.owned] = np.asarray(xl)[:self.n_owned]
+
+
+def local_halo_arrays(dsys):
+    """The halo plan of `vlfs_dist_set_halo` for the rank of `dsys`, computed without communication
+    (every rank knows the global tables): peers, send_ptr/send_idx (owned local ids each peer
+    needs, in the order of ITS ghost block = ascending global id) and recv_ptr (ranges of this
+    rank's ghost block, which is grouped by owner)."""
+    owner, r = dsys.owner, dsys.rank
+    own = owner[dsys.ghosts]
+    recv = {int(p): int((own == p).sum()) for p in np.unique(own)}
+    # what peer q needs from me: my owned DOFs inside cells that touch a DOF q owns
+    need = {}
+    for d in dsys.domains:
+        alld = d.touch_dofs()                                 # (ncells, DOFs of the used slots)
+        own_c = owner[alld]
+        has_mine = (own_c == r).any(axis=1)
+        for q in np.unique(own_c[has_mine]):
+            if q == r:
+                continue
+            cells = has_mine & (own_c == q).any(axis=1)
+            g = alld[cells][own_c[cells] == r]
+            need.setdefault(int(q), []).append(np.unique(g))
+    send = {q: np.unique(np.concatenate(v)) for q, v in need.items()}
+    peers = sorted(set(recv) | set(send))
+    send_ptr, recv_ptr, send_idx = [0], [0], []
+    # the ghost block is grouped by owner in ascending owner order: recv ranges follow that order
+    for p in peers:
+        ids = send.get(p, np.zeros(0, dtype=np.int64))
+        send_idx.append(dsys.g2l[ids])
+        send_ptr.append(send_ptr[-1] + len(ids))
+        recv_ptr.append(recv_ptr[-1] + recv.get(p, 0))
+    send_idx = np.concatenate(send_idx) if send_idx else np.zeros(0, dtype=np.int64)
+    return (np.asarray(peers, dtype=np.int32), np.asarray(send_ptr, dtype=np.int64),
+            send_idx.astype(np.int32), np.asarray(recv_ptr, dtype=np.int64))
 
 
 def halo_plan(owner, rank, ghosts):
@@ -715,3 +850,204 @@ class SchurSolver:
         for m, z in zip(F.members, zs):          # (in-process fleets share one device)
             xk = m.ops.take(self.xg, m.ops.long_index(m.keep_pos))
             m.ops.schur_backward(xk, z)
+
+
+# ---------------------------------------------------------------------------------------------
+# the multi-GPU system behind the C ABI: communicator, halo exchange, Krylov reductions and the
+# substructuring solve all live in libvlfs_b200 (csrc/dist.cu); this class only partitions the
+# tables and marshals them
+# ---------------------------------------------------------------------------------------------
+class _FanoutDomain:
+    def __init__(self, parts):
+        self.parts = parts
+
+    def _fan(self, name, *a, **k):
+        out = [getattr(p, name)(*a, **k) for p in self.parts]
+        return out[0]
+
+    def add_term(self, *a, **k): return self._fan("add_term", *a, **k)
+    def add_rhs(self, *a, **k): return self._fan("add_rhs", *a, **k)
+    def set_coef(self, *a, **k): return self._fan("set_coef", *a, **k)
+    def set_rhs_coef(self, *a, **k): return self._fan("set_rhs_coef", *a, **k)
+    def set_weights(self, *a, **k): return self._fan("set_weights", *a, **k)
+
+    @property
+    def cells(self):
+        return self.parts[0].cells
+
+
+class MultiSystem:
+    """`B200System` surface over `nranks` GPUs.  `local_ranks` are the ranks this process hosts:
+    all of them (one process, one host thread per rank inside the library - what the Julia shim
+    does through `ccall`: `vlfs_multi_create`) or one (one process per GPU: pass the 128-byte
+    `unique_id` rank 0 got from `MultiSystem.unique_id()`).  Case modules use it unchanged:
+    `YagoProblem(params, system_cls=lambda *a, **k: MultiSystem(*a, nranks=2, devices=[0, 1], **k))`."""
+
+    @staticmethod
+    def unique_id():
+        from . import _lib as L
+        buf = (C.c_char * 128)()
+        rc = L.load().vlfs_dist_unique_id(C.cast(buf, C.c_void_p))
+        if rc != 0:
+            raise L.VlfsError("vlfs_dist_unique_id failed (status %d): NCCL not available" % rc)
+        return bytes(buf)
+
+    def __init__(self, ndofs, is_complex, nmat=1, nvec=1, device=None, nranks=1, devices=None, local_ranks=None,
+                 unique_id=None, partition="cells", rcb_axes=(0,), axis=0):
+        from . import _lib as L
+        from .assembler import B200System
+        self.lib = L.load()
+        self.ndofs, self.is_complex, self.nmat, self.nvec = int(ndofs), bool(is_complex), nmat, nvec
+        self.dtype = np.complex128 if is_complex else np.float64
+        self.nranks = nranks
+        self.local_ranks = list(range(nranks)) if local_ranks is None else list(local_ranks)
+        nl = len(self.local_ranks)
+        devices = list(devices) if devices is not None else [device or 0] * nl
+        assert len(devices) == nl
+        self._ctx_arr = (C.c_void_p * nl)()
+        if nl == nranks:                                    # every rank in this process
+            dv = (C.c_int * nl)(*devices)
+            rc = self.lib.vlfs_multi_create(self._ctx_arr, nl, dv)
+            if rc != 0:
+                raise L.VlfsError("vlfs_multi_create failed (status %d): needs %d usable sm_100 GPUs and NCCL; "
+                                  "there is no CPU fallback" % (rc, nl))
+            self._created = "multi"
+        else:                                               # one rank per process
+            assert nl == 1 and unique_id is not None and len(unique_id) == 128
+            ctx = C.c_void_p()
+            rc = self.lib.vlfs_create(C.byref(ctx), devices[0])
+            if rc != 0:
+                raise L.VlfsError("vlfs_create failed (status %d): no usable sm_100 GPU" % rc)
+            self._ctx_arr[0] = ctx
+            self._created = "rank"
+            self._uid = unique_id
+        self.parts = []
+        for k, r in enumerate(self.local_ranks):
+            ctx = C.c_void_p(self._ctx_arr[k])
+            mk = (lambda c: (lambda n, cplx, nmat=1, nvec=1, device=0: B200System.adopt(c, n, cplx, nmat, nvec)))(ctx)
+            self.parts.append(DistributedSystem(ndofs, is_complex, nmat=nmat, nvec=nvec, device=devices[k], rank=r,
+                                                nranks=nranks, axis=axis, backend=mk, partition=partition,
+                                                rcb_axes=rcb_axes))
+        self.nnz = self.ncoo = None
+
+    # -- registration fans out to the ranks (each keeps its own cells) ------------------------------
+    def add_domain(self, *a, **k):
+        return _FanoutDomain([p.add_domain(*a, **k) for p in self.parts])
+
+    def set_dof_coords(self, coords):
+        for p in self.parts:
+            p.set_dof_coords(coords)
+
+    def _check(self, rc, allow=(0,)):
+        if rc not in allow:
+            msgs = [self.lib.vlfs_last_error(C.c_void_p(self._ctx_arr[k])) for k in range(len(self.parts))]
+            from . import _lib as L
+            raise L.VlfsError("libvlfs_b200 status %d: %s" % (rc, " | ".join(m.decode() for m in msgs if m)))
+        return rc
+
+    def build_pattern(self):
+        from . import _lib as L
+        for k, p in enumerate(self.parts):                 # host partition + table extraction per rank
+            if self._created == "rank":
+                # the communicator needs the context's scalar type: after the local system exists
+                pass
+            p.build_pattern()
+        if self._created == "rank":
+            ctx = C.c_void_p(self._ctx_arr[0])
+            uid = (C.c_char * 128).from_buffer_copy(self._uid)
+            self._check(self.lib.vlfs_dist_init(ctx, self.local_ranks[0], self.nranks, C.cast(uid, C.c_void_p)))
+        for k, p in enumerate(self.parts):
+            peers, sp, si, rp = local_halo_arrays(p)
+            self._check(self.lib.vlfs_dist_set_halo(C.c_void_p(self._ctx_arr[k]), p.n_owned, len(peers), L.iptr(peers),
+                                                    sp.ctypes.data_as(C.POINTER(C.c_int64)), L.iptr(si),
+                                                    rp.ctypes.data_as(C.POINTER(C.c_int64))))
+            p.halo = (peers, sp, si, rp)
+        rps = [p.local.get_pattern()[0] for p in self.parts]
+        self.nnz_owned = [int(rp[p.n_owned]) for rp, p in zip(rps, self.parts)]
+        self.nnz = sum(self.nnz_owned)                     # of the ranks hosted here
+        self.ncoo = sum(p.ncoo or 0 for p in self.parts)
+        return self.nnz
+
+    def assemble(self, matrices=True, vectors=True):
+        if matrices and vectors:
+            self._check(self.lib.vlfs_multi_assemble(self._ctx_arr, len(self.parts)))
+        else:
+            for p in self.parts:
+                p.local.assemble(matrices, vectors)
+
+    def solver_setup(self, mat=0, method=None, precond=None, restart=20, maxit=40, rtol=1e-10, block_size_hint=0, sweeps=0):
+        from . import _lib as L
+        o = L.SolverOpts(L.SOLVER_GMRES if method is None else method, L.PRECOND_SPARSE_LU if precond is None else precond,
+                         restart, maxit, rtol, block_size_hint, sweeps)
+        self.factor_status = self._check(self.lib.vlfs_multi_solver_setup(self._ctx_arr, len(self.parts), mat, C.byref(o)),
+                                         allow=(0, L.PIVOT_PERTURBED))
+
+    def refactor(self, mat=0):
+        from . import _lib as L
+        self.factor_status = self._check(self.lib.vlfs_multi_solver_refactor(self._ctx_arr, len(self.parts), mat),
+                                         allow=(0, L.PIVOT_PERTURBED))
+
+    def solve(self, vec=0):
+        """Solves with the assembled right-hand side `vec`; returns the GLOBAL vector (entries owned by
+        the ranks hosted here; the others are zero) and the statistics of the first local rank."""
+        from . import _lib as L
+        n = len(self.parts)
+        xs = [np.zeros(p.n_local, dtype=self.dtype) for p in self.parts]
+        ptrs = (C.c_void_p * n)(*[x.ctypes.data_as(C.c_void_p).value for x in xs])
+        st = (L.SolveStats * n)()
+        self._check(self.lib.vlfs_multi_solve_vec(self._ctx_arr, n, vec, ptrs, st), allow=(0, L.NOT_CONVERGED))
+        xg = np.zeros(self.ndofs, dtype=self.dtype)
+        for p, x in zip(self.parts, xs):
+            p.scatter_owned(x, xg)
+        s0 = st[0]
+        return xg, dict(iterations=s0.iterations, converged=bool(s0.converged), rel_residual=s0.rel_residual,
+                        setup_ms=s0.setup_ms, solve_ms=max(s.solve_ms for s in st))
+
+    def spmv(self, x, mat=0):
+        """y = A x for a GLOBAL host vector (entries of the rows owned here)."""
+        n = len(self.parts)
+        xs = [p.to_local(x) for p in self.parts]
+        ys = [np.zeros(p.n_local, dtype=self.dtype) for p in self.parts]
+        xp = (C.c_void_p * n)(*[v.ctypes.data_as(C.c_void_p).value for v in xs])
+        yp = (C.c_void_p * n)(*[v.ctypes.data_as(C.c_void_p).value for v in ys])
+        self._check(self.lib.vlfs_multi_spmv(self._ctx_arr, n, mat, xp, yp))
+        yg = np.zeros(self.ndofs, dtype=self.dtype)
+        for p, y in zip(self.parts, ys):
+            p.scatter_owned(y, yg)
+        return yg
+
+    def spmv_device_ms(self, mat=0, reps=10):
+        n = len(self.parts)
+        ms = (C.c_float * n)()
+        self._check(self.lib.vlfs_multi_spmv_device(self._ctx_arr, n, mat, reps, ms))
+        return max(ms) / reps
+
+    def get_vector(self, vec=0):
+        bg = np.zeros(self.ndofs, dtype=self.dtype)
+        for p in self.parts:
+            p.scatter_owned(p.local.get_vector(vec), bg)
+        return bg
+
+    def dist_info(self):
+        out = []
+        for k in range(len(self.parts)):
+            a = np.zeros(4)
+            self.lib.vlfs_dist_info(C.c_void_p(self._ctx_arr[k]), a.ctypes.data_as(C.POINTER(C.c_double)))
+            out.append(dict(n_left=int(a[0]), n_right=int(a[1]), chain_ms=float(a[2]), boundary_rows=int(a[3])))
+        return out
+
+    def launches(self):
+        return sum(p.local.launches() for p in self.parts)
+
+    def close(self):
+        for k in range(len(self.parts)):
+            if self._ctx_arr[k]:
+                self.lib.vlfs_destroy(C.c_void_p(self._ctx_arr[k]))
+                self._ctx_arr[k] = None
+        self.parts = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
