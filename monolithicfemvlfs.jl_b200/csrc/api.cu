@@ -40,12 +40,13 @@ void build_row_incidence(const std::vector<DomainDev>& doms, long long ndofs, De
                          long long* launches);
 void launch_count_row_entries(const unsigned long long* src, const int* incptr, long long nrows,
                               const GatherDom* doms, uint32_t* cnt, cudaStream_t s);
-void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, const uint32_t* rowstart,
-                               long long nrows, const GatherDom* doms, const int* dom_late, RowInc* out,
-                               unsigned char* late, const int* dest, int* dest_rows, cudaStream_t s);
-bool launch_assemble_rows(const int* rowptr, const int* incptr, const RowInc* inc, const int* dest_rows,
-                          double* const* ctab_all, long long nrows, double* const* mats, int nmat, int is_complex,
-                          int maxrow, const unsigned char* late, int phase, int nsm, cudaStream_t s);
+void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, const int* rowptr,
+                               const uint32_t* rowstart, long long nrows, const GatherDom* doms, const int* dom_late,
+                               uint32_t* tabs, unsigned char* late, const int* dest, uint32_t* entries, int* bad,
+                               cudaStream_t s);
+bool launch_assemble_rows(const RowMeta* meta, long long nrows, const uint32_t* tabs, const uint32_t* entries,
+                          double* const* ctab_all, double* const* mats, int nmat, int is_complex, int maxrow,
+                          int nsm, cudaStream_t s);
 double measure_fp64_fma_tflops(int nsm, int reps, cudaStream_t s);
 void build_csc_device(const int* rowind, const int* colind, long long nnz, long long ndofs,
                       DevBuf<int>& colptr, DevBuf<int>& rowval, DevBuf<int>& csr_slot,
@@ -150,11 +151,16 @@ struct vlfs_ctx {
   DevBuf<double> ctab_all[4];              // per matrix: the class tables of all domains, contiguous
   bool rec32_valid = false;
   // row-centric numeric pass: incidence records of every row (pattern.cu: build_row_incidence)
-  DevBuf<int> incptr, dom_late, dest_rows;   // dest_rows: the COO->slot permutation re-laid row by row
-  DevBuf<uint32_t> rowstart;                 // first entry of every row's run in dest_rows
+  DevBuf<int> incptr, dom_late;
+  DevBuf<uint32_t> row_entries;              // packed entry stream: the COO->slot permutation re-laid row by row
+  DevBuf<uint32_t> rowstart;                 // first entry of every row's run in row_entries
   DevBuf<unsigned long long> inc_src;
-  DevBuf<RowInc> inc;
+  DevBuf<uint32_t> inc_tabs;                 // class-table position of every incidence record (+32 padding)
   DevBuf<unsigned char> row_late;
+  DevBuf<RowMeta> row_meta;                  // rows in processing order: tables ready early first, then the others
+  std::vector<unsigned> rowstart_host;
+  std::vector<int> rowptr_host, incptr_host;
+  long long n_early = 0;
   long long ninc = 0;
   int maxrow = 0;
   bool rows_valid = false, rows_two_phase = false;
@@ -699,25 +705,53 @@ void rebuild_row_records(vlfs_ctx* ctx) {
   }
   if (total >= 0xffffffffll) return;
   ctx->dom_late.upload(late.data(), late.size(), ctx->stream);
-  if (ctx->inc.n != (size_t)ctx->ninc) ctx->inc.alloc((size_t)ctx->ninc);
-  if (ctx->row_late.n != (size_t)ctx->ndofs) ctx->row_late.alloc((size_t)ctx->ndofs);
-  const bool first = ctx->dest_rows.n != (size_t)ctx->ncoo;
-  if (first) {                                // once per pattern: row-major copy of the slot permutation
+  const bool first = ctx->row_entries.n != (size_t)ctx->ncoo;
+  DevBuf<int> bad;
+  bad.alloc(1); bad.zero(ctx->stream);
+  if (first) {                                // once per pattern: packed entry stream in row-major order
     DevBuf<uint32_t> cnt, total;
     cnt.alloc((size_t)ctx->ndofs); total.alloc(1);
     ctx->rowstart.alloc((size_t)ctx->ndofs);
     launch_count_row_entries(ctx->inc_src.p, ctx->incptr.p, ctx->ndofs, ctx->gather_doms.p, cnt.p, ctx->stream);
     exclusive_scan_u32(cnt.p, ctx->rowstart.p, (size_t)ctx->ndofs, total.p, ctx->stream);
-    ctx->dest_rows.alloc((size_t)ctx->ncoo);
+    ctx->row_entries.alloc((size_t)ctx->ncoo);
+    ctx->inc_tabs.alloc((size_t)ctx->ninc + 32);
+    CUDA_TRY(cudaMemsetAsync(ctx->inc_tabs.p, 0xff, ((size_t)ctx->ninc + 32) * sizeof(uint32_t), ctx->stream));
     ctx->launches += 3;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->rowstart_host.resize((size_t)ctx->ndofs);
+    ctx->incptr_host.resize((size_t)ctx->ndofs + 1);
+    CUDA_TRY(cudaMemcpy(ctx->rowstart_host.data(), ctx->rowstart.p, ctx->rowstart_host.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ctx->incptr_host.data(), ctx->incptr.p, ctx->incptr_host.size() * sizeof(int), cudaMemcpyDeviceToHost));
   }
-  launch_fill_row_incidence(ctx->inc_src.p, ctx->incptr.p, ctx->rowstart.p, ctx->ndofs, ctx->gather_doms.p,
-                            ctx->dom_late.p, ctx->inc.p, ctx->row_late.p, ctx->dest_all.p,
-                            first ? ctx->dest_rows.p : nullptr, ctx->stream);
+  if (ctx->row_late.n != (size_t)ctx->ndofs) ctx->row_late.alloc((size_t)ctx->ndofs);
+  launch_fill_row_incidence(ctx->inc_src.p, ctx->incptr.p, ctx->rowptr.p, ctx->rowstart.p, ctx->ndofs, ctx->gather_doms.p,
+                            ctx->dom_late.p, ctx->inc_tabs.p, ctx->row_late.p, ctx->dest_all.p,
+                            first ? ctx->row_entries.p : nullptr, bad.p, ctx->stream);
   ++ctx->launches;
+  int hbad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&hbad, bad.p, sizeof hbad, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  ctx->rows_two_phase = any_late && any_early;
+  if (hbad) { ctx->row_entries.release(); return; }      // a row beyond the packed fields: slot-centric pass
+  {                                           // row metadata in processing order (host: once per classification)
+    std::vector<unsigned char> lf((size_t)ctx->ndofs);
+    CUDA_TRY(cudaMemcpy(lf.data(), ctx->row_late.p, lf.size(), cudaMemcpyDeviceToHost));
+    std::vector<RowMeta> list;
+    list.reserve(lf.size());
+    const std::vector<int>& rp = ctx->rowptr_host;
+    auto push = [&](long long r) {
+      const unsigned e0 = ctx->rowstart_host[(size_t)r];
+      const unsigned e1 = r + 1 < ctx->ndofs ? ctx->rowstart_host[(size_t)r + 1] : (unsigned)ctx->ncoo;
+      list.push_back(RowMeta{rp[(size_t)r], e0, (unsigned)ctx->incptr_host[(size_t)r],
+                             (unsigned)(rp[(size_t)r + 1] - rp[(size_t)r]) | ((e1 - e0) << 12)});
+    };
+    for (long long r = 0; r < ctx->ndofs; ++r) if (!lf[(size_t)r]) push(r);
+    ctx->n_early = (long long)list.size();
+    for (long long r = 0; r < ctx->ndofs; ++r) if (lf[(size_t)r]) push(r);
+    ctx->row_meta.upload(list.data(), list.size(), ctx->stream);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->rows_two_phase = any_late && any_early && ctx->n_early > 0 && ctx->n_early < ctx->ndofs;
   ctx->rows_valid = true;
 }
 
@@ -807,9 +841,11 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   if (use_rows) {
     {
       double* ca[4] = {ctx->ctab_all[0].p, ctx->ctab_all[1].p, ctx->ctab_all[2].p, ctx->ctab_all[3].p};
-      auto rows = [&](int phase) {
-        if (!launch_assemble_rows(ctx->rowptr.p, ctx->incptr.p, ctx->inc.p, ctx->dest_rows.p, ca, ctx->ndofs, mp.data(),
-                                  (int)mp.size(), ctx->is_complex, ctx->maxrow, ctx->row_late.p, phase, ctx->nsm, s))
+      auto rows = [&](int phase) {        // 0: all rows, 1: the early part of the list, 2: the late part
+        const RowMeta* list = ctx->row_meta.p + (phase == 2 ? ctx->n_early : 0);
+        const long long n = phase == 0 ? ctx->ndofs : (phase == 1 ? ctx->n_early : ctx->ndofs - ctx->n_early);
+        if (!launch_assemble_rows(list, n, ctx->inc_tabs.p, ctx->row_entries.p, ca, mp.data(),
+                                  (int)mp.size(), ctx->is_complex, ctx->maxrow, ctx->nsm, s))
           throw std::string("row-centric pass: a matrix row does not fit the shared memory");
         ++ctx->launches;
       };
@@ -1153,7 +1189,8 @@ int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
       // row-centric numeric pass: incidence lists of every row, longest row (its shared-memory segment)
       build_row_incidence(devs, ctx->ndofs, ctx->incptr, ctx->inc_src, &ctx->ninc, ctx->stream, &ctx->launches);
       {
-        std::vector<int> rp((size_t)ctx->ndofs + 1);
+        std::vector<int>& rp = ctx->rowptr_host;
+        rp.resize((size_t)ctx->ndofs + 1);
         CUDA_TRY(cudaMemcpy(rp.data(), ctx->rowptr.p, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
         int mx = 0;
         for (long long i = 0; i < ctx->ndofs; ++i) mx = std::max(mx, rp[i + 1] - rp[i]);

@@ -955,35 +955,37 @@ gather_compact(const uint32_t* __restrict__ run_start, const uint32_t* __restric
   }
 }
 
-// packed (domain, block, local row, cell) sources -> RowInc records; once per pattern and again when
-// the element-block classes change.  late[row] = 1 when a contributing domain's class tables come
-// out of the quadrature kernel (they are ready later than the directly tabulated ones).
-// dest_rows (optional, once per pattern): the records' dest entries copied into row-major order.
+// packed (domain, block, local row, cell) sources -> class-table positions tabs[k] of the incidence
+// records (once per pattern and again when the element-block classes change); late[row] = 1 when a
+// contributing domain's class tables come out of the quadrature kernel (ready later than the directly
+// tabulated ones).  With `entries` != nullptr (once per pattern) the packed entry stream and the
+// row's entry count are written too.
 __global__ void fill_row_incidence(const unsigned long long* __restrict__ src, const int* __restrict__ incptr,
-                                   const uint32_t* __restrict__ rowstart, long long nrows,
+                                   const int* __restrict__ rowptr, const uint32_t* __restrict__ rowstart, long long nrows,
                                    const GatherDom* __restrict__ doms, const int* __restrict__ dom_late,
-                                   RowInc* __restrict__ out, unsigned char* __restrict__ late,
-                                   const int* __restrict__ dest, int* __restrict__ dest_rows) {
+                                   uint32_t* __restrict__ tabs, unsigned char* __restrict__ late,
+                                   const int* __restrict__ dest, uint32_t* __restrict__ entries, int* __restrict__ bad) {
   for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < nrows;
        row += (long long)gridDim.x * blockDim.x) {
     unsigned char l = 0;
     uint32_t pos = rowstart[row];
-    for (int k = incptr[row]; k < incptr[row + 1]; ++k) {
+    const int k0 = incptr[row], k1 = incptr[row + 1], r0 = rowptr[row];
+    if (entries && (k1 - k0 > VLFS_ROW_MAXREC + 1 || rowptr[row + 1] - r0 > VLFS_ROW_MAXLEN)) atomicExch(bad, 1);
+    for (int k = k0; k < k1; ++k) {
       const unsigned long long r = src[k];
       const unsigned d = (unsigned)(r >> 60), b = (unsigned)((r >> 58) & 3u), a = (unsigned)((r >> 32) & 0x3fffu);
       const unsigned e = (unsigned)(r & 0xffffffffull);
       const GatherDom& G = doms[d];
       const int nc = G.blk[b].nc;
-      RowInc R;
-      R.start = pos;
-      R.nc = (uint32_t)nc;
-      R.tab = (G.ncls > 0 && G.ctab_off[b] >= 0)
-                  ? (uint32_t)(G.ctab_base + G.ctab_off[b] + (long long)G.cls[e] * (G.blk[b].nr * nc) + (long long)a * nc)
-                  : 0xffffffffu;
-      out[k] = R;
-      if (dest_rows) {
+      tabs[k] = (G.ncls > 0 && G.ctab_off[b] >= 0)
+                    ? (uint32_t)(G.ctab_base + G.ctab_off[b] + (long long)G.cls[e] * (G.blk[b].nr * nc) + (long long)a * nc)
+                    : 0xffffffffu;
+      if (entries) {
+        if (nc > VLFS_ROW_MAXNC + 1) atomicExch(bad, 1);
         const long long coo = G.coo_lo + (long long)e * G.epc + G.blk[b].off + (long long)a * nc;
-        for (int j = 0; j < nc; ++j) dest_rows[pos + j] = dest[coo + j];
+        const uint32_t rec = (uint32_t)(k - k0) & VLFS_ROW_MAXREC;
+        for (int j = 0; j < nc; ++j)
+          entries[pos + j] = ((uint32_t)(dest[coo + j] - r0) << 20) | (rec << 10) | ((uint32_t)j & VLFS_ROW_MAXNC);
       }
       pos += nc;
       l |= (unsigned char)dom_late[d];
@@ -1007,124 +1009,102 @@ __global__ void count_row_entries(const unsigned long long* __restrict__ src, co
 }
 
 // Row-centric numeric pass (every domain class-tabulated): one warp per CSR row.  The row's value
-// segment lives in shared memory.  The row's contributions are ONE contiguous run of dest_rows
-// (slots) described by its incidence records (class-table position of every element-matrix row):
-// the lanes stream the run with coalesced loads (4 windows of 32 entries in flight), look up the
-// record of their entry with shuffles, read the class-table value (contiguous inside a record, L2
-// resident) and add into the segment - record by record, i.e. in COO order, the order in which
-// Julia's sparse(I,J,V) adds duplicates, so the result is bitwise repeatable without atomics.  The
-// finished segment is written to the CSR values in one coalesced pass: every value is written exactly
-// once (this is also the zero fill), every dest entry is read exactly once, nothing else streams
-// from HBM.  phase: 0 all rows, 1 rows whose tables are ready early (late[row] == 0), 2 the others.
+// segment lives in shared memory.  The row's contributions are ONE contiguous run of the packed
+// entry stream (slot inside the row, element-matrix row = record, column inside the record): the lanes
+// stream the run with coalesced loads, fetch the record's class-table position, read the table value
+// (contiguous inside a record, L2 resident) and add into the segment - record by record, i.e. in
+// COO order, the order in which Julia's sparse(I,J,V) adds duplicates, so the result is bitwise
+// repeatable without atomics.  The finished segment is written to the CSR values in one coalesced
+// pass: every value is written exactly once (this is also the zero fill), every COO entry is read
+// exactly once (4 bytes), nothing else streams from HBM.  Rows are taken in the order of `meta`
+// (early rows first); the meta of row i+2 and the first windows of row i+1 travel while row i is summed.
 template <int NMAT, bool CPLX>
 __global__ void __launch_bounds__(256, NMAT == 1 ? 4 : (NMAT == 2 ? 3 : 2))
-assemble_rows(const int* __restrict__ rowptr, const int* __restrict__ incptr, const RowInc* __restrict__ inc,
-              const int* __restrict__ dest_rows, AsmPtrs ctab_all, long long nrows, AsmPtrs ptrs, int maxrow,
-              const unsigned char* __restrict__ late, int phase) {
+assemble_rows(const RowMeta* __restrict__ meta, long long nlist, const uint32_t* __restrict__ tabs,
+              const uint32_t* __restrict__ entries, AsmPtrs ctab_all, AsmPtrs ptrs, int maxrow) {
   using T = typename std::conditional<CPLX, double2, double>::type;
-  constexpr int W = 4;                 // windows of 32 entries in flight
+  constexpr int W = 2;                 // windows of 32 entries prefetched per row
   extern __shared__ __align__(16) double seg_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   T* seg = reinterpret_cast<T*>(seg_raw) + (size_t)wib * NMAT * maxrow;
-  const long long nwarps = (long long)gridDim.x * wpb;
-  auto next_row = [&](long long r) {    // next row of this warp that belongs to the phase
-    while (r < nrows && phase != 0 && (__ldg(late + r) != 0) != (phase == 2)) r += nwarps;
-    return r;
+  const long long nwarps = (long long)gridDim.x * wpb, w = (long long)blockIdx.x * wpb + wib;
+  const int4 nometa = make_int4(0, 0, 0, 0);
+  auto load_meta = [&](long long i) {
+    const long long q = w + i * nwarps;
+    return q < nlist ? __ldg(reinterpret_cast<const int4*>(meta) + q) : nometa;
   };
-  const RowInc none{0u, 0xffffffffu, 0u};
-  long long row = next_row((long long)blockIdx.x * wpb + wib);
-  int r0 = 0, r1 = 0, k0 = 0, k1 = 0;
-  RowInc mine = none;
-  if (row < nrows) {
-    r0 = __ldg(rowptr + row); r1 = __ldg(rowptr + row + 1);
-    k0 = __ldg(incptr + row); k1 = __ldg(incptr + row + 1);
-    if (k0 + lane < k1) mine = inc[k0 + lane];
-  }
-  while (row < nrows) {
-    // the next row's pointers and first records travel while this row is summed
-    const long long nrow = next_row(row + nwarps);
-    int nr0 = 0, nr1 = 0, nk0 = 0, nk1 = 0;
-    if (nrow < nrows) {
-      nr0 = __ldg(rowptr + nrow); nr1 = __ldg(rowptr + nrow + 1);
-      nk0 = __ldg(incptr + nrow); nk1 = __ldg(incptr + nrow + 1);
-    }
-    RowInc nmine = none;
-    bool nfetched = false;
-    const int L = r1 - r0;
+  auto load_windows = [&](const int4& m, uint32_t (&pk)[W], uint32_t& tab) {
+    const uint32_t total = (uint32_t)m.w >> 12;
+#pragma unroll
+    for (int t = 0; t < W; ++t) pk[t] = (uint32_t)(32 * t + lane) < total ? __ldg(entries + (uint32_t)m.y + 32 * t + lane) : 0xffffffffu;
+    tab = total ? __ldg(tabs + (uint32_t)m.z + lane) : 0xffffffffu;   // (padded: reading 32 records is always in range)
+  };
+  int4 m2 = load_meta(2), m1 = load_meta(1), m0 = load_meta(0);
+  uint32_t pk1[W], pk0[W], tab1, tab0;
+  load_windows(m1, pk1, tab1);
+  load_windows(m0, pk0, tab0);
+  for (long long i = 0; w + i * nwarps < nlist; ++i) {
+    const int4 m3 = load_meta(i + 3);
+    uint32_t pk2[W], tab2;
+    load_windows(m2, pk2, tab2);
+    const int r0 = m0.x, L = m0.w & 0xfff;
+    const uint32_t e0 = (uint32_t)m0.y, k0 = (uint32_t)m0.z, total = (uint32_t)m0.w >> 12;
     for (int sidx = lane; sidx < L; sidx += 32) {
 #pragma unroll
       for (int m = 0; m < NMAT; ++m) seg[m * maxrow + sidx] = T{};
     }
     __syncwarp();
-    for (int kb = k0; kb < k1; kb += 32) {
-      if (kb > k0) { mine = none; if (kb + lane < k1) mine = inc[kb + lane]; }
-      const int cnt = min(32, k1 - kb);
-      const uint32_t e0 = __shfl_sync(0xffffffffu, mine.start, 0);
-      const uint32_t rs = mine.start - e0;                          // my record's first entry, relative
-      const uint32_t re = lane < cnt ? rs + mine.nc : 0xffffffffu;   // ... and one past its last
-      const int total = (int)__shfl_sync(0xffffffffu, re, cnt - 1);
-      for (int w0 = 0; w0 < total; w0 += 32 * W) {
-        int slot[W], g[W], gb[W], npass[W];
-        uint32_t tix[W];
-        T v[W][NMAT];
+    for (uint32_t q0 = 0; q0 < total; q0 += 32 * W) {
+      uint32_t pk[W];
+      T v[W][NMAT];
+      uint32_t tix[W];
 #pragma unroll
-        for (int t = 0; t < W; ++t) {                    // W coalesced loads of the slot stream
-          const int q = w0 + 32 * t + lane;
-          slot[t] = q < total ? __ldg(dest_rows + e0 + q) - r0 : -1;
-        }
-        if (!nfetched) {                                 // first records of the next row
-          nfetched = true;
-          if (nrow < nrows && nk0 + lane < nk1) nmine = inc[nk0 + lane];
-        }
+      for (int t = 0; t < W; ++t) {
+        const uint32_t q = q0 + 32 * t + lane;
+        pk[t] = q0 == 0 ? pk0[t] : (q < total ? __ldg(entries + e0 + q) : 0xffffffffu);
+      }
 #pragma unroll
-        for (int t = 0; t < W; ++t) {                    // record of every entry (shuffles only)
-          const int qf = w0 + 32 * t;
-          gb[t] = 0; npass[t] = 0; g[t] = 0; tix[t] = 0xffffffffu;
-          if (qf >= total) continue;                     // (uniform)
-          const int ql = min(qf + 31, total - 1), q = qf + lane;
-          gb[t] = __ffs(__ballot_sync(0xffffffffu, re > (uint32_t)qf)) - 1;       // first record reaching the window
-          const int gl = __ffs(__ballot_sync(0xffffffffu, re > (uint32_t)ql)) - 1; // record of its last entry
-          npass[t] = gl - gb[t] + 1;
-          int gg = gb[t];
-          for (int p = 0; p + 1 < npass[t]; ++p) {
-            const uint32_t e = __shfl_sync(0xffffffffu, re, min(gg, 31));
-            if (e <= (uint32_t)q) ++gg;
-          }
-          gg = min(gg, cnt - 1);
-          g[t] = gg;
-          const uint32_t s_ = __shfl_sync(0xffffffffu, rs, gg);
-          const uint32_t tb = __shfl_sync(0xffffffffu, mine.tab, gg);
-          if (q < total && tb != 0xffffffffu) tix[t] = tb + ((uint32_t)q - s_);
+      for (int t = 0; t < W; ++t) {                      // class-table position of my entry
+        const uint32_t rec = (pk[t] >> 10) & VLFS_ROW_MAXREC;
+        uint32_t tb = __shfl_sync(0xffffffffu, tab0, rec & 31);
+        if (rec >= 32 && pk[t] != 0xffffffffu) tb = __ldg(tabs + k0 + rec);     // rows with > 32 records (rare)
+        tix[t] = (pk[t] != 0xffffffffu && tb != 0xffffffffu) ? tb + (pk[t] & VLFS_ROW_MAXNC) : 0xffffffffu;
+      }
+#pragma unroll
+      for (int t = 0; t < W; ++t)
+        if (tix[t] != 0xffffffffu) {
+#pragma unroll
+          for (int m = 0; m < NMAT; ++m) v[t][m] = __ldg(reinterpret_cast<const T*>(ctab_all.mat[m]) + tix[t]);
         }
 #pragma unroll
-        for (int t = 0; t < W; ++t)                      // class-table values (L2 resident)
-          if (tix[t] != 0xffffffffu) {
+      for (int t = 0; t < W; ++t) {                      // adds, one record at a time (COO order)
+        if (q0 + 32 * t >= total) continue;                // (uniform)
+        const uint32_t rec = (pk[t] >> 10) & VLFS_ROW_MAXREC;
+        const uint32_t nvalid = min(32u, total - (q0 + 32 * t));
+        const uint32_t rfirst = __shfl_sync(0xffffffffu, rec, 0), rlast = __shfl_sync(0xffffffffu, rec, nvalid - 1);
+        for (uint32_t p = rfirst; p <= rlast; ++p) {
+          if (rec == p && tix[t] != 0xffffffffu) {
 #pragma unroll
-            for (int m = 0; m < NMAT; ++m) v[t][m] = __ldg(reinterpret_cast<const T*>(ctab_all.mat[m]) + tix[t]);
-          }
-#pragma unroll
-        for (int t = 0; t < W; ++t)                      // adds, one record at a time (COO order)
-          for (int p = 0; p < npass[t]; ++p) {
-            if (g[t] == gb[t] + p && tix[t] != 0xffffffffu) {
-#pragma unroll
-              for (int m = 0; m < NMAT; ++m) {
-                T* ptr = seg + m * maxrow + slot[t];
-                if constexpr (CPLX) { T o = *ptr; o.x += v[t][m].x; o.y += v[t][m].y; *ptr = o; }
-                else *ptr += v[t][m];
-              }
+            for (int m = 0; m < NMAT; ++m) {
+              T* ptr = seg + m * maxrow + (pk[t] >> 20);
+              if constexpr (CPLX) { T o = *ptr; o.x += v[t][m].x; o.y += v[t][m].y; *ptr = o; }
+              else *ptr += v[t][m];
             }
-            __syncwarp();        // the next record may hit the same slots from other lanes
           }
+          __syncwarp();          // the next record may hit the same slots from other lanes
+        }
       }
     }
-    if (!nfetched && nrow < nrows && nk0 + lane < nk1) nmine = inc[nk0 + lane];
     __syncwarp();
     for (int sidx = lane; sidx < L; sidx += 32) {
 #pragma unroll
       for (int m = 0; m < NMAT; ++m) reinterpret_cast<T*>(ptrs.mat[m])[r0 + sidx] = seg[m * maxrow + sidx];
     }
     __syncwarp();
-    row = nrow; r0 = nr0; r1 = nr1; k0 = nk0; k1 = nk1; mine = nmine;
+    m0 = m1; m1 = m2; m2 = m3;
+    tab0 = tab1; tab1 = tab2;
+#pragma unroll
+    for (int t = 0; t < W; ++t) { pk0[t] = pk1[t]; pk1[t] = pk2[t]; }
   }
 }
 
@@ -1139,21 +1119,22 @@ void launch_count_row_entries(const unsigned long long* src, const int* incptr, 
   CUDA_TRY(cudaGetLastError());
 }
 
-void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, const uint32_t* rowstart,
-                               long long nrows, const GatherDom* doms, const int* dom_late, RowInc* out,
-                               unsigned char* late, const int* dest, int* dest_rows, cudaStream_t s) {
+void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, const int* rowptr,
+                               const uint32_t* rowstart, long long nrows, const GatherDom* doms, const int* dom_late,
+                               uint32_t* tabs, unsigned char* late, const int* dest, uint32_t* entries, int* bad,
+                               cudaStream_t s) {
   if (nrows == 0) return;
   long long grid = (nrows + 255) / 256;
   if (grid > 148 * 32) grid = 148 * 32;
-  fill_row_incidence<<<(unsigned)grid, 256, 0, s>>>(src, incptr, rowstart, nrows, doms, dom_late, out, late, dest, dest_rows);
+  fill_row_incidence<<<(unsigned)grid, 256, 0, s>>>(src, incptr, rowptr, rowstart, nrows, doms, dom_late, tabs, late, dest, entries, bad);
   CUDA_TRY(cudaGetLastError());
 }
 
-// returns false when a row segment does not fit the shared memory of a CTA (the caller then uses
-// the slot-centric gather)
-bool launch_assemble_rows(const int* rowptr, const int* incptr, const RowInc* inc, const int* dest_rows,
-                          double* const* ctab_all, long long nrows, double* const* mats, int nmat, int is_complex,
-                          int maxrow, const unsigned char* late, int phase, int nsm, cudaStream_t s) {
+// rows [first, first + nrows) of the meta list; returns false when a row segment does not fit the
+// shared memory of a CTA (the caller then uses the slot-centric gather)
+bool launch_assemble_rows(const RowMeta* meta, long long nrows, const uint32_t* tabs, const uint32_t* entries,
+                          double* const* ctab_all, double* const* mats, int nmat, int is_complex, int maxrow,
+                          int nsm, cudaStream_t s) {
   if (nrows == 0) return true;
   AsmPtrs P{}, CT{};
   for (int m = 0; m < nmat && m < 4; ++m) { P.mat[m] = mats[m]; CT.mat[m] = ctab_all[m]; }
@@ -1172,7 +1153,13 @@ bool launch_assemble_rows(const int* rowptr, const int* incptr, const RowInc* in
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)nsm * per_sm;
     if (grid > need) grid = need;
-    kern<<<(unsigned)grid, 32 * wpb, smem, s>>>(rowptr, incptr, inc, dest_rows, CT, nrows, P, maxrow, late, phase);
+    static bool said = false;
+    if (!said && getenv("VLFS_DEBUG")) {
+      said = true;
+      fprintf(stderr, "[vlfs] assemble_rows: %lld rows, maxrow %d, %d warps/CTA, %zu B smem/CTA, %d CTAs/SM, grid %lld\n",
+              nrows, maxrow, wpb, smem, per_sm, grid);
+    }
+    kern<<<(unsigned)grid, 32 * wpb, smem, s>>>(meta, nrows, tabs, entries, CT, P, maxrow);
   };
   switch (nmat * 2 + (is_complex ? 1 : 0)) {
     case 2: go(assemble_rows<1, false>); break;
