@@ -50,6 +50,20 @@ class Domain:
         self.system, self.id, self.nslots, self.D = system, did, nslots, D
         self.nterms = 0
         self.nrhs = 0
+        self.slot_ndofs = []          # bookkeeping for the byte / flop counts of bench.py
+        self.table_bytes = 0
+        self.term_flops = 0           # flops per (cell, quadrature point) of the bilinear contractions
+
+    def _count_term(self, coef, test_op, test_slots, trial_slots):
+        ncomp = {L.OP_VAL: 1, L.OP_DDIR: 1, L.OP_LAPL: 1, L.OP_GRAD_NOWN: 1, L.OP_GRAD: self.D,
+                 L.OP_CHESS_NPLUS: self.D}.get(test_op, self.D * (self.D + 1) // 2)
+        used = lambda spec: [int(k) for k, v in spec.items() if v != 0] if isinstance(spec, dict) else [int(spec)]
+        if not self.slot_ndofs:
+            return
+        nr = sum(self.slot_ndofs[k] for k in used(test_slots))
+        nc = sum(self.slot_ndofs[k] for k in used(trial_slots))
+        parts = (np.real(coef) != 0) + (np.imag(coef) != 0)
+        self.term_flops += 2 * ncomp * nr * nc * max(int(parts), 1)
 
     def _scales(self, spec):
         out = (C.c_double * L.MAX_SLOTS)()
@@ -64,6 +78,7 @@ class Domain:
                  test_dir=(0, 0, 0), trial_dir=(0, 0, 0)):
         """mat += coef ∫ w (Σ_s scale_s OP_test)(Σ_s scale_s OP_trial) dμ; *_slots is a slot
         index or a {slot: scale} dict (skeleton jumps/means)."""
+        self._count_term(coef, test_op, test_slots, trial_slots)
         t = L.TermDesc()
         t.mat, t.weight = mat, weight
         t.coef_re, t.coef_im = float(np.real(coef)), float(np.imag(coef))
@@ -212,13 +227,18 @@ class B200System:
         self._check(self.lib.vlfs_add_domain(self.ctx, C.byref(d), C.byref(did)))
         dom = Domain(self, did.value, len(slots), D)
         dom.ncells, dom.nq = ncells, nq
+        dom.slot_ndofs = [int(s["ndofs"]) for s in slots]
+        dom.table_bytes = ncells * (sum(4 * int(s["ndofs"]) + 8 * D * int(s["nv"]) for s in slots) + 8 * nq * len(weights))
         self.domains.append(dom)
         return dom
 
     # ------------------------------------------------------------------------------
     def build_pattern(self):
+        import time
         nnz, ncoo = C.c_int64(0), C.c_int64(0)
+        t0 = time.perf_counter()
         self._check(self.lib.vlfs_build_pattern(self.ctx, C.byref(nnz), C.byref(ncoo)))
+        self.pattern_build_ms = (time.perf_counter() - t0) * 1e3     # symbolic phase, once per mesh
         self.nnz, self.ncoo = nnz.value, ncoo.value
         return self.nnz
 

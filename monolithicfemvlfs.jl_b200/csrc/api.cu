@@ -48,6 +48,13 @@ bool launch_assemble_rows(const RowMeta* meta, long long nrows, const uint32_t* 
                           double* const* ctab_all, double* const* mats, int nmat, int is_complex, int maxrow,
                           int nsm, cudaStream_t s);
 double measure_fp64_fma_tflops(int nsm, int reps, cudaStream_t s);
+size_t tile_meta_bytes();
+void launch_build_sorted_tiles(const uint32_t* run_start, const uint32_t* rec32, long long nnz, const long long* late_lo,
+                               const long long* late_hi, int nlate, void* meta, unsigned char* perm, uint32_t* tile_rec,
+                               unsigned char* tile_late, int* bad, cudaStream_t s);
+void launch_gather_tiles(const int* tile_list, long long ntiles, const void* meta, const unsigned char* perm,
+                         const uint32_t* tile_rec, double* const* ctab_all, long long nnz, double* const* mats, int nmat,
+                         int is_complex, int nsm, cudaStream_t s);
 void build_csc_device(const int* rowind, const int* colind, long long nnz, long long ndofs,
                       DevBuf<int>& colptr, DevBuf<int>& rowval, DevBuf<int>& csr_slot,
                       cudaStream_t s, long long* launches);
@@ -161,6 +168,12 @@ struct vlfs_ctx {
   std::vector<unsigned> rowstart_host;
   std::vector<int> rowptr_host, incptr_host;
   long long n_early = 0;
+  // slot-centric pass on length-sorted tiles (integrate.cu: gather_tiles)
+  DevBuf<unsigned char> tile_meta, tile_perm, tile_late;
+  DevBuf<uint32_t> tile_rec;
+  DevBuf<int> tile_list;                     // tiles whose tables are ready early, then the others
+  long long ntiles = 0, ntiles_early = 0;
+  bool tiles_valid = false, tiles_two_phase = false;
   long long ninc = 0;
   int maxrow = 0;
   bool rows_valid = false, rows_two_phase = false;
@@ -674,6 +687,56 @@ void rebuild_compact_records(vlfs_ctx* ctx) {
   ctx->rec32_valid = true;
 }
 
+// Length-sorted tiles of the slot-centric pass, from the 32-bit class records (every domain
+// class-tabulated).  Rebuilt when the element-block classes change.
+void rebuild_tiles(vlfs_ctx* ctx) {
+  ctx->tiles_valid = false;
+  static const bool enabled = !(getenv("VLFS_ASM_TILES") && atoi(getenv("VLFS_ASM_TILES")) == 0);
+  if (!enabled || !ctx->rec32_valid || ctx->nnz == 0) return;
+  for (auto& d : ctx->doms)
+    if (d->dev.ncells * (long long)d->dev.entries_per_cell > 0 && !d->terms_host.empty() && !d->cls_full) return;
+  const long long ntiles = (ctx->nnz + 255) / 256;
+  ctx->ntiles = ntiles;
+  std::vector<long long> lo, hi;
+  bool any_early = false;
+  for (auto& d : ctx->doms) {
+    if (d->ncls == 0 || d->ctab_entries == 0) continue;
+    if (d->cls_full) { lo.push_back(d->ctab_base); hi.push_back(d->ctab_base + d->ctab_entries); }
+    else any_early = true;
+  }
+  DevBuf<long long> dlo, dhi;
+  DevBuf<int> bad;
+  dlo.upload(lo.data(), std::max<size_t>(lo.size(), 1), ctx->stream);
+  dhi.upload(hi.data(), std::max<size_t>(hi.size(), 1), ctx->stream);
+  bad.alloc(1); bad.zero(ctx->stream);
+  if (ctx->tile_meta.n != (size_t)ntiles * tile_meta_bytes()) {
+    ctx->tile_meta.alloc((size_t)ntiles * tile_meta_bytes());
+    ctx->tile_perm.alloc((size_t)ntiles * 256);
+    ctx->tile_late.alloc((size_t)ntiles);
+    ctx->tile_rec.alloc((size_t)ctx->ncoo);
+  }
+  launch_build_sorted_tiles(ctx->run_start.p, ctx->gather_rec32.p, ctx->nnz, dlo.p, dhi.p, (int)lo.size(), ctx->tile_meta.p,
+                            ctx->tile_perm.p, ctx->tile_rec.p, ctx->tile_late.p, bad.p, ctx->stream);
+  ++ctx->launches;
+  int hbad = 0;
+  std::vector<unsigned char> lf((size_t)ntiles);
+  CUDA_TRY(cudaMemcpyAsync(&hbad, bad.p, sizeof hbad, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(lf.data(), ctx->tile_late.p, lf.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (hbad) return;                          // a run longer than the tile layout holds: plain gather
+  std::vector<int> list;
+  list.reserve((size_t)ntiles);
+  for (long long t = 0; t < ntiles; ++t) if (!lf[(size_t)t]) list.push_back((int)t);
+  ctx->ntiles_early = (long long)list.size();
+  for (long long t = 0; t < ntiles; ++t) if (lf[(size_t)t]) list.push_back((int)t);
+  ctx->tile_list.upload(list.data(), list.size(), ctx->stream);
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->tiles_two_phase = !lo.empty() && any_early && ctx->ntiles_early > 0 && ctx->ntiles_early < ntiles;
+  ctx->tiles_valid = true;
+  ctx->gather_rec32.release();               // the tiles hold the same records
+  ctx->rec32_valid = false;
+}
+
 // slot-centric fallback records, built on demand from the sorted COO order
 void ensure_gather_records(vlfs_ctx* ctx) {
   if (ctx->gather_rec.n == (size_t)ctx->ncoo || ctx->ncoo == 0) return;
@@ -755,6 +818,23 @@ void rebuild_row_records(vlfs_ctx* ctx) {
   ctx->rows_valid = true;
 }
 
+// Which numeric pass runs when every domain is class-tabulated: length-sorted tiles (default), the
+// row-centric pass (VLFS_ASM_TILES=0), else the plain slot-centric gather with 32- or 64-bit records.
+void choose_numeric_pass(vlfs_ctx* ctx) {
+  static const bool tiles_on = !(getenv("VLFS_ASM_TILES") && atoi(getenv("VLFS_ASM_TILES")) == 0);
+  ctx->tiles_valid = ctx->rows_valid = false;
+  if (tiles_on) {
+    ensure_gather_records(ctx);
+    rebuild_compact_records(ctx);
+    rebuild_tiles(ctx);
+    if (ctx->tiles_valid) return;
+  }
+  rebuild_row_records(ctx);
+  if (ctx->rows_valid) return;
+  ensure_gather_records(ctx);
+  if (!ctx->rec32_valid) rebuild_compact_records(ctx);
+}
+
 void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   if (!ctx->pattern_built) throw std::string("vlfs_build_pattern must be called first");
   if (ctx->imported) throw std::string("the matrix was imported (vlfs_import_csr): nothing to assemble");
@@ -769,11 +849,12 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
       if (dp->cls_dirty) { classify_domain(ctx, *dp); reclass = true; }
     if (reclass) {
       upload_gather_doms(ctx);
-      rebuild_row_records(ctx);
-      if (!ctx->rows_valid) { ensure_gather_records(ctx); rebuild_compact_records(ctx); }
+      choose_numeric_pass(ctx);
     }
   }
-  const bool use_rows = do_mat && ctx->rows_valid;
+  const bool use_tiles = do_mat && ctx->tiles_valid;
+  const bool use_rows = do_mat && ctx->rows_valid && !use_tiles;
+  const bool two_phase = (use_tiles && ctx->tiles_two_phase) || (use_rows && ctx->rows_two_phase);
   // linear forms of constant-Jacobian domains touch only the vectors: they run on their own stream
   // beside the matrix passes (when both are assembled and nobody is timing kernels one by one)
   const bool vec_aside = do_vec && do_mat && !ctx->profile;
@@ -820,7 +901,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
       if (d.ncls == 0) continue;
       // row-centric pass in two phases: the directly tabulated domains share stream 0 (their tables
       // are ready first), the quadrature-tabulated ones alternate between streams 1 and 2
-      const int q = (use_rows && ctx->rows_two_phase) ? (d.cls_full ? 1 + (k++ & 1) : 0) : (k++ % 3);
+      const int q = two_phase ? (d.cls_full ? 1 + (k++ & 1) : 0) : (k++ % 3);
       cudaStream_t a = ctx->aux[q];
       if (!used[q]) { CUDA_TRY(cudaStreamWaitEvent(a, ctx->ev_fork, 0)); used[q] = true; }
       launch_build_class_tables(ctx->gather_doms.p, (int)di, d.ctab_work, ctx->nmat, ctx->is_complex, a);
@@ -835,8 +916,28 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     for (int q = 0; q < 3; ++q)
       if (used[q]) {
         CUDA_TRY(cudaEventRecord(ctx->ev_join[q], ctx->aux[q]));
-        if (!(use_rows && ctx->rows_two_phase && q > 0)) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
+        if (!(two_phase && q > 0)) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
       }
+  }
+  if (use_tiles) {
+    double* ca[4] = {ctx->ctab_all[0].p, ctx->ctab_all[1].p, ctx->ctab_all[2].p, ctx->ctab_all[3].p};
+    auto tiles = [&](int phase) {         // 0: all tiles, 1: the early part of the list, 2: the late part
+      const int* list = phase == 0 ? nullptr : ctx->tile_list.p + (phase == 2 ? ctx->ntiles_early : 0);
+      const long long n = phase == 0 ? ctx->ntiles : (phase == 1 ? ctx->ntiles_early : ctx->ntiles - ctx->ntiles_early);
+      launch_gather_tiles(list, n, ctx->tile_meta.p, ctx->tile_perm.p, ctx->tile_rec.p, ca, ctx->nnz, mp.data(),
+                          (int)mp.size(), ctx->is_complex, ctx->nsm, s);
+      ++ctx->launches;
+    };
+    if (ctx->tiles_two_phase) {
+      { ProfScope p1(ctx, "gather_tiles:early"); tiles(1); }
+      {
+        ProfScope pw(ctx, "class_tables:quadrature_wait");
+        for (int q = 1; q < 3; ++q) if (used[q]) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
+      }
+      { ProfScope p2(ctx, "gather_tiles:late"); tiles(2); }
+    } else {
+      ProfScope p0(ctx, "gather_tiles"); tiles(0);
+    }
   }
   if (use_rows) {
     {
@@ -864,8 +965,8 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   {
     // slot-centric pass: writes every CSR value (zero fill included) with the tabulated /
     // reference-type contributions summed in COO order; the cell-centric kernels then add the rest
-    ProfScope ps(ctx, use_rows ? "vector_zero" : "gather_reference");
-    if (do_mat && !use_rows) {
+    ProfScope ps(ctx, (use_rows || use_tiles) ? "vector_zero" : "gather_reference");
+    if (do_mat && !use_rows && !use_tiles) {
       double* ca[4] = {ctx->ctab_all[0].p, ctx->ctab_all[1].p, ctx->ctab_all[2].p, ctx->ctab_all[3].p};
       launch_gather_reference(ctx->run_start.p, ctx->gather_rec.p,
                               ctx->rec32_valid ? ctx->gather_rec32.p : nullptr, ca, ctx->nnz, ctx->gather_doms.p,
@@ -1196,10 +1297,7 @@ int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
         for (long long i = 0; i < ctx->ndofs; ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
         ctx->maxrow = mx;
       }
-      rebuild_row_records(ctx);
-      // the slot-centric records (0.9 GB on the paper-size Yago mesh) are only built when the
-      // row-centric pass cannot run; the sorted COO order stays for a later fallback
-      if (!ctx->rows_valid) { ensure_gather_records(ctx); rebuild_compact_records(ctx); }
+      choose_numeric_pass(ctx);
     }
     ctx->nnz = n1; ctx->ncoo = n2;
     for (size_t di = 0; di < ctx->doms.size(); ++di) {

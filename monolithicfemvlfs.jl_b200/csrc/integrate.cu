@@ -1108,7 +1108,200 @@ assemble_rows(const RowMeta* __restrict__ meta, long long nlist, const uint32_t*
   }
 }
 
+// ---- slot-centric pass on length-sorted tiles -----------------------------------------------------
+// A tile = VLFS_TILE consecutive CSR slots.  Inside a tile the slots are handed to the threads in
+// order of DEcreasing run length (number of COO contributions), and the tile's records (class-table
+// positions) are stored step-major: step j holds the j-th contribution of every thread whose run is
+// longer than j - a dense prefix of the threads.  So every load of the record stream is coalesced,
+// idle lanes only exist in the one warp that straddles the end of a step, no per-slot run pointer is
+// read (one byte per slot for the permutation, 64 bytes per tile for the step offsets), and a thread
+// still adds its run in COO order (bitwise repeatable, the order of Julia's sparse(I,J,V)).
+#define VLFS_TILE 256
+#define VLFS_TILE_MAXLEN 31
+struct TileMeta { uint32_t rec0; unsigned short off[VLFS_TILE_MAXLEN + 1]; };     // 4 + 64 bytes
+
+// once per pattern / classification: one CTA per tile
+__global__ void __launch_bounds__(VLFS_TILE)
+build_sorted_tiles(const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ rec32, long long nnz,
+                   const long long* __restrict__ late_lo, const long long* __restrict__ late_hi, int nlate,
+                   TileMeta* __restrict__ meta, unsigned char* __restrict__ perm, uint32_t* __restrict__ tile_rec,
+                   unsigned char* __restrict__ tile_late, int* __restrict__ bad) {
+  __shared__ int hist[VLFS_TILE_MAXLEN + 2];      // threads per run length
+  __shared__ int start_of_len[VLFS_TILE_MAXLEN + 2];
+  __shared__ int s_late;
+  __shared__ unsigned short s_off[VLFS_TILE_MAXLEN + 2];
+  __shared__ int rank_in_len[VLFS_TILE];
+  const long long tile = blockIdx.x, base = tile * VLFS_TILE;
+  const int t = threadIdx.x;
+  const long long slot = base + t;
+  if (t <= VLFS_TILE_MAXLEN + 1) hist[t] = 0;
+  if (t == 0) s_late = 0;
+  __syncthreads();
+  uint32_t p0 = 0, len = 0;
+  if (slot < nnz) { p0 = run_start[slot]; len = run_start[slot + 1] - p0; }
+  if (len > VLFS_TILE_MAXLEN) { atomicExch(bad, 1); len = VLFS_TILE_MAXLEN; }
+  // stable counting sort by decreasing length: position = #threads with longer runs + #earlier threads of equal length
+  // (the rank among equal lengths comes from a ballot-based scan: deterministic)
+  {
+    int r = 0;
+    for (int w0 = 0; w0 < VLFS_TILE; w0 += 32) {          // every warp ranks its lanes against all earlier threads
+      __syncthreads();
+      if (t >= w0 && t < w0 + 32) {
+        const unsigned same = __match_any_sync(0xffffffffu, len);
+        r = hist[len] + __popc(same & ((1u << (t & 31)) - 1));
+        __syncwarp();                                                            // every lane has read its count
+        if ((same & ((1u << (t & 31)) - 1)) == 0) hist[len] += __popc(same);     // one lane per distinct length
+      }
+    }
+    __syncthreads();
+    rank_in_len[t] = r;
+  }
+  if (t == 0) {
+    int acc = 0;
+    for (int l = VLFS_TILE_MAXLEN; l >= 0; --l) { start_of_len[l] = acc; acc += hist[l]; }
+    // step offsets: cnt_j = threads with len > j
+    int off = 0;
+    for (int j = 0; j <= VLFS_TILE_MAXLEN; ++j) {
+      s_off[j] = (unsigned short)off;
+      int cnt = 0;
+      for (int l = j + 1; l <= VLFS_TILE_MAXLEN; ++l) cnt += hist[l];
+      off += cnt;
+    }
+    s_off[VLFS_TILE_MAXLEN + 1] = (unsigned short)off;
+  }
+  __syncthreads();
+  const int pos = start_of_len[len] + rank_in_len[t];       // thread that takes this slot
+  if (slot < nnz) perm[base + pos] = (unsigned char)t;      // perm[thread] = slot offset inside the tile
+  const uint32_t rec0 = run_start[base < nnz ? base : nnz];
+  bool late = false;
+  for (uint32_t j = 0; j < len; ++j) {
+    const uint32_t r = rec32[p0 + j];
+    tile_rec[rec0 + s_off[j] + pos] = r;
+    for (int q = 0; q < nlate; ++q) late |= r != 0xffffffffu && (long long)r >= late_lo[q] && (long long)r < late_hi[q];
+  }
+  if (late) s_late = 1;
+  __syncthreads();
+  if (t <= VLFS_TILE_MAXLEN) meta[tile].off[t] = s_off[t];
+  if (t == 0) { meta[tile].rec0 = rec0; tile_late[tile] = (unsigned char)s_late; }
+}
+
+// One WARP per tile, no barriers: lane l owns the thread positions l, l+32, ..., l+224 of the sorted
+// tile, i.e. up to 8 independent record -> table-value chains per lane are in flight (G of them at a
+// time), which is what hides the HBM / L2 latency; every load of the record stream is a full
+// coalesced line; the finished values go straight to their slots (the tile's 4 KB are written by
+// this warp alone within a few hundred cycles, so the partial sectors merge in L2).
+template <int NMAT, bool CPLX, int G>
+__global__ void __launch_bounds__(256)
+gather_tiles(const int* __restrict__ tile_list, long long ntiles, const TileMeta* __restrict__ meta,
+             const unsigned char* __restrict__ perm, const uint32_t* __restrict__ tile_rec, AsmPtrs ctab_all,
+             long long nnz, AsmPtrs ptrs) {
+  using T = typename std::conditional<CPLX, double2, double>::type;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  long long k = w;
+  // metadata of the first tile; afterwards the next tile's metadata travels while this one is summed
+  auto tile_of = [&](long long kk) { return kk < ntiles ? (tile_list ? (long long)__ldg(tile_list + kk) : kk) : -1; };
+  long long tile = tile_of(k);
+  uint32_t rec0 = 0, off_l = 0;
+  if (tile >= 0) { rec0 = __ldg(&meta[tile].rec0); off_l = __ldg(&meta[tile].off[lane]); }
+  while (tile >= 0) {
+    const long long ntile = tile_of(k + nwarps);
+    uint32_t nrec0 = 0, noff_l = 0;
+    if (ntile >= 0) { nrec0 = __ldg(&meta[ntile].rec0); noff_l = __ldg(&meta[ntile].off[lane]); }
+    const long long base = tile * VLFS_TILE;
+#pragma unroll 1
+    for (int g0 = 0; g0 < VLFS_TILE / 32; g0 += G) {
+      if ((long long)g0 * 32 + base >= nnz) break;
+      T acc[G][NMAT];
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int m = 0; m < NMAT; ++m) acc[g][m] = T{};
+      for (int j = 0; j < VLFS_TILE_MAXLEN; ++j) {
+        const int oj = (int)__shfl_sync(0xffffffffu, off_l, j), cnt = (int)__shfl_sync(0xffffffffu, off_l, j + 1) - oj;
+        if (cnt <= g0 * 32) break;                       // (uniform) no thread position of this pass is active any more
+        uint32_t r[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int t = (g0 + g) * 32 + lane;
+          r[g] = t < cnt ? __ldg(tile_rec + rec0 + oj + t) : 0xffffffffu;
+        }
+        T v[G][NMAT];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (r[g] != 0xffffffffu) {
+#pragma unroll
+            for (int m = 0; m < NMAT; ++m) v[g][m] = __ldg(reinterpret_cast<const T*>(ctab_all.mat[m]) + r[g]);
+          }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (r[g] != 0xffffffffu) {
+#pragma unroll
+            for (int m = 0; m < NMAT; ++m) {
+              if constexpr (CPLX) { acc[g][m].x += v[g][m].x; acc[g][m].y += v[g][m].y; }
+              else acc[g][m] += v[g][m];
+            }
+          }
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const long long t = base + (g0 + g) * 32 + lane;
+        if (t < nnz) {
+          const long long slot = base + __ldg(perm + t);
+#pragma unroll
+          for (int m = 0; m < NMAT; ++m) reinterpret_cast<T*>(ptrs.mat[m])[slot] = acc[g][m];
+        }
+      }
+    }
+    k += nwarps; tile = ntile; rec0 = nrec0; off_l = noff_l;
+  }
+}
+
 }  // namespace
+
+size_t tile_meta_bytes() { return sizeof(TileMeta); }
+void launch_build_sorted_tiles(const uint32_t* run_start, const uint32_t* rec32, long long nnz, const long long* late_lo,
+                               const long long* late_hi, int nlate, void* meta, unsigned char* perm, uint32_t* tile_rec,
+                               unsigned char* tile_late, int* bad, cudaStream_t s) {
+  const long long ntiles = (nnz + VLFS_TILE - 1) / VLFS_TILE;
+  if (ntiles == 0) return;
+  build_sorted_tiles<<<(unsigned)ntiles, VLFS_TILE, 0, s>>>(run_start, rec32, nnz, late_lo, late_hi, nlate,
+                                                           reinterpret_cast<TileMeta*>(meta), perm, tile_rec, tile_late, bad);
+  CUDA_TRY(cudaGetLastError());
+}
+
+void launch_gather_tiles(const int* tile_list, long long ntiles, const void* meta, const unsigned char* perm,
+                         const uint32_t* tile_rec, double* const* ctab_all, long long nnz, double* const* mats, int nmat,
+                         int is_complex, int nsm, cudaStream_t s) {
+  if (ntiles == 0) return;
+  AsmPtrs P{}, CT{};
+  for (int m = 0; m < nmat && m < 4; ++m) { P.mat[m] = mats[m]; CT.mat[m] = ctab_all[m]; }
+  static const int per_sm_env = getenv("VLFS_TILES_CTAS") ? atoi(getenv("VLFS_TILES_CTAS")) : 0;
+  static const int g_env = getenv("VLFS_TILES_G") ? atoi(getenv("VLFS_TILES_G")) : 0;
+  auto go = [&](auto kern) {
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+    if (per_sm_env > 0) per_sm = per_sm_env;
+    long long grid = (long long)nsm * (per_sm < 1 ? 1 : per_sm);            // persistent: one warp walks its tiles
+    const long long need = (ntiles + 7) / 8;
+    if (grid > need) grid = need;
+    static bool said = false;
+    if (!said && getenv("VLFS_DEBUG")) { said = true; fprintf(stderr, "[vlfs] gather_tiles: %lld tiles, %d CTAs/SM, grid %lld\n", ntiles, per_sm, grid); }
+    kern<<<(unsigned)grid, 256, 0, s>>>(tile_list, ntiles, reinterpret_cast<const TileMeta*>(meta), perm, tile_rec, CT, nnz, P);
+  };
+  switch (nmat * 2 + (is_complex ? 1 : 0)) {
+    case 2: if (g_env == 4) go(gather_tiles<1, false, 4>); else go(gather_tiles<1, false, 8>); break;
+    case 3: if (g_env == 4) go(gather_tiles<1, true, 4>); else if (g_env == 2) go(gather_tiles<1, true, 2>); else go(gather_tiles<1, true, 8>); break;
+    case 4: go(gather_tiles<2, false, 4>); break;
+    case 5: go(gather_tiles<2, true, 4>); break;
+    case 6: go(gather_tiles<3, false, 4>); break;
+    case 7: go(gather_tiles<3, true, 2>); break;
+    case 8: go(gather_tiles<4, false, 2>); break;
+    default: go(gather_tiles<4, true, 2>); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+}
 
 void launch_count_row_entries(const unsigned long long* src, const int* incptr, long long nrows,
                               const GatherDom* doms, uint32_t* cnt, cudaStream_t s) {

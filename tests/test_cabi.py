@@ -59,3 +59,63 @@ def test_julia_shim_binds_the_reference_facing_calls():
               "vlfs_newmark_run", "vlfs_eval_functional"]
     assert [n for n in needed if ":" + n not in jl] == []
     assert "UNTESTED" in jl
+
+
+def _harness(tmp_path_factory):
+    import subprocess
+    exe = str(tmp_path_factory.mktemp("cabi") / "cabi_harness")
+    pkg = os.path.join(ROOT, "monolithicfemvlfs.jl_b200")
+    subprocess.run(["g++", "-O1", "-std=c++17", os.path.join(ROOT, "tests", "cabi_harness.cpp"), "-o", exe,
+                    "-L" + pkg, "-lvlfs_b200", "-Wl,-rpath," + pkg], check=True)
+    return exe
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    return _harness(tmp_path_factory)
+
+
+def test_struct_layouts_of_the_header_match_ctypes_and_julia(harness):
+    """A C++ program compiled against include/vlfs_b200.h reports sizeof/offsetof of every struct; the
+    ctypes mirror (what the tests call through) must agree field for field, and the Julia shim declares
+    the same fields in the same order."""
+    import subprocess
+    out = subprocess.run([harness, "--layout"], capture_output=True, text=True, check=True).stdout
+    got = {}
+    for line in out.strip().splitlines():
+        t = line.split()
+        got[t[0]] = dict(size=int(t[1]), **{t[k]: int(t[k + 1]) for k in range(2, len(t), 2)})
+    pairs = {"vlfs_slot_desc": L.SlotDesc, "vlfs_domain_desc": L.DomainDesc, "vlfs_term_desc": L.TermDesc,
+             "vlfs_rhs_desc": L.RhsDesc, "vlfs_solver_opts": L.SolverOpts, "vlfs_solve_stats": L.SolveStats,
+             "vlfs_functional_desc": L.FunctionalDesc}
+    for name, cls in pairs.items():
+        assert C.sizeof(cls) == got[name]["size"], name
+        for field, off in got[name].items():
+            if field != "size":
+                assert getattr(cls, field).offset == off, (name, field)
+    jl = open(os.path.join(ROOT, "julia", "VLFSB200.jl")).read()
+    for cls, jname in ((L.SlotDesc, "SlotDesc"), (L.TermDesc, "TermDesc"), (L.RhsDesc, "RhsDesc"), (L.SolverOpts, "SolverOpts")):
+        body = jl[jl.index("struct " + jname):]
+        body = body[:body.index("\nend")]
+        order = [f for f, _ in cls._fields_]
+        pos = [re.search(r"\b" + f + r"::", body).start() for f in order]
+        assert pos == sorted(pos), jname
+
+
+def test_harness_refuses_to_run_without_a_gpu(harness):
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert subprocess.run([harness, "--run"]).returncode == 77
+
+
+@pytest.mark.gpu
+def test_cabi_harness_on_the_gpu(tmp_path_factory):
+    """The ABI exercised from C++ exactly as `ccall` would: assembly from hand-written tables against
+    the analytic matrix, SpMV, solve, the imported-matrix LinearSolver path and a two-rank system."""
+    import subprocess
+    exe = _harness(tmp_path_factory)
+    out = subprocess.run([exe, "--run"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "all checks passed" in out.stdout
