@@ -237,11 +237,11 @@ def quadrature_flops(S):
 
 
 def numeric_pass(prof):
-    """(kernel name, ms) of the numeric pass: both launches of the two-phase kernels together."""
-    for key in ("gather_tiles", "assemble_rows"):
-        ms = sum(t for n, t in prof if n.startswith(key))
-        if ms > 0:
-            return key, ms
+    """(kernel name, ms) of the numeric pass: all launches of the pass together (template gather in
+    two phases + row expansion, or the plain chunk gather / the slot-centric fallback)."""
+    names = sorted({n.split(":")[0] for n, t in prof if n.startswith(("gather_chunks", "expand_rows")) and t > 0})
+    if names:
+        return "+".join(names), sum(t for n, t in prof if n.split(":")[0] in names)
     for n, t in prof:
         if n.startswith("gather_reference"):
             return "gather_reference", t

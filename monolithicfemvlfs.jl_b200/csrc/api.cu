@@ -35,26 +35,20 @@ void launch_compact_gather_records(const unsigned long long* rec, long long ncoo
 void launch_gather_reference(const uint32_t* run_start, const unsigned long long* rec, const uint32_t* rec32,
                              double* const* ctab_all, long long nnz, const GatherDom* doms, int ndom, int nrp_total, long long tab_total,
                              double* const* mats, int nmat, int is_complex, int nsm, cudaStream_t s);
-void build_row_incidence(const std::vector<DomainDev>& doms, long long ndofs, DevBuf<int>& incptr,
-                         DevBuf<unsigned long long>& inc_src, long long* nrec_out, cudaStream_t s,
-                         long long* launches);
-void launch_count_row_entries(const unsigned long long* src, const int* incptr, long long nrows,
-                              const GatherDom* doms, uint32_t* cnt, cudaStream_t s);
-void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, const int* rowptr,
-                               const uint32_t* rowstart, long long nrows, const GatherDom* doms, const int* dom_late,
-                               uint32_t* tabs, unsigned char* late, const int* dest, uint32_t* entries, int* bad,
-                               cudaStream_t s);
-bool launch_assemble_rows(const RowMeta* meta, long long nrows, const uint32_t* tabs, const uint32_t* entries,
-                          double* const* ctab_all, double* const* mats, int nmat, int is_complex, int maxrow,
-                          int nsm, cudaStream_t s);
 double measure_fp64_fma_tflops(int nsm, int reps, cudaStream_t s);
-size_t tile_meta_bytes();
-void launch_build_sorted_tiles(const uint32_t* run_start, const uint32_t* rec32, long long nnz, const long long* late_lo,
-                               const long long* late_hi, int nlate, void* meta, unsigned char* perm, uint32_t* tile_rec,
-                               unsigned char* tile_late, int* bad, cudaStream_t s);
-void launch_gather_tiles(const int* tile_list, long long ntiles, const void* meta, const unsigned char* perm,
-                         const uint32_t* tile_rec, double* const* ctab_all, long long nnz, double* const* mats, int nmat,
-                         int is_complex, int nsm, cudaStream_t s);
+unsigned chunk_longest_run(const uint32_t* run_start, long long nnz, cudaStream_t s);
+void launch_chunk_mark_heads(const uint32_t* run_start, long long nnz, uint32_t* rec, cudaStream_t s);
+void build_chunks(const uint32_t* run_start, long long slot_lo, long long slot_hi, unsigned maxrun, const uint32_t* rec,
+                  const long long* late_lo, const long long* late_hi, int nlate, DevBuf<unsigned char>& meta_out,
+                  long long* nchunks_out, long long* nearly_out, cudaStream_t s, long long* launches);
+void launch_gather_chunks(const void* meta, long long first, long long nchunks, const uint32_t* rec,
+                          double* const* ctab_all, double* const* mats, int nmat, int is_complex, cudaStream_t s);
+bool build_row_templates(const int* rowptr, const uint32_t* run_start, long long nrows, long long nnz, const uint32_t* rec,
+                         const long long* late_lo, const long long* late_hi, int nlate, DevBuf<uint32_t>& trec,
+                         DevBuf<uint32_t>& trun, long long* T_out, long long* T_early_out, DevBuf<unsigned char>& list,
+                         long long* rows_early_out, long long* nclasses_out, cudaStream_t s, long long* launches);
+void launch_expand_rows(const void* list, long long first, long long nlist, double* const* tmpl, double* const* mats, int nmat,
+                        int is_complex, cudaStream_t s);
 void build_csc_device(const int* rowind, const int* colind, long long nnz, long long ndofs,
                       DevBuf<int>& colptr, DevBuf<int>& rowval, DevBuf<int>& csr_slot,
                       cudaStream_t s, long long* launches);
@@ -136,12 +130,13 @@ struct Domain {
 
 }  // namespace
 
+#define VLFS_NAUX 5
 struct vlfs_ctx {
   int device = 0;
   int nsm = 148;
   cudaStream_t stream = nullptr;
-  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // class tables of different domains in parallel
-  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t aux[VLFS_NAUX] = {};   // class tables of different domains in parallel
+  cudaEvent_t ev_fork = nullptr, ev_join[VLFS_NAUX] = {};
   cudaStream_t aux_vec = nullptr;                      // linear forms next to the matrix passes
   cudaEvent_t ev_vec_fork = nullptr, ev_vec_join = nullptr;
   std::string err;
@@ -157,26 +152,19 @@ struct vlfs_ctx {
   DevBuf<uint32_t> gather_rec32;           // index of the entry's class-table value (all domains tabulated)
   DevBuf<double> ctab_all[4];              // per matrix: the class tables of all domains, contiguous
   bool rec32_valid = false;
-  // row-centric numeric pass: incidence records of every row (pattern.cu: build_row_incidence)
-  DevBuf<int> incptr, dom_late;
-  DevBuf<uint32_t> row_entries;              // packed entry stream: the COO->slot permutation re-laid row by row
-  DevBuf<uint32_t> rowstart;                 // first entry of every row's run in row_entries
-  DevBuf<unsigned long long> inc_src;
-  DevBuf<uint32_t> inc_tabs;                 // class-table position of every incidence record (+32 padding)
-  DevBuf<unsigned char> row_late;
-  DevBuf<RowMeta> row_meta;                  // rows in processing order: tables ready early first, then the others
-  std::vector<unsigned> rowstart_host;
-  std::vector<int> rowptr_host, incptr_host;
-  long long n_early = 0;
-  // slot-centric pass on length-sorted tiles (integrate.cu: gather_tiles)
-  DevBuf<unsigned char> tile_meta, tile_perm, tile_late;
-  DevBuf<uint32_t> tile_rec;
-  DevBuf<int> tile_list;                     // tiles whose tables are ready early, then the others
-  long long ntiles = 0, ntiles_early = 0;
-  bool tiles_valid = false, tiles_two_phase = false;
-  long long ninc = 0;
-  int maxrow = 0;
-  bool rows_valid = false, rows_two_phase = false;
+  // chunked slot-centric pass (gather.cu: gather_chunks) in two segments: chunks whose class tables are
+  // ready early, then the others.  Without row templates the records live in gather_rec32 and the
+  // values go to the matrices; with row templates (tmpl_valid) the pass runs on the template stream
+  // (trec / trun) into tmpl_vals and expand_rows copies the template of every row into the matrices.
+  DevBuf<unsigned char> chunk_meta[2];
+  const unsigned char* seg_meta[2] = {nullptr, nullptr};
+  long long seg_first[2] = {0, 0}, seg_count[2] = {0, 0};
+  bool chunks_valid = false, chunks_two_phase = false;
+  bool tmpl_valid = false;
+  DevBuf<uint32_t> trec, trun;
+  DevBuf<double> tmpl_vals[4];
+  DevBuf<unsigned char> row_list;            // uint4 per row in processing order (early rows first)
+  long long tmpl_slots = 0, tmpl_classes = 0, rows_early = 0;
   int nrp_total = 0;
   long long tab_total = 0;
   DevBuf<GatherDom> gather_doms;
@@ -687,16 +675,23 @@ void rebuild_compact_records(vlfs_ctx* ctx) {
   ctx->rec32_valid = true;
 }
 
-// Length-sorted tiles of the slot-centric pass, from the 32-bit class records (every domain
-// class-tabulated).  Rebuilt when the element-block classes change.
-void rebuild_tiles(vlfs_ctx* ctx) {
-  ctx->tiles_valid = false;
-  static const bool enabled = !(getenv("VLFS_ASM_TILES") && atoi(getenv("VLFS_ASM_TILES")) == 0);
+// Chunk tables of the slot-centric pass, from the 32-bit class records (every domain
+// class-tabulated).  Rebuilt when the element-block classes change.  The records are converted in
+// place to the chunk format (head bit), so the plain compact gather no longer applies afterwards.
+// Rows with identical record streams share one template (VLFS_ASM_TEMPLATES=0 switches that off).
+void rebuild_chunks(vlfs_ctx* ctx) {
+  ctx->chunks_valid = ctx->tmpl_valid = false;
+  static const bool enabled = !(getenv("VLFS_ASM_CHUNKS") && atoi(getenv("VLFS_ASM_CHUNKS")) == 0);
+  static const bool templates = !(getenv("VLFS_ASM_TEMPLATES") && atoi(getenv("VLFS_ASM_TEMPLATES")) == 0);
   if (!enabled || !ctx->rec32_valid || ctx->nnz == 0) return;
-  for (auto& d : ctx->doms)
+  long long total = 0;
+  for (auto& d : ctx->doms) {
     if (d->dev.ncells * (long long)d->dev.entries_per_cell > 0 && !d->terms_host.empty() && !d->cls_full) return;
-  const long long ntiles = (ctx->nnz + 255) / 256;
-  ctx->ntiles = ntiles;
+    total += d->ctab_entries;
+  }
+  if (total >= 0x7fffffffll) return;
+  const unsigned maxrun = chunk_longest_run(ctx->run_start.p, ctx->nnz, ctx->stream);
+  if (maxrun == 0) return;                    // a run longer than the shared-memory window: plain gather
   std::vector<long long> lo, hi;
   bool any_early = false;
   for (auto& d : ctx->doms) {
@@ -705,36 +700,44 @@ void rebuild_tiles(vlfs_ctx* ctx) {
     else any_early = true;
   }
   DevBuf<long long> dlo, dhi;
-  DevBuf<int> bad;
-  dlo.upload(lo.data(), std::max<size_t>(lo.size(), 1), ctx->stream);
-  dhi.upload(hi.data(), std::max<size_t>(hi.size(), 1), ctx->stream);
-  bad.alloc(1); bad.zero(ctx->stream);
-  if (ctx->tile_meta.n != (size_t)ntiles * tile_meta_bytes()) {
-    ctx->tile_meta.alloc((size_t)ntiles * tile_meta_bytes());
-    ctx->tile_perm.alloc((size_t)ntiles * 256);
-    ctx->tile_late.alloc((size_t)ntiles);
-    ctx->tile_rec.alloc((size_t)ctx->ncoo);
-  }
-  launch_build_sorted_tiles(ctx->run_start.p, ctx->gather_rec32.p, ctx->nnz, dlo.p, dhi.p, (int)lo.size(), ctx->tile_meta.p,
-                            ctx->tile_perm.p, ctx->tile_rec.p, ctx->tile_late.p, bad.p, ctx->stream);
+  const long long none = 0;
+  dlo.upload(lo.empty() ? &none : lo.data(), std::max<size_t>(lo.size(), 1), ctx->stream);
+  dhi.upload(hi.empty() ? &none : hi.data(), std::max<size_t>(hi.size(), 1), ctx->stream);
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  launch_chunk_mark_heads(ctx->run_start.p, ctx->nnz, ctx->gather_rec32.p, ctx->stream);
   ++ctx->launches;
-  int hbad = 0;
-  std::vector<unsigned char> lf((size_t)ntiles);
-  CUDA_TRY(cudaMemcpyAsync(&hbad, bad.p, sizeof hbad, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaMemcpyAsync(lf.data(), ctx->tile_late.p, lf.size(), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  if (hbad) return;                          // a run longer than the tile layout holds: plain gather
-  std::vector<int> list;
-  list.reserve((size_t)ntiles);
-  for (long long t = 0; t < ntiles; ++t) if (!lf[(size_t)t]) list.push_back((int)t);
-  ctx->ntiles_early = (long long)list.size();
-  for (long long t = 0; t < ntiles; ++t) if (lf[(size_t)t]) list.push_back((int)t);
-  ctx->tile_list.upload(list.data(), list.size(), ctx->stream);
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  ctx->tiles_two_phase = !lo.empty() && any_early && ctx->ntiles_early > 0 && ctx->ntiles_early < ntiles;
-  ctx->tiles_valid = true;
-  ctx->gather_rec32.release();               // the tiles hold the same records
-  ctx->rec32_valid = false;
+  ctx->rec32_valid = false;                   // the records now carry the head bit
+  long long T = 0, Te = 0;
+  if (templates && build_row_templates(ctx->rowptr.p, ctx->run_start.p, ctx->ndofs, ctx->nnz, ctx->gather_rec32.p, dlo.p, dhi.p,
+                                       (int)lo.size(), ctx->trec, ctx->trun, &T, &Te, ctx->row_list, &ctx->rows_early,
+                                       &ctx->tmpl_classes, ctx->stream, &ctx->launches)) {
+    ctx->tmpl_slots = T;
+    for (int m = 0; m < ctx->nmat; ++m)
+      if (ctx->tmpl_vals[m].n != (size_t)T * ctx->scalar()) ctx->tmpl_vals[m].alloc((size_t)T * ctx->scalar());
+    long long ne = 0;
+    build_chunks(ctx->trun.p, 0, Te, maxrun, ctx->trec.p, dlo.p, dhi.p, 0, ctx->chunk_meta[0], &ctx->seg_count[0], &ne,
+                 ctx->stream, &ctx->launches);
+    build_chunks(ctx->trun.p, Te, T, maxrun, ctx->trec.p, dlo.p, dhi.p, 0, ctx->chunk_meta[1], &ctx->seg_count[1], &ne,
+                 ctx->stream, &ctx->launches);
+    ctx->seg_meta[0] = ctx->chunk_meta[0].p; ctx->seg_meta[1] = ctx->chunk_meta[1].p;
+    ctx->seg_first[0] = ctx->seg_first[1] = 0;
+    ctx->tmpl_valid = true;
+    if (getenv("VLFS_DEBUG"))
+      fprintf(stderr, "[vlfs] row templates: %lld classes of rows for %lld rows, %lld template slots for %lld values (%lld early)\n",
+              ctx->tmpl_classes, ctx->ndofs, T, ctx->nnz, Te);
+  } else {
+    ctx->trec.release(); ctx->trun.release(); ctx->row_list.release();
+    for (int m = 0; m < 4; ++m) ctx->tmpl_vals[m].release();
+    long long nchunks = 0, ne = 0;
+    build_chunks(ctx->run_start.p, 0, ctx->nnz, maxrun, ctx->gather_rec32.p, dlo.p, dhi.p, (int)lo.size(), ctx->chunk_meta[0],
+                 &nchunks, &ne, ctx->stream, &ctx->launches);
+    ctx->chunk_meta[1].release();
+    ctx->seg_meta[0] = ctx->seg_meta[1] = ctx->chunk_meta[0].p;
+    ctx->seg_first[0] = 0; ctx->seg_count[0] = ne;
+    ctx->seg_first[1] = ne; ctx->seg_count[1] = nchunks - ne;
+  }
+  ctx->chunks_two_phase = !lo.empty() && any_early && ctx->seg_count[0] > 0 && ctx->seg_count[1] > 0;
+  ctx->chunks_valid = true;
 }
 
 // slot-centric fallback records, built on demand from the sorted COO order
@@ -747,92 +750,13 @@ void ensure_gather_records(vlfs_ctx* ctx) {
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
 }
 
-// RowInc records of the row-centric pass: possible when every domain that owns COO entries is
-// class-tabulated (same condition as the 32-bit gather records)
-void rebuild_row_records(vlfs_ctx* ctx) {
-  ctx->rows_valid = false;
-  static const bool enabled = !(getenv("VLFS_ASM_ROWS") && atoi(getenv("VLFS_ASM_ROWS")) == 0);
-  if (!enabled || ctx->ninc == 0 || ctx->maxrow == 0) return;
-  if ((size_t)ctx->nmat * ctx->maxrow * ctx->scalar() * sizeof(double) > 200 * 1024) return;   // row segment > shared memory
-  long long total = 0;
-  std::vector<int> late(ctx->doms.size(), 0);
-  bool any_late = false, any_early = false;
-  for (size_t di = 0; di < ctx->doms.size(); ++di) {
-    Domain& d = *ctx->doms[di];
-    if (d.dev.ncells * (long long)d.dev.entries_per_cell == 0) continue;
-    if (d.ncls == 0) return;
-    if (!d.terms_host.empty() && !d.cls_full) return;      // cell-centric terms left: they need the zero fill first
-    total += d.ctab_entries;
-    late[di] = d.cls_full ? 1 : 0;
-    (d.cls_full ? any_late : any_early) = true;
-  }
-  if (total >= 0xffffffffll) return;
-  ctx->dom_late.upload(late.data(), late.size(), ctx->stream);
-  const bool first = ctx->row_entries.n != (size_t)ctx->ncoo;
-  DevBuf<int> bad;
-  bad.alloc(1); bad.zero(ctx->stream);
-  if (first) {                                // once per pattern: packed entry stream in row-major order
-    DevBuf<uint32_t> cnt, total;
-    cnt.alloc((size_t)ctx->ndofs); total.alloc(1);
-    ctx->rowstart.alloc((size_t)ctx->ndofs);
-    launch_count_row_entries(ctx->inc_src.p, ctx->incptr.p, ctx->ndofs, ctx->gather_doms.p, cnt.p, ctx->stream);
-    exclusive_scan_u32(cnt.p, ctx->rowstart.p, (size_t)ctx->ndofs, total.p, ctx->stream);
-    ctx->row_entries.alloc((size_t)ctx->ncoo);
-    ctx->inc_tabs.alloc((size_t)ctx->ninc + 32);
-    CUDA_TRY(cudaMemsetAsync(ctx->inc_tabs.p, 0xff, ((size_t)ctx->ninc + 32) * sizeof(uint32_t), ctx->stream));
-    ctx->launches += 3;
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    ctx->rowstart_host.resize((size_t)ctx->ndofs);
-    ctx->incptr_host.resize((size_t)ctx->ndofs + 1);
-    CUDA_TRY(cudaMemcpy(ctx->rowstart_host.data(), ctx->rowstart.p, ctx->rowstart_host.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(ctx->incptr_host.data(), ctx->incptr.p, ctx->incptr_host.size() * sizeof(int), cudaMemcpyDeviceToHost));
-  }
-  if (ctx->row_late.n != (size_t)ctx->ndofs) ctx->row_late.alloc((size_t)ctx->ndofs);
-  launch_fill_row_incidence(ctx->inc_src.p, ctx->incptr.p, ctx->rowptr.p, ctx->rowstart.p, ctx->ndofs, ctx->gather_doms.p,
-                            ctx->dom_late.p, ctx->inc_tabs.p, ctx->row_late.p, ctx->dest_all.p,
-                            first ? ctx->row_entries.p : nullptr, bad.p, ctx->stream);
-  ++ctx->launches;
-  int hbad = 0;
-  CUDA_TRY(cudaMemcpyAsync(&hbad, bad.p, sizeof hbad, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  if (hbad) { ctx->row_entries.release(); return; }      // a row beyond the packed fields: slot-centric pass
-  {                                           // row metadata in processing order (host: once per classification)
-    std::vector<unsigned char> lf((size_t)ctx->ndofs);
-    CUDA_TRY(cudaMemcpy(lf.data(), ctx->row_late.p, lf.size(), cudaMemcpyDeviceToHost));
-    std::vector<RowMeta> list;
-    list.reserve(lf.size());
-    const std::vector<int>& rp = ctx->rowptr_host;
-    auto push = [&](long long r) {
-      const unsigned e0 = ctx->rowstart_host[(size_t)r];
-      const unsigned e1 = r + 1 < ctx->ndofs ? ctx->rowstart_host[(size_t)r + 1] : (unsigned)ctx->ncoo;
-      list.push_back(RowMeta{rp[(size_t)r], e0, (unsigned)ctx->incptr_host[(size_t)r],
-                             (unsigned)(rp[(size_t)r + 1] - rp[(size_t)r]) | ((e1 - e0) << 12)});
-    };
-    for (long long r = 0; r < ctx->ndofs; ++r) if (!lf[(size_t)r]) push(r);
-    ctx->n_early = (long long)list.size();
-    for (long long r = 0; r < ctx->ndofs; ++r) if (lf[(size_t)r]) push(r);
-    ctx->row_meta.upload(list.data(), list.size(), ctx->stream);
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  }
-  ctx->rows_two_phase = any_late && any_early && ctx->n_early > 0 && ctx->n_early < ctx->ndofs;
-  ctx->rows_valid = true;
-}
-
-// Which numeric pass runs when every domain is class-tabulated: length-sorted tiles (default), the
-// row-centric pass (VLFS_ASM_TILES=0), else the plain slot-centric gather with 32- or 64-bit records.
+// Which numeric pass runs: with every domain class-tabulated the chunked slot-centric pass, else the
+// plain slot-centric gather (32- or 64-bit records) followed by the cell-centric kernels.
 void choose_numeric_pass(vlfs_ctx* ctx) {
-  static const bool tiles_on = !(getenv("VLFS_ASM_TILES") && atoi(getenv("VLFS_ASM_TILES")) == 0);
-  ctx->tiles_valid = ctx->rows_valid = false;
-  if (tiles_on) {
-    ensure_gather_records(ctx);
-    rebuild_compact_records(ctx);
-    rebuild_tiles(ctx);
-    if (ctx->tiles_valid) return;
-  }
-  rebuild_row_records(ctx);
-  if (ctx->rows_valid) return;
+  ctx->chunks_valid = false;
   ensure_gather_records(ctx);
-  if (!ctx->rec32_valid) rebuild_compact_records(ctx);
+  rebuild_compact_records(ctx);
+  rebuild_chunks(ctx);
 }
 
 void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
@@ -852,9 +776,8 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
       choose_numeric_pass(ctx);
     }
   }
-  const bool use_tiles = do_mat && ctx->tiles_valid;
-  const bool use_rows = do_mat && ctx->rows_valid && !use_tiles;
-  const bool two_phase = (use_tiles && ctx->tiles_two_phase) || (use_rows && ctx->rows_two_phase);
+  const bool use_chunks = do_mat && ctx->chunks_valid;
+  const bool two_phase = use_chunks && ctx->chunks_two_phase;
   // linear forms of constant-Jacobian domains touch only the vectors: they run on their own stream
   // beside the matrix passes (when both are assembled and nobody is timing kernels one by one)
   const bool vec_aside = do_vec && do_mat && !ctx->profile;
@@ -881,7 +804,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     for (auto& dp : ctx->doms) if (!dp->rhs_host.empty() && !dp->rhs_fast) vec_join_early = true;
     if (vec_join_early) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_vec_join, 0));
   }
-  bool used[3] = {false, false, false};
+  bool used[VLFS_NAUX] = {};
   if (do_mat) {
     // per-class element blocks: reference products tabulated directly, general (quadrature) terms
     // integrated on the class representatives only, reduced into the class tables.  These are
@@ -889,7 +812,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
     ProfScope ps(ctx, "class_tables");
     if (!ctx->ev_fork) {
       CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-      for (int k = 0; k < 3; ++k) {
+      for (int k = 0; k < VLFS_NAUX; ++k) {
         CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming));
       }
@@ -900,8 +823,8 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
       Domain& d = *ctx->doms[di];
       if (d.ncls == 0) continue;
       // row-centric pass in two phases: the directly tabulated domains share stream 0 (their tables
-      // are ready first), the quadrature-tabulated ones alternate between streams 1 and 2
-      const int q = two_phase ? (d.cls_full ? 1 + (k++ & 1) : 0) : (k++ % 3);
+      // are ready first), the quadrature-tabulated ones take the other streams in turn
+      const int q = two_phase ? (d.cls_full ? 1 + (k++ % (VLFS_NAUX - 1)) : 0) : (k++ % VLFS_NAUX);
       cudaStream_t a = ctx->aux[q];
       if (!used[q]) { CUDA_TRY(cudaStreamWaitEvent(a, ctx->ev_fork, 0)); used[q] = true; }
       launch_build_class_tables(ctx->gather_doms.p, (int)di, d.ctab_work, ctx->nmat, ctx->is_complex, a);
@@ -913,60 +836,46 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
         ++ctx->launches;
       }
     }
-    for (int q = 0; q < 3; ++q)
+    for (int q = 0; q < VLFS_NAUX; ++q)
       if (used[q]) {
         CUDA_TRY(cudaEventRecord(ctx->ev_join[q], ctx->aux[q]));
         if (!(two_phase && q > 0)) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
       }
   }
-  if (use_tiles) {
+  if (use_chunks) {
     double* ca[4] = {ctx->ctab_all[0].p, ctx->ctab_all[1].p, ctx->ctab_all[2].p, ctx->ctab_all[3].p};
-    auto tiles = [&](int phase) {         // 0: all tiles, 1: the early part of the list, 2: the late part
-      const int* list = phase == 0 ? nullptr : ctx->tile_list.p + (phase == 2 ? ctx->ntiles_early : 0);
-      const long long n = phase == 0 ? ctx->ntiles : (phase == 1 ? ctx->ntiles_early : ctx->ntiles - ctx->ntiles_early);
-      launch_gather_tiles(list, n, ctx->tile_meta.p, ctx->tile_perm.p, ctx->tile_rec.p, ca, ctx->nnz, mp.data(),
-                          (int)mp.size(), ctx->is_complex, ctx->nsm, s);
+    double* tv[4] = {ctx->tmpl_vals[0].p, ctx->tmpl_vals[1].p, ctx->tmpl_vals[2].p, ctx->tmpl_vals[3].p};
+    const bool tm = ctx->tmpl_valid;
+    auto chunks = [&](int seg) {
+      if (ctx->seg_count[seg] == 0) return;
+      launch_gather_chunks(ctx->seg_meta[seg], ctx->seg_first[seg], ctx->seg_count[seg], tm ? ctx->trec.p : ctx->gather_rec32.p,
+                           ca, tm ? tv : mp.data(), (int)mp.size(), ctx->is_complex, s);
       ++ctx->launches;
     };
-    if (ctx->tiles_two_phase) {
-      { ProfScope p1(ctx, "gather_tiles:early"); tiles(1); }
+    auto expand = [&](long long first, long long n) {
+      if (n == 0) return;
+      launch_expand_rows(ctx->row_list.p, first, n, tv, mp.data(), (int)mp.size(), ctx->is_complex, s);
+      ++ctx->launches;
+    };
+    if (two_phase) {
+      { ProfScope p1(ctx, "gather_chunks:early"); chunks(0); }
+      if (tm) { ProfScope p1(ctx, "expand_rows:early"); expand(0, ctx->rows_early); }
       {
         ProfScope pw(ctx, "class_tables:quadrature_wait");
-        for (int q = 1; q < 3; ++q) if (used[q]) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
+        for (int q = 1; q < VLFS_NAUX; ++q) if (used[q]) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
       }
-      { ProfScope p2(ctx, "gather_tiles:late"); tiles(2); }
+      { ProfScope p2(ctx, "gather_chunks:late"); chunks(1); }
+      if (tm) { ProfScope p2(ctx, "expand_rows:late"); expand(ctx->rows_early, ctx->ndofs - ctx->rows_early); }
     } else {
-      ProfScope p0(ctx, "gather_tiles"); tiles(0);
-    }
-  }
-  if (use_rows) {
-    {
-      double* ca[4] = {ctx->ctab_all[0].p, ctx->ctab_all[1].p, ctx->ctab_all[2].p, ctx->ctab_all[3].p};
-      auto rows = [&](int phase) {        // 0: all rows, 1: the early part of the list, 2: the late part
-        const RowMeta* list = ctx->row_meta.p + (phase == 2 ? ctx->n_early : 0);
-        const long long n = phase == 0 ? ctx->ndofs : (phase == 1 ? ctx->n_early : ctx->ndofs - ctx->n_early);
-        if (!launch_assemble_rows(list, n, ctx->inc_tabs.p, ctx->row_entries.p, ca, mp.data(),
-                                  (int)mp.size(), ctx->is_complex, ctx->maxrow, ctx->nsm, s))
-          throw std::string("row-centric pass: a matrix row does not fit the shared memory");
-        ++ctx->launches;
-      };
-      if (ctx->rows_two_phase) {
-        { ProfScope p1(ctx, "assemble_rows:early"); rows(1); }
-        {
-          ProfScope pw(ctx, "class_tables:quadrature_wait");
-          for (int q = 1; q < 3; ++q) if (used[q]) CUDA_TRY(cudaStreamWaitEvent(s, ctx->ev_join[q], 0));
-        }
-        { ProfScope p2(ctx, "assemble_rows:late"); rows(2); }
-      } else {
-        ProfScope p0(ctx, "assemble_rows"); rows(0);
-      }
+      { ProfScope p0(ctx, "gather_chunks"); chunks(0); chunks(1); }
+      if (tm) { ProfScope p0(ctx, "expand_rows"); expand(0, ctx->ndofs); }
     }
   }
   {
     // slot-centric pass: writes every CSR value (zero fill included) with the tabulated /
     // reference-type contributions summed in COO order; the cell-centric kernels then add the rest
-    ProfScope ps(ctx, (use_rows || use_tiles) ? "vector_zero" : "gather_reference");
-    if (do_mat && !use_rows && !use_tiles) {
+    ProfScope ps(ctx, use_chunks ? "vector_zero" : "gather_reference");
+    if (do_mat && !use_chunks) {
       double* ca[4] = {ctx->ctab_all[0].p, ctx->ctab_all[1].p, ctx->ctab_all[2].p, ctx->ctab_all[3].p};
       launch_gather_reference(ctx->run_start.p, ctx->gather_rec.p,
                               ctx->rec32_valid ? ctx->gather_rec32.p : nullptr, ca, ctx->nnz, ctx->gather_doms.p,
@@ -1094,7 +1003,7 @@ int vlfs_destroy(vlfs_ctx* ctx) {
   if (ctx->aux_vec) cudaStreamDestroy(ctx->aux_vec);
   if (ctx->ev_vec_fork) cudaEventDestroy(ctx->ev_vec_fork);
   if (ctx->ev_vec_join) cudaEventDestroy(ctx->ev_vec_join);
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < VLFS_NAUX; ++k) {
     if (ctx->aux[k]) cudaStreamDestroy(ctx->aux[k]);
     if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
   }
@@ -1287,16 +1196,6 @@ int vlfs_build_pattern(vlfs_ctx* ctx, int64_t* nnz, int64_t* ncoo) {
       ctx->tab_total = 0;
       for (auto& d : ctx->doms) { ctx->nrp_total += (int)d->refprods_host.size(); ctx->tab_total += (long long)d->reftabs.n; }
       if ((int)ctx->doms.size() > 16) throw std::string("more than 16 integration domains");
-      // row-centric numeric pass: incidence lists of every row, longest row (its shared-memory segment)
-      build_row_incidence(devs, ctx->ndofs, ctx->incptr, ctx->inc_src, &ctx->ninc, ctx->stream, &ctx->launches);
-      {
-        std::vector<int>& rp = ctx->rowptr_host;
-        rp.resize((size_t)ctx->ndofs + 1);
-        CUDA_TRY(cudaMemcpy(rp.data(), ctx->rowptr.p, rp.size() * sizeof(int), cudaMemcpyDeviceToHost));
-        int mx = 0;
-        for (long long i = 0; i < ctx->ndofs; ++i) mx = std::max(mx, rp[i + 1] - rp[i]);
-        ctx->maxrow = mx;
-      }
       choose_numeric_pass(ctx);
     }
     ctx->nnz = n1; ctx->ncoo = n2;

@@ -174,20 +174,6 @@ struct GatherDom {
   long long ctab_off[VLFS_MAX_BLOCKS];   // entry offset of every block inside a class table
 };
 
-// ---- row-centric numeric pass (integrate.cu: assemble_rows) --------------------------------------
-// RowMeta (one per CSR row, stored in processing order: rows whose class tables are ready early first):
-//   r0     first CSR slot of the row
-//   e0     first entry of the row's run in the packed entry stream
-//   k0     first incidence record of the row (tabs[k0 + rec] = class-table position of element-matrix
-//          row `rec`; 0xffffffff: the block has no class table, its terms come from the cell-centric kernel)
-//   lt     row length (12 bits) | number of entries of the run << 12
-// entry stream (one 32-bit word per COO entry, the COO->slot permutation re-laid row by row and in
-// COO order inside a row):  slot - r0 (12 bits) << 20 | record (10 bits) << 10 | column inside the record (10 bits)
-struct RowMeta { int r0; uint32_t e0, k0, lt; };
-#define VLFS_ROW_MAXLEN 4095
-#define VLFS_ROW_MAXREC 1023
-#define VLFS_ROW_MAXNC 1023
-
 // ---- primitives -------------------------------------------------------------------
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev,
                         cudaStream_t s);

@@ -955,418 +955,7 @@ gather_compact(const uint32_t* __restrict__ run_start, const uint32_t* __restric
   }
 }
 
-// packed (domain, block, local row, cell) sources -> class-table positions tabs[k] of the incidence
-// records (once per pattern and again when the element-block classes change); late[row] = 1 when a
-// contributing domain's class tables come out of the quadrature kernel (ready later than the directly
-// tabulated ones).  With `entries` != nullptr (once per pattern) the packed entry stream and the
-// row's entry count are written too.
-__global__ void fill_row_incidence(const unsigned long long* __restrict__ src, const int* __restrict__ incptr,
-                                   const int* __restrict__ rowptr, const uint32_t* __restrict__ rowstart, long long nrows,
-                                   const GatherDom* __restrict__ doms, const int* __restrict__ dom_late,
-                                   uint32_t* __restrict__ tabs, unsigned char* __restrict__ late,
-                                   const int* __restrict__ dest, uint32_t* __restrict__ entries, int* __restrict__ bad) {
-  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < nrows;
-       row += (long long)gridDim.x * blockDim.x) {
-    unsigned char l = 0;
-    uint32_t pos = rowstart[row];
-    const int k0 = incptr[row], k1 = incptr[row + 1], r0 = rowptr[row];
-    if (entries && (k1 - k0 > VLFS_ROW_MAXREC + 1 || rowptr[row + 1] - r0 > VLFS_ROW_MAXLEN)) atomicExch(bad, 1);
-    for (int k = k0; k < k1; ++k) {
-      const unsigned long long r = src[k];
-      const unsigned d = (unsigned)(r >> 60), b = (unsigned)((r >> 58) & 3u), a = (unsigned)((r >> 32) & 0x3fffu);
-      const unsigned e = (unsigned)(r & 0xffffffffull);
-      const GatherDom& G = doms[d];
-      const int nc = G.blk[b].nc;
-      tabs[k] = (G.ncls > 0 && G.ctab_off[b] >= 0)
-                    ? (uint32_t)(G.ctab_base + G.ctab_off[b] + (long long)G.cls[e] * (G.blk[b].nr * nc) + (long long)a * nc)
-                    : 0xffffffffu;
-      if (entries) {
-        if (nc > VLFS_ROW_MAXNC + 1) atomicExch(bad, 1);
-        const long long coo = G.coo_lo + (long long)e * G.epc + G.blk[b].off + (long long)a * nc;
-        const uint32_t rec = (uint32_t)(k - k0) & VLFS_ROW_MAXREC;
-        for (int j = 0; j < nc; ++j)
-          entries[pos + j] = ((uint32_t)(dest[coo + j] - r0) << 20) | (rec << 10) | ((uint32_t)j & VLFS_ROW_MAXNC);
-      }
-      pos += nc;
-      l |= (unsigned char)dom_late[d];
-    }
-    late[row] = l;
-  }
-}
-
-// contributions (COO entries) per row -> cnt[row]  (scanned into rowstart by the caller)
-__global__ void count_row_entries(const unsigned long long* __restrict__ src, const int* __restrict__ incptr,
-                                  long long nrows, const GatherDom* __restrict__ doms, uint32_t* __restrict__ cnt) {
-  for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < nrows;
-       row += (long long)gridDim.x * blockDim.x) {
-    uint32_t c = 0;
-    for (int k = incptr[row]; k < incptr[row + 1]; ++k) {
-      const unsigned long long r = src[k];
-      c += (uint32_t)doms[(unsigned)(r >> 60)].blk[(unsigned)((r >> 58) & 3u)].nc;
-    }
-    cnt[row] = c;
-  }
-}
-
-// Row-centric numeric pass (every domain class-tabulated): one warp per CSR row.  The row's value
-// segment lives in shared memory.  The row's contributions are ONE contiguous run of the packed
-// entry stream (slot inside the row, element-matrix row = record, column inside the record): the lanes
-// stream the run with coalesced loads, fetch the record's class-table position, read the table value
-// (contiguous inside a record, L2 resident) and add into the segment - record by record, i.e. in
-// COO order, the order in which Julia's sparse(I,J,V) adds duplicates, so the result is bitwise
-// repeatable without atomics.  The finished segment is written to the CSR values in one coalesced
-// pass: every value is written exactly once (this is also the zero fill), every COO entry is read
-// exactly once (4 bytes), nothing else streams from HBM.  Rows are taken in the order of `meta`
-// (early rows first); the meta of row i+2 and the first windows of row i+1 travel while row i is summed.
-template <int NMAT, bool CPLX>
-__global__ void __launch_bounds__(256, NMAT == 1 ? 4 : (NMAT == 2 ? 3 : 2))
-assemble_rows(const RowMeta* __restrict__ meta, long long nlist, const uint32_t* __restrict__ tabs,
-              const uint32_t* __restrict__ entries, AsmPtrs ctab_all, AsmPtrs ptrs, int maxrow) {
-  using T = typename std::conditional<CPLX, double2, double>::type;
-  constexpr int W = 2;                 // windows of 32 entries prefetched per row
-  extern __shared__ __align__(16) double seg_raw[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  T* seg = reinterpret_cast<T*>(seg_raw) + (size_t)wib * NMAT * maxrow;
-  const long long nwarps = (long long)gridDim.x * wpb, w = (long long)blockIdx.x * wpb + wib;
-  const int4 nometa = make_int4(0, 0, 0, 0);
-  auto load_meta = [&](long long i) {
-    const long long q = w + i * nwarps;
-    return q < nlist ? __ldg(reinterpret_cast<const int4*>(meta) + q) : nometa;
-  };
-  auto load_windows = [&](const int4& m, uint32_t (&pk)[W], uint32_t& tab) {
-    const uint32_t total = (uint32_t)m.w >> 12;
-#pragma unroll
-    for (int t = 0; t < W; ++t) pk[t] = (uint32_t)(32 * t + lane) < total ? __ldg(entries + (uint32_t)m.y + 32 * t + lane) : 0xffffffffu;
-    tab = total ? __ldg(tabs + (uint32_t)m.z + lane) : 0xffffffffu;   // (padded: reading 32 records is always in range)
-  };
-  int4 m2 = load_meta(2), m1 = load_meta(1), m0 = load_meta(0);
-  uint32_t pk1[W], pk0[W], tab1, tab0;
-  load_windows(m1, pk1, tab1);
-  load_windows(m0, pk0, tab0);
-  for (long long i = 0; w + i * nwarps < nlist; ++i) {
-    const int4 m3 = load_meta(i + 3);
-    uint32_t pk2[W], tab2;
-    load_windows(m2, pk2, tab2);
-    const int r0 = m0.x, L = m0.w & 0xfff;
-    const uint32_t e0 = (uint32_t)m0.y, k0 = (uint32_t)m0.z, total = (uint32_t)m0.w >> 12;
-    for (int sidx = lane; sidx < L; sidx += 32) {
-#pragma unroll
-      for (int m = 0; m < NMAT; ++m) seg[m * maxrow + sidx] = T{};
-    }
-    __syncwarp();
-    for (uint32_t q0 = 0; q0 < total; q0 += 32 * W) {
-      uint32_t pk[W];
-      T v[W][NMAT];
-      uint32_t tix[W];
-#pragma unroll
-      for (int t = 0; t < W; ++t) {
-        const uint32_t q = q0 + 32 * t + lane;
-        pk[t] = q0 == 0 ? pk0[t] : (q < total ? __ldg(entries + e0 + q) : 0xffffffffu);
-      }
-#pragma unroll
-      for (int t = 0; t < W; ++t) {                      // class-table position of my entry
-        const uint32_t rec = (pk[t] >> 10) & VLFS_ROW_MAXREC;
-        uint32_t tb = __shfl_sync(0xffffffffu, tab0, rec & 31);
-        if (rec >= 32 && pk[t] != 0xffffffffu) tb = __ldg(tabs + k0 + rec);     // rows with > 32 records (rare)
-        tix[t] = (pk[t] != 0xffffffffu && tb != 0xffffffffu) ? tb + (pk[t] & VLFS_ROW_MAXNC) : 0xffffffffu;
-      }
-#pragma unroll
-      for (int t = 0; t < W; ++t)
-        if (tix[t] != 0xffffffffu) {
-#pragma unroll
-          for (int m = 0; m < NMAT; ++m) v[t][m] = __ldg(reinterpret_cast<const T*>(ctab_all.mat[m]) + tix[t]);
-        }
-#pragma unroll
-      for (int t = 0; t < W; ++t) {                      // adds, one record at a time (COO order)
-        if (q0 + 32 * t >= total) continue;                // (uniform)
-        const uint32_t rec = (pk[t] >> 10) & VLFS_ROW_MAXREC;
-        const uint32_t nvalid = min(32u, total - (q0 + 32 * t));
-        const uint32_t rfirst = __shfl_sync(0xffffffffu, rec, 0), rlast = __shfl_sync(0xffffffffu, rec, nvalid - 1);
-        for (uint32_t p = rfirst; p <= rlast; ++p) {
-          if (rec == p && tix[t] != 0xffffffffu) {
-#pragma unroll
-            for (int m = 0; m < NMAT; ++m) {
-              T* ptr = seg + m * maxrow + (pk[t] >> 20);
-              if constexpr (CPLX) { T o = *ptr; o.x += v[t][m].x; o.y += v[t][m].y; *ptr = o; }
-              else *ptr += v[t][m];
-            }
-          }
-          __syncwarp();          // the next record may hit the same slots from other lanes
-        }
-      }
-    }
-    __syncwarp();
-    for (int sidx = lane; sidx < L; sidx += 32) {
-#pragma unroll
-      for (int m = 0; m < NMAT; ++m) reinterpret_cast<T*>(ptrs.mat[m])[r0 + sidx] = seg[m * maxrow + sidx];
-    }
-    __syncwarp();
-    m0 = m1; m1 = m2; m2 = m3;
-    tab0 = tab1; tab1 = tab2;
-#pragma unroll
-    for (int t = 0; t < W; ++t) { pk0[t] = pk1[t]; pk1[t] = pk2[t]; }
-  }
-}
-
-// ---- slot-centric pass on length-sorted tiles -----------------------------------------------------
-// A tile = VLFS_TILE consecutive CSR slots.  Inside a tile the slots are handed to the threads in
-// order of DEcreasing run length (number of COO contributions), and the tile's records (class-table
-// positions) are stored step-major: step j holds the j-th contribution of every thread whose run is
-// longer than j - a dense prefix of the threads.  So every load of the record stream is coalesced,
-// idle lanes only exist in the one warp that straddles the end of a step, no per-slot run pointer is
-// read (one byte per slot for the permutation, 64 bytes per tile for the step offsets), and a thread
-// still adds its run in COO order (bitwise repeatable, the order of Julia's sparse(I,J,V)).
-#define VLFS_TILE 256
-#define VLFS_TILE_MAXLEN 31
-struct TileMeta { uint32_t rec0; unsigned short off[VLFS_TILE_MAXLEN + 1]; };     // 4 + 64 bytes
-
-// once per pattern / classification: one CTA per tile
-__global__ void __launch_bounds__(VLFS_TILE)
-build_sorted_tiles(const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ rec32, long long nnz,
-                   const long long* __restrict__ late_lo, const long long* __restrict__ late_hi, int nlate,
-                   TileMeta* __restrict__ meta, unsigned char* __restrict__ perm, uint32_t* __restrict__ tile_rec,
-                   unsigned char* __restrict__ tile_late, int* __restrict__ bad) {
-  __shared__ int hist[VLFS_TILE_MAXLEN + 2];      // threads per run length
-  __shared__ int start_of_len[VLFS_TILE_MAXLEN + 2];
-  __shared__ int s_late;
-  __shared__ unsigned short s_off[VLFS_TILE_MAXLEN + 2];
-  __shared__ int rank_in_len[VLFS_TILE];
-  const long long tile = blockIdx.x, base = tile * VLFS_TILE;
-  const int t = threadIdx.x;
-  const long long slot = base + t;
-  if (t <= VLFS_TILE_MAXLEN + 1) hist[t] = 0;
-  if (t == 0) s_late = 0;
-  __syncthreads();
-  uint32_t p0 = 0, len = 0;
-  if (slot < nnz) { p0 = run_start[slot]; len = run_start[slot + 1] - p0; }
-  if (len > VLFS_TILE_MAXLEN) { atomicExch(bad, 1); len = VLFS_TILE_MAXLEN; }
-  // stable counting sort by decreasing length: position = #threads with longer runs + #earlier threads of equal length
-  // (the rank among equal lengths comes from a ballot-based scan: deterministic)
-  {
-    int r = 0;
-    for (int w0 = 0; w0 < VLFS_TILE; w0 += 32) {          // every warp ranks its lanes against all earlier threads
-      __syncthreads();
-      if (t >= w0 && t < w0 + 32) {
-        const unsigned same = __match_any_sync(0xffffffffu, len);
-        r = hist[len] + __popc(same & ((1u << (t & 31)) - 1));
-        __syncwarp();                                                            // every lane has read its count
-        if ((same & ((1u << (t & 31)) - 1)) == 0) hist[len] += __popc(same);     // one lane per distinct length
-      }
-    }
-    __syncthreads();
-    rank_in_len[t] = r;
-  }
-  if (t == 0) {
-    int acc = 0;
-    for (int l = VLFS_TILE_MAXLEN; l >= 0; --l) { start_of_len[l] = acc; acc += hist[l]; }
-    // step offsets: cnt_j = threads with len > j
-    int off = 0;
-    for (int j = 0; j <= VLFS_TILE_MAXLEN; ++j) {
-      s_off[j] = (unsigned short)off;
-      int cnt = 0;
-      for (int l = j + 1; l <= VLFS_TILE_MAXLEN; ++l) cnt += hist[l];
-      off += cnt;
-    }
-    s_off[VLFS_TILE_MAXLEN + 1] = (unsigned short)off;
-  }
-  __syncthreads();
-  const int pos = start_of_len[len] + rank_in_len[t];       // thread that takes this slot
-  if (slot < nnz) perm[base + pos] = (unsigned char)t;      // perm[thread] = slot offset inside the tile
-  const uint32_t rec0 = run_start[base < nnz ? base : nnz];
-  bool late = false;
-  for (uint32_t j = 0; j < len; ++j) {
-    const uint32_t r = rec32[p0 + j];
-    tile_rec[rec0 + s_off[j] + pos] = r;
-    for (int q = 0; q < nlate; ++q) late |= r != 0xffffffffu && (long long)r >= late_lo[q] && (long long)r < late_hi[q];
-  }
-  if (late) s_late = 1;
-  __syncthreads();
-  if (t <= VLFS_TILE_MAXLEN) meta[tile].off[t] = s_off[t];
-  if (t == 0) { meta[tile].rec0 = rec0; tile_late[tile] = (unsigned char)s_late; }
-}
-
-// One WARP per tile, no barriers: lane l owns the thread positions l, l+32, ..., l+224 of the sorted
-// tile, i.e. up to 8 independent record -> table-value chains per lane are in flight (G of them at a
-// time), which is what hides the HBM / L2 latency; every load of the record stream is a full
-// coalesced line; the finished values go straight to their slots (the tile's 4 KB are written by
-// this warp alone within a few hundred cycles, so the partial sectors merge in L2).
-template <int NMAT, bool CPLX, int G>
-__global__ void __launch_bounds__(256)
-gather_tiles(const int* __restrict__ tile_list, long long ntiles, const TileMeta* __restrict__ meta,
-             const unsigned char* __restrict__ perm, const uint32_t* __restrict__ tile_rec, AsmPtrs ctab_all,
-             long long nnz, AsmPtrs ptrs) {
-  using T = typename std::conditional<CPLX, double2, double>::type;
-  const int lane = threadIdx.x & 31;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  long long k = w;
-  // metadata of the first tile; afterwards the next tile's metadata travels while this one is summed
-  auto tile_of = [&](long long kk) { return kk < ntiles ? (tile_list ? (long long)__ldg(tile_list + kk) : kk) : -1; };
-  long long tile = tile_of(k);
-  uint32_t rec0 = 0, off_l = 0;
-  if (tile >= 0) { rec0 = __ldg(&meta[tile].rec0); off_l = __ldg(&meta[tile].off[lane]); }
-  while (tile >= 0) {
-    const long long ntile = tile_of(k + nwarps);
-    uint32_t nrec0 = 0, noff_l = 0;
-    if (ntile >= 0) { nrec0 = __ldg(&meta[ntile].rec0); noff_l = __ldg(&meta[ntile].off[lane]); }
-    const long long base = tile * VLFS_TILE;
-#pragma unroll 1
-    for (int g0 = 0; g0 < VLFS_TILE / 32; g0 += G) {
-      if ((long long)g0 * 32 + base >= nnz) break;
-      T acc[G][NMAT];
-#pragma unroll
-      for (int g = 0; g < G; ++g)
-#pragma unroll
-        for (int m = 0; m < NMAT; ++m) acc[g][m] = T{};
-      for (int j = 0; j < VLFS_TILE_MAXLEN; ++j) {
-        const int oj = (int)__shfl_sync(0xffffffffu, off_l, j), cnt = (int)__shfl_sync(0xffffffffu, off_l, j + 1) - oj;
-        if (cnt <= g0 * 32) break;                       // (uniform) no thread position of this pass is active any more
-        uint32_t r[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int t = (g0 + g) * 32 + lane;
-          r[g] = t < cnt ? __ldg(tile_rec + rec0 + oj + t) : 0xffffffffu;
-        }
-        T v[G][NMAT];
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-          if (r[g] != 0xffffffffu) {
-#pragma unroll
-            for (int m = 0; m < NMAT; ++m) v[g][m] = __ldg(reinterpret_cast<const T*>(ctab_all.mat[m]) + r[g]);
-          }
-#pragma unroll
-        for (int g = 0; g < G; ++g)
-          if (r[g] != 0xffffffffu) {
-#pragma unroll
-            for (int m = 0; m < NMAT; ++m) {
-              if constexpr (CPLX) { acc[g][m].x += v[g][m].x; acc[g][m].y += v[g][m].y; }
-              else acc[g][m] += v[g][m];
-            }
-          }
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const long long t = base + (g0 + g) * 32 + lane;
-        if (t < nnz) {
-          const long long slot = base + __ldg(perm + t);
-#pragma unroll
-          for (int m = 0; m < NMAT; ++m) reinterpret_cast<T*>(ptrs.mat[m])[slot] = acc[g][m];
-        }
-      }
-    }
-    k += nwarps; tile = ntile; rec0 = nrec0; off_l = noff_l;
-  }
-}
-
 }  // namespace
-
-size_t tile_meta_bytes() { return sizeof(TileMeta); }
-void launch_build_sorted_tiles(const uint32_t* run_start, const uint32_t* rec32, long long nnz, const long long* late_lo,
-                               const long long* late_hi, int nlate, void* meta, unsigned char* perm, uint32_t* tile_rec,
-                               unsigned char* tile_late, int* bad, cudaStream_t s) {
-  const long long ntiles = (nnz + VLFS_TILE - 1) / VLFS_TILE;
-  if (ntiles == 0) return;
-  build_sorted_tiles<<<(unsigned)ntiles, VLFS_TILE, 0, s>>>(run_start, rec32, nnz, late_lo, late_hi, nlate,
-                                                           reinterpret_cast<TileMeta*>(meta), perm, tile_rec, tile_late, bad);
-  CUDA_TRY(cudaGetLastError());
-}
-
-void launch_gather_tiles(const int* tile_list, long long ntiles, const void* meta, const unsigned char* perm,
-                         const uint32_t* tile_rec, double* const* ctab_all, long long nnz, double* const* mats, int nmat,
-                         int is_complex, int nsm, cudaStream_t s) {
-  if (ntiles == 0) return;
-  AsmPtrs P{}, CT{};
-  for (int m = 0; m < nmat && m < 4; ++m) { P.mat[m] = mats[m]; CT.mat[m] = ctab_all[m]; }
-  static const int per_sm_env = getenv("VLFS_TILES_CTAS") ? atoi(getenv("VLFS_TILES_CTAS")) : 0;
-  static const int g_env = getenv("VLFS_TILES_G") ? atoi(getenv("VLFS_TILES_G")) : 0;
-  auto go = [&](auto kern) {
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
-    if (per_sm_env > 0) per_sm = per_sm_env;
-    long long grid = (long long)nsm * (per_sm < 1 ? 1 : per_sm);            // persistent: one warp walks its tiles
-    const long long need = (ntiles + 7) / 8;
-    if (grid > need) grid = need;
-    static bool said = false;
-    if (!said && getenv("VLFS_DEBUG")) { said = true; fprintf(stderr, "[vlfs] gather_tiles: %lld tiles, %d CTAs/SM, grid %lld\n", ntiles, per_sm, grid); }
-    kern<<<(unsigned)grid, 256, 0, s>>>(tile_list, ntiles, reinterpret_cast<const TileMeta*>(meta), perm, tile_rec, CT, nnz, P);
-  };
-  switch (nmat * 2 + (is_complex ? 1 : 0)) {
-    case 2: if (g_env == 4) go(gather_tiles<1, false, 4>); else go(gather_tiles<1, false, 8>); break;
-    case 3: if (g_env == 4) go(gather_tiles<1, true, 4>); else if (g_env == 2) go(gather_tiles<1, true, 2>); else go(gather_tiles<1, true, 8>); break;
-    case 4: go(gather_tiles<2, false, 4>); break;
-    case 5: go(gather_tiles<2, true, 4>); break;
-    case 6: go(gather_tiles<3, false, 4>); break;
-    case 7: go(gather_tiles<3, true, 2>); break;
-    case 8: go(gather_tiles<4, false, 2>); break;
-    default: go(gather_tiles<4, true, 2>); break;
-  }
-  CUDA_TRY(cudaGetLastError());
-}
-
-void launch_count_row_entries(const unsigned long long* src, const int* incptr, long long nrows,
-                              const GatherDom* doms, uint32_t* cnt, cudaStream_t s) {
-  if (nrows == 0) return;
-  long long grid = (nrows + 255) / 256;
-  if (grid > 148 * 32) grid = 148 * 32;
-  count_row_entries<<<(unsigned)grid, 256, 0, s>>>(src, incptr, nrows, doms, cnt);
-  CUDA_TRY(cudaGetLastError());
-}
-
-void launch_fill_row_incidence(const unsigned long long* src, const int* incptr, const int* rowptr,
-                               const uint32_t* rowstart, long long nrows, const GatherDom* doms, const int* dom_late,
-                               uint32_t* tabs, unsigned char* late, const int* dest, uint32_t* entries, int* bad,
-                               cudaStream_t s) {
-  if (nrows == 0) return;
-  long long grid = (nrows + 255) / 256;
-  if (grid > 148 * 32) grid = 148 * 32;
-  fill_row_incidence<<<(unsigned)grid, 256, 0, s>>>(src, incptr, rowptr, rowstart, nrows, doms, dom_late, tabs, late, dest, entries, bad);
-  CUDA_TRY(cudaGetLastError());
-}
-
-// rows [first, first + nrows) of the meta list; returns false when a row segment does not fit the
-// shared memory of a CTA (the caller then uses the slot-centric gather)
-bool launch_assemble_rows(const RowMeta* meta, long long nrows, const uint32_t* tabs, const uint32_t* entries,
-                          double* const* ctab_all, double* const* mats, int nmat, int is_complex, int maxrow,
-                          int nsm, cudaStream_t s) {
-  if (nrows == 0) return true;
-  AsmPtrs P{}, CT{};
-  for (int m = 0; m < nmat && m < 4; ++m) { P.mat[m] = mats[m]; CT.mat[m] = ctab_all[m]; }
-  const size_t per_warp = (size_t)nmat * maxrow * (is_complex ? 16 : 8);
-  int wpb = 8;
-  while (wpb > 1 && per_warp * wpb > 64 * 1024) wpb >>= 1;      // keep several CTAs per SM
-  const size_t smem = per_warp * wpb;
-  if (smem > 200 * 1024) return false;
-  static const int cta_per_sm = getenv("VLFS_ROWS_CTAS") ? atoi(getenv("VLFS_ROWS_CTAS")) : 0;
-  const long long need = (nrows + wpb - 1) / wpb;
-  auto go = [&](auto kern) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;                      // resident CTAs per SM (registers and shared memory): a persistent grid
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * wpb, smem));
-    if (cta_per_sm > 0) per_sm = cta_per_sm;
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)nsm * per_sm;
-    if (grid > need) grid = need;
-    static bool said = false;
-    if (!said && getenv("VLFS_DEBUG")) {
-      said = true;
-      fprintf(stderr, "[vlfs] assemble_rows: %lld rows, maxrow %d, %d warps/CTA, %zu B smem/CTA, %d CTAs/SM, grid %lld\n",
-              nrows, maxrow, wpb, smem, per_sm, grid);
-    }
-    kern<<<(unsigned)grid, 32 * wpb, smem, s>>>(meta, nrows, tabs, entries, CT, P, maxrow);
-  };
-  switch (nmat * 2 + (is_complex ? 1 : 0)) {
-    case 2: go(assemble_rows<1, false>); break;
-    case 3: go(assemble_rows<1, true>); break;
-    case 4: go(assemble_rows<2, false>); break;
-    case 5: go(assemble_rows<2, true>); break;
-    case 6: go(assemble_rows<3, false>); break;
-    case 7: go(assemble_rows<3, true>); break;
-    case 8: go(assemble_rows<4, false>); break;
-    default: go(assemble_rows<4, true>); break;
-  }
-  CUDA_TRY(cudaGetLastError());
-  return true;
-}
 
 void launch_cell_geometry(const DomainDev& dom, int want_gradgrad, double* out, cudaStream_t s) {
   if (dom.ncells == 0) return;

@@ -107,40 +107,6 @@ __global__ void retile_dest(DomainDev dom, const int* __restrict__ dest, int* __
   }
 }
 
-// ---- row -> (domain, cell, block, local row) incidence of the row-centric numeric pass ----------
-// one record per (cell, touched block, local test row), generated in COO order; key = global row
-__global__ void gen_incidence(DomainDev dom, int rows_per_cell, unsigned long long rec_base,
-                              uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
-  const long long total = dom.ncells * (long long)rows_per_cell;
-  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
-       g += (long long)gridDim.x * blockDim.x) {
-    const long long c = g / rows_per_cell;
-    int t = (int)(g - c * rows_per_cell), b = 0;
-    while (t >= dom.blk[b].nr) { t -= dom.blk[b].nr; ++b; }
-    const SlotDev& S = dom.slot[dom.blk[b].ts];
-    keys[rec_base + g] = (uint64_t)(uint32_t)S.dofs[c * S.ndofs + t];
-    idx[rec_base + g] = (uint32_t)(rec_base + g);
-  }
-}
-
-// sorted record -> packed source (domain:4 | block:2 | local row:14 | cell:32), row of the record
-__global__ void decode_incidence(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idx, long long nrec,
-                                 const DomainDev* __restrict__ doms, const long long* __restrict__ rec_base,
-                                 const int* __restrict__ rows_per_cell, int ndom,
-                                 unsigned long long* __restrict__ src, int* __restrict__ rows) {
-  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nrec; k += (long long)gridDim.x * blockDim.x) {
-    const long long g = idx[k];
-    int d = 0;
-    while (d + 1 < ndom && g >= rec_base[d + 1]) ++d;
-    const long long r = g - rec_base[d];
-    const long long c = r / rows_per_cell[d];
-    int t = (int)(r - c * rows_per_cell[d]), b = 0;
-    while (t >= doms[d].blk[b].nr) { t -= doms[d].blk[b].nr; ++b; }
-    src[k] = ((unsigned long long)d << 60) | ((unsigned long long)b << 58) | ((unsigned long long)t << 32) | (unsigned long long)c;
-    rows[k] = (int)(uint32_t)keys[k];
-  }
-}
-
 int bits_for(long long n) {
   int b = 1;
   while ((1ll << b) < n) ++b;
@@ -205,48 +171,6 @@ void build_pattern_device(const std::vector<DomainDev>& doms, long long ndofs,
   perm_out = std::move(idx);          // sorted position -> COO index (slot-centric gather)
   *nnz_out = nnz;
   *ncoo_out = ncoo;
-}
-
-// Row incidence lists of the row-centric numeric pass: for every row the (domain, cell, block,
-// local row) records that contribute to it, in COO order (stable sort on the row).  inc_src holds
-// the packed sources, incptr[row] the first record of each row.
-void build_row_incidence(const std::vector<DomainDev>& doms, long long ndofs, DevBuf<int>& incptr,
-                         DevBuf<unsigned long long>& inc_src, long long* nrec_out, cudaStream_t s,
-                         long long* launches) {
-  const int ndom = (int)doms.size();
-  std::vector<long long> base(ndom + 1, 0);
-  std::vector<int> rpc(ndom, 0);
-  for (int d = 0; d < ndom; ++d) {
-    for (int b = 0; b < doms[d].nblocks; ++b) rpc[d] += doms[d].blk[b].nr;
-    base[d + 1] = base[d] + doms[d].ncells * (long long)rpc[d];
-  }
-  const long long nrec = base[ndom];
-  *nrec_out = nrec;
-  incptr.alloc(ndofs + 1);
-  if (nrec == 0) { incptr.zero(s); return; }
-  if (nrec >= (1ll << 32)) throw std::string("row incidence count exceeds 2^32 on one GPU");
-  DevBuf<uint64_t> keys, keys_tmp;
-  DevBuf<uint32_t> idx, idx_tmp;
-  DevBuf<DomainDev> ddev;
-  DevBuf<long long> dbase;
-  DevBuf<int> drpc, rows;
-  keys.alloc(nrec); keys_tmp.alloc(nrec); idx.alloc(nrec); idx_tmp.alloc(nrec);
-  for (int d = 0; d < ndom; ++d) {
-    const long long n = base[d + 1] - base[d];
-    if (n == 0) continue;
-    gen_incidence<<<grid_for(n), 256, 0, s>>>(doms[d], rpc[d], (unsigned long long)base[d], keys.p, idx.p);
-    if (launches) ++*launches;
-  }
-  int lo[1] = {0}, hi[1] = {bits_for(ndofs)};
-  radix_sort_pairs(keys.p, idx.p, keys_tmp.p, idx_tmp.p, (size_t)nrec, 1, lo, hi, s, launches);
-  keys_tmp.release(); idx_tmp.release();
-  ddev.upload(doms.data(), ndom, s); dbase.upload(base.data(), ndom + 1, s); drpc.upload(rpc.data(), ndom, s);
-  inc_src.alloc(nrec); rows.alloc(nrec);
-  decode_incidence<<<grid_for(nrec), 256, 0, s>>>(keys.p, idx.p, nrec, ddev.p, dbase.p, drpc.p, ndom, inc_src.p, rows.p);
-  build_rowptr<<<grid_for(ndofs + 1), 256, 0, s>>>(rows.p, nrec, incptr.p, ndofs);
-  if (launches) *launches += 2;
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(s));
 }
 
 void build_tiled_dest(const DomainDev& dom, const int* dest, DevBuf<int>& tiled, cudaStream_t s,
