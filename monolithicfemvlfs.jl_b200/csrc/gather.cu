@@ -294,57 +294,40 @@ __global__ void row_early_flags(const uint32_t* __restrict__ row_class, const ui
     row_early[row] = class_early[row_class[row]];
 }
 
-// One warp per 32 list entries (consecutive CSR rows inside the early / late part of the list): the
-// slots of the 32 rows are handled as one flat range, lane t of step u copies item 32u + t - the
-// row of an item comes from a 5-step search over the rows' prefix sums held across the lanes.  U
-// independent template loads per lane are in flight; the stores of a step are one contiguous
-// 512-byte piece of the value array wherever the rows are consecutive.  SPLIT warps share a group
-// (warp `sub` takes the steps sub, sub + SPLIT, ...): more, shorter warps fill the SMs evenly.
+// A group of 32 list entries (consecutive CSR rows inside the early / late part of the list) is shared
+// by SPLIT warps: every lane loads one entry (one coalesced 512-byte read), warp `sub` copies the rows
+// sub, sub + SPLIT, ... of the group.  A row is one contiguous piece of the template array and of the
+// value array: the lanes copy it 16 bytes each, up to U independent loads per lane in flight.
+// Measured alternatives (Y1, late rows: 853 MB written, 777 MB of template reads through L2, 183 us =
+// 72 % of the L2 slice throughput): a flat item -> row search over the group's prefix sums (8 shuffles
+// per item, L1 data pipe 72 % busy, same time); the list ordered class after class with the template
+// row kept in registers (L2 reads gone, but the scattered destination rows cost more DRAM write
+// efficiency than the reads saved: 200 us).
 template <int NMAT, bool CPLX, int U, int SPLIT>
 __global__ void __launch_bounds__(256)
 expand_rows(const uint4* __restrict__ list, long long nlist, MatPtrs tmpl, MatPtrs ptrs) {
   using T = typename std::conditional<CPLX, double2, double>::type;
   const int lane = threadIdx.x & 31;
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long first = (w / SPLIT) * 32;          // SPLIT warps share a group of 32 rows
-  const uint32_t sub = (uint32_t)(w % SPLIT);
+  const long long first = (w / SPLIT) * 32;
+  const int sub = (int)(w % SPLIT);
   if (first >= nlist) return;
-  const uint4 e = first + lane < nlist ? __ldcs(list + first + lane) : make_uint4(0u, 0u, 0u, 0u);
-  uint32_t incl = e.z;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  const uint32_t excl = incl - e.z;
-  for (uint32_t t0 = sub * 32 * U; t0 < total; t0 += SPLIT * 32 * U) {
-    uint32_t src[U], dst[U];
-    bool on[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t t = t0 + 32 * u + lane;
-      int r = 0;
-#pragma unroll
-      for (int step = 16; step; step >>= 1) {
-        const uint32_t v = __shfl_sync(0xffffffffu, incl, r + step - 1);
-        if (v <= t) r += step;
-      }
-      const uint32_t ex = __shfl_sync(0xffffffffu, excl, r);
-      const uint32_t d = __shfl_sync(0xffffffffu, e.x, r), s = __shfl_sync(0xffffffffu, e.y, r);
-      on[u] = t < total;
-      src[u] = s + (t - ex);
-      dst[u] = d + (t - ex);
-    }
+  const int cnt = (int)min(32ll, nlist - first);
+  const uint4 e = lane < cnt ? __ldcs(list + first + lane) : make_uint4(0u, 0u, 0u, 0u);
+  for (int r = sub; r < cnt; r += SPLIT) {
+    const uint32_t d = __shfl_sync(0xffffffffu, e.x, r), s = __shfl_sync(0xffffffffu, e.y, r);
+    const uint32_t len = __shfl_sync(0xffffffffu, e.z, r);
 #pragma unroll
     for (int mm = 0; mm < NMAT; ++mm) {
-      const T* __restrict__ in = reinterpret_cast<const T*>(tmpl.mat[mm]);
-      T* __restrict__ out = reinterpret_cast<T*>(ptrs.mat[mm]);
-      T v[U];
+      const T* __restrict__ in = reinterpret_cast<const T*>(tmpl.mat[mm]) + s;
+      T* __restrict__ out = reinterpret_cast<T*>(ptrs.mat[mm]) + d;
+      for (uint32_t k0 = lane; k0 < len; k0 += 32 * U) {
+        T v[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) if (on[u]) v[u] = __ldg(in + src[u]);
+        for (int u = 0; u < U; ++u) if (k0 + 32 * u < len) v[u] = __ldg(in + k0 + 32 * u);
 #pragma unroll
-      for (int u = 0; u < U; ++u) if (on[u]) __stcs(out + dst[u], v[u]);
+        for (int u = 0; u < U; ++u) if (k0 + 32 * u < len) __stcs(out + k0 + 32 * u, v[u]);
+      }
     }
   }
 }
