@@ -139,9 +139,12 @@ typedef struct {
 
 typedef struct {
   int32_t iterations;
-  int32_t converged;
-  double rel_residual;
+  int32_t converged;         /* 1: |b-Ax|/|b| <= rtol.  2: refinement stopped at the attainable accuracy of
+                                double precision, normwise backward error <= 1e-14 (what LUSolver() itself
+                                delivers).  0: neither (VLFS_NOT_CONVERGED)                               */
+  double rel_residual;       /* true residual |b-Ax|_2 / |b|_2                                           */
   double setup_ms, solve_ms;
+  double backward_error;     /* |b-Ax|_2 / (|A|_F |x|_2 + |b|_2); 0 when rtol was met without needing it */
 } vlfs_solve_stats;
 
 enum { VLFS_SOLVER_GMRES = 0, VLFS_SOLVER_BICGSTAB = 1, VLFS_SOLVER_CG = 2 };

@@ -66,8 +66,8 @@ end
 
 mutable struct SolveStats
   iterations::Int32; converged::Int32
-  rel_residual::Float64; setup_ms::Float64; solve_ms::Float64
-  SolveStats() = new(0, 0, 0.0, 0.0, 0.0)
+  rel_residual::Float64; setup_ms::Float64; solve_ms::Float64; backward_error::Float64
+  SolveStats() = new(0, 0, 0.0, 0.0, 0.0, 0.0)
 end
 
 # --- context ---------------------------------------------------------------------------------

@@ -125,7 +125,7 @@ function Gridap.Algebra.solve!(x::AbstractVector, ns::B200NumericalSetup, b::Abs
     rc = ccall((:vlfs_solve, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{VLFSB200.SolveStats}), ns.ctx, bb, xx, st)
   end
   _check(ns.ctx, rc; allow=(0, 3))              # 3 = VLFS_NOT_CONVERGED: statistics, not an exception
-  st.converged == 1 || @warn "B200LUSolver: refinement stopped at relative residual $(st.rel_residual)"
+  st.converged != 0 || @warn "B200LUSolver: refinement stopped at relative residual $(st.rel_residual), backward error $(st.backward_error)"
   copyto!(x, xx)
   x
 end

@@ -58,7 +58,7 @@ class SolverOpts(C.Structure):
 
 class SolveStats(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("rel_residual", C.c_double),
-                ("setup_ms", C.c_double), ("solve_ms", C.c_double)]
+                ("setup_ms", C.c_double), ("solve_ms", C.c_double), ("backward_error", C.c_double)]
 
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libvlfs_b200.so")

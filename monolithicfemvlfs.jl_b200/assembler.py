@@ -369,7 +369,8 @@ class B200System:
             rc = self.lib.vlfs_solve(self.ctx, b.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), C.byref(st))
         self._check(rc, allow=(0, L.NOT_CONVERGED))
         return x, dict(iterations=st.iterations, converged=bool(st.converged), rel_residual=st.rel_residual,
-                       setup_ms=st.setup_ms, solve_ms=st.solve_ms)
+                       setup_ms=st.setup_ms, solve_ms=st.solve_ms, backward_error=st.backward_error,
+                       at_attainable_accuracy=st.converged == 2)
 
     def newmark_run(self, matK, matC, matM, nsteps, dt, gamma, beta, tcoef, u0, v0, a0,
                     out_range=(0, 0), out_stride=1):

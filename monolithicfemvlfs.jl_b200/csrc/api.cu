@@ -1023,6 +1023,10 @@ int vlfs_system_init(vlfs_ctx* ctx, int64_t ndofs, int is_complex, int nmat, int
     ctx->doms.clear(); ctx->mats.clear(); ctx->vecs.clear();
     ctx->pattern_built = false; ctx->imported = false; ctx->solver.reset(); ctx->direct.reset(); ctx->dense.reset();
     ctx->dof_coords.clear(); ctx->coord_dim = 0; ctx->roles.clear(); ctx->solver_mat = -1;
+    ctx->chunks_valid = ctx->tmpl_valid = ctx->rec32_valid = false;       // numeric-pass tables of the old pattern
+    ctx->gather_rec.release(); ctx->gather_rec32.release(); ctx->trec.release(); ctx->trun.release(); ctx->row_list.release();
+    ctx->chunk_meta[0].release(); ctx->chunk_meta[1].release();
+    for (int m = 0; m < 4; ++m) ctx->tmpl_vals[m].release();
     ctx->vecs.resize(nvec);
     for (auto& v : ctx->vecs) { v.alloc((size_t)ndofs * ctx->scalar()); v.zero(ctx->stream); }
     return VLFS_OK;

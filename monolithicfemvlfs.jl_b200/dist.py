@@ -1001,7 +1001,8 @@ class MultiSystem:
             p.scatter_owned(x, xg)
         s0 = st[0]
         return xg, dict(iterations=s0.iterations, converged=bool(s0.converged), rel_residual=s0.rel_residual,
-                        setup_ms=s0.setup_ms, solve_ms=max(s.solve_ms for s in st))
+                        setup_ms=s0.setup_ms, solve_ms=max(s.solve_ms for s in st), backward_error=s0.backward_error,
+                        at_attainable_accuracy=s0.converged == 2)
 
     def spmv(self, x, mat=0):
         """y = A x for a GLOBAL host vector (entries of the rows owned here)."""

@@ -30,7 +30,7 @@ def test_struct_layouts_match_header_sizes():
     # 4 int32 + 9 pointers ; see vlfs_slot_desc
     assert C.sizeof(L.SlotDesc) == 16 + 9 * 8
     assert C.sizeof(L.TermDesc) == 8 + 16 + 8 + 16 + 16 + 24 + 24
-    assert C.sizeof(L.SolveStats) == 8 + 8 + 16
+    assert C.sizeof(L.SolveStats) == 8 + 8 + 16 + 8
 
 
 def test_no_gpu_means_loud_failure():
