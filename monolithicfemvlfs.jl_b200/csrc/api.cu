@@ -531,6 +531,10 @@ void finalize_domain(vlfs_ctx* ctx, Domain& d) {
     if (O.op == VLFS_OP_VAL && !dev.slot[O.slot].variant) {
       O.smem_off = p; O.buf_stride = 0;
       p += dev.nq * O.ncomp * O.ndp;
+    } else {
+      // per-cell table (marked before the reference-matrix pairs below are chosen: a stale 0 here
+      // made second-derivative products of the first cell stand in for every cell of a CTA)
+      O.buf_stride = -1;
     }
   }
   dev.smem_inv_len = p - dev.smem_inv_off;

@@ -306,6 +306,8 @@ struct DistState : DistHooks {
     launch_spmv_rows(rowptr, colind, vals, x, y, row_lists.p + n_int, n_bnd, nnz_bnd, cplx, alpha, beta, nsm, s);
   }
 
+  void exchange(double* x) override { exchange_on(x, s); }
+
   void allreduce_sum(double* dev, int ndoubles) override {
     if (nranks == 1) return;
     if (loop) {

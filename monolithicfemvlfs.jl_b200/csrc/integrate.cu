@@ -1113,7 +1113,7 @@ void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, con
   if (per_sm > by_regs) per_sm = by_regs;
   // persistent CTAs: exactly the resident set, each pipelining over its cells
   long long cap = (long long)nsm * per_sm;
-  if (grid > cap) grid = cap;
+  if (grid > cap && !getenv("VLFS_ASM_ONE_CELL_PER_CTA")) grid = cap;       // (diagnostic switch: no pipelining over cells)
   const int use_tref = ncells_run >= 2 * grid;      // at least two cells per CTA
   auto launch = [&](auto kern) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

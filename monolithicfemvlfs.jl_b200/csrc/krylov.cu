@@ -13,6 +13,9 @@
 #include <cstring>
 #include <limits>
 
+void launch_residual_dd(const int* rowptr, const int* colind, const void* vals, const double* xh, const double* xl,
+                        const double* b, double* r, long long nrows, long long nnz, int is_complex, int nsm, cudaStream_t s);
+void launch_dd_axpy(double* xh, double* xl, const double* d, long long n, int is_complex, int nsm, cudaStream_t s);
 void launch_spmv(const int* rowptr, const int* colind, const void* vals, const void* x, void* y,
                  long long nrows, long long nnz, int is_complex, const double* alpha,
                  const double* beta, int nsm, cudaStream_t s);
@@ -312,7 +315,7 @@ struct SolverState {
   long long* launches;
   size_t sc;                    // doubles per scalar
   int nred;                     // reduction blocks
-  DevBuf<double> dinv, V, Z, w, z, r, partial, hdev, tmp1, tmp2, tmp3, tmp4;
+  DevBuf<double> dinv, V, Z, w, z, r, partial, hdev, tmp1, tmp2, tmp3, tmp4, xlo;
   double setup_ms = 0;
   DirectSolver* direct = nullptr;
   DistHooks* dist = nullptr;    // row-partitioned system: n = owned rows, vectors have nalloc = owned + ghost entries
@@ -324,6 +327,12 @@ struct SolverState {
     const double a[2] = {are, 0}, b[2] = {bre, 0};
     if (dist) { dist->spmv(vals, const_cast<double*>(x), y, a, b); *launches += 4; return; }
     launch_spmv(rowptr, colind, vals, x, y, n, nnz, cplx, a, b, nsm, s);
+    ++*launches;
+  }
+  // r = b - A (xh + xl) in twice the working precision (spmv.cu: csr_residual_dd)
+  void residual_dd(double* xh, double* xl, const double* b, double* r) {
+    if (dist) { dist->exchange(xh); dist->exchange(xl); *launches += 2; }
+    launch_residual_dd(rowptr, colind, vals, xh, xl, b, r, n, nnz, cplx, nsm, s);
     ++*launches;
   }
   void axpby_(cd a, const double* x, cd b, double* y) {
@@ -461,18 +470,22 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
   // factor 4 (the attainable accuracy eps*|A||x|/|b| is reached).
   const bool direct = S.opts.precond == VLFS_PRECOND_SPARSE_LU;
   if (direct && S.Z.n != (size_t)m * ld) { S.Z.alloc((size_t)m * ld); S.Z.zero(S.s); }
+  double* xlo = nullptr;
+  if (direct) { xlo = S.vec(S.xlo); CUDA_TRY(cudaMemsetAsync(xlo, 0, ld * sizeof(double), S.s)); }
   bool stagnated = false;
   double prev_cycle_rel = 1e300;
   static const bool dbg = getenv("VLFS_DEBUG") != nullptr;
   static const bool nostag = getenv("VLFS_GMRES_NOSTAG") != nullptr;       // diagnostic: iterate to rtol / maxit
   while (true) {
-    // r = b - A x
-    S.copy(b, r);
-    S.spmv(x, r, -1.0, 1.0);
+    // r = b - A x; with the exact factorisation as preconditioner the iterate is carried as an
+    // unevaluated pair x + xlo and the residual is formed in twice the working precision, so the
+    // refinement converges to the solution of the system (not to cond(A)*eps of it)
+    if (direct) S.residual_dd(x, xlo, b, r);
+    else { S.copy(b, r); S.spmv(x, r, -1.0, 1.0); }
     double beta = S.nrm2(r);
     rel = beta / bnorm;
     if (dbg) fprintf(stderr, "[vlfs] gmres: true residual %.3e after %d iterations\n", rel, it);
-    if (!(rel > S.opts.rtol) || it >= S.opts.maxit || (stagnated && !nostag)) break;     // (NaN ends the loop too)
+    if (!(rel > S.opts.rtol) || it >= S.opts.maxit || stagnated) break;     // (NaN ends the loop too)
     if (direct && !nostag && rel > 0.25 * prev_cycle_rel) break;
     prev_cycle_rel = rel;
     S.axpby_(cd(1.0 / beta, 0), r, cd(0, 0), S.V.p);      // V_0
@@ -525,7 +538,9 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
       rel = std::abs(g[j + 1]) / bnorm;
       if (!(rel > S.opts.rtol) || hn == 0.0) { ++j; ++it; break; }
       if (dbg) fprintf(stderr, "[vlfs] gmres:   it %d Arnoldi estimate %.3e\n", it, rel);
-      if (direct && j >= 1 && rel > 0.25 * prev) { stagnated = true; ++j; ++it; break; }
+      // the Arnoldi estimate of a cycle cannot fall below the accuracy of the double-precision sweeps:
+      // end the cycle, the next one starts from the residual formed in twice the precision
+      if (direct && j >= 1 && rel > 0.25 * prev) { ++j; ++it; break; }
     }
     // y = H^{-1} g ; x += M^{-1} V y
     for (int k = j - 1; k >= 0; --k) {
@@ -539,7 +554,8 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
     if (j == 0) continue;
     if (direct) {                               // x += Z y: no further application of the LU sweeps
       S.gemv_sub_(S.Z.p, j, ny.data(), w);
-      S.axpby_(cd(1, 0), w, cd(1, 0), x);
+      launch_dd_axpy(x, xlo, w, n, S.cplx, S.nsm, S.s);
+      ++*S.launches;
     } else {
       S.gemv_sub_(S.V.p, j, ny.data(), w);     // w = V y
       S.precond(w, z);

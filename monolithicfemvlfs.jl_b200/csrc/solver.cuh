@@ -13,6 +13,7 @@ struct DistHooks {
   // y = alpha A x + beta y over the owned rows; fills the ghost block of x first (halo exchange
   // overlapped with the rows that need no ghost value)
   virtual void spmv(const double* vals, double* x, double* y, const double* alpha, const double* beta) = 0;
+  virtual void exchange(double* x) = 0;                             // ghost block of x <- owners (on the context's stream)
   virtual void allreduce_sum(double* dev, int ndoubles) = 0;        // in place, over all ranks
   virtual bool has_exact_apply() const = 0;                         // substructuring solver set up
   virtual void apply(const double* r, double* z) = 0;               // z = A^-1 r (all ranks together)
