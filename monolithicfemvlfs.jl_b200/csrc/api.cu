@@ -568,7 +568,11 @@ void finalize_domain(vlfs_ctx* ctx, Domain& d) {
     if (dev.opi[o].buf_stride < 0) dev.opi[o].buf_stride = q;
   // three table buffers allow the split-phase pipeline barrier; fall back to two when the
   // per-cell tables are large (second-derivative operators)
-  dev.nbuf = ((size_t)(p + 3 * q) * sizeof(double) <= 200 * 1024) ? 3 : 2;
+  // (large tables: two buffers when that lets one more CTA share the SM)
+  {
+    auto ctas = [&](int nb) { return (int)((220 * 1024) / ((size_t)(p + nb * q) * sizeof(double) + 1024)); };
+    dev.nbuf = ((size_t)(p + 3 * q) * sizeof(double) <= 200 * 1024 && ctas(3) >= std::min(ctas(2), 3)) ? 3 : 2;
+  }
   p += dev.nbuf * q;
   dev.smem_total = p;
   if ((size_t)p * sizeof(double) > 227 * 1024)
@@ -1174,11 +1178,13 @@ int vlfs_set_weights(vlfs_ctx* ctx, int domain_id, int weight, const double* val
     size_t n = (size_t)d.dev.ncells * d.dev.nq;
     CUDA_TRY(cudaMemcpyAsync(d.weights.p + (size_t)weight * n, values, n * sizeof(double),
                              cudaMemcpyHostToDevice, ctx->stream));
-    // a changed field that a bilinear term uses changes the element-block classes
-    if (memcmp(d.weights_host.data() + (size_t)weight * n, values, n * sizeof(double)) != 0) {
+    // a changed field that a bilinear term uses changes the element-block classes; fields that only
+    // linear forms use (the incident-wave data of a frequency sweep) need no host copy and no compare
+    bool in_matrix = false;
+    for (const vlfs_term_desc& T : d.terms) in_matrix |= T.weight == weight;
+    if (in_matrix && memcmp(d.weights_host.data() + (size_t)weight * n, values, n * sizeof(double)) != 0) {
       memcpy(d.weights_host.data() + (size_t)weight * n, values, n * sizeof(double));
-      for (const vlfs_term_desc& T : d.terms)
-        if (T.weight == weight) d.cls_dirty = true;
+      d.cls_dirty = true;
     }
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return VLFS_OK;

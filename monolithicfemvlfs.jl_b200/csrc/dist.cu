@@ -407,7 +407,13 @@ void dist_init_all(int n, const int* devs, std::vector<DistPtr>& out) {
 void dist_bind(DistState& D, cudaStream_t s, int is_complex, int nsm, long long* launches) {
   D.s = s; D.cplx = is_complex; D.sc = is_complex ? 2 : 1; D.nsm = nsm; D.launches = launches;
   if (!D.cs) {
-    CUDA_TRY(cudaStreamCreateWithFlags(&D.cs, cudaStreamNonBlocking));
+    {
+      // the halo stream outranks the product: its pack kernel and the NCCL send/recv kernels get their
+      // CTAs as soon as one retires instead of queueing behind the interior rows
+      int lo = 0, hi = 0;
+      CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUDA_TRY(cudaStreamCreateWithPriority(&D.cs, cudaStreamNonBlocking, hi));
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&D.ev_x, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&D.ev_halo, cudaEventDisableTiming));
   }

@@ -314,20 +314,30 @@ expand_rows(const uint4* __restrict__ list, long long nlist, MatPtrs tmpl, MatPt
   if (first >= nlist) return;
   const int cnt = (int)min(32ll, nlist - first);
   const uint4 e = lane < cnt ? __ldcs(list + first + lane) : make_uint4(0u, 0u, 0u, 0u);
-  for (int r = sub; r < cnt; r += SPLIT) {
-    const uint32_t d = __shfl_sync(0xffffffffu, e.x, r), s = __shfl_sync(0xffffffffu, e.y, r);
-    const uint32_t len = __shfl_sync(0xffffffffu, e.z, r);
+  // two rows per step: the loads of both rows are issued before the first store (twice the bytes in flight)
+  for (int r = sub; r < cnt; r += 2 * SPLIT) {
+    const int r2 = r + SPLIT < cnt ? r + SPLIT : r;
+    const uint32_t dA = __shfl_sync(0xffffffffu, e.x, r), sA = __shfl_sync(0xffffffffu, e.y, r);
+    const uint32_t lenA = __shfl_sync(0xffffffffu, e.z, r);
+    const uint32_t dB = __shfl_sync(0xffffffffu, e.x, r2), sB = __shfl_sync(0xffffffffu, e.y, r2);
+    const uint32_t lenB = r2 != r ? __shfl_sync(0xffffffffu, e.z, r2) : (__shfl_sync(0xffffffffu, e.z, r2), 0u);
 #pragma unroll
     for (int mm = 0; mm < NMAT; ++mm) {
-      const T* __restrict__ in = reinterpret_cast<const T*>(tmpl.mat[mm]) + s;
-      T* __restrict__ out = reinterpret_cast<T*>(ptrs.mat[mm]) + d;
-      for (uint32_t k0 = lane; k0 < len; k0 += 32 * U) {
-        T v[U];
+      const T* __restrict__ inA = reinterpret_cast<const T*>(tmpl.mat[mm]) + sA;
+      const T* __restrict__ inB = reinterpret_cast<const T*>(tmpl.mat[mm]) + sB;
+      T* __restrict__ outA = reinterpret_cast<T*>(ptrs.mat[mm]) + dA;
+      T* __restrict__ outB = reinterpret_cast<T*>(ptrs.mat[mm]) + dB;
+      T vA[U], vB[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) if (k0 + 32 * u < len) v[u] = __ldg(in + k0 + 32 * u);
+      for (int u = 0; u < U; ++u) if (lane + 32 * u < lenA) vA[u] = __ldg(inA + lane + 32 * u);
 #pragma unroll
-        for (int u = 0; u < U; ++u) if (k0 + 32 * u < len) __stcs(out + k0 + 32 * u, v[u]);
-      }
+      for (int u = 0; u < U; ++u) if (lane + 32 * u < lenB) vB[u] = __ldg(inB + lane + 32 * u);
+#pragma unroll
+      for (int u = 0; u < U; ++u) if (lane + 32 * u < lenA) __stcs(outA + lane + 32 * u, vA[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) if (lane + 32 * u < lenB) __stcs(outB + lane + 32 * u, vB[u]);
+      for (uint32_t k = 32 * U + lane; k < lenA; k += 32) __stcs(outA + k, __ldg(inA + k));      // rows longer than 32 U
+      for (uint32_t k = 32 * U + lane; k < lenB; k += 32) __stcs(outB + k, __ldg(inB + k));
     }
   }
 }

@@ -25,6 +25,7 @@
 //  functional_cells<D>: ∑∫|OP(u_h) − f|² dμ of FE functions (L2 errors, energies).
 #include "common.cuh"
 #include <cstdlib>
+#include <algorithm>
 #include <cuda/barrier>
 
 namespace {
@@ -1096,7 +1097,15 @@ void launch_integrate(const DomainDev& dom, const RhsDev* rhs_dev, int nrhs, con
   size_t smem = (size_t)dom.smem_total * sizeof(double);
   // one thread per 4x4 tile of the cell's touched blocks, whole warps, at most 256
   int ntiles = do_mat ? dom.tile_base[dom.nblocks] : 0;
-  int threads = ((ntiles + 31) / 32) * 32;
+  // ... or one thread per (point, local DOF) entry of the largest per-cell operator table, whichever is
+  // more: with few tiles and second-derivative tables (MultiGeo plate: 16 tiles, 240 Hessian entries of
+  // ~100 flops each) the staging is the work, and 64 threads left 2 warps per SM (ncu: FP64 pipe 4 %)
+  int staging = 0;
+  for (int o = 0; o < dom.nopi; ++o)
+    if (dom.opi[o].buf_stride != 0 && (stage_mask >> o & 1u) &&
+        (dom.opi[o].op == VLFS_OP_HESS || dom.opi[o].op == VLFS_OP_CHESS || dom.opi[o].op == VLFS_OP_CHESS_NPLUS || dom.opi[o].op == VLFS_OP_LAPL))
+      staging = std::max(staging, dom.nq * dom.slot[dom.opi[o].slot].ndofs);     // (value / gradient tables are cheap to stage)
+  int threads = ((std::max(ntiles, staging) + 31) / 32) * 32;
   if (threads < 64) threads = 64;
   if (threads > 256) threads = 256;
   if (const char* e = getenv("VLFS_ASM_THREADS")) {      // tuning hook

@@ -6,6 +6,7 @@ usage: ncu -i gpurun_out/r1_prof_assembly_spmv.ncu-rep --page raw --csv > /tmp/r
 """
 import csv
 import json
+import os
 import sys
 
 METRICS = [
@@ -27,8 +28,10 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def label(name, seen):
-    for key, lab in (("build_class_tables", "class_tables:build"), ("integrate_cells", "class_tables:integrate"),
-                     ("gather_compact", "gather_reference"), ("gather_reference", "gather_reference"), ("rhs_affine", "rhs_affine"), ("csr_spmv", "csr_spmv")):
+    for key, lab in (("build_class_tables", "class_tables:build"), ("integrate_cells", "integrate_cells"),
+                     ("gather_chunks", "gather_chunks"), ("expand_rows", "expand_rows"),
+                     ("gather_compact", "gather_reference"), ("gather_reference", "gather_reference"), ("rhs_affine", "rhs_affine"),
+                     ("csr_spmv_cplx", "csr_spmv"), ("csr_spmv_real", "csr_spmv_real")):
         if key in name:
             seen[lab] = seen.get(lab, 0) + 1
             return lab, seen[lab]
@@ -53,8 +56,20 @@ def main(raw, out_csv, out_json):
             traffic.setdefault(lab, []).append(b)
     # per launch: mean over the captured launches of the same kernel
     per = {lab: sum(v) / len(v) for lab, v in traffic.items()}
-    out = {"gather_reference": per.get("gather_reference"), "csr_spmv": per.get("csr_spmv"),
-           "captured_launches": {lab: len(v) for lab, v in traffic.items()}, "per_launch_mean_bytes": per}
+    out = {"captured_launches": {lab: len(v) for lab, v in traffic.items()}, "per_launch_mean_bytes": per}
+    for k in ("gather_reference", "csr_spmv", "csr_spmv_real", "integrate_cells"):
+        if k in per:
+            out[k] = per[k]
+    # the numeric pass of one assembly = 2 gather_chunks + 2 expand_rows launches (early / late): captured in
+    # step order, so the first four launches are one pass
+    if "gather_chunks" in traffic and "expand_rows" in traffic and len(traffic["gather_chunks"]) >= 2 and len(traffic["expand_rows"]) >= 2:
+        out["expand_rows+gather_chunks"] = sum(traffic["gather_chunks"][:2]) + sum(traffic["expand_rows"][:2])
+    if os.path.exists(out_json) and len(sys.argv) > 4 and sys.argv[4] == "merge":
+        old = json.load(open(out_json))
+        for k in ("captured_launches", "per_launch_mean_bytes"):
+            old.setdefault(k, {}).update(out.pop(k))
+        old.update(out)
+        out = old
     json.dump(out, open(out_json, "w"), indent=1)
 
 
