@@ -363,6 +363,130 @@ schur_update(const FrontMeta* __restrict__ meta, const int* __restrict__ list, i
   }
 }
 
+// The same update on the FP64 tensor cores (mma.sync.m8n8k4.f64; measured on this B200: 37.1 TFLOP/s
+// against 33.6 of the FMA pipe, scripts/ubench/dmma_peak.cu) with the operand tiles brought in by
+// cp.async into a double-buffered shared-memory ring.  The register-tiled version above loads one
+// shared-memory operand per 2 real FMAs and waits for its global loads between two barriers (ncu:
+// long-scoreboard 14 cycles per issue, 17 % issue slots); here a warp-level 8x8x4 product needs 2
+// operand loads per thread for 16 FMAs and the loads of stage s+1 fly during the products of stage s.
+// Tile 64 x 64 per CTA, 8 warps as 2 x 4, a warp owns 32 x 16 = 4 x 2 mma tiles, depth 16 per stage.
+// Row strides of 20 (A) and 66 / 68 (B, complex / real) scalars keep the fragment loads of a quarter /
+// half warp in distinct banks.  The accumulators collect +A*B and are subtracted at the end.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? BYTES : 0;                   // src-size 0: the destination is zero filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(d), "l"(gsrc), "n"(BYTES), "r"(n) : "memory");
+}
+constexpr int MMA_KD = 16;                           // depth of a stage
+constexpr int MMA_LDA = MMA_KD + 4;
+template <bool C> struct MmaLd { static constexpr int B = C ? TS + 2 : TS + 4; };
+template <bool C> constexpr size_t mma_smem() { return 2 * (size_t)(TS * MMA_LDA + MMA_KD * MmaLd<C>::B) * sizeof(typename Num<C>::T); }
+
+template <bool C>
+__global__ void __launch_bounds__(256, 2)
+schur_update_mma(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int kf, int nk, int mode,
+                 int kend_panel, typename Num<C>::T* __restrict__ pool) {
+  using N = Num<C>;
+  using T = typename N::T;
+  constexpr int P = C ? 2 : 1;
+  constexpr int LDB = MmaLd<C>::B;
+  constexpr int STAGE = TS * MMA_LDA + MMA_KD * LDB;           // scalars per stage
+  extern __shared__ __align__(16) double smraw[];
+  T* sm = reinterpret_cast<T*>(smraw);
+  const FrontMeta F = meta[list[blockIdx.z]];
+  const int d0 = kf * NB;
+  if (d0 >= F.np) return;
+  const int d1 = min((kf + nk) * NB, F.np);
+  const int Kend = min(kend_panel * NB, F.np);
+  int i0, j0, ilim, jlim;
+  if (mode == 0) { i0 = Kend + blockIdx.y * TS; j0 = Kend + blockIdx.x * TS; ilim = F.nf; jlim = F.nf; }
+  else if (mode == 1) { i0 = d1 + blockIdx.y * TS; j0 = d1 + blockIdx.x * TS; ilim = F.nf; jlim = Kend; }
+  else { i0 = d1 + blockIdx.y * TS; j0 = Kend + blockIdx.x * TS; ilim = Kend; jlim = F.nf; }
+  if (i0 >= ilim || j0 >= jlim) return;
+  T* Fp = pool + F.off;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = warp >> 2, wc = warp & 3;           // warp tile: rows wr*32.., columns wc*16..
+  const int g = lane >> 2, t4 = lane & 3;            // groupID, threadID_in_group of the fragment layouts
+  double acc[4][2][P][2];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int p = 0; p < P; ++p) acc[m][n][p][0] = acc[m][n][p][1] = 0.0;
+  const int nstage = (d1 - d0 + MMA_KD - 1) / MMA_KD;
+  auto issue = [&](int st) {
+    const int kb0 = d0 + st * MMA_KD, kb = min(MMA_KD, d1 - kb0);
+    T* sA = sm + (size_t)(st & 1) * STAGE;
+    T* sB = sA + TS * MMA_LDA;
+#pragma unroll
+    for (int t = tid; t < TS * MMA_KD; t += 256) {               // A: rows i0.., columns kb0..
+      const int r = t / MMA_KD, c = t % MMA_KD;
+      const bool ok = i0 + r < ilim && c < kb;
+      cp_async_zfill<sizeof(T)>(sA + r * MMA_LDA + c, ok ? Fp + (long long)(i0 + r) * F.nf + kb0 + c : Fp, ok);
+    }
+#pragma unroll
+    for (int t = tid; t < MMA_KD * TS; t += 256) {               // B: rows kb0.., columns j0..
+      const int r = t / TS, c = t % TS;
+      const bool ok = j0 + c < jlim && r < kb;
+      cp_async_zfill<sizeof(T)>(sB + r * LDB + c, ok ? Fp + (long long)(kb0 + r) * F.nf + j0 + c : Fp, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0);
+  for (int st = 0; st < nstage; ++st) {
+    if (st + 1 < nstage) { issue(st + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const T* sA = sm + (size_t)(st & 1) * STAGE;
+    const T* sB = sA + TS * MMA_LDA;
+#pragma unroll
+    for (int k4 = 0; k4 < MMA_KD / 4; ++k4) {
+      T a[4], b[2];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) a[m] = sA[(wr * 32 + m * 8 + g) * MMA_LDA + k4 * 4 + t4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) b[n] = sB[(k4 * 4 + t4) * LDB + wc * 16 + n * 8 + g];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          if constexpr (C) {
+            dmma884(acc[m][n][0], a[m].x, b[n].x);
+            dmma884(acc[m][n][0], -a[m].y, b[n].y);
+            dmma884(acc[m][n][1], a[m].x, b[n].y);
+            dmma884(acc[m][n][1], a[m].y, b[n].x);
+          } else {
+            dmma884(acc[m][n][0], a[m], b[n]);
+          }
+        }
+    }
+    __syncthreads();                                   // the next issue overwrites this buffer
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int i = i0 + wr * 32 + m * 8 + g;
+    if (i >= ilim) continue;
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const int j = j0 + wc * 16 + n * 8 + 2 * t4;
+      T* p = Fp + (long long)i * F.nf + j;
+      if constexpr (C) {
+        if (j < jlim) p[0] = make_double2(p[0].x - acc[m][n][0][0], p[0].y - acc[m][n][1][0]);
+        if (j + 1 < jlim) p[1] = make_double2(p[1].x - acc[m][n][0][1], p[1].y - acc[m][n][1][1]);
+      } else {
+        if (j < jlim) p[0] -= acc[m][n][0][0];
+        if (j + 1 < jlim) p[1] -= acc[m][n][0][1];
+      }
+    }
+  }
+}
+
 // ---- solve kernels --------------------------------------------------------------------
 // b (original numbering, n_total entries) -> bp (eliminated positions only)
 template <bool C>
@@ -740,8 +864,10 @@ static void factor_levels(DirectSolver& D) {
   using T = typename Num<C>::T;
   cudaStream_t s = D.s;
   T* pool = reinterpret_cast<T*>(D.pool.p);
-  const size_t smem = (size_t)(TS * (NB + 1) + NB * TS) * sizeof(T);
-  CUDA_TRY(cudaFuncSetAttribute(schur_update<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool use_mma = !(getenv("VLFS_LU_MMA") && atoi(getenv("VLFS_LU_MMA")) == 0);
+  const size_t smem = use_mma ? mma_smem<C>() : (size_t)(TS * (NB + 1) + NB * TS) * sizeof(T);
+  auto schur = use_mma ? schur_update_mma<C> : schur_update<C>;
+  CUDA_TRY(cudaFuncSetAttribute(schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const int outer_env = getenv("VLFS_LU_OUTER") ? atoi(getenv("VLFS_LU_OUTER")) : 4;
   const int outer = outer_env < 1 ? 1 : outer_env;   // panels per outer block (4 = 128 pivots)
   D.d_info.zero(s);
@@ -771,16 +897,16 @@ static void factor_levels(DirectSolver& D) {
         const int strip = (K1 - k - 1) * NB;              // rest of the outer block after panel k
         if (strip > 0) {
           dim3 gc((strip + TS - 1) / TS, (rem + TS - 1) / TS, nfr);
-          schur_update<C><<<gc, 256, smem, s>>>(D.d_meta.p, list, k, 1, 1, K1, pool);
+          schur<<<gc, 256, smem, s>>>(D.d_meta.p, list, k, 1, 1, K1, pool);
           dim3 gr((rem + TS - 1) / TS, (strip + TS - 1) / TS, nfr);
-          schur_update<C><<<gr, 256, smem, s>>>(D.d_meta.p, list, k, 1, 2, K1, pool);
+          schur<<<gr, 256, smem, s>>>(D.d_meta.p, list, k, 1, 2, K1, pool);
           *D.launches += 2;
         }
       }
       const int rem = maxnf - K0 * NB;                    // >= nf - Kend of every front still active
       if (rem > 0) {
         dim3 g3((rem + TS - 1) / TS, (rem + TS - 1) / TS, nfr);
-        schur_update<C><<<g3, 256, smem, s>>>(D.d_meta.p, list, K0, K1 - K0, 0, K1, pool);
+        schur<<<g3, 256, smem, s>>>(D.d_meta.p, list, K0, K1 - K0, 0, K1, pool);
         ++*D.launches;
       }
     }
