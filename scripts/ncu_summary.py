@@ -31,7 +31,7 @@ def label(name, seen):
     for key, lab in (("build_class_tables", "class_tables:build"), ("integrate_cells", "integrate_cells"),
                      ("gather_chunks", "gather_chunks"), ("expand_rows", "expand_rows"),
                      ("gather_compact", "gather_reference"), ("gather_reference", "gather_reference"), ("rhs_affine", "rhs_affine"),
-                     ("csr_spmv_cplx", "csr_spmv"), ("csr_spmv_real", "csr_spmv_real")):
+                     ("csr_spmv_cplx", "csr_spmv"), ("csr_spmv_real", "csr_spmv_real"), ("schur_update", "schur_update")):
         if key in name:
             seen[lab] = seen.get(lab, 0) + 1
             return lab, seen[lab]
