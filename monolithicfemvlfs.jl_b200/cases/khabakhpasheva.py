@@ -216,6 +216,12 @@ def run_Khabakhpasheva_freq_domain(params, device=0, solver=None):
     opts.update(solver or {})
     prob.sys.solver_setup(0, **opts)
     x, prob.stats = prob.sys.solve(vec=0)
+    if params.vtk_output:                                   # src/Khabakhpasheva_freq_domain.jl:244-246
+        from ..vtk import writevtk
+        phi, kap, et = prob.X.split(x)
+        writevtk(prob.Om, params.name + "_O_solution", [("phi_re", prob.V_Om, phi.real), ("phi_im", prob.V_Om, phi.imag)], nsubcells=10)
+        writevtk(prob.Gkap, params.name + "_Gk_solution", [("eta_re", prob.V_Gk, kap.real), ("eta_im", prob.V_Gk, kap.imag)], nsubcells=10)
+        writevtk(prob.Geta, params.name + "_Ge_solution", [("eta_re", prob.V_Ge, et.real), ("eta_im", prob.V_Ge, et.imag)], nsubcells=10)
     return prob.postprocess(x)
 
 

@@ -125,4 +125,11 @@ def run_MultiGeo_freq_domain(params, device=0, solver=None):
     opts.update(solver or {})
     prob.sys.solver_setup(0, **opts)
     x, prob.stats = prob.sys.solve(vec=0)
+    if params.vtk_output:                                   # src/Multi_geo_freq_domain.jl:145-147
+        from ..vtk import writevtk
+        phi, kap, et = prob.X.split(x)
+        name = getattr(params, "name", "MultiGeo")
+        writevtk(prob.Om, name + "_O", [("phi_re", prob.V_Om, phi.real), ("phi_im", prob.V_Om, phi.imag)], nsubcells=10)
+        writevtk(prob.Gf, name + "_Gk", [("eta_re", prob.V_Gk, kap.real), ("eta_im", prob.V_Gk, kap.imag)], nsubcells=10)
+        writevtk(prob.Gb, name + "_Ge", [("eta_re", prob.V_Ge, et.real), ("eta_im", prob.V_Ge, et.imag)], nsubcells=10)
     return prob.X.split(x)

@@ -212,4 +212,11 @@ def run_Yago_freq_domain(params, device=0, solver=None):
     x, stats = prob.sys.solve(vec=0)
     prob.stats = stats
     xps, eta = prob.rao(x)
+    if params.vtk_output:                                   # src/Yago_freq_domain.jl:201-205
+        from ..vtk import writevtk
+        phi, kap, et = prob.X.split(x)
+        name = getattr(params, "name", "Yago")
+        writevtk(prob.Om, name + "_O", [("phi_re", prob.V_Om, phi.real), ("phi_im", prob.V_Om, phi.imag)], nsubcells=10)
+        writevtk(prob.Gf, name + "_Gk", [("eta_re", prob.V_Gk, kap.real), ("eta_im", prob.V_Gk, kap.imag)], nsubcells=10)
+        writevtk(prob.Gb, name + "_Ge", [("eta_re", prob.V_Ge, et.real), ("eta_im", prob.V_Ge, et.imag)], nsubcells=10)
     return xps, eta

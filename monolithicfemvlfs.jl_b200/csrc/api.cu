@@ -114,6 +114,7 @@ struct Domain {
   double* ctab_ptr[4] = {nullptr, nullptr, nullptr, nullptr};   // this domain's slice of vlfs_ctx::ctab_all
   long long ctab_base = 0;                                      // its first entry there
   std::vector<double> jt_host, cellgeo_host, weights_host;
+  std::vector<int> cls_host, reps_host;      // class of every cell / representative cell of every class
   long long ctab_off[VLFS_MAX_BLOCKS] = {-1, -1, -1, -1};
   long long ctab_entries = 0, ctab_work = 0;
   DevBuf<RhsDev> rhs_dev;
@@ -350,7 +351,7 @@ void build_reference_products(vlfs_ctx* ctx, Domain& d) {
 void classify_domain(vlfs_ctx* ctx, Domain& d) {
   DomainDev& dev = d.dev;
   d.cls_dirty = false;
-  d.ncls = 0; d.cls_full = false;
+  d.ncls = 0; d.cls_full = false; d.cls_host.clear(); d.reps_host.clear();
   for (int b = 0; b < VLFS_MAX_BLOCKS; ++b) d.ctab_off[b] = -1;
   const bool any_general = !d.terms_host.empty();
   if (!dev.affine || dev.ncells == 0 || (d.refprods_host.empty() && !any_general)) return;
@@ -403,6 +404,7 @@ void classify_domain(vlfs_ctx* ctx, Domain& d) {
   d.cls_full = any_general && (long long)ncls * 4 <= dev.ncells;
   d.cls.upload(cls.data(), cls.size(), ctx->stream);
   d.reps.upload(reps.data(), reps.size(), ctx->stream);
+  d.cls_host = cls; d.reps_host = reps;
   if (!d.cellgeo_host.empty()) {
     std::vector<double> cg((size_t)ncls * VLFS_CELLGEO);
     for (int c = 0; c < ncls; ++c)
@@ -1184,7 +1186,19 @@ int vlfs_set_weights(vlfs_ctx* ctx, int domain_id, int weight, const double* val
     for (const vlfs_term_desc& T : d.terms) in_matrix |= T.weight == weight;
     if (in_matrix && memcmp(d.weights_host.data() + (size_t)weight * n, values, n * sizeof(double)) != 0) {
       memcpy(d.weights_host.data() + (size_t)weight * n, values, n * sizeof(double));
-      d.cls_dirty = true;
+      // The classes stay valid when the new field is still constant over every class (e.g. μ₂ = k μ₁ in
+      // a frequency sweep: the same partition, new values): the class tables are recomputed from the
+      // representatives at every assembly anyway, so nothing has to be rebuilt.
+      bool same_partition = d.ncls > 0 && d.cls_host.size() == (size_t)d.dev.ncells;
+      if (same_partition) {
+        const size_t nq = (size_t)d.dev.nq;
+        const double* w = values;
+        for (long long e = 0; e < d.dev.ncells && same_partition; ++e) {
+          const size_t r = (size_t)d.reps_host[(size_t)d.cls_host[(size_t)e]];
+          same_partition = memcmp(w + (size_t)e * nq, w + r * nq, nq * sizeof(double)) == 0;
+        }
+      }
+      if (!same_partition) d.cls_dirty = true;
     }
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return VLFS_OK;

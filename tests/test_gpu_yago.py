@@ -139,3 +139,39 @@ def test_general_quadrature_path_equals_fast_path(kw):
     v_gen, b_gen = prob2.sys.get_values(0), prob2.sys.get_vector(0)
     assert np.abs(v_fast - v_gen).max() <= 1e-13 * np.abs(v_gen).max()
     assert np.abs(b_fast - b_gen).max() <= 1e-13 * np.abs(b_gen).max()
+
+
+def test_scaled_coefficient_field_keeps_the_classes():
+    """A frequency sweep fed with μ₂ = k μ₁ as a FIELD (what a Gridap-side caller would send) changes the
+    weight of bilinear terms every step.  The new field induces the same cell classes, so nothing is
+    re-classified or rebuilt (the class tables are recomputed from the representatives at every assembly
+    anyway); a field that breaks the classes does trigger the rebuild and still gives the right matrix."""
+    from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
+    prob = YagoProblem(Yago_freq_domain_params(nx=6, ny=2, nz=2, order=4, lfactor=0.6, dfactor=4), device=0)
+    prob.assemble()
+    v0 = prob.sys.get_values(0)
+    inp = prob.frequency_inputs(0.6)
+    t = prob.t_Gf
+    mu1, kk = inp["weights_Gf"][0], 3.7
+    steady = []
+    for _ in range(2):                                # launches of a plain re-assembly
+        l0 = prob.sys.launches(); prob.sys.assemble(); steady.append(prob.sys.launches() - l0)
+    # the same bilinear form written with the field k μ₁ and the coefficients divided by k
+    prob.dom_Gf.set_weights(0, kk * mu1)
+    prob.dom_Gf.set_coef(t["upn"], 1.0 / kk)
+    prob.dom_Gf.set_coef(t["wkm"], inp["coef_Gf"][t["wkm"]] / kk)
+    prob.dom_Gf.set_coef(t["wpn"], inp["coef_Gf"][t["wpn"]] / kk)
+    l0 = prob.sys.launches(); prob.sys.assemble(); scaled = prob.sys.launches() - l0
+    v1 = prob.sys.get_values(0)
+    assert np.abs(v1 - v0).max() <= 1e-13 * np.abs(v0).max()
+    assert scaled == steady[-1], (scaled, steady)     # no classification / record / template kernels
+    # a field that differs in every cell breaks the classes: rebuild, and still the right values
+    rng = np.random.default_rng(0)
+    bumpy = kk * mu1 * (1.0 + 1e-3 * rng.random(mu1.shape[0]))[:, None]
+    prob.dom_Gf.set_weights(0, bumpy)
+    l0 = prob.sys.launches(); prob.sys.assemble(); rebuilt = prob.sys.launches() - l0
+    assert rebuilt > scaled
+    prob.dom_Gf.set_weights(0, kk * mu1)
+    prob.sys.assemble()
+    v2 = prob.sys.get_values(0)
+    assert np.abs(v2 - v0).max() <= 1e-13 * np.abs(v0).max()
