@@ -7,16 +7,16 @@ The reference is a serial Julia program; this module is the partitioned twin of 
   with its own libvlfs_b200 context only the cells that touch one of its DOFs, with local DOF
   ids [owned | ghost]; every owned row of the local CSR is then complete - no matrix entry ever
   crosses GPUs and nothing is reduced between ranks during assembly.
-* y = A x needs the ghost values of x: one halo exchange (pack kernel + NCCL send/recv through
-  torch.distributed) before the local SpMV over the owned rows.
-* The solve is right-preconditioned GMRES (CGS2, all dots of a pass batched into one all-reduce)
-  with the GPU multifrontal LU of each rank's owned block as block-Jacobi preconditioner.
+* The PRODUCT path is `MultiSystem` (bottom of this file): partition and local numbering here on the
+  host, everything else - halo exchange overlapped with the interior rows, all-reduce, distributed
+  GMRES, substructuring on the chain of slab cuts - inside the library (csrc/dist.cu, behind
+  `vlfs_multi_*` / `vlfs_dist_*`).  `bench.py --gpus N` and tests/test_gpu_multi.py use it.
 
-`Fleet` runs any number of ranks inside one process in lockstep (all members local: used by the
-1-GPU tests, no waiting between kernels of different ranks) or one member per process with
-torch.distributed carrying halos and reductions (real multi-GPU).  Arithmetic goes through a
-`LocalOps` object: `GpuOps` below (libvlfs_b200 device entry points on torch CUDA tensors); the
-NumPy twin used by the gloo CPU tests lives in oracle/dist_cpu.py and is test infrastructure.
+`Fleet` / `GpuOps` / `SchurSolver` are the round-1 Python prototype of the same algorithms (lockstep
+ranks inside one process, torch.distributed between processes).  They are kept as the executable
+specification of the host logic: the gloo world_size-2 CPU tests (tests/test_dist_cpu.py, with the
+NumPy arithmetic twin oracle/dist_cpu.py, test infrastructure) and tests/test_gpu_dist.py run them;
+nothing in the product path or the bench does.
 """
 import ctypes as C
 import numpy as np
