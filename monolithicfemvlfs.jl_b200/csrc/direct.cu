@@ -373,8 +373,8 @@ schur_update(const FrontMeta* __restrict__ meta, const int* __restrict__ list, i
 // Row strides of 20 (A) and 66 / 68 (B, complex / real) scalars keep the fragment loads of a quarter /
 // half warp in distinct banks.  The accumulators collect +A*B and are subtracted at the end.
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 template <int BYTES>
 __device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc, bool valid) {
@@ -388,7 +388,7 @@ template <bool C> struct MmaLd { static constexpr int B = C ? TS + 2 : TS + 4; }
 template <bool C> constexpr size_t mma_smem() { return 2 * (size_t)(TS * MMA_LDA + MMA_KD * MmaLd<C>::B) * sizeof(typename Num<C>::T); }
 
 template <bool C>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 2)       // (3 CTAs/SM fit the shared memory but spill at 80 registers: 221 vs 215 ms)
 schur_update_mma(const FrontMeta* __restrict__ meta, const int* __restrict__ list, int kf, int nk, int mode,
                  int kend_panel, typename Num<C>::T* __restrict__ pool) {
   using N = Num<C>;
@@ -452,19 +452,23 @@ schur_update_mma(const FrontMeta* __restrict__ meta, const int* __restrict__ lis
       for (int m = 0; m < 4; ++m) a[m] = sA[(wr * 32 + m * 8 + g) * MMA_LDA + k4 * 4 + t4];
 #pragma unroll
       for (int n = 0; n < 2; ++n) b[n] = sB[(k4 * 4 + t4) * LDB + wc * 16 + n * 8 + g];
+      // (the two products into the same accumulator are issued 16 DMMAs apart: ncu showed the pipe
+      //  throttling on the dependent back-to-back pairs)
+      if constexpr (C) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < 4; ++m)
 #pragma unroll
-        for (int n = 0; n < 2; ++n) {
-          if constexpr (C) {
-            dmma884(acc[m][n][0], a[m].x, b[n].x);
-            dmma884(acc[m][n][0], -a[m].y, b[n].y);
-            dmma884(acc[m][n][1], a[m].x, b[n].y);
-            dmma884(acc[m][n][1], a[m].y, b[n].x);
-          } else {
-            dmma884(acc[m][n][0], a[m], b[n]);
-          }
-        }
+          for (int n = 0; n < 2; ++n) { dmma884(acc[m][n][0], a[m].x, b[n].x); dmma884(acc[m][n][1], a[m].x, b[n].y); }
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int n = 0; n < 2; ++n) { dmma884(acc[m][n][0], -a[m].y, b[n].y); dmma884(acc[m][n][1], a[m].y, b[n].x); }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int n = 0; n < 2; ++n) dmma884(acc[m][n][0], a[m], b[n]);
+      }
     }
     __syncthreads();                                   // the next issue overwrites this buffer
   }

@@ -472,7 +472,6 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
   if (direct && S.Z.n != (size_t)m * ld) { S.Z.alloc((size_t)m * ld); S.Z.zero(S.s); }
   double* xlo = nullptr;
   if (direct) { xlo = S.vec(S.xlo); CUDA_TRY(cudaMemsetAsync(xlo, 0, ld * sizeof(double), S.s)); }
-  bool stagnated = false;
   double prev_cycle_rel = 1e300;
   static const bool dbg = getenv("VLFS_DEBUG") != nullptr;
   static const bool nostag = getenv("VLFS_GMRES_NOSTAG") != nullptr;       // diagnostic: iterate to rtol / maxit
@@ -485,7 +484,7 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
     double beta = S.nrm2(r);
     rel = beta / bnorm;
     if (dbg) fprintf(stderr, "[vlfs] gmres: true residual %.3e after %d iterations\n", rel, it);
-    if (!(rel > S.opts.rtol) || it >= S.opts.maxit || stagnated) break;     // (NaN ends the loop too)
+    if (!(rel > S.opts.rtol) || it >= S.opts.maxit) break;     // (NaN ends the loop too)
     if (direct && !nostag && rel > 0.25 * prev_cycle_rel) break;
     prev_cycle_rel = rel;
     S.axpby_(cd(1.0 / beta, 0), r, cd(0, 0), S.V.p);      // V_0
