@@ -194,8 +194,13 @@ int vlfs_import_csr(vlfs_ctx* ctx, int64_t ndofs, int is_complex, int nmat, cons
                     const int32_t* colind);
 int vlfs_set_values(vlfs_ctx* ctx, int mat, const void* values);
 int vlfs_set_vector(vlfs_ctx* ctx, int vec, const void* values);
-/* mat[target] = sum_k coef[k] * mat[src[k]]   (Newmark: K + γ/(βΔt) C + 1/(βΔt²) M)       */
+/* mat[target] = sum_k coef[k] * mat[src[k]], n <= 4  (Newmark: K + γ/(βΔt) C + 1/(βΔt²) M; ω sweeps by
+ * basis matrices: A(ω) = B₀ + ω B₁ + ω² B₂ + k B₃, src/Yago_freq_domain.jl:69-94,162-165)          */
 int vlfs_combine(vlfs_ctx* ctx, int target, int n, const int* src, const double* coef_re_im);
+/* One more value array on the built pattern that no term targets (zero-filled): the target of
+ * vlfs_combine when all nmat <= 4 assembled matrices are sources.  *mat receives its index (>= nmat),
+ * valid wherever a matrix index is taken except vlfs_add_term.  Dropped by vlfs_system_init.      */
+int vlfs_add_work_matrix(vlfs_ctx* ctx, int* mat);
 
 /* ---- algebra -------------------------------------------------------------------- */
 int vlfs_spmv(vlfs_ctx* ctx, int mat, const void* x, void* y);         /* host in/out   */

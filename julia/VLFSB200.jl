@@ -192,6 +192,13 @@ function combine!(s::System, target::Integer, src::Vector{<:Integer}, coef::Vect
                  s.ctx, target, length(src), Cint.(src), c))
 end
 
+# a value array no term targets: A(ω) = B₀ + ω B₁ + ω² B₂ + k B₃ of a sweep by basis matrices
+function add_work_matrix!(s::System)
+  m = Ref{Cint}(-1)
+  check(s, ccall((:vlfs_add_work_matrix, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}), s.ctx, m))
+  Int(m[])
+end
+
 function spmv(s::System, x::Vector, mat::Integer=0)
   y = similar(x)
   check(s, ccall((:vlfs_spmv, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), s.ctx, mat, x, y))

@@ -287,6 +287,12 @@ class B200System:
         cf[1::2] = np.imag(coefs)
         self._check(self.lib.vlfs_combine(self.ctx, target, len(sources), L.iptr(src), L.dptr(cf)))
 
+    def add_work_matrix(self):
+        """One more value array on the pattern that no term targets (`vlfs_add_work_matrix`)."""
+        m = C.c_int(-1)
+        self._check(self.lib.vlfs_add_work_matrix(self.ctx, C.byref(m)))
+        return m.value
+
     def spmv(self, x, mat=0):
         x = np.ascontiguousarray(x, dtype=self.dtype)
         y = np.empty_like(x)

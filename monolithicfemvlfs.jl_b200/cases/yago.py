@@ -21,6 +21,9 @@ class Yago_freq_domain_params:          # src/Yago_freq_domain.jl:11-20
     vtk_output: bool = False
 
 
+MAT_B0, MAT_B1, MAT_B2, MAT_BK = 0, 1, 2, 3     # basis matrices of the ω sweep; A(ω) is a work matrix (prob.MAT_A)
+
+
 def wave_constants(L_, H, g, lfactor):
     k = 2 * np.pi / (L_ * lfactor)
     om = np.sqrt(g * k * np.tanh(k * H))
@@ -30,10 +33,18 @@ def wave_constants(L_, H, g, lfactor):
 class YagoProblem:
     """Everything up to and including `op = AffineFEOperator(a,b,X,Y)`."""
 
-    def __init__(self, params, device=0, system_cls=B200System, affine=None):
+    def __init__(self, params, device=0, system_cls=B200System, affine=None, basis=False):
         """affine=None: detect constant-Jacobian domains; False: force the general per-point
-        geometry path everywhere (parity check of the fast paths)."""
+        geometry path everywhere (parity check of the fast paths).
+
+        basis=True: ω-sweep by basis matrices.  ω enters the bilinear form only through
+        the scalars ω, ω² and k (src/Yago_freq_domain.jl:69-94,162-165), so
+        A(ω) = B₀ + ω B₁ + ω² B₂ + k B₃ with ω-independent B_k: the terms are registered on the matrices
+        MAT_B0..MAT_BK of ONE union pattern with their ω-independent factors, `assemble_basis` integrates
+        them once, and `combine_frequency` forms the work matrix `self.MAT_A` with one `vlfs_combine` per
+        frequency."""
         p = self.params = params
+        self.basis = bool(basis)
         nx, ny, nz, order = p.nx, p.ny, p.nz, p.order
         # fixed parameters (:29-50)
         Lb, B, H, hb = 300, 60, 58.5, 2.0
@@ -86,12 +97,17 @@ class YagoProblem:
         self.X = X = MultiFieldFESpace([TrialFESpace(V_Om), TrialFESpace(V_Gk), TrialFESpace(V_Ge)])
         self.V_Om, self.V_Gk, self.V_Ge = V_Om, V_Gk, V_Ge
 
-        sys_ = self.sys = system_cls(X.ndofs, True, nmat=1, nvec=1, device=device)
+        sys_ = self.sys = system_cls(X.ndofs, True, nmat=4 if self.basis else 1, nvec=1, device=device)
         ez = (0.0, 0.0, 1.0)
+        # target matrix of a term by its ω-class: everything on matrix 0 unless `basis`
+        M0, M1, M2, MK = (MAT_B0, MAT_B1, MAT_B2, MAT_BK) if self.basis else (0, 0, 0, 0)
+        bh = c["bh"]
+        fb = self._basis_factors = self.basis_factors(bh, g, c["d0"])
+        fac = (lambda name: fb[name]) if self.basis else (lambda name: 0)
         # ---- Ω : ∫ ∇(ϕ)⋅∇(w) (:162)
         s_phi = dOm.own_slot(V_Om)
         self.dom_Om = sys_.add_domain(3, dOm.nq, dOm.wq, [s_phi], affine=affine)
-        self.dom_Om.add_term(0, 1.0, L.OP_GRAD, 0, L.OP_GRAD, 0)
+        self.dom_Om.add_term(M0, 1.0, L.OP_GRAD, 0, L.OP_GRAD, 0)
         # ---- Γf (:163): slot 0 = ϕ trace, slot 1 = κ ; weights: 0 = μ₁, 1 = Re/Im of rhs fields
         xq = dGf.points()
         self._xq_Gf = xq[..., 0].copy()
@@ -100,13 +116,13 @@ class YagoProblem:
         d = self.dom_Gf
         PHI, KAP = 0, 1
         self.t_Gf = dict(
-            uk=d.add_term(0, 0, L.OP_VAL, KAP, L.OP_VAL, KAP),                        # βₕ g κ u
-            up=d.add_term(0, 0, L.OP_VAL, KAP, L.OP_VAL, PHI),                        # -iωβₕ ϕ u
-            upn=d.add_term(0, 1.0, L.OP_VAL, KAP, L.OP_DDIR, PHI, weight=0, trial_dir=ez),   # μ₁ ∇ₙϕ u
-            wk=d.add_term(0, 0, L.OP_VAL, PHI, L.OP_VAL, KAP),                        # (βₕ g αₕ + iω) κ w
-            wkm=d.add_term(0, 0, L.OP_VAL, PHI, L.OP_VAL, KAP, weight=0),             # -k μ₁ κ w
-            wp=d.add_term(0, 0, L.OP_VAL, PHI, L.OP_VAL, PHI),                        # -iωβₕαₕ ϕ w
-            wpn=d.add_term(0, 0, L.OP_VAL, PHI, L.OP_DDIR, PHI, weight=0, trial_dir=ez))   # αₕ μ₁ ∇ₙϕ w
+            uk=d.add_term(M0, fac("uk"), L.OP_VAL, KAP, L.OP_VAL, KAP),                # βₕ g κ u
+            up=d.add_term(M1, fac("up"), L.OP_VAL, KAP, L.OP_VAL, PHI),                # -iωβₕ ϕ u
+            upn=d.add_term(M0, 1.0, L.OP_VAL, KAP, L.OP_DDIR, PHI, weight=0, trial_dir=ez),   # μ₁ ∇ₙϕ u
+            wk=d.add_term(M1, fac("wk"), L.OP_VAL, PHI, L.OP_VAL, KAP),                # (βₕ g αₕ + iω) κ w
+            wkm=d.add_term(MK, fac("wkm"), L.OP_VAL, PHI, L.OP_VAL, KAP, weight=0),    # -k μ₁ κ w
+            wp=d.add_term(M2, fac("wp"), L.OP_VAL, PHI, L.OP_VAL, PHI),                # -iωβₕαₕ ϕ w
+            wpn=d.add_term(M1, fac("wpn"), L.OP_VAL, PHI, L.OP_DDIR, PHI, weight=0, trial_dir=ez))   # αₕ μ₁ ∇ₙϕ w
         # rhs (:166): -∫(ηd w - ∇ₙϕd (u + αₕ w)); complex fields sampled at the points
         self.r_Gf = dict(
             w1=d.add_rhs(0, -1.0, L.OP_VAL, PHI, weight_re=1, weight_im=2),           # -ηd w
@@ -118,19 +134,21 @@ class YagoProblem:
                                           measure_slot=1, Ctensor=Ct, affine=affine)
         ETA = 1
         self.t_Gb = dict(
-            vv=d.add_term(0, 0, L.OP_VAL, ETA, L.OP_VAL, ETA),                        # (g-ω²d₀) η v
-            bend=d.add_term(0, 1.0, L.OP_HESS, ETA, L.OP_CHESS, ETA),                 # ∇∇v⊙(C⊙∇∇η)
-            vp=d.add_term(0, 0, L.OP_VAL, ETA, L.OP_VAL, PHI),                        # -iω ϕ v
-            we=d.add_term(0, 0, L.OP_VAL, PHI, L.OP_VAL, ETA))                        # iω η w
+            vv=d.add_term(M0, fac("vv0"), L.OP_VAL, ETA, L.OP_VAL, ETA),               # (g-ω²d₀) η v
+            bend=d.add_term(M0, 1.0, L.OP_HESS, ETA, L.OP_CHESS, ETA),                # ∇∇v⊙(C⊙∇∇η)
+            vp=d.add_term(M1, fac("vp"), L.OP_VAL, ETA, L.OP_VAL, PHI),                # -iω ϕ v
+            we=d.add_term(M1, fac("we"), L.OP_VAL, PHI, L.OP_VAL, ETA))                # iω η w
+        if self.basis:
+            d.add_term(M2, fb["vv2"], L.OP_VAL, ETA, L.OP_VAL, ETA)                   # -ω²d₀ η v
         # ---- Λb (:165): slot 0 = η⁺, slot 1 = η⁻
         self.dom_Lb = d = sys_.add_domain(3, dLb.nq, dLb.wq,
                                           [dLb.skeleton_slot(V_Ge, "plus"), dLb.skeleton_slot(V_Ge, "minus")],
                                           measure_slot=0, measure_kind=L.MEASURE_FACET, Ctensor=Ct, affine=affine)
         jump, mean = {0: 1.0, 1: -1.0}, {0: 0.5, 1: 0.5}
         gamma = 1.0 * order * (order + 1) / c["h"]
-        d.add_term(0, -1.0, L.OP_GRAD, jump, L.OP_CHESS_NPLUS, mean)
-        d.add_term(0, -1.0, L.OP_CHESS_NPLUS, mean, L.OP_GRAD, jump)
-        d.add_term(0, D_ / rho * gamma, L.OP_GRAD, jump, L.OP_GRAD, jump)
+        d.add_term(M0, -1.0, L.OP_GRAD, jump, L.OP_CHESS_NPLUS, mean)
+        d.add_term(M0, -1.0, L.OP_CHESS_NPLUS, mean, L.OP_GRAD, jump)
+        d.add_term(M0, D_ / rho * gamma, L.OP_GRAD, jump, L.OP_GRAD, jump)
         # ---- Γin rhs (:166): ∫ vin w ; slot 0 = ϕ trace, slot 1 = Q1 face (measure only)
         V_aux = TestFESpace(Gin, ReferenceFE(lagrangian, float, 1))
         V_aux.offset = 0
@@ -141,7 +159,30 @@ class YagoProblem:
         if hasattr(sys_, "set_dof_coords"):
             sys_.set_dof_coords(X.dof_coords()[:, :2])       # quasi-2-D: dissect in the (x,y)
         self.nnz = sys_.build_pattern()
+        self.MAT_A = sys_.add_work_matrix() if self.basis and hasattr(sys_, "add_work_matrix") else (4 if self.basis else 0)
         self.set_frequency(p.lfactor)
+
+    @staticmethod
+    def basis_factors(bh, g, d0):
+        """ω-independent factors of the ω-dependent terms: with αₕ = -iω/g (1-βₕ)/βₕ
+        (src/Yago_freq_domain.jl:89-94) every coefficient of `frequency_inputs` is one of
+        {1, ω, ω², k} times the number below."""
+        a1 = -1j / g * (1 - bh) / bh                       # αₕ / ω
+        return dict(uk=bh * g, up=-1j * bh, wk=bh * g * a1 + 1j, wkm=-1.0, wp=-1j * bh * a1,
+                    wpn=a1, vv0=g, vv2=-d0, vp=-1j, we=1j)
+
+    def assemble_basis(self):
+        """Integrates B₀..B₃ (and the right-hand side of the current frequency) once."""
+        assert self.basis
+        self.sys.assemble()
+
+    def combine_frequency(self, lfactor=None):
+        """A(ω) = B₀ + ω B₁ + ω² B₂ + k B₃ into the work matrix `MAT_A` (`vlfs_combine`); the right-hand side still
+        comes from `set_frequency` + `assemble(matrices=False)`: it holds ω inside exp(ikx) fields."""
+        assert self.basis
+        if lfactor is not None:
+            self.set_frequency(lfactor)
+        self.sys.combine(self.MAT_A, [MAT_B0, MAT_B1, MAT_B2, MAT_BK], [1.0, self.om, self.om ** 2, self.k])
 
     # ω-dependent scalars and coefficient fields only (the sweep of scripts/5-4-1-Yago.jl:33-71)
     def frequency_inputs(self, lfactor):
@@ -176,13 +217,16 @@ class YagoProblem:
         """Host → device: `vlfs_set_weights` / `vlfs_set_term_coef` / `vlfs_set_rhs_coef`."""
         self.k, self.om = inp["k"], inp["om"]
         for i, w in enumerate(inp["weights_Gf"]):
-            self.dom_Gf.set_weights(i, w)
-        for tid, v in inp["coef_Gf"].items():
-            self.dom_Gf.set_coef(tid, v)
+            if not (self.basis and i == 0 and getattr(self, "_mu1_set", False)):
+                self.dom_Gf.set_weights(i, w)       # μ₁ (field 0) does not depend on ω
+        self._mu1_set = True
+        if not self.basis:                          # basis mode: the factors of B_k are fixed
+            for tid, v in inp["coef_Gf"].items():
+                self.dom_Gf.set_coef(tid, v)
+            for tid, v in inp["coef_Gb"].items():
+                self.dom_Gb.set_coef(tid, v)
         for rid, v in inp["rhs_Gf"].items():
             self.dom_Gf.set_rhs_coef(rid, v)
-        for tid, v in inp["coef_Gb"].items():
-            self.dom_Gb.set_coef(tid, v)
         for i, w in enumerate(inp["weights_Gin"]):
             self.dom_Gin.set_weights(i, w)
 

@@ -142,7 +142,8 @@ struct vlfs_ctx {
   cudaEvent_t ev_vec_fork = nullptr, ev_vec_join = nullptr;
   std::string err;
   long long ndofs = 0;
-  int is_complex = 0, nmat = 0, nvec = 0;
+  int is_complex = 0, nmat = 0, nvec = 0;   // nmat: matrices the terms assemble; mats may hold work matrices after them
+  int nmat_all() const { return (int)mats.size() > nmat ? (int)mats.size() : nmat; }
   std::vector<std::unique_ptr<Domain>> doms;
   bool pattern_built = false;
   bool imported = false;                // pattern given by vlfs_import_csr: no domains, nothing to assemble
@@ -774,7 +775,7 @@ void assemble_impl(vlfs_ctx* ctx, bool do_mat, bool do_vec) {
   if (ctx->imported) throw std::string("the matrix was imported (vlfs_import_csr): nothing to assemble");
   cudaStream_t s = ctx->stream;
   std::vector<double*> mp, vp;
-  for (auto& m : ctx->mats) mp.push_back(m.p);
+  for (int m = 0; m < ctx->nmat; ++m) mp.push_back(ctx->mats[m].p);     // work matrices are not assembled
   for (auto& v : ctx->vecs) vp.push_back(v.p);
   for (auto& dp : ctx->doms) refresh_coefs(ctx, *dp);
   {
@@ -1279,7 +1280,7 @@ int vlfs_import_csr(vlfs_ctx* ctx, int64_t ndofs, int is_complex, int nmat, cons
 
 int vlfs_set_values(vlfs_ctx* ctx, int mat, const void* values) {
   return guarded(ctx, [&]() {
-    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !values) return fail(ctx, VLFS_ERR_ARG, "bad matrix");
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat_all() || !values) return fail(ctx, VLFS_ERR_ARG, "bad matrix");
     CUDA_TRY(cudaMemcpyAsync(ctx->mats[mat].p, values, ctx->nnz * ctx->scalar() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return VLFS_OK;
@@ -1329,7 +1330,7 @@ int vlfs_assemble_vectors(vlfs_ctx* ctx) {
 
 int vlfs_get_values(vlfs_ctx* ctx, int mat, void* values) {
   return guarded(ctx, [&]() {
-    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !values) return fail(ctx, VLFS_ERR_ARG, "bad matrix");
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat_all() || !values) return fail(ctx, VLFS_ERR_ARG, "bad matrix");
     CUDA_TRY(cudaMemcpy(values, ctx->mats[mat].p, ctx->nnz * ctx->scalar() * sizeof(double), cudaMemcpyDeviceToHost));
     return VLFS_OK;
   });
@@ -1345,11 +1346,11 @@ int vlfs_get_vector(vlfs_ctx* ctx, int vec, void* values) {
 
 int vlfs_combine(vlfs_ctx* ctx, int target, int n, const int* src, const double* coef) {
   return guarded(ctx, [&]() {
-    if (!ctx->pattern_built || target < 0 || target >= ctx->nmat || n < 1 || n > 4 || !src || !coef)
+    if (!ctx->pattern_built || target < 0 || target >= ctx->nmat_all() || n < 1 || n > 4 || !src || !coef)
       return fail(ctx, VLFS_ERR_ARG, "vlfs_combine: bad arguments");
     double* sp[4];
     for (int k = 0; k < n; ++k) {
-      if (src[k] < 0 || src[k] >= ctx->nmat) return fail(ctx, VLFS_ERR_ARG, "vlfs_combine: bad source");
+      if (src[k] < 0 || src[k] >= ctx->nmat_all()) return fail(ctx, VLFS_ERR_ARG, "vlfs_combine: bad source");
       sp[k] = ctx->mats[src[k]].p;
     }
     launch_axpby_vals(ctx->mats[target].p, (size_t)ctx->nnz, n, sp, coef, ctx->is_complex, ctx->stream);
@@ -1359,9 +1360,23 @@ int vlfs_combine(vlfs_ctx* ctx, int target, int n, const int* src, const double*
   });
 }
 
+int vlfs_add_work_matrix(vlfs_ctx* ctx, int* mat) {
+  return guarded(ctx, [&]() {
+    if (!ctx->pattern_built || !mat) return fail(ctx, VLFS_ERR_ARG, "vlfs_add_work_matrix: after vlfs_build_pattern / vlfs_import_csr");
+    if (ctx->mats.size() >= 16) return fail(ctx, VLFS_ERR_STATE, "vlfs_add_work_matrix: at most 16 value arrays");
+    if (ctx->mats.capacity() < 16) ctx->mats.reserve(16);
+    ctx->mats.emplace_back();
+    ctx->mats.back().alloc((size_t)ctx->nnz * ctx->scalar());
+    ctx->mats.back().zero(ctx->stream);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *mat = (int)ctx->mats.size() - 1;
+    return VLFS_OK;
+  });
+}
+
 int vlfs_spmv(vlfs_ctx* ctx, int mat, const void* x, void* y) {
   return guarded(ctx, [&]() {
-    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !x || !y) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat_all() || !x || !y) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
     size_t nb = (size_t)ctx->ndofs * ctx->scalar();
     DevBuf<double> dx, dy;
     dx.upload((const double*)x, nb, ctx->stream);
@@ -1379,7 +1394,7 @@ int vlfs_spmv(vlfs_ctx* ctx, int mat, const void* x, void* y) {
 
 int vlfs_spmv_device(vlfs_ctx* ctx, int mat, int reps, float* ms_total) {
   return guarded(ctx, [&]() {
-    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || reps < 1) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat_all() || reps < 1) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
     size_t nb = (size_t)ctx->ndofs * ctx->scalar();
     DevBuf<double> dx, dy;
     std::vector<double> hx(nb);
@@ -1475,7 +1490,7 @@ int vlfs_last_kernel_launches(vlfs_ctx* ctx, int64_t* n) {
 }
 
 int vlfs_device_ptrs(vlfs_ctx* ctx, int mat, void** rowptr, void** colind, void** values) {
-  if (!ctx || !ctx->pattern_built || mat < 0 || mat >= ctx->nmat) return VLFS_ERR_ARG;
+  if (!ctx || !ctx->pattern_built || mat < 0 || mat >= ctx->nmat_all()) return VLFS_ERR_ARG;
   if (rowptr) *rowptr = ctx->rowptr.p;
   if (colind) *colind = ctx->colind.p;
   if (values) *values = ctx->mats[mat].p;
@@ -1484,7 +1499,7 @@ int vlfs_device_ptrs(vlfs_ctx* ctx, int mat, void** rowptr, void** colind, void*
 
 int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
   return guarded(ctx, [&]() {
-    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !opts) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat_all() || !opts) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
     vlfs_solver_opts o2 = *opts;
     // the per-GPU block preconditioner factorises its block exactly (multifrontal LU): ILU(0) and
     // Jacobi stall on these indefinite operators
@@ -1534,7 +1549,7 @@ int vlfs_set_dof_coords(vlfs_ctx* ctx, int dim, const double* coords) {
 
 int vlfs_solver_refactor(vlfs_ctx* ctx, int mat) {
   return guarded(ctx, [&]() {
-    if (!ctx->solver || !ctx->direct || mat < 0 || mat >= ctx->nmat)
+    if (!ctx->solver || !ctx->direct || mat < 0 || mat >= ctx->nmat_all())
       return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup with VLFS_PRECOND_SPARSE_LU first");
     direct_numeric(*ctx->direct, ctx->rowind.p, ctx->colind.p, ctx->mats[mat].p);
     if (ctx->dist_active() && dist_nranks(*ctx->dist) > 1)
@@ -1599,7 +1614,7 @@ int vlfs_newmark_run(vlfs_ctx* ctx, int matK, int matC, int matM, int nsteps, do
   return guarded(ctx, [&]() {
     if (!ctx->solver) return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup first");
     if (ctx->is_complex) return fail(ctx, VLFS_ERR_ARG, "Newmark stepping is real-valued");
-    if (matK < 0 || matC < 0 || matM < 0 || matK >= ctx->nmat || matC >= ctx->nmat || matM >= ctx->nmat ||
+    if (matK < 0 || matC < 0 || matM < 0 || matK >= ctx->nmat_all() || matC >= ctx->nmat_all() || matM >= ctx->nmat_all() ||
         nsteps < 1 || nb < 0 || nb > ctx->nvec || (nb && !tcoef) || !u0 || !v0 || !a0 ||
         out_lo < 0 || out_hi < out_lo || out_hi > ctx->ndofs || out_stride < 1 || (out_hi > out_lo && !out))
       return fail(ctx, VLFS_ERR_ARG, "vlfs_newmark_run: bad arguments");
@@ -1634,7 +1649,7 @@ int vlfs_set_owned_rows(vlfs_ctx* ctx, int64_t n_owned) {
 
 int vlfs_dev_spmv(vlfs_ctx* ctx, int mat, const void* x_dev, void* y_dev) {
   return guarded(ctx, [&]() {
-    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat || !x_dev || !y_dev) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
+    if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat_all() || !x_dev || !y_dev) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
     const double one[2] = {1, 0}, zero[2] = {0, 0};
     if (ctx->dist_active()) dist_hooks(*ctx->dist)->spmv(ctx->mats[mat].p, (double*)const_cast<void*>(x_dev), (double*)y_dev, one, zero);
     else launch_spmv(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, x_dev, y_dev, ctx->nowned, ctx->nnz,

@@ -136,6 +136,21 @@ static int run_single(int n, double sigma, std::vector<double>& x_out) {
     double ref = diag[i] * x[i] + (i > 0 ? off[i - 1] * x[i - 1] : 0) + (i < n ? off[i] * x[i + 1] : 0);
     if (std::fabs(y[i] - ref) > 1e-12 * std::fabs(diag[1])) { fprintf(stderr, "spmv row %d\n", i); return 1; }
   }
+  // a work matrix as the target of vlfs_combine: W = 2.5 A, multiplied through the same entry point
+  {
+    int wm = -1;
+    const int src0 = 0;
+    const double c25[2] = {2.5, 0.0};
+    CHECK(vlfs_add_work_matrix(ctx, &wm));
+    if (wm != 1) { fprintf(stderr, "work matrix index %d\n", wm); return 1; }
+    CHECK(vlfs_combine(ctx, wm, 1, &src0, c25));
+    std::vector<double> yw(n + 1);
+    CHECK(vlfs_spmv(ctx, wm, x.data(), yw.data()));
+    for (int i = 0; i <= n; ++i)
+      if (std::fabs(yw[i] - 2.5 * y[i]) > 1e-12 * std::fabs(diag[1])) { fprintf(stderr, "work matrix row %d\n", i); return 1; }
+    vlfs_term_desc bad; memset(&bad, 0, sizeof bad); bad.mat = wm;
+    if (vlfs_add_term(ctx, 0, &bad, nullptr) == VLFS_OK) { fprintf(stderr, "term on a work matrix accepted\n"); return 1; }
+  }
   std::vector<double> xyz(n + 1);
   for (int i = 0; i <= n; ++i) xyz[i] = (double)i / n;
   CHECK(vlfs_set_dof_coords(ctx, 1, xyz.data()));

@@ -176,3 +176,37 @@ def test_scaled_coefficient_field_keeps_the_classes():
     prob.sys.assemble()
     v2 = prob.sys.get_values(0)
     assert np.abs(v2 - v0).max() <= 1e-13 * np.abs(v0).max()          # ... and comes back
+
+
+def test_frequency_sweep_by_basis_matrices():
+    """A(ω) = B₀ + ω B₁ + ω² B₂ + k B₃ (src/Yago_freq_domain.jl:69-94,162-165).  The B_k are
+    integrated ONCE on the union pattern; every λfactor of the sweep (scripts/5-4-1-Yago.jl:33-71, subset) is one
+    `vlfs_combine` + the right-hand side, a refactorisation and a solve - pattern bit-exact, entries ≤ 1e-12,
+    solution ≤ 1e-8 against the oracle's literal form at that frequency."""
+    from vlfs_b200 import _lib as L
+    from vlfs_b200.cases.yago import YagoProblem, Yago_freq_domain_params
+    from oracle.cases.yago import YagoCase
+    prob = YagoProblem(Yago_freq_domain_params(**KW1), device=0, basis=True)
+    prob.assemble_basis()
+    rp, ci = prob.sys.get_pattern()
+    first = True
+    for lf in (0.4, 0.6, 0.8):
+        l0 = prob.sys.launches()
+        prob.combine_frequency(lf)
+        n_combine = prob.sys.launches() - l0
+        prob.sys.assemble(matrices=False)
+        A, b = YagoCase(**dict(KW1, lfactor=lf)).assemble()
+        A = A.tocsr(); A.sort_indices()
+        assert np.array_equal(rp, A.indptr) and np.array_equal(ci, A.indices)
+        v = prob.sys.get_values(prob.MAT_A)
+        assert np.abs(v - A.data).max() <= 1e-12 * np.abs(A.data).max()
+        assert np.abs(prob.sys.get_vector(0) - b).max() <= 1e-12 * np.abs(b).max()
+        assert n_combine == 1, n_combine               # no quadrature, no gather: one streaming kernel
+        if first:
+            prob.sys.solver_setup(prob.MAT_A, method=L.SOLVER_GMRES, precond=L.PRECOND_SPARSE_LU, restart=30, maxit=60, rtol=1e-12)
+            first = False
+        else:
+            prob.sys.refactor(prob.MAT_A)
+        x, st = prob.sys.solve(vec=0)
+        xr = lu_reference(A, b)
+        assert st["converged"] and np.linalg.norm(x - xr) <= 1e-8 * np.linalg.norm(xr)

@@ -76,6 +76,26 @@ def test_yago_descriptors_reproduce_oracle_matrix(kw):
     assert np.abs(b - vecs[0]).max() <= 1e-12 * np.abs(b).max()
 
 
+def test_yago_basis_matrices_reproduce_oracle_over_a_sweep():
+    """ω-sweep by basis matrices: A(ω) = B₀ + ω B₁ + ω² B₂ + k B₃ with the B_k integrated once
+    reproduces the oracle's literal form at every λfactor of scripts/5-4-1-Yago.jl:33-71 (subset)."""
+    from vlfs_b200.cases.yago import MAT_B0, MAT_B1, MAT_B2, MAT_BK
+    kw = dict(nx=2, ny=2, nz=1, order=2, lfactor=0.4, dfactor=3)
+    p = YagoProblem(Yago_freq_domain_params(**kw), system_cls=RecordingSystem, basis=True)
+    mats, _ = p.sys.evaluate()
+    for lf in (0.4, 0.6, 0.8):
+        p.set_frequency(lf)
+        _, vecs = p.sys.evaluate()
+        A, b = YagoCase(**dict(kw, lfactor=lf)).assemble()
+        A = A.tocsr(); A.sort_indices()
+        M = mats[MAT_B0] + p.om * mats[MAT_B1] + p.om ** 2 * mats[MAT_B2] + p.k * mats[MAT_BK]
+        for B in mats:            # one union pattern, explicit zeros kept
+            assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+        D = (M - A).tocsr()
+        assert (abs(D).max() if D.nnz else 0.0) <= 1e-12 * np.abs(A.data).max()
+        assert np.abs(b - vecs[0]).max() <= 1e-12 * np.abs(b).max()
+
+
 # ---- the other configurations of BASELINE.json: product descriptors vs the oracle's literal forms
 def _same_pattern_and_values(M, A, tol=1e-12):
     A = A.tocsr(); A.sort_indices()
