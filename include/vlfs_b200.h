@@ -149,10 +149,12 @@ typedef struct {
 
 enum { VLFS_SOLVER_GMRES = 0, VLFS_SOLVER_BICGSTAB = 1, VLFS_SOLVER_CG = 2 };
 enum { VLFS_PRECOND_NONE = 0, VLFS_PRECOND_JACOBI = 1,
-       VLFS_PRECOND_BLOCK_ILU0 = 2, /* per-GPU block preconditioner; the block (the owned rows of
-                                       this context) is factorised EXACTLY, i.e. identical to
-                                       VLFS_PRECOND_SPARSE_LU - zero-fill ILU stalls on these
-                                       operators */
+       VLFS_PRECOND_BLOCK_ILU0 = 2, /* per-GPU block preconditioner: zero-fill incomplete LU (IKJ order on
+                                       the CSR pattern) of the block owned rows x owned columns of this
+                                       context, level-scheduled factorisation and triangular solves
+                                       (ilu0.cu).  Converges on the Newmark matrices; stalls on the
+                                       indefinite frequency-domain operators, where
+                                       VLFS_PRECOND_SPARSE_LU is the solver */
        VLFS_PRECOND_SPARSE_LU = 3 /* GPU multifrontal LU of the matrix (the LUSolver() twin) */ };
 
 typedef struct vlfs_ctx vlfs_ctx;
@@ -209,13 +211,18 @@ int vlfs_spmv(vlfs_ctx* ctx, int mat, const void* x, void* y);         /* host i
  * from three far-apart unknowns are used instead (level-structure dissection). */
 int vlfs_set_dof_coords(vlfs_ctx* ctx, int dim, const double* coords);
 int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts);
-/* refactorise the current values of `mat` keeping the symbolic analysis (ω sweeps) */
+/* refactorise the current values of `mat` keeping the symbolic analysis (ω sweeps): the elimination tree of
+ * VLFS_PRECOND_SPARSE_LU, the dependency levels of VLFS_PRECOND_BLOCK_ILU0 */
 int vlfs_solver_refactor(vlfs_ctx* ctx, int mat);
 /* {nfronts, nlevels, maxfront, fill entries, flops, pool bytes, symbolic ms, numeric ms} */
 int vlfs_direct_info(vlfs_ctx* ctx, double* out8);
-/* pivot statistics of the last (re)factorisation: pivots replaced by the static perturbation
- * after the in-block threshold partial pivoting, and non-finite pivots */
+/* pivot statistics of the last (re)factorisation (sparse LU or ILU(0), whichever the solver uses): pivots
+ * replaced by the static perturbation (LU: after the in-block threshold partial pivoting), non-finite pivots */
 int vlfs_direct_status(vlfs_ctx* ctx, int64_t* perturbed, int64_t* nonfinite);
+/* z = M^-1 r with the preconditioner of the last vlfs_solver_setup (host buffers, ndofs entries in,
+ * owned entries out); {lower levels, upper levels, lower launches, upper launches} of the ILU(0) */
+int vlfs_precond_apply(vlfs_ctx* ctx, const void* r, void* z);
+int vlfs_precond_info(vlfs_ctx* ctx, double* out4);
 int vlfs_solve(vlfs_ctx* ctx, const void* b, void* x, vlfs_solve_stats* stats);   /* host */
 int vlfs_solve_vec(vlfs_ctx* ctx, int vec, void* x, vlfs_solve_stats* stats); /* assembled rhs */
 

@@ -80,7 +80,7 @@ EXPORTS = [
     "vlfs_dist_unique_id", "vlfs_dist_init", "vlfs_multi_create", "vlfs_dist_set_halo", "vlfs_dist_info",
     "vlfs_multi_build_pattern", "vlfs_multi_assemble", "vlfs_multi_solver_setup", "vlfs_multi_solver_refactor",
     "vlfs_multi_solve_vec", "vlfs_multi_spmv", "vlfs_multi_spmv_device", "vlfs_measure_fp64_peak",
-    "vlfs_add_work_matrix",
+    "vlfs_add_work_matrix", "vlfs_precond_apply", "vlfs_precond_info",
 ]
 
 _lib = None
@@ -123,6 +123,8 @@ def load():
     lib.vlfs_get_vector.argtypes = [vp, C.c_int, vp]
     lib.vlfs_combine.argtypes = [vp, C.c_int, C.c_int, _ip, _dp]
     lib.vlfs_add_work_matrix.argtypes = [vp, C.POINTER(C.c_int)]
+    lib.vlfs_precond_apply.argtypes = [vp, vp, vp]
+    lib.vlfs_precond_info.argtypes = [vp, _dp]
     lib.vlfs_spmv.argtypes = [vp, C.c_int, vp, vp]
     lib.vlfs_solver_setup.argtypes = [vp, C.c_int, C.POINTER(SolverOpts)]
     lib.vlfs_set_dof_coords.argtypes = [vp, C.c_int, _dp]

@@ -287,6 +287,18 @@ class B200System:
         cf[1::2] = np.imag(coefs)
         self._check(self.lib.vlfs_combine(self.ctx, target, len(sources), L.iptr(src), L.dptr(cf)))
 
+    def precond_apply(self, r):
+        """z = M⁻¹ r with the preconditioner of the last `solver_setup` (`vlfs_precond_apply`)."""
+        r = np.ascontiguousarray(r, dtype=self.dtype)
+        z = np.zeros_like(r)
+        self._check(self.lib.vlfs_precond_apply(self.ctx, r.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p)))
+        return z
+
+    def precond_info(self):
+        out = np.zeros(4)
+        self._check(self.lib.vlfs_precond_info(self.ctx, L.dptr(out)))
+        return dict(zip(("levels_lower", "levels_upper", "launches_lower", "launches_upper"), out.astype(int)))
+
     def add_work_matrix(self):
         """One more value array on the pattern that no term targets (`vlfs_add_work_matrix`)."""
         m = C.c_int(-1)

@@ -177,6 +177,8 @@ struct vlfs_ctx {
   std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
   SolverPtr solver;
   DirectPtr direct;
+  std::unique_ptr<Ilu0> ilu;            // VLFS_PRECOND_BLOCK_ILU0 (ilu0.cu)
+  int precond_kind = VLFS_PRECOND_NONE; // of ctx->solver
   std::vector<double> dof_coords;
   int coord_dim = 0;
   int solver_mat = -1;
@@ -941,6 +943,19 @@ int pivot_status(vlfs_ctx* ctx) {
   return VLFS_OK;
 }
 
+int ilu_status(vlfs_ctx* ctx) {
+  char buf[160];
+  if (ctx->ilu->nonfinite > 0) {
+    snprintf(buf, sizeof buf, "ILU(0): %lld non-finite pivots", ctx->ilu->nonfinite);
+    return fail(ctx, VLFS_ERR_SINGULAR, buf);
+  }
+  if (ctx->ilu->perturbed > 0) {
+    snprintf(buf, sizeof buf, "ILU(0): %lld tiny pivots replaced", ctx->ilu->perturbed);
+    return fail(ctx, VLFS_PIVOT_PERTURBED, buf);
+  }
+  return VLFS_OK;
+}
+
 template <typename T>
 void upload_opt(DevBuf<T>& b, const T* h, size_t n, cudaStream_t s) {
   if (h && n) b.upload(h, n, s);
@@ -1005,7 +1020,7 @@ int vlfs_destroy(vlfs_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ctx->solver.reset();
   ctx->dist.reset();
-  ctx->direct.reset();
+  ctx->direct.reset(); ctx->ilu.reset();
   ctx->dense.reset();
   ctx->doms.clear();
   ctx->mats.clear();
@@ -1032,7 +1047,7 @@ int vlfs_system_init(vlfs_ctx* ctx, int64_t ndofs, int is_complex, int nmat, int
     ctx->ndofs = ndofs; ctx->is_complex = is_complex ? 1 : 0; ctx->nmat = nmat; ctx->nvec = nvec;
     ctx->nowned = ndofs;
     ctx->doms.clear(); ctx->mats.clear(); ctx->vecs.clear();
-    ctx->pattern_built = false; ctx->imported = false; ctx->solver.reset(); ctx->direct.reset(); ctx->dense.reset();
+    ctx->pattern_built = false; ctx->imported = false; ctx->solver.reset(); ctx->direct.reset(); ctx->ilu.reset(); ctx->dense.reset();
     ctx->dof_coords.clear(); ctx->coord_dim = 0; ctx->roles.clear(); ctx->solver_mat = -1;
     ctx->chunks_valid = ctx->tmpl_valid = ctx->rec32_valid = false;       // numeric-pass tables of the old pattern
     ctx->gather_rec.release(); ctx->gather_rec32.release(); ctx->trec.release(); ctx->trun.release(); ctx->row_list.release();
@@ -1500,11 +1515,13 @@ int vlfs_device_ptrs(vlfs_ctx* ctx, int mat, void** rowptr, void** colind, void*
 int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
   return guarded(ctx, [&]() {
     if (!ctx->pattern_built || mat < 0 || mat >= ctx->nmat_all() || !opts) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
-    vlfs_solver_opts o2 = *opts;
-    // the per-GPU block preconditioner factorises its block exactly (multifrontal LU): ILU(0) and
-    // Jacobi stall on these indefinite operators
-    if (o2.precond == VLFS_PRECOND_BLOCK_ILU0) o2.precond = VLFS_PRECOND_SPARSE_LU;
-    opts = &o2;
+    if (opts->precond < VLFS_PRECOND_NONE || opts->precond > VLFS_PRECOND_SPARSE_LU)
+      return fail(ctx, VLFS_ERR_ARG, "vlfs_solver_setup: unknown preconditioner");
+    if (opts->precond == VLFS_PRECOND_BLOCK_ILU0) {
+      // zero-fill incomplete LU of the block of owned rows x owned columns; level analysis once per pattern
+      if (!ctx->ilu) ctx->ilu = ilu0_symbolic(ctx->rowptr.p, ctx->colind.p, ctx->nowned, ctx->is_complex, ctx->stream);
+      ilu0_numeric(*ctx->ilu, ctx->mats[mat].p, &ctx->launches);
+    }
     if (opts->precond == VLFS_PRECOND_SPARSE_LU) {
       const bool chain = ctx->dist_active() && dist_nranks(*ctx->dist) > 1;
       if (chain && !ctx->direct) dist_roles(*ctx->dist, ctx->roles);     // cuts kept, lower ghosts ignored
@@ -1531,8 +1548,10 @@ int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
     }
     ctx->solver = solver_create(ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p, ctx->nowned, ctx->nnz,
                                 ctx->is_complex, *opts, ctx->nsm, ctx->stream, &ctx->launches,
-                                ctx->direct.get(), ctx->dist_active() ? dist_hooks(*ctx->dist) : nullptr);
+                                ctx->direct.get(), ctx->dist_active() ? dist_hooks(*ctx->dist) : nullptr, ctx->ilu.get());
     ctx->solver_mat = mat;
+    ctx->precond_kind = opts->precond;
+    if (opts->precond == VLFS_PRECOND_BLOCK_ILU0) return ilu_status(ctx);
     return opts->precond == VLFS_PRECOND_SPARSE_LU ? pivot_status(ctx) : VLFS_OK;
   });
 }
@@ -1542,15 +1561,21 @@ int vlfs_set_dof_coords(vlfs_ctx* ctx, int dim, const double* coords) {
     if (dim < 1 || dim > 3 || !coords || ctx->ndofs == 0) return fail(ctx, VLFS_ERR_ARG, "bad arguments");
     ctx->dof_coords.assign(coords, coords + (size_t)ctx->ndofs * dim);
     ctx->coord_dim = dim;
-    ctx->direct.reset();
+    ctx->direct.reset(); ctx->ilu.reset();
     return VLFS_OK;
   });
 }
 
 int vlfs_solver_refactor(vlfs_ctx* ctx, int mat) {
   return guarded(ctx, [&]() {
+    if (ctx->solver && ctx->ilu && ctx->precond_kind == VLFS_PRECOND_BLOCK_ILU0 && mat >= 0 && mat < ctx->nmat_all()) {
+      ilu0_numeric(*ctx->ilu, ctx->mats[mat].p, &ctx->launches);      // same levels, new values
+      solver_set_matrix(*ctx->solver, ctx->mats[mat].p);
+      ctx->solver_mat = mat;
+      return ilu_status(ctx);
+    }
     if (!ctx->solver || !ctx->direct || mat < 0 || mat >= ctx->nmat_all())
-      return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup with VLFS_PRECOND_SPARSE_LU first");
+      return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup with VLFS_PRECOND_SPARSE_LU or VLFS_PRECOND_BLOCK_ILU0 first");
     direct_numeric(*ctx->direct, ctx->rowind.p, ctx->colind.p, ctx->mats[mat].p);
     if (ctx->dist_active() && dist_nranks(*ctx->dist) > 1)
       dist_schur_factor(*ctx->dist, *ctx->direct, ctx->rowptr.p, ctx->colind.p, ctx->mats[mat].p);
@@ -1562,9 +1587,10 @@ int vlfs_solver_refactor(vlfs_ctx* ctx, int mat) {
 }
 
 int vlfs_direct_status(vlfs_ctx* ctx, int64_t* perturbed, int64_t* nonfinite) {
-  if (!ctx || !ctx->direct) return VLFS_ERR_ARG;
+  if (!ctx || (!ctx->direct && !ctx->ilu)) return VLFS_ERR_ARG;
   long long a = 0, b = 0;
-  direct_pivot_status(*ctx->direct, &a, &b);
+  if (ctx->ilu && ctx->precond_kind == VLFS_PRECOND_BLOCK_ILU0) { a = ctx->ilu->perturbed; b = ctx->ilu->nonfinite; }
+  else if (ctx->direct) direct_pivot_status(*ctx->direct, &a, &b);
   if (perturbed) *perturbed = a;
   if (nonfinite) *nonfinite = b;
   return VLFS_OK;
@@ -1642,7 +1668,7 @@ int vlfs_set_owned_rows(vlfs_ctx* ctx, int64_t n_owned) {
   return guarded(ctx, [&]() {
     if (n_owned < 1 || n_owned > ctx->ndofs) return fail(ctx, VLFS_ERR_ARG, "vlfs_set_owned_rows: 1 <= n_owned <= ndofs");
     ctx->nowned = n_owned;
-    ctx->solver.reset(); ctx->direct.reset();
+    ctx->solver.reset(); ctx->direct.reset(); ctx->ilu.reset();
     return VLFS_OK;
   });
 }
@@ -1665,6 +1691,27 @@ int vlfs_dev_precond(vlfs_ctx* ctx, const void* r_dev, void* z_dev) {
     solver_precond(*ctx->solver, (const double*)r_dev, (double*)z_dev);
     return VLFS_OK;
   });
+}
+
+int vlfs_precond_apply(vlfs_ctx* ctx, const void* r, void* z) {
+  return guarded(ctx, [&]() {
+    if (!ctx->solver || !r || !z) return fail(ctx, VLFS_ERR_STATE, "vlfs_solver_setup first");
+    const size_t nb = (size_t)ctx->ndofs * ctx->scalar(), no = (size_t)ctx->nowned * ctx->scalar();
+    DevBuf<double> dr, dz;
+    dr.upload((const double*)r, nb, ctx->stream);
+    dz.alloc(nb); dz.zero(ctx->stream);
+    solver_precond(*ctx->solver, dr.p, dz.p);
+    CUDA_TRY(cudaMemcpyAsync(z, dz.p, no * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return VLFS_OK;
+  });
+}
+
+int vlfs_precond_info(vlfs_ctx* ctx, double* out4) {
+  if (!ctx || !out4 || !ctx->ilu) return VLFS_ERR_ARG;
+  out4[0] = (double)ctx->ilu->nlevels_lower; out4[1] = (double)ctx->ilu->nlevels_upper;
+  out4[2] = (double)ctx->ilu->lplan.size(); out4[3] = (double)ctx->ilu->uplan.size();
+  return VLFS_OK;
 }
 
 int vlfs_dev_multidot(vlfs_ctx* ctx, const void* V_dev, int64_t ldv, int nv, const void* w_dev, int64_t n,
@@ -1766,7 +1813,7 @@ int vlfs_set_roles(vlfs_ctx* ctx, const int8_t* role) {
     for (long long i = 0; i < ctx->ndofs; ++i)
       if (role[i] < 0 || role[i] > 2) return fail(ctx, VLFS_ERR_ARG, "vlfs_set_roles: role must be 0, 1 or 2");
     ctx->roles.assign(role, role + ctx->ndofs);
-    ctx->solver.reset(); ctx->direct.reset();
+    ctx->solver.reset(); ctx->direct.reset(); ctx->ilu.reset();
     return VLFS_OK;
   });
 }
@@ -1863,7 +1910,7 @@ int vlfs_dist_set_halo(vlfs_ctx* ctx, int64_t n_owned, int npeers, const int32_t
     if (n_owned < 1 || n_owned > ctx->ndofs || npeers < 0 || (npeers && (!peers || !send_ptr || !recv_ptr)))
       return fail(ctx, VLFS_ERR_ARG, "vlfs_dist_set_halo: bad arguments");
     ctx->nowned = n_owned;
-    ctx->solver.reset(); ctx->direct.reset(); ctx->roles.clear();
+    ctx->solver.reset(); ctx->direct.reset(); ctx->ilu.reset(); ctx->roles.clear();
     dist_bind(*ctx->dist, ctx->stream, ctx->is_complex, ctx->nsm, &ctx->launches);
     std::vector<long long> sp(npeers + 1, 0), rp(npeers + 1, 0);
     for (int p = 0; p <= npeers && npeers > 0; ++p) { sp[p] = send_ptr[p]; rp[p] = recv_ptr[p]; }

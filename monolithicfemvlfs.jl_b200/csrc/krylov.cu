@@ -318,6 +318,7 @@ struct SolverState {
   DevBuf<double> dinv, V, Z, w, z, r, partial, hdev, tmp1, tmp2, tmp3, tmp4, xlo;
   double setup_ms = 0;
   DirectSolver* direct = nullptr;
+  Ilu0* ilu = nullptr;          // VLFS_PRECOND_BLOCK_ILU0: factorisation of the owned block (ilu0.cu)
   DistHooks* dist = nullptr;    // row-partitioned system: n = owned rows, vectors have nalloc = owned + ghost entries
   long long nalloc = 0;
 
@@ -392,6 +393,7 @@ struct SolverState {
     if (opts.precond == VLFS_PRECOND_NONE) { copy(rin, zout); return; }
     if (opts.precond == VLFS_PRECOND_SPARSE_LU && dist && dist->has_exact_apply()) { dist->apply(rin, zout); return; }
     if (opts.precond == VLFS_PRECOND_SPARSE_LU) { direct_solve(*direct, rin, zout); return; }
+    if (opts.precond == VLFS_PRECOND_BLOCK_ILU0) { ilu0_apply(*ilu, rin, zout, launches); return; }
     if (cplx) pointwise_mul<true><<<vgrid(n, nsm), 256, 0, s>>>((const double2*)dinv.p, (const double2*)rin, (double2*)zout, n);
     else pointwise_mul<false><<<vgrid(n, nsm), 256, 0, s>>>(dinv.p, rin, zout, n);
     ++*launches;
@@ -401,9 +403,10 @@ struct SolverState {
 SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals,
                                            long long n, long long nnz, int is_complex,
                                            const vlfs_solver_opts& opts, int nsm, cudaStream_t s,
-                                           long long* launches, DirectSolver* direct, DistHooks* dist) {
+                                           long long* launches, DirectSolver* direct, DistHooks* dist, Ilu0* ilu) {
   SolverPtr S(new SolverState());
   S->dist = dist;
+  S->ilu = ilu;
   S->nalloc = dist ? dist->n_local : n;
   S->rowptr = rowptr; S->colind = colind; S->vals = vals; S->n = n; S->nnz = nnz;
   S->cplx = is_complex; S->opts = opts; S->nsm = nsm; S->s = s; S->launches = launches;

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <memory>
 #include "direct.cuh"
+#include "ilu0.cuh"
 
 // Rank-local view of a row-partitioned system (dist.cu): the Krylov loops call these instead of the
 // plain local operations when the context belongs to a multi-GPU system.  Everything is ordered
@@ -27,7 +28,8 @@ using SolverPtr = std::unique_ptr<SolverState, SolverDeleter>;
 SolverPtr solver_create(const int* rowptr, const int* colind, const double* vals,
                         long long n, long long nnz, int is_complex,
                                            const vlfs_solver_opts& opts, int nsm, cudaStream_t s,
-                                           long long* launches, DirectSolver* direct, DistHooks* dist = nullptr);
+                                           long long* launches, DirectSolver* direct, DistHooks* dist = nullptr,
+                                           Ilu0* ilu = nullptr);
 void solver_set_matrix(SolverState& S, const double* vals);   // after a refactorisation of another matrix
 int solver_solve(SolverState& S, const double* b_dev, double* x_dev, vlfs_solve_stats* stats);
 int newmark_run(SolverState& S, const int* rowptr, const int* colind, const double* Kvals, const double* Cvals,
