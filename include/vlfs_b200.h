@@ -220,9 +220,10 @@ int vlfs_direct_info(vlfs_ctx* ctx, double* out8);
  * replaced by the static perturbation (LU: after the in-block threshold partial pivoting), non-finite pivots */
 int vlfs_direct_status(vlfs_ctx* ctx, int64_t* perturbed, int64_t* nonfinite);
 /* z = M^-1 r with the preconditioner of the last vlfs_solver_setup (host buffers, ndofs entries in,
- * owned entries out); {lower levels, upper levels, lower launches, upper launches} of the ILU(0) */
+ * owned entries out); {lower levels, upper levels, lower launches, upper launches, level analysis ms (host),
+ * factorisation ms, last vlfs_precond_apply ms (CUDA events), entries of the block rows} of the ILU(0) */
 int vlfs_precond_apply(vlfs_ctx* ctx, const void* r, void* z);
-int vlfs_precond_info(vlfs_ctx* ctx, double* out4);
+int vlfs_precond_info(vlfs_ctx* ctx, double* out8);
 int vlfs_solve(vlfs_ctx* ctx, const void* b, void* x, vlfs_solve_stats* stats);   /* host */
 int vlfs_solve_vec(vlfs_ctx* ctx, int vec, void* x, vlfs_solve_stats* stats); /* assembled rhs */
 

@@ -295,9 +295,11 @@ class B200System:
         return z
 
     def precond_info(self):
-        out = np.zeros(4)
+        out = np.zeros(8)
         self._check(self.lib.vlfs_precond_info(self.ctx, L.dptr(out)))
-        return dict(zip(("levels_lower", "levels_upper", "launches_lower", "launches_upper"), out.astype(int)))
+        d = dict(zip(("levels_lower", "levels_upper", "launches_lower", "launches_upper"), out[:4].astype(int).tolist()))
+        d.update(symbolic_ms=out[4], numeric_ms=out[5], apply_ms=out[6], nnz=int(out[7]))
+        return d
 
     def add_work_matrix(self):
         """One more value array on the pattern that no term targets (`vlfs_add_work_matrix`)."""

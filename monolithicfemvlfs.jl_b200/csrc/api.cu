@@ -179,6 +179,7 @@ struct vlfs_ctx {
   DirectPtr direct;
   std::unique_ptr<Ilu0> ilu;            // VLFS_PRECOND_BLOCK_ILU0 (ilu0.cu)
   int precond_kind = VLFS_PRECOND_NONE; // of ctx->solver
+  double precond_apply_ms = 0;          // last vlfs_precond_apply (CUDA events)
   std::vector<double> dof_coords;
   int coord_dim = 0;
   int solver_mat = -1;
@@ -1519,7 +1520,10 @@ int vlfs_solver_setup(vlfs_ctx* ctx, int mat, const vlfs_solver_opts* opts) {
       return fail(ctx, VLFS_ERR_ARG, "vlfs_solver_setup: unknown preconditioner");
     if (opts->precond == VLFS_PRECOND_BLOCK_ILU0) {
       // zero-fill incomplete LU of the block of owned rows x owned columns; level analysis once per pattern
-      if (!ctx->ilu) ctx->ilu = ilu0_symbolic(ctx->rowptr.p, ctx->colind.p, ctx->nowned, ctx->is_complex, ctx->stream);
+      // block_size_hint = B > 0: block Jacobi of ILU(0) blocks of B consecutive rows, one CTA per block
+      const int B = opts->block_size_hint > 0 && opts->block_size_hint < ctx->nowned ? opts->block_size_hint : 0;
+      if (!ctx->ilu || ctx->ilu->block_rows != B)
+        ctx->ilu = ilu0_symbolic(ctx->rowptr.p, ctx->colind.p, ctx->nowned, ctx->is_complex, B, ctx->stream);
       ilu0_numeric(*ctx->ilu, ctx->mats[mat].p, &ctx->launches);
     }
     if (opts->precond == VLFS_PRECOND_SPARSE_LU) {
@@ -1700,17 +1704,27 @@ int vlfs_precond_apply(vlfs_ctx* ctx, const void* r, void* z) {
     DevBuf<double> dr, dz;
     dr.upload((const double*)r, nb, ctx->stream);
     dz.alloc(nb); dz.zero(ctx->stream);
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, ctx->stream));
     solver_precond(*ctx->solver, dr.p, dz.p);
+    CUDA_TRY(cudaEventRecord(e1, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(z, dz.p, no * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->precond_apply_ms = ms;
     return VLFS_OK;
   });
 }
 
-int vlfs_precond_info(vlfs_ctx* ctx, double* out4) {
-  if (!ctx || !out4 || !ctx->ilu) return VLFS_ERR_ARG;
-  out4[0] = (double)ctx->ilu->nlevels_lower; out4[1] = (double)ctx->ilu->nlevels_upper;
-  out4[2] = (double)ctx->ilu->lplan.size(); out4[3] = (double)ctx->ilu->uplan.size();
+int vlfs_precond_info(vlfs_ctx* ctx, double* out8) {
+  if (!ctx || !out8 || !ctx->ilu) return VLFS_ERR_ARG;
+  out8[0] = (double)ctx->ilu->nlevels_lower; out8[1] = (double)ctx->ilu->nlevels_upper;
+  out8[2] = (double)ctx->ilu->lplan.size(); out8[3] = (double)ctx->ilu->uplan.size();
+  out8[4] = ctx->ilu->symbolic_ms; out8[5] = ctx->ilu->numeric_ms; out8[6] = ctx->precond_apply_ms;
+  out8[7] = (double)ctx->ilu->nnz;
   return VLFS_OK;
 }
 

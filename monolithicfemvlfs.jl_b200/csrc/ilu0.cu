@@ -2,7 +2,9 @@
 //
 // north_star (5): "a preconditioned Krylov solve (CG / GMRES / BiCGStab with Jacobi or block-ILU0)".  The
 // block is the square matrix of the rows AND columns this context owns (n = owned rows; ghost columns
-// >= n are dropped: block Jacobi over the GPUs, ILU(0) inside a block).  ILU(0) in the IKJ order on the
+// >= n are dropped: block Jacobi over the GPUs, ILU(0) inside a block).  With block_size_hint = B > 0 the
+// owned block is cut further into diagonal blocks of B consecutive rows (block Jacobi of ILU(0) blocks): the
+// dependency chains end at the block boundaries, and ONE launch runs every block on its own CTA.  ILU(0) in the IKJ order on the
 // CSR pattern:   for i: for k < i in row i (ascending): a_ik /= a_kk;  a_ij -= a_ik a_kj  for j > k in
 // row k that row i also holds.  Row i needs the finished rows k of its strict lower pattern only, so
 // rows are grouped into dependency LEVELS (host analysis, once per pattern) and a level is processed
@@ -19,6 +21,7 @@
 #include "ilu0.cuh"
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 
 namespace {
 
@@ -73,7 +76,7 @@ __device__ __forceinline__ int find_col(const int* __restrict__ colind, int lo, 
 
 // ---- one row of the factorisation (whole warp) --------------------------------------------------------
 template <bool CX>
-__device__ void factor_row(int i, int n, const int* __restrict__ rowptr, const int* __restrict__ colind,
+__device__ void factor_row(int i, int r0, int r1, const int* __restrict__ rowptr, const int* __restrict__ colind,
                            const int* __restrict__ diag, typename Num<CX>::T* lu, double tiny2, int* info) {
   using N = Num<CX>;
   using T = typename N::T;
@@ -81,12 +84,13 @@ __device__ void factor_row(int i, int n, const int* __restrict__ rowptr, const i
   const int lo = rowptr[i], hi = rowptr[i + 1], d = diag[i];
   for (int p = lo; p < d; ++p) {
     const int k = colind[p];
+    if (k < r0) continue;                                  // coupling to another diagonal block: dropped (k is warp-uniform)
     const int dk = diag[k];
     const T lik = N::div(lu[p], lu[dk]);
     const int ke = rowptr[k + 1];
     for (int q = dk + 1 + lane; q < ke; q += 32) {
       const int j = colind[q];
-      if (j >= n) break;                                   // ghost columns close a sorted row
+      if (j >= r1) break;                                  // other blocks / ghost columns close a sorted row
       const int pos = find_col(colind, p + 1, hi, j);
       if (pos >= 0) lu[pos] = N::sub(lu[pos], N::mul(lik, lu[q]));
     }
@@ -102,19 +106,22 @@ __device__ void factor_row(int i, int n, const int* __restrict__ rowptr, const i
 }
 
 template <bool CX>
-__device__ void lower_row(int i, const int* __restrict__ rowptr, const int* __restrict__ colind,
+__device__ void lower_row(int i, int r0, const int* __restrict__ rowptr, const int* __restrict__ colind,
                           const int* __restrict__ diag, const typename Num<CX>::T* lu,
                           const typename Num<CX>::T* r, typename Num<CX>::T* z) {
   using N = Num<CX>;
   const int lane = threadIdx.x & 31;
   typename N::T s = N::zero();
-  for (int p = rowptr[i] + lane; p < diag[i]; p += 32) s = N::add(s, N::mul(lu[p], z[colind[p]]));
+  for (int p = rowptr[i] + lane; p < diag[i]; p += 32) {
+    const int k = colind[p];
+    if (k >= r0) s = N::add(s, N::mul(lu[p], z[k]));
+  }
   s = warp_sum<CX>(s);
   if (lane == 0) z[i] = N::sub(r[i], s);
 }
 
 template <bool CX>
-__device__ void upper_row(int i, int n, const int* __restrict__ rowptr, const int* __restrict__ colind,
+__device__ void upper_row(int i, int r1, const int* __restrict__ rowptr, const int* __restrict__ colind,
                           const int* __restrict__ diag, const typename Num<CX>::T* lu, typename Num<CX>::T* z) {
   using N = Num<CX>;
   const int lane = threadIdx.x & 31;
@@ -122,7 +129,7 @@ __device__ void upper_row(int i, int n, const int* __restrict__ rowptr, const in
   const int d = diag[i];
   for (int p = d + 1 + lane; p < rowptr[i + 1]; p += 32) {
     const int j = colind[p];
-    if (j < n) s = N::add(s, N::mul(lu[p], z[j]));
+    if (j < r1) s = N::add(s, N::mul(lu[p], z[j]));
   }
   s = warp_sum<CX>(s);
   if (lane == 0) z[i] = N::div(N::sub(z[i], s), lu[d]);
@@ -131,12 +138,12 @@ __device__ void upper_row(int i, int n, const int* __restrict__ rowptr, const in
 enum { ST_FACTOR = 0, ST_LOWER = 1, ST_UPPER = 2 };
 
 template <bool CX, int STAGE>
-__device__ __forceinline__ void do_row(int i, int n, const int* rowptr, const int* colind, const int* diag,
+__device__ __forceinline__ void do_row(int i, int r0, int r1, const int* rowptr, const int* colind, const int* diag,
                                        typename Num<CX>::T* lu, const typename Num<CX>::T* r, typename Num<CX>::T* z,
                                        double tiny2, int* info) {
-  if (STAGE == ST_FACTOR) factor_row<CX>(i, n, rowptr, colind, diag, lu, tiny2, info);
-  else if (STAGE == ST_LOWER) lower_row<CX>(i, rowptr, colind, diag, lu, r, z);
-  else upper_row<CX>(i, n, rowptr, colind, diag, lu, z);
+  if (STAGE == ST_FACTOR) factor_row<CX>(i, r0, r1, rowptr, colind, diag, lu, tiny2, info);
+  else if (STAGE == ST_LOWER) lower_row<CX>(i, r0, rowptr, colind, diag, lu, r, z);
+  else upper_row<CX>(i, r1, rowptr, colind, diag, lu, z);
 }
 
 // one (wide) level: one warp per row, any number of CTAs
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(256) ilu0_level(const int* __restrict__ rows, 
                                                   const typename Num<CX>::T* r, typename Num<CX>::T* z, double tiny2, int* info) {
   const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (w >= nrows) return;
-  do_row<CX, STAGE>(rows[w], n, rowptr, colind, diag, lu, r, z, tiny2, info);
+  do_row<CX, STAGE>(rows[w], 0, n, rowptr, colind, diag, lu, r, z, tiny2, info);
 }
 
 // a run of small levels [l0, l1) (each <= 32 rows): one CTA of 32 warps walks them
@@ -159,8 +166,27 @@ __global__ void __launch_bounds__(1024) ilu0_chain(const int* __restrict__ rows,
   const int w = threadIdx.x >> 5;
   for (int l = l0; l < l1; ++l) {
     const int b = lptr[l], e = lptr[l + 1];
-    if (b + w < e) do_row<CX, STAGE>(rows[b + w], n, rowptr, colind, diag, lu, r, z, tiny2, info);
+    if (b + w < e) do_row<CX, STAGE>(rows[b + w], 0, n, rowptr, colind, diag, lu, r, z, tiny2, info);
     __syncthreads();                 // the next level reads what this one wrote (same CTA: ordered by the barrier)
+  }
+}
+
+// block Jacobi of ILU(0) blocks (block_rows > 0): diagonal block b = rows and columns [b B, (b+1) B); one CTA per
+// block walks the block's own levels (rows of a block only depend on rows of the same block), all blocks at once
+template <bool CX, int STAGE>
+__global__ void __launch_bounds__(512) ilu0_blocks(const int* __restrict__ rows, const int* __restrict__ lptr,
+                                                   const int* __restrict__ blk_lev, int block_rows, int n,
+                                                   const int* __restrict__ rowptr, const int* __restrict__ colind,
+                                                   const int* __restrict__ diag, typename Num<CX>::T* lu,
+                                                   const typename Num<CX>::T* r, typename Num<CX>::T* z, double tiny2, int* info) {
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int r0 = blockIdx.x * block_rows;
+  const int r1 = min(n, r0 + block_rows);
+  const int l0 = blk_lev[blockIdx.x], l1 = blk_lev[blockIdx.x + 1] - 1;      // (one terminating entry per block)
+  for (int l = l0; l < l1; ++l) {
+    const int b = lptr[l], e = lptr[l + 1];
+    for (int q = b + w; q < e; q += nw) do_row<CX, STAGE>(rows[q], r0, r1, rowptr, colind, diag, lu, r, z, tiny2, info);
+    __syncthreads();
   }
 }
 
@@ -197,6 +223,41 @@ void plan_levels(const std::vector<int>& level, int nlev, std::vector<int>& rows
   }
 }
 
+// rows ordered by (block, level); lptr holds the level boundaries of every block followed by one terminating
+// entry per block, blk_lev[b] the first lptr entry of block b
+void plan_blocks(const std::vector<int>& level, long long n, int block_rows, std::vector<int>& rows, std::vector<int>& lptr,
+                 std::vector<int>& blk_lev, int* max_levels) {
+  const int nb = (int)((n + block_rows - 1) / block_rows);
+  rows.resize((size_t)n);
+  lptr.clear(); blk_lev.assign((size_t)nb + 1, 0);
+  *max_levels = 0;
+  std::vector<int> cnt;
+  for (int b = 0; b < nb; ++b) {
+    const long long r0 = (long long)b * block_rows, r1 = std::min(n, r0 + block_rows);
+    int nl = 0;
+    for (long long i = r0; i < r1; ++i) nl = std::max(nl, level[(size_t)i] + 1);
+    cnt.assign((size_t)nl + 1, 0);
+    for (long long i = r0; i < r1; ++i) ++cnt[(size_t)level[(size_t)i] + 1];
+    for (int l = 0; l < nl; ++l) cnt[(size_t)l + 1] += cnt[l];
+    blk_lev[b] = (int)lptr.size();
+    for (int l = 0; l <= nl; ++l) lptr.push_back((int)r0 + cnt[l]);
+    for (long long i = r0; i < r1; ++i) rows[(size_t)(r0 + cnt[level[(size_t)i]]++)] = (int)i;
+    *max_levels = std::max(*max_levels, nl);
+  }
+  blk_lev[nb] = (int)lptr.size();
+}
+
+template <bool CX, int STAGE>
+void run_blocks(const Ilu0& P, const int* rows, const int* lptr, const int* blk_lev, const double* r, double* z,
+                double tiny2, cudaStream_t s, long long* launches) {
+  using T = typename Num<CX>::T;
+  ilu0_blocks<CX, STAGE><<<(unsigned)P.nblocks, 512, 0, s>>>(rows, lptr, blk_lev, P.block_rows, (int)P.n, P.rowptr, P.colind, P.diag.p,
+                                                            reinterpret_cast<T*>(P.lu.p), reinterpret_cast<const T*>(r),
+                                                            reinterpret_cast<T*>(z), tiny2, P.info.p);
+  if (launches) ++*launches;
+  CUDA_TRY(cudaGetLastError());
+}
+
 template <bool CX, int STAGE>
 void run_plan(const Ilu0& P, const std::vector<Ilu0Launch>& plan, const std::vector<int>& lptr_host, const int* rows,
               const int* lptr, const double* r, double* z, double tiny2, cudaStream_t s, long long* launches) {
@@ -219,9 +280,15 @@ void run_plan(const Ilu0& P, const std::vector<Ilu0Launch>& plan, const std::vec
 }  // namespace
 
 // ---- host analysis (once per pattern) ---------------------------------------------------------------
-std::unique_ptr<Ilu0> ilu0_symbolic(const int* rowptr_dev, const int* colind_dev, long long n, int is_complex, cudaStream_t s) {
+std::unique_ptr<Ilu0> ilu0_symbolic(const int* rowptr_dev, const int* colind_dev, long long n, int is_complex, int block_rows,
+                                    cudaStream_t s) {
+  const auto t0 = std::chrono::steady_clock::now();
   std::unique_ptr<Ilu0> P(new Ilu0());
   P->n = n; P->cplx = is_complex; P->rowptr = rowptr_dev; P->colind = colind_dev; P->s = s;
+  if (block_rows < 0 || block_rows >= n) block_rows = 0;                 // one block: the ILU(0) of the whole owned block
+  P->block_rows = block_rows;
+  P->nblocks = block_rows ? (int)((n + block_rows - 1) / block_rows) : 1;
+  const long long B = block_rows ? block_rows : (n > 0 ? n : 1);
   std::vector<int> rp((size_t)n + 1);
   CUDA_TRY(cudaMemcpyAsync(rp.data(), rowptr_dev, rp.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -237,7 +304,7 @@ std::unique_ptr<Ilu0> ilu0_symbolic(const int* rowptr_dev, const int* colind_dev
     for (int p = rp[(size_t)i]; p < rp[(size_t)i + 1]; ++p) {
       const int c = ci[(size_t)p];
       if (p > rp[(size_t)i] && c <= ci[(size_t)p - 1]) throw std::string("ILU0: column indices of a row must be strictly ascending");
-      if (c < i) lev = std::max(lev, ll[(size_t)c] + 1);
+      if (c < i) { if (c >= i / B * B) lev = std::max(lev, ll[(size_t)c] + 1); }     // couplings inside the diagonal block only
       else if (c == i) d = p;
     }
     if (d < 0) throw std::string("ILU0: structurally zero diagonal in row ") + std::to_string(i);
@@ -247,32 +314,51 @@ std::unique_ptr<Ilu0> ilu0_symbolic(const int* rowptr_dev, const int* colind_dev
     int lev = 0;
     for (int p = diag[(size_t)i] + 1; p < rp[(size_t)i + 1]; ++p) {
       const int c = ci[(size_t)p];
-      if (c < n) lev = std::max(lev, ul[(size_t)c] + 1);
+      if (c < std::min(n, (i / B + 1) * B)) lev = std::max(lev, ul[(size_t)c] + 1);
     }
     ul[(size_t)i] = lev; nu = std::max(nu, lev + 1);
   }
   if (n == 0) { nl = nu = 0; }
   std::vector<int> rows, lptr;
-  plan_levels(ll, nl, rows, P->lptr_host, P->lplan);
-  P->lrows.upload(rows.data(), rows.size(), s);
-  P->lptr.upload(P->lptr_host.data(), P->lptr_host.size(), s);
-  plan_levels(ul, nu, rows, P->uptr_host, P->uplan);
-  P->urows.upload(rows.data(), rows.size(), s);
-  P->uptr.upload(P->uptr_host.data(), P->uptr_host.size(), s);
+  if (block_rows) {
+    std::vector<int> bl;
+    plan_blocks(ll, n, block_rows, rows, P->lptr_host, bl, &nl);
+    P->lrows.upload(rows.data(), rows.size(), s);
+    P->lptr.upload(P->lptr_host.data(), P->lptr_host.size(), s);
+    P->lblk.upload(bl.data(), bl.size(), s);
+    plan_blocks(ul, n, block_rows, rows, P->uptr_host, bl, &nu);
+    P->urows.upload(rows.data(), rows.size(), s);
+    P->uptr.upload(P->uptr_host.data(), P->uptr_host.size(), s);
+    P->ublk.upload(bl.data(), bl.size(), s);
+    P->lplan.assign(1, Ilu0Launch{0, nl, 1});
+    P->uplan.assign(1, Ilu0Launch{0, nu, 1});
+    CUDA_TRY(cudaStreamSynchronize(s));     // bl dies at scope exit
+  } else {
+    plan_levels(ll, nl, rows, P->lptr_host, P->lplan);
+    P->lrows.upload(rows.data(), rows.size(), s);
+    P->lptr.upload(P->lptr_host.data(), P->lptr_host.size(), s);
+    plan_levels(ul, nu, rows, P->uptr_host, P->uplan);
+    P->urows.upload(rows.data(), rows.size(), s);
+    P->uptr.upload(P->uptr_host.data(), P->uptr_host.size(), s);
+  }
   P->diag.upload(diag.data(), diag.size(), s);
   P->lu.alloc((size_t)nnz * (is_complex ? 2 : 1));
   P->info.alloc(2);
   P->scale.alloc(1);
   CUDA_TRY(cudaStreamSynchronize(s));       // the host vectors die here
   P->nlevels_lower = nl; P->nlevels_upper = nu;
+  P->symbolic_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return P;
 }
 
 void ilu0_numeric(Ilu0& P, const double* vals, long long* launches) {
   const size_t bytes = (size_t)P.nnz * (P.cplx ? 2 : 1) * sizeof(double);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, P.s));
   if (bytes) CUDA_TRY(cudaMemcpyAsync(P.lu.p, vals, bytes, cudaMemcpyDeviceToDevice, P.s));
   P.info.zero(P.s);
-  if (P.n == 0) return;
+  if (P.n == 0) { cudaEventDestroy(e0); cudaEventDestroy(e1); return; }
   if (P.cplx) max_abs2_diag<true><<<1, 256, 0, P.s>>>(P.diag.p, reinterpret_cast<const double2*>(P.lu.p), (int)P.n, P.scale.p);
   else max_abs2_diag<false><<<1, 256, 0, P.s>>>(P.diag.p, P.lu.p, (int)P.n, P.scale.p);
   double m2 = 0.0;
@@ -281,17 +367,35 @@ void ilu0_numeric(Ilu0& P, const double* vals, long long* launches) {
   // a pivot below eps * max|a_ii| is replaced (counted in info[0]); non-finite pivots are counted in info[1]
   const double tiny2 = m2 * 2.3e-16 * 2.3e-16;
   if (launches) ++*launches;
-  if (P.cplx) run_plan<true, ST_FACTOR>(P, P.lplan, P.lptr_host, P.lrows.p, P.lptr.p, nullptr, nullptr, tiny2, P.s, launches);
+  if (P.block_rows) {
+    if (P.cplx) run_blocks<true, ST_FACTOR>(P, P.lrows.p, P.lptr.p, P.lblk.p, nullptr, nullptr, tiny2, P.s, launches);
+    else run_blocks<false, ST_FACTOR>(P, P.lrows.p, P.lptr.p, P.lblk.p, nullptr, nullptr, tiny2, P.s, launches);
+  } else if (P.cplx) run_plan<true, ST_FACTOR>(P, P.lplan, P.lptr_host, P.lrows.p, P.lptr.p, nullptr, nullptr, tiny2, P.s, launches);
   else run_plan<false, ST_FACTOR>(P, P.lplan, P.lptr_host, P.lrows.p, P.lptr.p, nullptr, nullptr, tiny2, P.s, launches);
   int info[2] = {0, 0};
   CUDA_TRY(cudaMemcpyAsync(info, P.info.p, sizeof info, cudaMemcpyDeviceToHost, P.s));
+  CUDA_TRY(cudaEventRecord(e1, P.s));
   CUDA_TRY(cudaStreamSynchronize(P.s));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  P.numeric_ms = ms;
   P.perturbed = info[0]; P.nonfinite = info[1];
 }
 
 // z = U^-1 L^-1 r   (r and z may not alias)
 void ilu0_apply(Ilu0& P, const double* r, double* z, long long* launches) {
   if (P.n == 0) return;
+  if (P.block_rows) {
+    if (P.cplx) {
+      run_blocks<true, ST_LOWER>(P, P.lrows.p, P.lptr.p, P.lblk.p, r, z, 0.0, P.s, launches);
+      run_blocks<true, ST_UPPER>(P, P.urows.p, P.uptr.p, P.ublk.p, r, z, 0.0, P.s, launches);
+    } else {
+      run_blocks<false, ST_LOWER>(P, P.lrows.p, P.lptr.p, P.lblk.p, r, z, 0.0, P.s, launches);
+      run_blocks<false, ST_UPPER>(P, P.urows.p, P.uptr.p, P.ublk.p, r, z, 0.0, P.s, launches);
+    }
+    return;
+  }
   if (P.cplx) {
     run_plan<true, ST_LOWER>(P, P.lplan, P.lptr_host, P.lrows.p, P.lptr.p, r, z, 0.0, P.s, launches);
     run_plan<true, ST_UPPER>(P, P.uplan, P.uptr_host, P.urows.p, P.uptr.p, r, z, 0.0, P.s, launches);

@@ -450,8 +450,10 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
   // Right-preconditioned restarted GMRES with ONE batched reduction per iteration: w = A M^-1 v_j is
   // written into the next basis slot, <v_0..v_j, w> and <w, w> come out of one multidot (and, on a
   // row-partitioned system, one all-reduce); the norm of the orthogonalised vector follows from
-  // Pythagoras.  When that difference cancels (less than 5 % of |w|^2 left) a second classical
-  // Gram-Schmidt pass is made (CGS2).
+  // Pythagoras.  When that difference cancels (less than half of |w|^2 left: the Daniel-Gragg-Kaufman-
+  // Stewart criterion) a second classical Gram-Schmidt pass is made (CGS2).  A laxer test (5 %) lost
+  // the orthogonality of the basis with a good preconditioner (A M^-1 close to the identity: every
+  // w is nearly parallel to v_j) - ILU(0)-GMRES then needed 87 iterations where CG needs 35.
   const int m = S.opts.restart;
   const long long n = S.n;
   const size_t ld = (size_t)S.nalloc * S.sc;
@@ -508,7 +510,7 @@ int gmres(SolverState& S, const double* b, double* x, vlfs_solve_stats* st) {
       };
       double hn2 = tail2(h);
       S.gemv_sub_(S.V.p, j + 1, h.data(), wj);
-      if (!(hn2 > 0.05 * h[j + 1].real())) {                // cancellation: second Gram-Schmidt pass
+      if (!(hn2 > 0.5 * h[j + 1].real())) {                 // cancellation (|w_orth| < |w|/sqrt 2, the 'twice is enough' test): second Gram-Schmidt pass
         S.multidot(S.V.p, j + 2, wj, h2.data());
         hn2 = tail2(h2);
         S.gemv_sub_(S.V.p, j + 1, h2.data(), wj);
