@@ -634,6 +634,12 @@ def cpu_solve_baseline():
             "spmv_GBs": sp_bytes / sp_s / 1e9, "spmv_ms": sp_s * 1e3,
             "solve_s_per_step": lu_s, "solver": "scipy.sparse.linalg.splu (SuperLU) + triangular solves",
             "fill_entries": int(lu.L.nnz + lu.U.nnz),
+            # same-config estimate: the sample is Y1 coarsened 4 x 2 in the plane (quasi-2-D mesh, 3 layers deep);
+            # a sparse LU of a 2-D-like mesh costs ~ n^1.5 flops (nested dissection bound; SuperLU's COLAMD
+            # ordering does not do better), so the whole workload is >= 8^1.5 = 22.6 x this time on one core
+            "extrapolated_full_workload_s": lu_s * 8 ** 1.5,
+            "extrapolation_basis": "measured sample time x (N_Y1/N_sample)^1.5 = x 22.6 (flops of a sparse LU on a "
+                                   "quasi-2-D mesh); lower bound, SuperLU is single-threaded here",
             "rel_residual": float(np.linalg.norm(A @ xs - b) / np.linalg.norm(b))}
 
 
