@@ -4,10 +4,11 @@
 // (src/Khabakhpasheva_time_domain.jl:258-266, src/Periodic_Beam.jl:107-116) and
 // inside every Krylov iteration of the solve that stands in for `LUSolver()`
 // (src/Yago_freq_domain.jl:171).  HBM-bound: nnz*(sT+4) + 4(N+1) + 2*N*sT bytes.
-// A group of TPR lanes owns a row; values are streamed with 128-bit loads, x is
+// A group of TPR lanes owns a row (8 lanes for the 30-100 entries per row of these operators); values are streamed, x is
 // gathered through the read-only path (it lives in the 126 MB L2), the row sum is a
 // shuffle reduction.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -186,7 +187,7 @@ void launch_residual_dd(const int* rowptr, const int* colind, const void* vals, 
                         const double* b, double* r, long long nrows, long long nnz, int is_complex, int nsm, cudaStream_t s) {
   if (nrows == 0) return;
   const double avg = (double)nnz / (double)nrows;
-  const int tpr = avg >= 24 ? 32 : 8;
+  const int tpr = avg >= 128 ? 32 : 8;      // (same finding as for the plain product: few lanes per row)
   long long grid = (nrows + 256 / tpr - 1) / (256 / tpr);
   if (grid > (long long)nsm * 64) grid = (long long)nsm * 64;
   const double* v = (const double*)vals;
@@ -226,7 +227,15 @@ void launch_spmv_rows(const int* rowptr, const int* colind, const void* vals, co
                       const double* beta, int nsm, cudaStream_t s) {
   if (nrows == 0) return;
   double avg = (double)nnz / (double)nrows;
-  int tpr = avg >= 48 ? 32 : avg >= 24 ? 16 : avg >= 12 ? 8 : 4;
+  // lanes per row: about 8-10 entries per lane.  Measured on Y1 (76 entries per row, B200, profiles/r2_spmv_lanes.md):
+  // 32 lanes 0.79 / 0.64 of the HBM peak (complex / real), 16 lanes 0.94 / 0.78, 8 lanes 0.95 / 0.85, 4 lanes 0.87 / 0.77 -
+  // with 32 lanes a 76-entry row leaves a 12-entry tail on a quarter of the warp and pays a 5-step reduction per row
+  int tpr = avg >= 256 ? 32 : avg >= 128 ? 16 : avg >= 20 ? 8 : 4;
+  // tuning hooks (lanes per row of the real / complex product)
+  static const int tpr_real = getenv("VLFS_SPMV_TPR_REAL") ? atoi(getenv("VLFS_SPMV_TPR_REAL")) : 0;
+  static const int tpr_cplx = getenv("VLFS_SPMV_TPR_CPLX") ? atoi(getenv("VLFS_SPMV_TPR_CPLX")) : 0;
+  const int forced = is_complex ? tpr_cplx : tpr_real;
+  if (forced == 4 || forced == 8 || forced == 16 || forced == 32) tpr = forced;
   long long rows_per_block = 256 / tpr;
   long long grid = (nrows + rows_per_block - 1) / rows_per_block;
   long long cap = (long long)nsm * 8 * 8;
