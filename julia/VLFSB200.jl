@@ -167,9 +167,18 @@ function get_vector(s::System, vec::Integer=0)
   b
 end
 
-function solver_setup!(s::System, mat=0; method=SOLVER_GMRES, precond=PRECOND_SPARSE_LU, restart=30, maxit=60, rtol=1e-12)
-  o = SolverOpts(method, precond, restart, maxit, rtol, 0, 0)
-  check(s, ccall((:vlfs_solver_setup, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{SolverOpts}), s.ctx, mat, o))
+# block_rows > 0 with PRECOND_BLOCK_ILU0: block Jacobi of ILU(0) blocks of that many consecutive rows
+function solver_setup!(s::System, mat=0; method=SOLVER_GMRES, precond=PRECOND_SPARSE_LU, restart=30, maxit=60, rtol=1e-12,
+                       block_rows=0)
+  o = SolverOpts(method, precond, restart, maxit, rtol, block_rows, 0)
+  check(s, ccall((:vlfs_solver_setup, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{SolverOpts}), s.ctx, mat, o); allow=(VLFS_OK, 4))
+end
+
+# z = M⁻¹ r with the preconditioner of the last solver_setup! (Jacobi, ILU(0), sparse LU)
+function precond_apply(s::System, r::Vector)
+  z = similar(r)
+  check(s, ccall((:vlfs_precond_apply, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), s.ctx, r, z))
+  z
 end
 
 function solve!(x::Vector, s::System, b::Vector)
