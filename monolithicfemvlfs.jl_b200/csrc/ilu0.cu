@@ -202,51 +202,6 @@ __global__ void max_abs2_diag(const int* __restrict__ diag, const typename Num<C
   if (threadIdx.x == 0) *out = sm[0];
 }
 
-// rows ordered by level (counting sort); launch plan = wide levels alone, runs of small levels together
-void plan_levels(const std::vector<int>& level, int nlev, std::vector<int>& rows, std::vector<int>& lptr,
-                 std::vector<Ilu0Launch>& plan) {
-  const int n = (int)level.size();
-  lptr.assign((size_t)nlev + 1, 0);
-  for (int i = 0; i < n; ++i) ++lptr[(size_t)level[i] + 1];
-  for (int l = 0; l < nlev; ++l) lptr[(size_t)l + 1] += lptr[l];
-  rows.resize(n);
-  std::vector<int> fill(lptr.begin(), lptr.end() - 1);
-  for (int i = 0; i < n; ++i) rows[(size_t)fill[level[i]]++] = i;          // ascending row id inside a level
-  plan.clear();
-  for (int l = 0; l < nlev;) {
-    const int sz = lptr[(size_t)l + 1] - lptr[l];
-    if (sz > 32) { plan.push_back({l, l + 1, 0}); ++l; continue; }
-    int e = l;
-    while (e < nlev && lptr[(size_t)e + 1] - lptr[e] <= 32) ++e;
-    plan.push_back({l, e, 1});
-    l = e;
-  }
-}
-
-// rows ordered by (block, level); lptr holds the level boundaries of every block followed by one terminating
-// entry per block, blk_lev[b] the first lptr entry of block b
-void plan_blocks(const std::vector<int>& level, long long n, int block_rows, std::vector<int>& rows, std::vector<int>& lptr,
-                 std::vector<int>& blk_lev, int* max_levels) {
-  const int nb = (int)((n + block_rows - 1) / block_rows);
-  rows.resize((size_t)n);
-  lptr.clear(); blk_lev.assign((size_t)nb + 1, 0);
-  *max_levels = 0;
-  std::vector<int> cnt;
-  for (int b = 0; b < nb; ++b) {
-    const long long r0 = (long long)b * block_rows, r1 = std::min(n, r0 + block_rows);
-    int nl = 0;
-    for (long long i = r0; i < r1; ++i) nl = std::max(nl, level[(size_t)i] + 1);
-    cnt.assign((size_t)nl + 1, 0);
-    for (long long i = r0; i < r1; ++i) ++cnt[(size_t)level[(size_t)i] + 1];
-    for (int l = 0; l < nl; ++l) cnt[(size_t)l + 1] += cnt[l];
-    blk_lev[b] = (int)lptr.size();
-    for (int l = 0; l <= nl; ++l) lptr.push_back((int)r0 + cnt[l]);
-    for (long long i = r0; i < r1; ++i) rows[(size_t)(r0 + cnt[level[(size_t)i]]++)] = (int)i;
-    *max_levels = std::max(*max_levels, nl);
-  }
-  blk_lev[nb] = (int)lptr.size();
-}
-
 template <bool CX, int STAGE>
 void run_blocks(const Ilu0& P, const int* rows, const int* lptr, const int* blk_lev, const double* r, double* z,
                 double tiny2, cudaStream_t s, long long* launches) {
@@ -259,13 +214,13 @@ void run_blocks(const Ilu0& P, const int* rows, const int* lptr, const int* blk_
 }
 
 template <bool CX, int STAGE>
-void run_plan(const Ilu0& P, const std::vector<Ilu0Launch>& plan, const std::vector<int>& lptr_host, const int* rows,
+void run_plan(const Ilu0& P, const std::vector<vlfs_ilu::Launch>& plan, const std::vector<int>& lptr_host, const int* rows,
               const int* lptr, const double* r, double* z, double tiny2, cudaStream_t s, long long* launches) {
   using T = typename Num<CX>::T;
   T* lu = reinterpret_cast<T*>(P.lu.p);
   const T* rr = reinterpret_cast<const T*>(r);
   T* zz = reinterpret_cast<T*>(z);
-  for (const Ilu0Launch& L : plan) {
+  for (const vlfs_ilu::Launch& L : plan) {
     if (L.chain) {
       ilu0_chain<CX, STAGE><<<1, 1024, 0, s>>>(rows, lptr, L.l0, L.l1, (int)P.n, P.rowptr, P.colind, P.diag.p, lu, rr, zz, tiny2, P.info.p);
     } else {
@@ -285,10 +240,6 @@ std::unique_ptr<Ilu0> ilu0_symbolic(const int* rowptr_dev, const int* colind_dev
   const auto t0 = std::chrono::steady_clock::now();
   std::unique_ptr<Ilu0> P(new Ilu0());
   P->n = n; P->cplx = is_complex; P->rowptr = rowptr_dev; P->colind = colind_dev; P->s = s;
-  if (block_rows < 0 || block_rows >= n) block_rows = 0;                 // one block: the ILU(0) of the whole owned block
-  P->block_rows = block_rows;
-  P->nblocks = block_rows ? (int)((n + block_rows - 1) / block_rows) : 1;
-  const long long B = block_rows ? block_rows : (n > 0 ? n : 1);
   std::vector<int> rp((size_t)n + 1);
   CUDA_TRY(cudaMemcpyAsync(rp.data(), rowptr_dev, rp.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -297,49 +248,20 @@ std::unique_ptr<Ilu0> ilu0_symbolic(const int* rowptr_dev, const int* colind_dev
   if (nnz) CUDA_TRY(cudaMemcpyAsync(ci.data(), colind_dev, ci.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   P->nnz = nnz;
-  std::vector<int> diag((size_t)n), ll((size_t)n, 0), ul((size_t)n, 0);
-  int nl = 0, nu = 0;
-  for (long long i = 0; i < n; ++i) {
-    int d = -1, lev = 0;
-    for (int p = rp[(size_t)i]; p < rp[(size_t)i + 1]; ++p) {
-      const int c = ci[(size_t)p];
-      if (p > rp[(size_t)i] && c <= ci[(size_t)p - 1]) throw std::string("ILU0: column indices of a row must be strictly ascending");
-      if (c < i) { if (c >= i / B * B) lev = std::max(lev, ll[(size_t)c] + 1); }     // couplings inside the diagonal block only
-      else if (c == i) d = p;
-    }
-    if (d < 0) throw std::string("ILU0: structurally zero diagonal in row ") + std::to_string(i);
-    diag[(size_t)i] = d; ll[(size_t)i] = lev; nl = std::max(nl, lev + 1);
-  }
-  for (long long i = n - 1; i >= 0; --i) {
-    int lev = 0;
-    for (int p = diag[(size_t)i] + 1; p < rp[(size_t)i + 1]; ++p) {
-      const int c = ci[(size_t)p];
-      if (c < std::min(n, (i / B + 1) * B)) lev = std::max(lev, ul[(size_t)c] + 1);
-    }
-    ul[(size_t)i] = lev; nu = std::max(nu, lev + 1);
-  }
-  if (n == 0) { nl = nu = 0; }
-  std::vector<int> rows, lptr;
-  if (block_rows) {
-    std::vector<int> bl;
-    plan_blocks(ll, n, block_rows, rows, P->lptr_host, bl, &nl);
-    P->lrows.upload(rows.data(), rows.size(), s);
-    P->lptr.upload(P->lptr_host.data(), P->lptr_host.size(), s);
-    P->lblk.upload(bl.data(), bl.size(), s);
-    plan_blocks(ul, n, block_rows, rows, P->uptr_host, bl, &nu);
-    P->urows.upload(rows.data(), rows.size(), s);
-    P->uptr.upload(P->uptr_host.data(), P->uptr_host.size(), s);
-    P->ublk.upload(bl.data(), bl.size(), s);
-    P->lplan.assign(1, Ilu0Launch{0, nl, 1});
-    P->uplan.assign(1, Ilu0Launch{0, nu, 1});
-    CUDA_TRY(cudaStreamSynchronize(s));     // bl dies at scope exit
-  } else {
-    plan_levels(ll, nl, rows, P->lptr_host, P->lplan);
-    P->lrows.upload(rows.data(), rows.size(), s);
-    P->lptr.upload(P->lptr_host.data(), P->lptr_host.size(), s);
-    plan_levels(ul, nu, rows, P->uptr_host, P->uplan);
-    P->urows.upload(rows.data(), rows.size(), s);
-    P->uptr.upload(P->uptr_host.data(), P->uptr_host.size(), s);
+  vlfs_ilu::Analysis A = vlfs_ilu::analyze(n, rp.data(), ci.data(), block_rows);      // ilu0_host.hpp (CPU-tested)
+  P->block_rows = A.block_rows;
+  P->nblocks = A.nblocks;
+  const std::vector<int>& diag = A.diag;
+  const int nl = A.lower.nlevels, nu = A.upper.nlevels;
+  P->lptr_host = A.lower.lptr; P->uptr_host = A.upper.lptr;
+  P->lplan = A.lower.plan; P->uplan = A.upper.plan;
+  P->lrows.upload(A.lower.rows.data(), A.lower.rows.size(), s);
+  P->lptr.upload(A.lower.lptr.data(), A.lower.lptr.size(), s);
+  P->urows.upload(A.upper.rows.data(), A.upper.rows.size(), s);
+  P->uptr.upload(A.upper.lptr.data(), A.upper.lptr.size(), s);
+  if (A.block_rows) {
+    P->lblk.upload(A.lower.blk.data(), A.lower.blk.size(), s);
+    P->ublk.upload(A.upper.blk.data(), A.upper.blk.size(), s);
   }
   P->diag.upload(diag.data(), diag.size(), s);
   P->lu.alloc((size_t)nnz * (is_complex ? 2 : 1));

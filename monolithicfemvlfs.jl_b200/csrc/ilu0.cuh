@@ -2,8 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include <memory>
-
-struct Ilu0Launch { int l0, l1, chain; };     // levels [l0,l1): one wide level (chain = 0) or a run of small ones
+#include "ilu0_host.hpp"
 
 struct Ilu0 {
   long long n = 0, nnz = 0;                    // owned rows; entries of those rows
@@ -15,7 +14,7 @@ struct Ilu0 {
   DevBuf<int> diag, lrows, lptr, urows, uptr, lblk, ublk, info;
   DevBuf<double> lu, scale;
   std::vector<int> lptr_host, uptr_host;
-  std::vector<Ilu0Launch> lplan, uplan;
+  std::vector<vlfs_ilu::Launch> lplan, uplan;
   int nlevels_lower = 0, nlevels_upper = 0;
   long long perturbed = 0, nonfinite = 0;      // pivot statistics of the last factorisation
   double symbolic_ms = 0, numeric_ms = 0;      // host analysis (wall), last factorisation (CUDA events)
