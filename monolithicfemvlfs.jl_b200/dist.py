@@ -310,9 +310,13 @@ class GpuOps:
         self.device = torch.device("cuda", dsys.device)
         self.n_owned, self.n_local = dsys.n_owned, dsys.n_local
         self.lib, self.ctx = self.sys.lib, self.sys.ctx
+        # the torch ops of this class and the library's kernels must share ONE stream, or halo / Schur data
+        # race silently: bound here, not left to the caller (vlfs_set_stream refuses once a solver exists,
+        # so constructing GpuOps after solver_setup fails loudly instead)
+        self.bind_stream()
 
     def bind_stream(self):
-        """Run the library on torch's current stream (call before solver_setup)."""
+        """Run the library on torch's current stream (done by the constructor; before solver_setup)."""
         s = self.torch.cuda.current_stream(self.device).cuda_stream
         self.sys._check(self.lib.vlfs_set_stream(self.ctx, C.c_void_p(s)))
 
