@@ -150,6 +150,9 @@ function build_pattern!(s::System)
 end
 
 assemble!(s::System) = check(s, ccall((:vlfs_assemble, LIB), Cint, (Ptr{Cvoid},), s.ctx))
+# only the matrices / only the right-hand sides (a sweep by basis matrices re-integrates the vectors alone)
+assemble_matrices!(s::System) = check(s, ccall((:vlfs_assemble_matrices, LIB), Cint, (Ptr{Cvoid},), s.ctx))
+assemble_vectors!(s::System) = check(s, ccall((:vlfs_assemble_vectors, LIB), Cint, (Ptr{Cvoid},), s.ctx))
 
 # The matrix as Gridap's default type: SparseMatrixCSC{T,Int64}, 1-based, explicit zeros kept.
 function get_matrix(s::System, mat::Integer=0)
@@ -215,7 +218,7 @@ function spmv(s::System, x::Vector, mat::Integer=0)
 end
 
 # keep the symbolic analysis, refactorise the current values (next ω of a sweep)
-refactor!(s::System, mat::Integer=0) = check(s, ccall((:vlfs_solver_refactor, LIB), Cint, (Ptr{Cvoid}, Cint), s.ctx, mat))
+refactor!(s::System, mat::Integer=0) = check(s, ccall((:vlfs_solver_refactor, LIB), Cint, (Ptr{Cvoid}, Cint), s.ctx, mat); allow=(VLFS_OK, 4))
 
 function solve_vec!(x::Vector, s::System, vec::Integer=0)
   st = SolveStats()
