@@ -56,7 +56,8 @@ def test_julia_shim_binds_the_reference_facing_calls():
               "vlfs_add_rhs_term", "vlfs_set_term_coef", "vlfs_set_rhs_coef", "vlfs_set_weights", "vlfs_build_pattern",
               "vlfs_get_pattern_csc", "vlfs_assemble", "vlfs_get_values", "vlfs_get_vector", "vlfs_combine", "vlfs_spmv",
               "vlfs_set_dof_coords", "vlfs_solver_setup", "vlfs_solver_refactor", "vlfs_solve", "vlfs_solve_vec",
-              "vlfs_newmark_run", "vlfs_eval_functional"]
+              "vlfs_newmark_run", "vlfs_eval_functional", "vlfs_add_work_matrix", "vlfs_precond_apply",
+              "vlfs_assemble_vectors", "vlfs_assemble_matrices"]
     assert [n for n in needed if ":" + n not in jl] == []
     assert "UNTESTED" in jl
 
